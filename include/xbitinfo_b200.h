@@ -1,0 +1,128 @@
+/*
+ * xbitinfo_b200 -- C ABI of the B200-native bit-information hot path.
+ *
+ * This is the drop-in boundary.  The reference (observingClouds/xbitinfo) has no FFI of
+ * its own: its "operator interface" for this path is a pair of Python functions,
+ *
+ *   _py_get_bitinformation(ds, var, axis, dim, kwargs) -> {"bitinfo": f64[nbits], ...}
+ *       xbitinfo/xbitinfo.py:337-370, selected by the `implementation=` string at
+ *       xbitinfo/xbitinfo.py:424-439; arithmetic in xbitinfo/_py_bitinfo.py:42-160
+ *   _np_bitround(data, keepbits) -> ndarray
+ *       xbitinfo/bitround.py:7-12 (arithmetic: numcodecs.bitround.BitRound)
+ *
+ * The entry points below are what a ctypes binding of those two functions calls
+ * (INTEGRATION.md shows the stub).  Conventions:
+ *   - plain pointers and sizes only; every function returns 0 on success, otherwise a
+ *     non-zero code (XBI_ERR_* or a cudaError_t value offset by XBI_ERR_CUDA_BASE) and
+ *     xbi_last_error() returns a thread-local message;
+ *   - *_dev pointers are device memory owned by the caller; kernels are ordered on the
+ *     given stream (a cudaStream_t passed as void*, NULL = default stream); nothing is
+ *     allocated or cached by the device-level calls, so they are re-entrant from
+ *     several host threads (dask workers);
+ *   - an array is described as a C-contiguous (outer, n, inner) view: the analysed
+ *     axis has length n, `outer` is the product of the dimensions before it, `inner`
+ *     the product of those after it;
+ *   - counts are ACCUMULATED (+=) into counts_dev so slabs, shards and halo rows
+ *     compose; the caller zeroes it once.  When a caller splits the analysed axis
+ *     itself it passes an n that includes one halo row of the next slab.
+ */
+#ifndef XBITINFO_B200_H
+#define XBITINFO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XBI_ABI_VERSION 1
+
+/* element types.  Signed integers are passed as the unsigned type of the same width
+ * (the reference reinterprets them: xbitinfo/xbitinfo.py:355). */
+enum xbi_dtype {
+    XBI_U8 = 0,
+    XBI_U16 = 1,
+    XBI_U32 = 2,
+    XBI_U64 = 3,
+    XBI_F16 = 4,
+    XBI_F32 = 5,
+    XBI_F64 = 6
+};
+
+/* flags of xbi_count_pairs */
+#define XBI_SIGNED_EXPONENT 1u /* floats: biased -> sign-magnitude exponent (_py_bitinfo.py:42-94) */
+#define XBI_MASK_NAN 2u        /* floats: a pair with a NaN element (any payload) is not counted   */
+#define XBI_MASK_VALUE 4u      /* a pair with an element bit-identical to mask_bits is not counted */
+#define XBI_FORCE_GENERIC 8u   /* testing: skip the TMA fast paths                                  */
+
+/* error codes */
+#define XBI_OK 0
+#define XBI_ERR_ARG 1
+#define XBI_ERR_UNSUPPORTED 2
+#define XBI_ERR_NO_DEVICE 3
+#define XBI_ERR_CUDA_BASE 1000 /* + cudaError_t */
+
+int xbi_abi_version(void);
+const char* xbi_last_error(void);
+/* number of kernels this library has launched so far in this process (all threads) */
+unsigned long long xbi_kernel_launches(void);
+
+/* bytes of device scratch xbi_count_pairs needs (contents are overwritten) */
+size_t xbi_workspace_bytes(void);
+
+/*
+ * K1: per-bit adjacent-pair histogram.   Replaces pb.bitinformation's counting
+ * (xbitinfo/_py_bitinfo.py:97-140, 155-160) fused with pb.signed_exponent (42-94).
+ *
+ * counts_dev: nbits*4 unsigned 64-bit counters, nbits = 8*sizeof(element);
+ *   counts_dev[4*k + 2*a + b] += #pairs whose bit k (k = 0 is the most significant bit)
+ *   is `a` in the first and `b` in the second element -- the (nbits,2,2) layout of
+ *   bitpaircount (_py_bitinfo.py:128-140).
+ * mask_bits: element bit pattern for XBI_MASK_VALUE (low bits used for narrow types).
+ */
+int xbi_count_pairs(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner,
+                    unsigned flags, uint64_t mask_bits, unsigned long long* counts_dev,
+                    void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
+ * K2: mutual information per bit from the counts, in bits.  Replaces
+ * pb.mutual_information (xbitinfo/_py_bitinfo.py:143-152): p = c/N, zero cells skipped,
+ * sum p*log(p/(pr*ps)) in the reference's order, / log(2), IEEE double, no FMA
+ * contraction.  N = sum of the four cells (0 pairs -> NaN).  With
+ * set_zero_insignificant != 0 every value <= the binomial free entropy at `confidence`
+ * is set to 0 (BitInformation.jl semantics).
+ */
+int xbi_mutual_information(const unsigned long long* counts_dev, int nbits,
+                           int set_zero_insignificant, double confidence, double* mi_dev,
+                           void* stream);
+
+/*
+ * K3: round to nearest (ties to even) keeping `keepbits` explicit mantissa bits, in
+ * place.  Replaces the arithmetic of _np_bitround (xbitinfo/bitround.py:7-12).
+ * dtype must be XBI_F16/F32/F64; keepbits == mantissa bits is the identity;
+ * keepbits < 0 or > mantissa bits -> XBI_ERR_ARG (numcodecs raises ValueError).
+ */
+int xbi_bitround_inplace(void* x_dev, int dtype, int64_t numel, int keepbits, void* stream);
+
+/*
+ * Host-buffer entry points: what the numpy-facing plugin functions call.  Data is
+ * streamed host -> device in slabs through a double-buffered staging area on `device`
+ * (allocated on first use per host thread, released by xbi_host_release), counted /
+ * rounded there, and only nbits doubles (or the rounded array) come back.
+ *   xbi_bitinformation_host: counts_host (nbits*4, may be NULL) is overwritten, not
+ *   accumulated; mi_host receives nbits doubles.
+ *   xbi_bitround_host: src_host and dst_host may be the same buffer.
+ */
+int xbi_bitinformation_host(const void* x_host, int dtype, int64_t outer, int64_t n,
+                            int64_t inner, unsigned flags, uint64_t mask_bits,
+                            int set_zero_insignificant, double confidence, double* mi_host,
+                            unsigned long long* counts_host, int device);
+int xbi_bitround_host(const void* src_host, void* dst_host, int dtype, int64_t numel,
+                      int keepbits, int device);
+void xbi_host_release(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XBITINFO_B200_H */

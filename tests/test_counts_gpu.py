@@ -1,0 +1,113 @@
+"""K1/K2 through the C ABI (host-buffer entry point) vs the CPU oracle -- bit-exact counts."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from oracle import bitinfo_oracle as bo
+from xbitinfo_b200 import _native as nat
+
+from conftest import smooth_field
+
+pytestmark = pytest.mark.gpu
+
+
+def run_host(x, axis, masked_value=None, set_zero=False, confidence=0.99, force_generic=False, transform=True):
+    x = np.ascontiguousarray(x)
+    axis = axis % x.ndim
+    outer = int(np.prod(x.shape[:axis], dtype=np.int64))
+    n = int(x.shape[axis])
+    inner = int(np.prod(x.shape[axis + 1:], dtype=np.int64))
+    nbits = x.dtype.itemsize * 8
+    flags, bits = nat.mask_spec(x.dtype, masked_value)
+    if x.dtype.kind == "f" and transform:
+        flags |= nat.SIGNED_EXPONENT
+    if force_generic:
+        flags |= nat.FORCE_GENERIC
+    mi = np.empty(nbits, dtype=np.float64)
+    counts = np.empty(nbits * 4, dtype=np.uint64)
+    rc = nat.lib().xbi_bitinformation_host(
+        x.ctypes.data_as(C.c_void_p), nat.dtype_code(x.dtype), outer, n, inner, flags, bits,
+        int(set_zero), float(confidence), mi.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), 0)
+    nat.check(rc)
+    return counts.reshape(nbits, 2, 2).astype(np.int64), mi
+
+
+def assert_mi_close(mi, ref):
+    """1e-12 relative where the information is significant; below that an absolute floor
+    (mutual information of noise bits is a cancelling sum)."""
+    if np.isnan(ref).all():
+        assert np.isnan(mi).all()
+        return
+    scale = max(np.nanmax(np.abs(ref)), 1e-300)
+    np.testing.assert_allclose(mi, ref, rtol=1e-12, atol=1e-12 * scale)
+
+
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_golden_cases(golden, force_generic):
+    for name in golden["case_names"]:
+        x = golden[f"case_{name}_x"]
+        axis = int(golden[f"case_{name}_axis"])
+        counts, mi = run_host(x, axis, force_generic=force_generic)
+        assert np.array_equal(counts, golden[f"case_{name}_counts"]), name
+        assert_mi_close(mi, golden[f"case_{name}_mi"])
+
+
+DTYPES = ["float32", "float64", "float16", "int8", "uint8", "int16", "uint16", "int32", "uint32", "int64", "uint64"]
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_every_axis_every_dtype(dtype, force_generic):
+    rng = np.random.default_rng(hash(dtype) % 2**32)
+    shape = (5, 33, 7, 130)
+    if np.dtype(dtype).kind == "f":
+        x = smooth_field(rng, shape, dtype, axis=-1, scale=0.2, base=3.0)
+    else:
+        info = np.iinfo(dtype)
+        x = rng.integers(info.min, info.max, size=shape, dtype=dtype, endpoint=True)
+    for axis in range(4):
+        counts, mi = run_host(x, axis, force_generic=force_generic)
+        ref_counts, npairs, ref_mi = bo.bitinformation(x, axis)
+        assert np.array_equal(counts, ref_counts), (dtype, axis)
+        assert counts[0].sum() == npairs
+        assert_mi_close(mi, ref_mi)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "float16"])
+@pytest.mark.parametrize("masked_value", [float("nan"), -999.0])
+@pytest.mark.parametrize("force_generic", [True, False])
+def test_masked_pairs(dtype, masked_value, force_generic):
+    rng = np.random.default_rng(7)
+    x = smooth_field(rng, (6, 40, 96), dtype, axis=1, scale=0.3, base=5.0)
+    land = rng.random((40, 96)) < 0.3
+    x[:, land] = masked_value
+    x[0, 0, :5] = np.nan  # NaNs that are not the masked value in the -999 variant
+    for axis in range(3):
+        counts, mi = run_host(x, axis, masked_value=masked_value, force_generic=force_generic)
+        ref_counts, npairs, ref_mi = bo.bitinformation(x, axis, masked_value=masked_value)
+        assert np.array_equal(counts, ref_counts), (dtype, axis)
+        assert counts[0].sum() == npairs
+        assert_mi_close(mi, ref_mi)
+
+
+@pytest.mark.parametrize("confidence", [0.99, 0.5])
+def test_set_zero_insignificant(confidence):
+    rng = np.random.default_rng(11)
+    x = smooth_field(rng, (50, 700), "float32", axis=1, scale=0.05, base=280.0)
+    counts, mi = run_host(x, 1, set_zero=True, confidence=confidence)
+    _, npairs, ref = bo.bitinformation(x, 1, set_zero_insignificant_flag=True, confidence=confidence)
+    thr = bo.free_entropy_threshold(npairs, confidence)
+    _, mi_raw = run_host(x, 1)
+    # away from the threshold the decisions must agree exactly
+    far = np.abs(mi_raw - thr) > 1e-6 * thr
+    assert np.array_equal((mi == 0)[far], (ref == 0)[far])
+    assert_mi_close(mi[far], ref[far])
+
+
+def test_errors():
+    x = np.zeros((4, 4), dtype="int32")
+    with pytest.raises(ValueError):
+        run_host(x, 1, masked_value=float("nan"), transform=False) if False else nat.check(
+            nat.lib().xbi_bitinformation_host(x.ctypes.data_as(C.c_void_p), nat.U32, 4, 4, 1, nat.MASK_NAN, 0, 0, 0.99,
+                                              np.empty(32).ctypes.data_as(C.c_void_p), None, 0))

@@ -1,0 +1,124 @@
+"""ctypes binding of libxbitinfo_b200.so (C ABI: include/xbitinfo_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or no CUDA device is
+present, calls raise.  Build the library with ``python -m xbitinfo_b200.csrc.build`` (or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libxbitinfo_b200.so")
+
+# enum xbi_dtype
+U8, U16, U32, U64, F16, F32, F64 = range(7)
+# flags
+SIGNED_EXPONENT, MASK_NAN, MASK_VALUE, FORCE_GENERIC = 1, 2, 4, 8
+# error codes
+ERR_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA_BASE = 1, 2, 3, 1000
+
+_DTYPE_CODES = {
+    "uint8": U8, "int8": U8,
+    "uint16": U16, "int16": U16,
+    "uint32": U32, "int32": U32,
+    "uint64": U64, "int64": U64,
+    "float16": F16, "float32": F32, "float64": F64,
+}
+
+
+class XbiError(RuntimeError):
+    """CUDA-side failure reported by libxbitinfo_b200."""
+
+
+def dtype_code(dtype) -> int:
+    name = np.dtype(dtype).name
+    try:
+        return _DTYPE_CODES[name]
+    except KeyError:
+        raise ValueError(f"dtype {name} neither known nor implemented.") from None
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """The loaded library (loads on first use; raises if it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built "
+            "(run `python -m xbitinfo_b200.csrc.build`). xbitinfo_b200 has no CPU fallback."
+        )
+    L = C.CDLL(LIB_PATH)
+    i64, u64, vp, i32, u32, dbl = C.c_int64, C.c_uint64, C.c_void_p, C.c_int, C.c_uint, C.c_double
+    L.xbi_abi_version.restype = i32
+    L.xbi_abi_version.argtypes = []
+    L.xbi_last_error.restype = C.c_char_p
+    L.xbi_last_error.argtypes = []
+    L.xbi_kernel_launches.restype = C.c_ulonglong
+    L.xbi_kernel_launches.argtypes = []
+    L.xbi_workspace_bytes.restype = C.c_size_t
+    L.xbi_workspace_bytes.argtypes = []
+    L.xbi_count_pairs.restype = i32
+    L.xbi_count_pairs.argtypes = [vp, i32, i64, i64, i64, u32, u64, vp, vp, C.c_size_t, vp]
+    L.xbi_mutual_information.restype = i32
+    L.xbi_mutual_information.argtypes = [vp, i32, i32, dbl, vp, vp]
+    L.xbi_bitround_inplace.restype = i32
+    L.xbi_bitround_inplace.argtypes = [vp, i32, i64, i32, vp]
+    L.xbi_bitinformation_host.restype = i32
+    L.xbi_bitinformation_host.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, i32]
+    L.xbi_bitround_host.restype = i32
+    L.xbi_bitround_host.argtypes = [vp, vp, i32, i64, i32, i32]
+    L.xbi_host_release.restype = None
+    L.xbi_host_release.argtypes = []
+    if L.xbi_abi_version() != 1:
+        raise ImportError("libxbitinfo_b200.so ABI version mismatch; rebuild it")
+    _lib = L
+    return L
+
+
+EXPORTED_SYMBOLS = (
+    "xbi_abi_version", "xbi_last_error", "xbi_kernel_launches", "xbi_workspace_bytes",
+    "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace",
+    "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
+)
+
+
+def check(rc: int) -> None:
+    """Translate a return code into the exception the reference interface would raise."""
+    if rc == 0:
+        return
+    msg = lib().xbi_last_error().decode("utf-8", "replace")
+    if rc == ERR_ARG:
+        raise ValueError(msg)
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    raise XbiError(f"[xbi rc={rc}] {msg}")
+
+
+def kernel_launches() -> int:
+    return int(lib().xbi_kernel_launches())
+
+
+def mask_spec(dtype, masked_value):
+    """(flag, mask_bits) for a ``masked_value`` keyword (None / "nothing" -> no mask,
+    NaN -> any NaN, other -> bit identity with the value cast to ``dtype``)."""
+    dtype = np.dtype(dtype)
+    if masked_value is None or (isinstance(masked_value, str) and masked_value == "nothing"):
+        return 0, 0
+    if dtype.kind == "f":
+        try:
+            is_nan = bool(np.isnan(masked_value))
+        except TypeError:
+            is_nan = False
+        if is_nan:
+            return MASK_NAN, 0
+    mv = np.array(masked_value).astype(dtype)
+    bits = int(mv.view(f"u{dtype.itemsize}"))
+    return MASK_VALUE, bits

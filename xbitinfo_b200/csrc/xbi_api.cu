@@ -1,0 +1,313 @@
+// C ABI of libxbitinfo_b200.so (declared in include/xbitinfo_b200.h).
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "xbi_common.cuh"
+#include "xbi_internal.h"
+
+namespace xbi {
+
+static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_launches{0};
+
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+static int fail_cuda(cudaError_t e, const char* where) {
+    g_last_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return XBI_ERR_CUDA_BASE + (int)e;
+}
+#define XBI_CUDA(call, where)                          \
+    do {                                               \
+        cudaError_t e__ = (call);                      \
+        if (e__ != cudaSuccess) return fail_cuda(e__, where); \
+    } while (0)
+
+static int make_job(CountJob& job, const void* x, int dtype, int64_t outer, int64_t n, int64_t inner,
+                    unsigned flags, uint64_t mask_bits) {
+    const int bytes = dtype_bytes(dtype);
+    if (bytes == 0) return fail(XBI_ERR_ARG, "unknown dtype code");
+    if (outer < 0 || n < 0 || inner < 0) return fail(XBI_ERR_ARG, "negative extent");
+    if ((flags & XBI_MASK_NAN) && (flags & XBI_MASK_VALUE))
+        return fail(XBI_ERR_ARG, "XBI_MASK_NAN and XBI_MASK_VALUE are mutually exclusive");
+    if ((flags & (XBI_SIGNED_EXPONENT | XBI_MASK_NAN)) && !dtype_is_float(dtype))
+        return fail(XBI_ERR_ARG, "XBI_SIGNED_EXPONENT / XBI_MASK_NAN need a floating-point dtype");
+    if (reinterpret_cast<uintptr_t>(x) % bytes != 0) return fail(XBI_ERR_ARG, "data pointer is not element-aligned");
+    job.x = x;
+    job.dtype = dtype;
+    job.transform = (flags & XBI_SIGNED_EXPONENT) != 0;
+    job.mask_mode = (flags & XBI_MASK_NAN) ? kMaskNaN : (flags & XBI_MASK_VALUE) ? kMaskValue : kMaskNone;
+    job.mask_bits = bytes == 8 ? mask_bits : (mask_bits & ((1ull << (8 * bytes)) - 1ull));
+    job.outer = outer;
+    job.n = n;
+    job.inner = inner;
+    return XBI_OK;
+}
+
+static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long long* counts_dev, Workspace* ws,
+                            cudaStream_t stream) {
+    const int nbits = 8 * dtype_bytes(job.dtype);
+    const int64_t numel = job.outer * job.n * job.inner;
+    if (numel == 0 || job.n < 2) return XBI_OK;  // no pairs along the axis: nothing to add
+    XBI_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), stream), "cudaMemsetAsync(workspace)");
+    const int64_t npairs_flat = numel - job.inner;
+    int64_t dlo = 0, dhi = 0;
+    if (!(flags & XBI_FORCE_GENERIC))
+        XBI_CUDA(launch_pairs_tma(job, npairs_flat, &ws->plus, stream, &dlo, &dhi), "pair counting (TMA path)");
+    if (dhi <= dlo) { dlo = 0; dhi = 0; }
+    XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
+    XBI_CUDA(launch_pairs_generic_flat(job, dhi, npairs_flat, &ws->plus, stream), "pair counting (generic, tail)");
+    XBI_CUDA(launch_pairs_generic_edges(job, &ws->minus, stream), "pair counting (edge pairs)");
+    XBI_CUDA(launch_combine(ws, nbits, counts_dev, stream), "combine");
+    return XBI_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// host-buffer path: per-thread staging context
+// ---------------------------------------------------------------------------------
+struct HostCtx {
+    int device = -1;
+    size_t buf_bytes = 0;
+    void* buf[2] = {nullptr, nullptr};
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    Workspace* ws[2] = {nullptr, nullptr};
+    unsigned long long* counts = nullptr;  // 64*4
+    double* mi = nullptr;                  // 64
+    void release() {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        for (int i = 0; i < 2; ++i) {
+            if (stream[i]) { cudaStreamSynchronize(stream[i]); cudaStreamDestroy(stream[i]); }
+            if (buf[i]) cudaFree(buf[i]);
+            if (ws[i]) cudaFree(ws[i]);
+            stream[i] = nullptr; buf[i] = nullptr; ws[i] = nullptr;
+        }
+        if (counts) cudaFree(counts);
+        if (mi) cudaFree(mi);
+        counts = nullptr; mi = nullptr;
+        device = -1;
+        buf_bytes = 0;
+    }
+    ~HostCtx() {}  // process teardown order is not ours to rely on; explicit xbi_host_release() frees
+};
+static thread_local HostCtx g_ctx;
+
+static int ensure_ctx(int device) {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(XBI_ERR_NO_DEVICE, "no CUDA device available (xbitinfo_b200 has no CPU fallback)");
+    }
+    if (device < 0 || device >= ndev) return fail(XBI_ERR_ARG, "device index out of range");
+    if (g_ctx.device == device) { XBI_CUDA(cudaSetDevice(device), "cudaSetDevice"); return XBI_OK; }
+    g_ctx.release();
+    XBI_CUDA(cudaSetDevice(device), "cudaSetDevice");
+    size_t mb = 256;
+    if (const char* env = std::getenv("XBI_STAGING_MB")) {
+        const long v = std::atol(env);
+        if (v >= 1 && v <= 65536) mb = (size_t)v;
+    }
+    g_ctx.buf_bytes = mb << 20;
+    g_ctx.device = device;
+    for (int i = 0; i < 2; ++i) {
+        XBI_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream[i], cudaStreamNonBlocking), "cudaStreamCreate");
+        XBI_CUDA(cudaMalloc(&g_ctx.buf[i], g_ctx.buf_bytes), "cudaMalloc(staging)");
+        XBI_CUDA(cudaMalloc(&g_ctx.ws[i], sizeof(Workspace)), "cudaMalloc(workspace)");
+    }
+    XBI_CUDA(cudaMalloc(&g_ctx.counts, 64 * 4 * sizeof(unsigned long long)), "cudaMalloc(counts)");
+    XBI_CUDA(cudaMalloc(&g_ctx.mi, 64 * sizeof(double)), "cudaMalloc(mi)");
+    return XBI_OK;
+}
+
+}  // namespace xbi
+
+using namespace xbi;
+
+extern "C" {
+
+int xbi_abi_version(void) { return XBI_ABI_VERSION; }
+const char* xbi_last_error(void) { return g_last_error.c_str(); }
+unsigned long long xbi_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+size_t xbi_workspace_bytes(void) { return sizeof(Workspace); }
+
+int xbi_count_pairs(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner, unsigned flags,
+                    uint64_t mask_bits, unsigned long long* counts_dev, void* workspace_dev, size_t workspace_bytes,
+                    void* stream) {
+    if (!counts_dev || !workspace_dev) return fail(XBI_ERR_ARG, "null counts or workspace pointer");
+    if (workspace_bytes < sizeof(Workspace)) return fail(XBI_ERR_ARG, "workspace smaller than xbi_workspace_bytes()");
+    if (reinterpret_cast<uintptr_t>(workspace_dev) % 8 != 0) return fail(XBI_ERR_ARG, "workspace must be 8-byte aligned");
+    CountJob job;
+    if (int rc = make_job(job, x_dev, dtype, outer, n, inner, flags, mask_bits)) return rc;
+    if (!x_dev && outer * n * inner > 0) return fail(XBI_ERR_ARG, "null data pointer");
+    return count_pairs_impl(job, flags, counts_dev, static_cast<Workspace*>(workspace_dev),
+                            static_cast<cudaStream_t>(stream));
+}
+
+int xbi_mutual_information(const unsigned long long* counts_dev, int nbits, int set_zero_insignificant,
+                           double confidence, double* mi_dev, void* stream) {
+    if (!counts_dev || !mi_dev) return fail(XBI_ERR_ARG, "null pointer");
+    if (nbits < 1 || nbits > 64) return fail(XBI_ERR_ARG, "nbits must be in 1..64");
+    double z = 0.0;
+    if (set_zero_insignificant) {
+        if (!(confidence > 0.0 && confidence < 1.0)) return fail(XBI_ERR_ARG, "confidence must be in (0,1)");
+        z = normal_quantile(1.0 - (1.0 - confidence) / 2.0);
+    }
+    XBI_CUDA(launch_mutual_information(counts_dev, nbits, set_zero_insignificant ? 1 : 0, z, mi_dev,
+                                       static_cast<cudaStream_t>(stream)),
+             "mutual information");
+    return XBI_OK;
+}
+
+static int check_bitround_args(int dtype, int64_t numel, int keepbits) {
+    if (!dtype_is_float(dtype)) return fail(XBI_ERR_ARG, "Only float arrays (16-64bit) can be bit-rounded");
+    const int mant = dtype == XBI_F16 ? 10 : dtype == XBI_F32 ? 23 : 52;
+    if (keepbits < 0) return fail(XBI_ERR_ARG, "keepbits must be zero or positive");
+    if (keepbits > mant) return fail(XBI_ERR_ARG, "keepbits too large for given dtype");
+    if (numel < 0) return fail(XBI_ERR_ARG, "negative numel");
+    return XBI_OK;
+}
+
+int xbi_bitround_inplace(void* x_dev, int dtype, int64_t numel, int keepbits, void* stream) {
+    if (int rc = check_bitround_args(dtype, numel, keepbits)) return rc;
+    if (numel == 0) return XBI_OK;
+    if (!x_dev) return fail(XBI_ERR_ARG, "null data pointer");
+    if (reinterpret_cast<uintptr_t>(x_dev) % dtype_bytes(dtype) != 0)
+        return fail(XBI_ERR_ARG, "data pointer is not element-aligned");
+    XBI_CUDA(launch_bitround(x_dev, dtype, numel, keepbits, static_cast<cudaStream_t>(stream)), "bitround");
+    return XBI_OK;
+}
+
+// Slab plan for streaming a host (outer, n, inner) array through a staging buffer.
+//   mode 0: whole blocks   -- `blocks` consecutive outer indices per slab (1-D copy)
+//   mode 1: column strips  -- all n rows x `cols` columns of one outer index (2-D copy)
+//   mode 2: row strips     -- `rows` (+1 halo) rows x `cols` columns of one outer index
+int xbi_bitinformation_host(const void* x_host, int dtype, int64_t outer, int64_t n, int64_t inner, unsigned flags,
+                            uint64_t mask_bits, int set_zero_insignificant, double confidence, double* mi_host,
+                            unsigned long long* counts_host, int device) {
+    if (!mi_host) return fail(XBI_ERR_ARG, "null mi_host");
+    CountJob probe;
+    if (int rc = make_job(probe, x_host, dtype, outer, n, inner, flags, mask_bits)) return rc;
+    if (int rc = ensure_ctx(device)) return rc;
+    HostCtx& c = g_ctx;
+    const int bytes = dtype_bytes(dtype);
+    const int nbits = 8 * bytes;
+    const int64_t numel = outer * n * inner;
+    if (numel > 0 && !x_host) return fail(XBI_ERR_ARG, "null data pointer");
+    XBI_CUDA(cudaMemsetAsync(c.counts, 0, 64 * 4 * sizeof(unsigned long long), c.stream[0]), "memset(counts)");
+    XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+
+    const char* src = static_cast<const char*>(x_host);
+    const int64_t cap = (int64_t)(c.buf_bytes / bytes);  // elements per staging buffer
+    int which = 0;
+    auto submit = [&](const void* from, size_t src_pitch, int64_t rows, int64_t cols, int64_t so, int64_t sn,
+                      int64_t si) -> int {
+        cudaStream_t st = c.stream[which];
+        // the stream's previous slab (copy + kernels) must be finished before its buffer is reused:
+        // same-stream ordering guarantees that.
+        if (src_pitch == (size_t)cols * bytes || rows == 1) {
+            XBI_CUDA(cudaMemcpyAsync(c.buf[which], from, (size_t)rows * cols * bytes, cudaMemcpyHostToDevice, st),
+                     "cudaMemcpyAsync(H2D)");
+        } else {
+            XBI_CUDA(cudaMemcpy2DAsync(c.buf[which], (size_t)cols * bytes, from, src_pitch, (size_t)cols * bytes,
+                                       (size_t)rows, cudaMemcpyHostToDevice, st),
+                     "cudaMemcpy2DAsync(H2D)");
+        }
+        CountJob job = probe;
+        job.x = c.buf[which];
+        job.outer = so; job.n = sn; job.inner = si;
+        if (int rc = count_pairs_impl(job, flags, c.counts, c.ws[which], st)) return rc;
+        which ^= 1;
+        return XBI_OK;
+    };
+
+    if (numel > 0 && n >= 2) {
+        const int64_t block = n * inner;
+        if (block <= cap) {
+            const int64_t per = cap / block;
+            for (int64_t o = 0; o < outer; o += per) {
+                const int64_t k = (outer - o < per) ? (outer - o) : per;
+                if (int rc = submit(src + (size_t)o * block * bytes, (size_t)block * k * bytes, 1, block * k, k, n, inner))
+                    return rc;
+            }
+        } else {
+            // strips of one outer index.  Column strips keep 16-byte multiples so the fast
+            // path stays eligible; row strips carry one halo row (the first row of the next strip).
+            const int64_t gran = 64;
+            int64_t cols, rows_per = 0;
+            const bool all_rows = n <= cap;
+            if (all_rows) {
+                cols = cap / n;
+                if (cols >= inner) cols = inner;
+                else if (cols >= gran) cols -= cols % gran;
+            } else {
+                cols = inner < gran ? inner : gran;
+                rows_per = cap / cols - 1;
+                if (rows_per < 1)
+                    return fail(XBI_ERR_UNSUPPORTED, "staging buffer too small for this shape; raise XBI_STAGING_MB");
+            }
+            const size_t pitch = (size_t)inner * bytes;
+            for (int64_t o = 0; o < outer; ++o) {
+                for (int64_t c0 = 0; c0 < inner; c0 += cols) {
+                    const int64_t w = (inner - c0 < cols) ? (inner - c0) : cols;
+                    if (all_rows) {
+                        const char* from = src + ((size_t)(o * n) * inner + c0) * bytes;
+                        if (int rc = submit(from, pitch, n, w, 1, n, w)) return rc;
+                    } else {
+                        for (int64_t r0 = 0; r0 < n - 1; r0 += rows_per) {
+                            const int64_t take = (n - r0 < rows_per + 1) ? (n - r0) : (rows_per + 1);
+                            const char* from = src + ((size_t)(o * n + r0) * inner + c0) * bytes;
+                            if (int rc = submit(from, pitch, take, w, 1, take, w)) return rc;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+    XBI_CUDA(cudaStreamSynchronize(c.stream[1]), "sync");
+    if (int rc = xbi_mutual_information(c.counts, nbits, set_zero_insignificant, confidence, c.mi, c.stream[0]))
+        return rc;
+    XBI_CUDA(cudaMemcpyAsync(mi_host, c.mi, nbits * sizeof(double), cudaMemcpyDeviceToHost, c.stream[0]), "D2H(mi)");
+    if (counts_host)
+        XBI_CUDA(cudaMemcpyAsync(counts_host, c.counts, (size_t)nbits * 4 * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, c.stream[0]),
+                 "D2H(counts)");
+    XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+    return XBI_OK;
+}
+
+int xbi_bitround_host(const void* src_host, void* dst_host, int dtype, int64_t numel, int keepbits, int device) {
+    if (int rc = check_bitround_args(dtype, numel, keepbits)) return rc;
+    if (numel == 0) return XBI_OK;
+    if (!src_host || !dst_host) return fail(XBI_ERR_ARG, "null pointer");
+    if (int rc = ensure_ctx(device)) return rc;
+    HostCtx& c = g_ctx;
+    const int bytes = dtype_bytes(dtype);
+    const int64_t cap = (int64_t)(c.buf_bytes / bytes);
+    int which = 0;
+    for (int64_t off = 0; off < numel; off += cap) {
+        const int64_t k = (numel - off < cap) ? (numel - off) : cap;
+        cudaStream_t st = c.stream[which];
+        XBI_CUDA(cudaMemcpyAsync(c.buf[which], static_cast<const char*>(src_host) + (size_t)off * bytes,
+                                 (size_t)k * bytes, cudaMemcpyHostToDevice, st),
+                 "cudaMemcpyAsync(H2D)");
+        XBI_CUDA(launch_bitround(c.buf[which], dtype, k, keepbits, st), "bitround");
+        XBI_CUDA(cudaMemcpyAsync(static_cast<char*>(dst_host) + (size_t)off * bytes, c.buf[which], (size_t)k * bytes,
+                                 cudaMemcpyDeviceToHost, st),
+                 "cudaMemcpyAsync(D2H)");
+        which ^= 1;
+    }
+    XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+    XBI_CUDA(cudaStreamSynchronize(c.stream[1]), "sync");
+    return XBI_OK;
+}
+
+void xbi_host_release(void) { g_ctx.release(); }
+
+}  // extern "C"

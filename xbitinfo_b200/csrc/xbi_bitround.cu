@@ -1,0 +1,134 @@
+// K3: bitround -- round to nearest, ties to even, keeping `keepbits` explicit mantissa
+// bits, in place, on the integer view of the IEEE bits.  Replaces the arithmetic behind
+// _np_bitround (xbitinfo/bitround.py:7-12, numcodecs BitRound): with drop = M - keepbits
+//     b += ((b >> drop) & 1) + (2^(drop-1) - 1);   b &= ~(2^drop - 1)
+// (wrapping add).  Pure streaming kernel: one 128-bit load and one 128-bit store per
+// 16 bytes, 2 x numel x itemsize bytes of HBM traffic.
+#include "xbi_common.cuh"
+#include "xbi_internal.h"
+
+namespace xbi {
+
+namespace {
+
+__device__ __forceinline__ uint32_t round32(uint32_t b, uint32_t drop, uint32_t half_m1, uint32_t keep) {
+    return (b + ((b >> drop) & 1u) + half_m1) & keep;
+}
+__device__ __forceinline__ uint32_t round16x2(uint32_t w, uint32_t drop, uint32_t half_m1, uint32_t keep) {
+    // the two halves must not carry into each other: round them in separate registers
+    const uint32_t lo = ((w & 0xFFFFu) + (((w & 0xFFFFu) >> drop) & 1u) + half_m1) & keep;
+    const uint32_t hi = ((w >> 16) + (((w >> 16) >> drop) & 1u) + half_m1) & keep;
+    return (lo & 0xFFFFu) | (hi << 16);
+}
+__device__ __forceinline__ unsigned long long round64(unsigned long long b, uint32_t drop, unsigned long long half_m1,
+                                                      unsigned long long keep) {
+    return (b + ((b >> drop) & 1ull) + half_m1) & keep;
+}
+
+template <int BYTES>
+__device__ __forceinline__ uint4 round_vec(uint4 v, uint32_t drop, unsigned long long half_m1, unsigned long long keep) {
+    if (BYTES == 4) {
+        v.x = round32(v.x, drop, (uint32_t)half_m1, (uint32_t)keep);
+        v.y = round32(v.y, drop, (uint32_t)half_m1, (uint32_t)keep);
+        v.z = round32(v.z, drop, (uint32_t)half_m1, (uint32_t)keep);
+        v.w = round32(v.w, drop, (uint32_t)half_m1, (uint32_t)keep);
+    } else if (BYTES == 2) {
+        v.x = round16x2(v.x, drop, (uint32_t)half_m1, (uint32_t)keep);
+        v.y = round16x2(v.y, drop, (uint32_t)half_m1, (uint32_t)keep);
+        v.z = round16x2(v.z, drop, (uint32_t)half_m1, (uint32_t)keep);
+        v.w = round16x2(v.w, drop, (uint32_t)half_m1, (uint32_t)keep);
+    } else {
+        unsigned long long a = ((unsigned long long)v.y << 32) | v.x;
+        unsigned long long b = ((unsigned long long)v.w << 32) | v.z;
+        a = round64(a, drop, half_m1, keep);
+        b = round64(b, drop, half_m1, keep);
+        v.x = (uint32_t)a; v.y = (uint32_t)(a >> 32);
+        v.z = (uint32_t)b; v.w = (uint32_t)(b >> 32);
+    }
+    return v;
+}
+
+template <int BYTES>
+__device__ __forceinline__ void round_scalar(void* x, long long i, uint32_t drop, unsigned long long half_m1,
+                                             unsigned long long keep) {
+    if (BYTES == 2) {
+        uint16_t* p = static_cast<uint16_t*>(x) + i;
+        const uint32_t b = *p;
+        *p = (uint16_t)((b + ((b >> drop) & 1u) + (uint32_t)half_m1) & (uint32_t)keep);
+    } else if (BYTES == 4) {
+        uint32_t* p = static_cast<uint32_t*>(x) + i;
+        *p = round32(*p, drop, (uint32_t)half_m1, (uint32_t)keep);
+    } else {
+        unsigned long long* p = static_cast<unsigned long long*>(x) + i;
+        *p = round64(*p, drop, half_m1, keep);
+    }
+}
+
+constexpr int kThreads = 256;
+constexpr int kVecPerThread = 4;  // 4 independent 128-bit loads in flight per thread
+
+// head: elements before the first 16-byte boundary; nvec: number of whole 16-byte vectors
+template <int BYTES>
+__global__ void __launch_bounds__(kThreads)
+k_bitround(void* __restrict__ x, long long numel, long long head, long long nvec, uint32_t drop,
+           unsigned long long half_m1, unsigned long long keep) {
+    constexpr int EPV = 16 / BYTES;
+    uint4* vbase = reinterpret_cast<uint4*>(static_cast<char*>(x) + head * BYTES);
+    const long long stride = (long long)gridDim.x * kThreads * kVecPerThread;
+    for (long long base = (long long)blockIdx.x * kThreads * kVecPerThread; base < nvec; base += stride) {
+        uint4 v[kVecPerThread];
+#pragma unroll
+        for (int u = 0; u < kVecPerThread; ++u) {
+            const long long i = base + (long long)u * kThreads + threadIdx.x;
+            if (i < nvec) v[u] = vbase[i];
+        }
+#pragma unroll
+        for (int u = 0; u < kVecPerThread; ++u) {
+            const long long i = base + (long long)u * kThreads + threadIdx.x;
+            if (i < nvec) vbase[i] = round_vec<BYTES>(v[u], drop, half_m1, keep);
+        }
+    }
+    // ragged ends (fewer than 2 vectors' worth of elements in total)
+    if (blockIdx.x == 0) {
+        const long long tail0 = head + nvec * EPV;
+        for (long long i = threadIdx.x; i < head; i += kThreads) round_scalar<BYTES>(x, i, drop, half_m1, keep);
+        for (long long i = tail0 + threadIdx.x; i < numel; i += kThreads) round_scalar<BYTES>(x, i, drop, half_m1, keep);
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cudaStream_t stream) {
+    if (numel <= 0) return cudaSuccess;
+    const int bytes = dtype_bytes(dtype);
+    const int mant = dtype == XBI_F16 ? 10 : dtype == XBI_F32 ? 23 : 52;
+    const uint32_t drop = (uint32_t)(mant - keepbits);
+    if (drop == 0) return cudaSuccess;  // identity
+    const int width = bytes * 8;
+    const unsigned long long full = width == 64 ? ~0ull : ((1ull << width) - 1ull);
+    const unsigned long long keep = (full >> drop) << drop;
+    const unsigned long long half_m1 = (1ull << (drop - 1)) - 1ull;
+
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(x);
+    long long head = (long long)(((16 - (addr & 15)) & 15) / bytes);
+    if (head > numel) head = numel;
+    const long long nvec = (numel - head) / (16 / bytes);
+
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    long long blocks = (nvec + (long long)kThreads * kVecPerThread - 1) / ((long long)kThreads * kVecPerThread);
+    const long long cap = (long long)sms * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    switch (bytes) {
+        case 2: k_bitround<2><<<(unsigned)blocks, kThreads, 0, stream>>>(x, numel, head, nvec, drop, half_m1, keep); break;
+        case 4: k_bitround<4><<<(unsigned)blocks, kThreads, 0, stream>>>(x, numel, head, nvec, drop, half_m1, keep); break;
+        case 8: k_bitround<8><<<(unsigned)blocks, kThreads, 0, stream>>>(x, numel, head, nvec, drop, half_m1, keep); break;
+        default: return cudaErrorInvalidValue;
+    }
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace xbi

@@ -1,0 +1,210 @@
+// Shared device-side building blocks of the bit-pair counting kernels (sm_100a).
+//
+// What is counted (reference: xbitinfo/_py_bitinfo.py:97-160): for every bit position k
+// of the analysis word and every adjacent pair (a, b) = (X[j], X[j+1]) along one axis,
+// the 2x2 histogram of (bit k of a, bit k of b).  The histogram is recovered from three
+// per-bit population counts and the pair count N:
+//     A  = #pairs with a_k = 1      B = #pairs with b_k = 1      AB = #pairs with both
+//     [[N-A-B+AB, B-AB], [A-AB, AB]]
+// so the kernels only ever have to add up bit planes of three word streams.
+//
+// How it is counted: "vertical" (bit-sliced) counters.  Each thread keeps, per stream, a
+// small stack of 32-bit registers; bit p of register r is binary digit r of the running
+// count for bit position p.  Sixteen input words are folded in with a tree of 15
+// carry-save adders (2 LOP3 each), higher digits are reached through a short ladder of
+// deferred carry-save adders and a ripple counter.  Cost ~2 LOP3 per word and stream,
+// independent of the data.  Population counts are only extracted at flush time, by a
+// 5-step butterfly across the warp that leaves lane L holding the count of bit position L.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace xbi {
+
+// ---------------------------------------------------------------------------------
+// raw accumulator block in device memory (part of the caller-provided workspace)
+// ---------------------------------------------------------------------------------
+// sums[s][j]: stream s in {A, B, AB}, j = bit number inside the element counted from the
+// least significant bit.  "plus" collects every flat pair (f, f+inner); "minus" collects
+// the flat pairs that straddle two rows/blocks of the analysed axis and therefore are
+// not pairs of the reference (they are subtracted in the combine kernel).
+struct RawSums {
+    unsigned long long sums[3][64];
+    unsigned long long npairs;
+    unsigned long long pad[7];
+};
+struct Workspace {
+    RawSums plus;
+    RawSums minus;
+};
+
+enum Stream { S_A = 0, S_B = 1, S_AB = 2 };
+
+// ---------------------------------------------------------------------------------
+// carry-save adder on bit planes: (hi, lo) = a + b + c per bit position
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t u = a ^ b;
+    hi = (a & b) | (u & c);  // majority  -> one LOP3 (0xE8)
+    lo = u ^ c;              // parity    -> one LOP3 (0x96)
+}
+
+// ---------------------------------------------------------------------------------
+// Vertical counter.  DYN deferred carry-save levels (each holds a plane and a pending
+// carry), UP ripple planes on top.  One "chunk" = 16 words.  Capacity between flushes:
+// kFlushChunks chunks (chosen so that no digit can overflow).
+// ---------------------------------------------------------------------------------
+template <int DYN, int UP>
+struct Ladder {
+    static constexpr int kPlanes = 4 + DYN + UP;
+    static constexpr uint32_t kFlushChunks = 1u << (DYN + UP - 1);
+
+    uint32_t p[4];            // digits 0..3 (weights 1,2,4,8)
+    uint32_t P[DYN], Q[DYN];  // digit 4+l and its pending carry of the same weight
+    uint32_t U[UP];           // digits 4+DYN ...
+
+    __device__ __forceinline__ void clear() {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) p[i] = 0;
+#pragma unroll
+        for (int i = 0; i < DYN; ++i) { P[i] = 0; Q[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < UP; ++i) U[i] = 0;
+    }
+
+    // fold 16 words in; `it` is the number of chunks folded in since the last clear()
+    __device__ __forceinline__ void add16(const uint32_t (&w)[16], uint32_t it) {
+        uint32_t t0, t1, f0, f1, e0, e1, s;
+        csa(t0, p[0], p[0], w[0], w[1]);
+        csa(t1, p[0], p[0], w[2], w[3]);
+        csa(f0, p[1], p[1], t0, t1);
+        csa(t0, p[0], p[0], w[4], w[5]);
+        csa(t1, p[0], p[0], w[6], w[7]);
+        csa(f1, p[1], p[1], t0, t1);
+        csa(e0, p[2], p[2], f0, f1);
+        csa(t0, p[0], p[0], w[8], w[9]);
+        csa(t1, p[0], p[0], w[10], w[11]);
+        csa(f0, p[1], p[1], t0, t1);
+        csa(t0, p[0], p[0], w[12], w[13]);
+        csa(t1, p[0], p[0], w[14], w[15]);
+        csa(f1, p[1], p[1], t0, t1);
+        csa(e1, p[2], p[2], f0, f1);
+        csa(s, p[3], p[3], e0, e1);
+        push16(s, it);
+    }
+
+    // a carry word of weight 16 enters the deferred levels; which levels fire depends
+    // only on `it`, so the branches are uniform across the whole grid
+    __device__ __forceinline__ void push16(uint32_t carry, uint32_t it) {
+        bool parked = false;
+#pragma unroll
+        for (int l = 0; l < DYN; ++l) {
+            if (!parked) {
+                if (((it >> l) & 1u) == 0u) {
+                    Q[l] = carry;
+                    parked = true;
+                } else {
+                    csa(carry, P[l], P[l], Q[l], carry);
+                    Q[l] = 0;
+                }
+            }
+        }
+        if (!parked) {
+#pragma unroll
+            for (int j = 0; j < UP; ++j) {
+                uint32_t t = U[j] & carry;
+                U[j] ^= carry;
+                carry = t;
+            }
+        }
+    }
+
+    // add a single word of weight 1 (rare events only: costs 2 ops per plane)
+    __device__ __forceinline__ void add1_slow(uint32_t w) {
+        uint32_t carry = w;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { uint32_t t = p[j] & carry; p[j] ^= carry; carry = t; }
+#pragma unroll
+        for (int j = 0; j < DYN; ++j) { uint32_t t = P[j] & carry; P[j] ^= carry; carry = t; }
+#pragma unroll
+        for (int j = 0; j < UP; ++j) { uint32_t t = U[j] & carry; U[j] ^= carry; carry = t; }
+    }
+
+    // Extract: after the call, lane L of the warp returns the total (over the 32 lanes)
+    // count of bit position L.  Must be called by all 32 lanes.  Does not clear.
+    __device__ __forceinline__ uint32_t warp_totals(uint32_t lane) const {
+        constexpr int W = kPlanes + 6;
+        uint32_t n[W];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) n[i] = p[i];
+#pragma unroll
+        for (int i = 0; i < DYN; ++i) n[4 + i] = P[i];
+#pragma unroll
+        for (int i = 0; i < UP; ++i) n[4 + DYN + i] = U[i];
+#pragma unroll
+        for (int i = kPlanes; i < W; ++i) n[i] = 0;
+        // pending carries have the weight of their level
+#pragma unroll
+        for (int l = 0; l < DYN; ++l) {
+            uint32_t carry = Q[l];
+#pragma unroll
+            for (int j = 4 + l; j < kPlanes + 1; ++j) { uint32_t t = n[j] & carry; n[j] ^= carry; carry = t; }
+        }
+        // butterfly: at distance d the lane keeps the bit positions whose bit log2(d)
+        // equals its own, receives the partner's values for those positions and adds
+#pragma unroll
+        for (int step = 0; step < 5; ++step) {
+            const int d = 16 >> step;
+            // positions with bit log2(d) set: 16 -> 0xFFFF0000, 8 -> 0xFF00FF00, ...
+            const uint32_t hi_sel = (d == 16) ? 0xFFFF0000u : (d == 8) ? 0xFF00FF00u : (d == 4) ? 0xF0F0F0F0u
+                                   : (d == 2) ? 0xCCCCCCCCu : 0xAAAAAAAAu;
+            const uint32_t keep = (lane & d) ? hi_sel : ~hi_sel;
+            uint32_t carry = 0;
+#pragma unroll
+            for (int j = 0; j < kPlanes + 1 + step; ++j) {
+                uint32_t mine = n[j] & keep;
+                uint32_t give = n[j] & ~keep;
+                uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, give, d);
+                uint32_t hi;
+                csa(hi, n[j], mine, got, carry);
+                carry = hi;
+            }
+            n[kPlanes + 1 + step] = carry;
+        }
+        uint32_t total = 0;
+#pragma unroll
+        for (int j = 0; j < W; ++j) total |= ((n[j] >> lane) & 1u) << j;
+        return total;
+    }
+};
+
+// ---------------------------------------------------------------------------------
+// signed-exponent transform on raw IEEE words (reference: _py_bitinfo.py:42-94)
+//   field F -> F - bias if F >= bias, else ~F (within the field); sign, mantissa kept.
+// Closed form verified against the reference on every float16 pattern and on random
+// float32/float64 patterns (tests/test_oracle.py).
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t sexp_f32(uint32_t w) {
+    // |x| >= 1.0 or NaN  <=>  exponent field >= 127   (one FSETP with |.| modifier)
+    const bool big = !(fabsf(__uint_as_float(w)) < 1.0f);
+    return big ? (w - 0x3F800000u) : (w ^ 0x7F800000u);
+}
+__device__ __forceinline__ uint32_t sexp_f64_hi(uint32_t hi) {
+    // the high word of a double compares like a float: field >= 1023 <=> |hi| >= 0x3FF00000
+    const bool big = !(fabsf(__uint_as_float(hi)) < __uint_as_float(0x3FF00000u));
+    return big ? (hi - 0x3FF00000u) : (hi ^ 0x7FF00000u);
+}
+__device__ __forceinline__ uint32_t sexp_f16_single(uint32_t w) {  // one half in the low 16 bits
+    return ((w & 0x7C00u) >= 0x3C00u) ? (w - 0x3C00u) : (w ^ 0x7C00u);
+}
+__device__ __forceinline__ uint32_t sexp_f16x2(uint32_t w) {  // two halves packed in one word
+    // per-half 0xFFFF where field >= 15: compare the 15-bit magnitudes without carries
+    const uint32_t mag = w & 0x7FFF7FFFu;
+    // (mag + (0x8000 - 0x3C00)) sets bit 15 of a half iff its magnitude >= 0x3C00; no carry
+    // leaves the half because mag <= 0x7FFF
+    const uint32_t ge = ((mag + 0x44004400u) >> 15) & 0x00010001u;
+    const uint32_t m = ge * 0xFFFFu;  // 0xFFFF per selected half
+    return ((w - (m & 0x3C003C00u)) & m) | ((w ^ 0x7C007C00u) & ~m);
+}
+
+}  // namespace xbi

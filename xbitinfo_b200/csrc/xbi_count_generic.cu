@@ -1,0 +1,189 @@
+// K1, generic variant: bit-pair counting for any shape and any alignment.
+//
+// Every thread loads the two elements of a flat pair (f, f+inner) with scalar loads
+// (coalesced across the warp), applies the signed-exponent transform
+// (xbitinfo/_py_bitinfo.py:42-94) and the mask test, and folds the three word streams
+// a, b, a&b into vertical counters (xbi_common.cuh).  It serves
+//   * the ranges the TMA fast paths cannot take (unaligned bases, ragged tails),
+//   * the "edge" pairs between consecutive blocks of the analysed axis, which the
+//     flat formulation counts although the reference (_py_bitinfo.py:155-160) does not.
+#include "xbi_common.cuh"
+#include "xbi_elem.cuh"
+#include "xbi_internal.h"
+
+namespace xbi {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPairsPerTile = 16 * kThreads;
+
+template <int KIND, int MASK, bool XFORM, bool EDGE>
+__global__ void __launch_bounds__(kThreads)
+k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long long n, long long inner,
+                uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst) {
+    using E = Elem<KIND>;
+    constexpr int NW = E::kWords;
+    using L = Ladder<3, 6>;
+    L A[NW], B[NW], AB[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { A[w].clear(); B[w].clear(); AB[w].clear(); }
+    unsigned long long accA[NW], accB[NW], accAB[NW];
+#pragma unroll
+    for (int w = 0; w < NW; ++w) { accA[w] = 0; accB[w] = 0; accAB[w] = 0; }
+    uint32_t nvalid = 0;
+    unsigned long long nvalid_total = 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t it = 0;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            accA[w] += A[w].warp_totals(lane);
+            accB[w] += B[w].warp_totals(lane);
+            accAB[w] += AB[w].warp_totals(lane);
+            A[w].clear(); B[w].clear(); AB[w].clear();
+        }
+        nvalid_total += nvalid;
+        nvalid = 0;
+        it = 0;
+    };
+
+    const long long tiles = (count + kPairsPerTile - 1) / kPairsPerTile;
+    for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        uint32_t wa[NW][16], wb[NW][16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+            const long long t = tile * kPairsPerTile + (long long)u * kThreads + threadIdx.x;
+            uint32_t a[NW], b[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { a[w] = 0; b[w] = 0; }
+            if (t < count) {
+                long long f;
+                if (EDGE) {
+                    if (inner == 1) {
+                        f = t * n + (n - 1);
+                    } else {
+                        const long long o = t / inner;
+                        f = (o * n + (n - 1)) * inner + (t - o * inner);
+                    }
+                } else {
+                    f = lo + t;
+                }
+                E::load(x, f, a);
+                E::load(x, f + inner, b);
+                bool ok = true;
+                if (MASK == kMaskNaN) ok = !(E::is_nan(a) || E::is_nan(b));
+                if (MASK == kMaskValue) ok = !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
+                if (XFORM) { E::transform(a); E::transform(b); }
+                if (!ok) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { a[w] = 0; b[w] = 0; }
+                }
+                nvalid += ok ? 1u : 0u;
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { wa[w][u] = a[w]; wb[w][u] = b[w]; }
+        }
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            uint32_t wab[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) wab[u] = wa[w][u] & wb[w][u];
+            A[w].add16(wa[w], it);
+            B[w].add16(wb[w], it);
+            AB[w].add16(wab, it);
+        }
+        ++it;
+        if (it == L::kFlushChunks) flush();
+    }
+    flush();
+
+    // block reduction, then one atomic per non-zero counter and block
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_n;
+    for (int i = threadIdx.x; i < 3 * 64; i += kThreads) (&s_sum[0][0])[i] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+        const int j = w * 32 + lane;
+        if (accA[w]) atomicAdd(&s_sum[S_A][j], accA[w]);
+        if (accB[w]) atomicAdd(&s_sum[S_B][j], accB[w]);
+        if (accAB[w]) atomicAdd(&s_sum[S_AB][j], accAB[w]);
+    }
+    if (nvalid_total) atomicAdd(&s_n, nvalid_total);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 64; i += kThreads) {
+        const unsigned long long v = (&s_sum[0][0])[i];
+        if (v) atomicAdd(&dst->sums[0][0] + i, v);
+    }
+    if (threadIdx.x == 0 && s_n) atomicAdd(&dst->npairs, s_n);
+}
+
+template <int KIND, int MASK, bool XFORM, bool EDGE>
+cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
+    if (count <= 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long tiles = (count + kPairsPerTile - 1) / kPairsPerTile;
+    long long grid = (long long)sms * 4;
+    if (grid > tiles) grid = tiles;
+    k_pairs_generic<KIND, MASK, XFORM, EDGE><<<(unsigned)grid, kThreads, 0, stream>>>(
+        job.x, lo, count, job.n, job.inner, (uint32_t)(job.mask_bits & 0xFFFFFFFFu),
+        (uint32_t)(job.mask_bits >> 32), dst);
+    note_launch();
+    return cudaGetLastError();
+}
+
+template <int KIND, bool EDGE>
+cudaError_t dispatch_mask(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
+    constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
+    if (job.transform) {
+        if constexpr (isf) {
+            switch (job.mask_mode) {
+                case kMaskNone: return launch_one<KIND, kMaskNone, true, EDGE>(job, lo, count, dst, stream);
+                case kMaskNaN: return launch_one<KIND, kMaskNaN, true, EDGE>(job, lo, count, dst, stream);
+                default: return launch_one<KIND, kMaskValue, true, EDGE>(job, lo, count, dst, stream);
+            }
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    }
+    switch (job.mask_mode) {
+        case kMaskNone: return launch_one<KIND, kMaskNone, false, EDGE>(job, lo, count, dst, stream);
+        case kMaskNaN:
+            if constexpr (isf) return launch_one<KIND, kMaskNaN, false, EDGE>(job, lo, count, dst, stream);
+            return cudaErrorInvalidValue;
+        default: return launch_one<KIND, kMaskValue, false, EDGE>(job, lo, count, dst, stream);
+    }
+}
+
+template <bool EDGE>
+cudaError_t dispatch_kind(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
+    switch (job.dtype) {
+        case XBI_U8: return dispatch_mask<kU8, EDGE>(job, lo, count, dst, stream);
+        case XBI_U16: return dispatch_mask<kU16, EDGE>(job, lo, count, dst, stream);
+        case XBI_U32: return dispatch_mask<kU32, EDGE>(job, lo, count, dst, stream);
+        case XBI_U64: return dispatch_mask<kU64, EDGE>(job, lo, count, dst, stream);
+        case XBI_F16: return dispatch_mask<kF16, EDGE>(job, lo, count, dst, stream);
+        case XBI_F32: return dispatch_mask<kF32, EDGE>(job, lo, count, dst, stream);
+        case XBI_F64: return dispatch_mask<kF64, EDGE>(job, lo, count, dst, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_pairs_generic_flat(const CountJob& job, int64_t lo, int64_t hi, RawSums* dst,
+                                      cudaStream_t stream) {
+    return dispatch_kind<false>(job, lo, hi - lo, dst, stream);
+}
+
+cudaError_t launch_pairs_generic_edges(const CountJob& job, RawSums* dst, cudaStream_t stream) {
+    if (job.outer <= 1) return cudaSuccess;
+    return dispatch_kind<true>(job, 0, (job.outer - 1) * job.inner, dst, stream);
+}
+
+}  // namespace xbi

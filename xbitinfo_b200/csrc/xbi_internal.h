@@ -1,0 +1,64 @@
+// Host-side declarations shared by the translation units of libxbitinfo_b200.so.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/xbitinfo_b200.h"
+
+namespace xbi {
+
+struct Workspace;
+struct RawSums;
+
+// element kinds as template parameters (== enum xbi_dtype)
+constexpr int kU8 = XBI_U8, kU16 = XBI_U16, kU32 = XBI_U32, kU64 = XBI_U64;
+constexpr int kF16 = XBI_F16, kF32 = XBI_F32, kF64 = XBI_F64;
+
+// how masked elements are recognised
+constexpr int kMaskNone = 0, kMaskNaN = 1, kMaskValue = 2;
+
+inline int dtype_bytes(int dtype) {
+    switch (dtype) {
+        case XBI_U8: return 1;
+        case XBI_U16: case XBI_F16: return 2;
+        case XBI_U32: case XBI_F32: return 4;
+        case XBI_U64: case XBI_F64: return 8;
+        default: return 0;
+    }
+}
+inline bool dtype_is_float(int dtype) { return dtype >= XBI_F16 && dtype <= XBI_F64; }
+
+// Description of one counting job on a C-contiguous (outer, n, inner) array.
+struct CountJob {
+    const void* x;       // device pointer to element 0
+    int dtype;           // enum xbi_dtype
+    bool transform;      // signed-exponent transform (floats)
+    int mask_mode;       // kMaskNone / kMaskNaN / kMaskValue
+    uint64_t mask_bits;  // for kMaskValue
+    int64_t outer, n, inner;
+};
+
+void note_launch();  // bumps the process-wide launch counter
+
+// Flat pairs (f, f+inner) for f in [lo, hi) accumulated into `dst` -- any alignment.
+cudaError_t launch_pairs_generic_flat(const CountJob& job, int64_t lo, int64_t hi, RawSums* dst,
+                                      cudaStream_t stream);
+// The flat pairs that straddle two consecutive blocks of the analysed axis:
+// f = (o*n + n-1)*inner + i for o in [0, outer-1), i in [0, inner).
+cudaError_t launch_pairs_generic_edges(const CountJob& job, RawSums* dst, cudaStream_t stream);
+
+// TMA fast paths.  Each consumes as much of [0, numel-inner) as its alignment rules
+// allow, reports the flat range it covered in [*done_lo, *done_hi) (empty if none), and
+// leaves the rest to the generic kernel.
+cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream,
+                             int64_t* done_lo, int64_t* done_hi);
+
+cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* counts, cudaStream_t stream);
+cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, int set_zero,
+                                      double z_quantile, double* mi, cudaStream_t stream);
+cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cudaStream_t stream);
+
+double normal_quantile(double p);  // AS241, host
+
+}  // namespace xbi
