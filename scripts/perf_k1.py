@@ -1,0 +1,75 @@
+"""Quick K1/K3 timing on one GPU (development aid; bench.py is the judged harness)."""
+import argparse
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, ".")
+from xbitinfo_b200 import _native as nat
+from xbitinfo_b200.device import PairCounter, bitround_
+
+
+def synth(shape, dtype, axis=-1, seed=1234):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.empty(shape, dtype=torch.float32, device="cuda")
+    x.normal_(0.0, 0.3, generator=g)
+    x = torch.cumsum(x, dim=axis, out=x)
+    x += 280.0
+    return x.to(dtype)
+
+
+def timeit(fn, iters=5, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    return min(ts), sorted(ts)[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="1024,721,1440")
+    ap.add_argument("--dtype", default="float32")
+    ap.add_argument("--axis", type=int, default=-1)
+    ap.add_argument("--mask", default="none")
+    ap.add_argument("--check", action="store_true")
+    ap.add_argument("--bitround", action="store_true")
+    a = ap.parse_args()
+    shape = tuple(int(s) for s in a.shape.split(","))
+    dtype = getattr(torch, a.dtype)
+    if dtype.is_floating_point:
+        x = synth(shape, dtype, a.axis)
+    else:
+        x = torch.randint(-2**30, 2**30, shape, device="cuda", dtype=torch.int64).to(dtype)
+    mv = None if a.mask == "none" else float(a.mask)
+    nbytes = x.numel() * x.element_size()
+    pc = PairCounter(x.dtype, x.device)
+    l0 = nat.kernel_launches()
+    pc.add(x, a.axis, masked_value=mv)
+    torch.cuda.synchronize()
+    print("launches per call:", nat.kernel_launches() - l0)
+    best, med = timeit(lambda: pc.add(x, a.axis, masked_value=mv))
+    print(f"K1 {a.dtype} {shape} axis={a.axis} mask={a.mask}: best {best*1e3:.3f} ms  median {med*1e3:.3f} ms  "
+          f"{nbytes/best/1e9:.1f} GB/s best, {nbytes/med/1e9:.1f} GB/s median ({nbytes/1e9:.2f} GB)")
+    if a.check:
+        pc.reset(); pc.add(x, a.axis, masked_value=mv); fast = pc.counts.clone()
+        pc.reset(); pc.add(x, a.axis, masked_value=mv, force_generic=True); gen = pc.counts.clone()
+        bg, _ = timeit(lambda: pc.add(x, a.axis, masked_value=mv, force_generic=True), iters=2, warm=1)
+        print("fast == generic:", bool(torch.equal(fast, gen)), f"(generic {nbytes/bg/1e9:.1f} GB/s)")
+        print("pairs:", int(fast[0].sum()), "expected", x.numel() // shape[a.axis] * (shape[a.axis] - 1))
+    if a.bitround and dtype.is_floating_point:
+        y = x.clone()
+        best, med = timeit(lambda: bitround_(y, 7))
+        print(f"K3 bitround: best {best*1e3:.3f} ms  {2*nbytes/best/1e9:.1f} GB/s (read+write)")
+
+
+if __name__ == "__main__":
+    main()

@@ -44,9 +44,13 @@ enum Stream { S_A = 0, S_B = 1, S_AB = 2 };
 // carry-save adder on bit planes: (hi, lo) = a + b + c per bit position
 // ---------------------------------------------------------------------------------
 __device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint32_t b, uint32_t c) {
-    uint32_t u = a ^ b;
-    hi = (a & b) | (u & c);  // majority  -> one LOP3 (0xE8)
-    lo = u ^ c;              // parity    -> one LOP3 (0x96)
+    // written as explicit LOP3s: left to the optimiser, the xor/and chains of a whole adder
+    // tree get re-associated into ~60% more two-input operations
+    uint32_t h, l;
+    asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(h) : "r"(a), "r"(b), "r"(c));  // majority
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(l) : "r"(a), "r"(b), "r"(c));  // parity
+    hi = h;
+    lo = l;
 }
 
 // ---------------------------------------------------------------------------------
@@ -94,30 +98,28 @@ struct Ladder {
     }
 
     // a carry word of weight 16 enters the deferred levels; which levels fire depends
-    // only on `it`, so the branches are uniform across the whole grid
-    __device__ __forceinline__ void push16(uint32_t carry, uint32_t it) {
-        bool parked = false;
-#pragma unroll
-        for (int l = 0; l < DYN; ++l) {
-            if (!parked) {
-                if (((it >> l) & 1u) == 0u) {
-                    Q[l] = carry;
-                    parked = true;
-                } else {
-                    csa(carry, P[l], P[l], Q[l], carry);
-                    Q[l] = 0;
-                }
-            }
-        }
-        if (!parked) {
+    // only on `it`, so the branches are uniform across the whole grid.  Level l holds a
+    // pending carry in Q[l] exactly when bit l of the number of chunks pushed so far is set.
+    template <int LVL>
+    __device__ __forceinline__ void push_level(uint32_t carry, uint32_t it) {
+        if constexpr (LVL == DYN) {
 #pragma unroll
             for (int j = 0; j < UP; ++j) {
-                uint32_t t = U[j] & carry;
+                const uint32_t t = U[j] & carry;
                 U[j] ^= carry;
                 carry = t;
             }
+        } else {
+            if (((it >> LVL) & 1u) == 0u) {
+                Q[LVL] = carry;
+            } else {
+                uint32_t up;
+                csa(up, P[LVL], P[LVL], Q[LVL], carry);
+                push_level<LVL + 1>(up, it);
+            }
         }
     }
+    __device__ __forceinline__ void push16(uint32_t carry, uint32_t it) { push_level<0>(carry, it); }
 
     // add a single word of weight 1 (rare events only: costs 2 ops per plane)
     __device__ __forceinline__ void add1_slow(uint32_t w) {
@@ -131,8 +133,9 @@ struct Ladder {
     }
 
     // Extract: after the call, lane L of the warp returns the total (over the 32 lanes)
-    // count of bit position L.  Must be called by all 32 lanes.  Does not clear.
-    __device__ __forceinline__ uint32_t warp_totals(uint32_t lane) const {
+    // count of bit position L.  `it` = chunks pushed since clear().  Must be called by all
+    // 32 lanes.  Does not clear.
+    __device__ __forceinline__ uint32_t warp_totals(uint32_t lane, uint32_t it) const {
         constexpr int W = kPlanes + 6;
         uint32_t n[W];
 #pragma unroll
@@ -146,7 +149,7 @@ struct Ladder {
         // pending carries have the weight of their level
 #pragma unroll
         for (int l = 0; l < DYN; ++l) {
-            uint32_t carry = Q[l];
+            uint32_t carry = ((it >> l) & 1u) ? Q[l] : 0u;
 #pragma unroll
             for (int j = 4 + l; j < kPlanes + 1; ++j) { uint32_t t = n[j] & carry; n[j] ^= carry; carry = t; }
         }

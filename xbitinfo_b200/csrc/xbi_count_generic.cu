@@ -39,9 +39,9 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
     auto flush = [&]() {
 #pragma unroll
         for (int w = 0; w < NW; ++w) {
-            accA[w] += A[w].warp_totals(lane);
-            accB[w] += B[w].warp_totals(lane);
-            accAB[w] += AB[w].warp_totals(lane);
+            accA[w] += A[w].warp_totals(lane, it);
+            accB[w] += B[w].warp_totals(lane, it);
+            accAB[w] += AB[w].warp_totals(lane, it);
             A[w].clear(); B[w].clear(); AB[w].clear();
         }
         nvalid_total += nvalid;

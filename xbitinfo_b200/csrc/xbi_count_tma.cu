@@ -1,11 +1,450 @@
-// K1 fast paths (TMA-staged) -- placeholder until the pipeline kernels land.
+// K1 fast path for adjacency along the LAST axis (inner == 1): TMA-staged rows.
+//
+// The flat array is viewed as rows of 128 bytes.  A persistent CTA (1 producer warp +
+// 15 counting warps) streams stages of 240 or 480 rows through a ring of shared-memory
+// buffers: one elected producer thread issues a 2-D tiled TMA load with the 128-byte
+// swizzle per stage (plus a 16-byte bulk copy of the halo: the first bytes of the row
+// after the stage) and the counting warps wait on the stage's mbarrier.  Each counting
+// thread owns a contiguous 64-byte (128-byte for 64-bit types) segment of a row, so the
+// neighbour of every element but the last is already in its registers; the swizzle makes
+// the per-thread 128-bit shared-memory reads bank-conflict free.  Words go through the
+// signed-exponent transform (xbitinfo/_py_bitinfo.py:42-94), the optional mask test and
+// into the bit-sliced counters of xbi_common.cuh.  HBM traffic: every byte is read once.
+//
+// Unmasked pairs need only two word streams: a (every element) and a&b.  The b-stream
+// total equals the a-stream total shifted by one element, i.e. A - bits(first element)
+// + bits(halo element of the last stage); block 0 applies that correction.
+#include <mutex>
+
 #include "xbi_common.cuh"
+#include "xbi_elem.cuh"
 #include "xbi_internal.h"
+#include "xbi_tma.cuh"
 
 namespace xbi {
-cudaError_t launch_pairs_tma(const CountJob&, int64_t, RawSums*, cudaStream_t, int64_t* done_lo, int64_t* done_hi) {
+
+namespace {
+
+constexpr int kCountThreads = 480;  // 15 counting warps + 1 producer warp = 512 threads -> 128 registers each
+constexpr int kCountWarps = kCountThreads / 32;
+constexpr int kThreads = kCountThreads + 32;  // + producer warp
+constexpr int kRowBytes = 128;
+constexpr int kBoxRows = 240;  // rows per TMA box (<= 256)
+
+template <int KIND>
+struct Seg {
+    static constexpr int kBytes = Elem<KIND>::kBytes;
+    static constexpr bool k64 = (kBytes == 8);
+    static constexpr int kSegWords = k64 ? 32 : 16;     // words a thread consumes per stage
+    static constexpr int kSegChunks = kSegWords / 4;    // 16-byte chunks
+    static constexpr int kExtra = k64 ? 2 : 1;          // neighbour words
+    static constexpr int kThreadsPerRow = 32 / kSegWords;  // 2 or 1
+    static constexpr int kRowsPerStage = kCountThreads / kThreadsPerRow;                 // 240 or 480
+    static constexpr int kStageBytes = kRowsPerStage * kRowBytes;                        // 30 KB or 60 KB
+    static constexpr int kStages = k64 ? 3 : 5;
+    static constexpr int kElemsPerStage = kStageBytes / kBytes;
+    static constexpr int kLaddersPerStream = k64 ? 2 : 1;
+    static constexpr int kBits = 8 * kBytes;
+};
+
+// shared memory: [stages][kStageBytes] (1024-aligned) | halo [stages][16] | full[stages] | empty[stages]
+template <int KIND>
+constexpr size_t smem_bytes() {
+    return 1024 + (size_t)Seg<KIND>::kStages * Seg<KIND>::kStageBytes + Seg<KIND>::kStages * 16 +
+           2 * Seg<KIND>::kStages * 8 + 64;
+}
+
+// ---- per-word helpers for types that fit one word -------------------------------------
+template <int KIND, bool XFORM>
+__device__ __forceinline__ uint32_t xform_word(uint32_t w) {
+    if (!XFORM) return w;
+    if (KIND == kF32) return sexp_f32(w);
+    if (KIND == kF16) return sexp_f16x2(w);
+    return w;
+}
+// the word holding, field by field, the successor element of every element of `cur`
+template <int BYTES>
+__device__ __forceinline__ uint32_t successor_word(uint32_t cur, uint32_t next) {
+    if (BYTES == 4) return next;
+    return __funnelshift_r(cur, next, 8 * BYTES);
+}
+// all-ones in the field of every element that is NOT masked
+template <int KIND, int MASK>
+__device__ __forceinline__ uint32_t keep_fields(uint32_t w, uint32_t mask_lo) {
+    if (MASK == kMaskNone) return 0xFFFFFFFFu;
+    constexpr int BYTES = Elem<KIND>::kBytes;
+    if (BYTES == 4) {
+        if (MASK == kMaskNaN) return ((w & 0x7FFFFFFFu) > 0x7F800000u) ? 0u : 0xFFFFFFFFu;
+        return (w == mask_lo) ? 0u : 0xFFFFFFFFu;
+    } else if (BYTES == 2) {
+        if (MASK == kMaskNaN) {
+            const uint32_t mag = w & 0x7FFF7FFFu;  // NaN <=> magnitude > 0x7C00
+            const uint32_t nan = ((mag + 0x03FF03FFu) >> 15) & 0x00010001u;
+            return ~(nan * 0xFFFFu);
+        }
+        const uint32_t x = w ^ (mask_lo * 0x00010001u);
+        const uint32_t nz = ((((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) >> 15) & 0x00010001u;
+        return nz * 0xFFFFu;
+    } else {
+        const uint32_t x = w ^ (mask_lo * 0x01010101u);
+        const uint32_t nz = ((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u;
+        return nz * 0xFFu;
+    }
+}
+template <int BYTES>
+__device__ __forceinline__ uint32_t count_fields(uint32_t v) {
+    if (BYTES == 4) return v & 1u;
+    if (BYTES == 2) return __popc(v & 0x00010001u);
+    return __popc(v & 0x01010101u);
+}
+
+template <int KIND, int MASK, bool XFORM>
+__global__ void __launch_bounds__(kThreads, 1)
+k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restrict__ region, long long nstages,
+                 uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst) {
+    using S = Seg<KIND>;
+    constexpr int BYTES = S::kBytes;
+    constexpr int NL = S::kLaddersPerStream;
+    constexpr bool MASKED = (MASK != kMaskNone);
+    constexpr int kNumLadders = NL * (MASKED ? 3 : 2);
+    using L = Ladder<3, (kNumLadders >= 6 ? 3 : kNumLadders >= 4 ? 5 : 8)>;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
+    const uint32_t halo0 = smem0 + S::kStages * S::kStageBytes;
+    const uint32_t full0 = halo0 + S::kStages * 16;
+    const uint32_t empty0 = full0 + S::kStages * 8;
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S::kStages; ++s) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kCountWarps);
+        }
+        mbar_fence_init();
+        tma_prefetch_descriptor(&tmap);
+    }
+    __syncthreads();
+
+    if (warp == 0) {
+        // ================= producer =================
+        if (lane == 0) {
+            uint32_t iter = 0;
+            for (long long g = blockIdx.x; g < nstages; g += gridDim.x, ++iter) {
+                const uint32_t s = iter % S::kStages;
+                const uint32_t ph = (iter / S::kStages) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                mbar_arrive_expect_tx(full0 + 8 * s, S::kStageBytes + 16);
+                const long long row0 = g * S::kRowsPerStage;
+#pragma unroll
+                for (int b = 0; b < S::kRowsPerStage / kBoxRows; ++b)
+                    tma_load_2d(smem0 + s * S::kStageBytes + b * kBoxRows * kRowBytes, &tmap, 0, (int32_t)(row0 + kBoxRows * b),
+                                full0 + 8 * s);
+                bulk_load_1d(halo0 + 16 * s, region + (row0 + S::kRowsPerStage) * kRowBytes, 16, full0 + 8 * s);
+            }
+        }
+        return;
+    }
+
+    // ================= counting warps =================
+    const uint32_t t = threadIdx.x - 32u;
+    const uint32_t row = t / S::kThreadsPerRow;
+    const uint32_t cbase = (t % S::kThreadsPerRow) * S::kSegChunks;
+    const uint32_t swz = row & 7u;
+    // where the neighbour words (first words of the next segment) live
+    const bool nb_same_row = (cbase + S::kSegChunks) < 8;
+    const bool nb_halo = (!nb_same_row) && (row == S::kRowsPerStage - 1);
+    const uint32_t nb_off = nb_same_row ? (row * kRowBytes + (((cbase + S::kSegChunks) ^ swz) << 4))
+                                        : ((row + 1) * kRowBytes + (((row + 1) & 7u) << 4));
+
+    L A[NL], AB[NL], B[MASKED ? NL : 1];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { A[i].clear(); AB[i].clear(); }
+    if (MASKED) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) B[i].clear();
+    }
+    unsigned long long accA[NL], accAB[NL], accB[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { accA[i] = 0; accAB[i] = 0; accB[i] = 0; }
+    uint32_t nvalid = 0;
+    unsigned long long nvalid_total = 0;
+    uint32_t it = 0;
+
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            accA[i] += A[i].warp_totals(lane, it);
+            accAB[i] += AB[i].warp_totals(lane, it);
+            A[i].clear(); AB[i].clear();
+            if (MASKED) { accB[i] += B[i].warp_totals(lane, it); B[i].clear(); }
+        }
+        nvalid_total += nvalid;
+        nvalid = 0;
+        it = 0;
+    };
+
+    uint32_t iter = 0;
+    for (long long g = blockIdx.x; g < nstages; g += gridDim.x, ++iter) {
+        const uint32_t s = iter % S::kStages;
+        const uint32_t ph = (iter / S::kStages) & 1u;
+        mbar_wait(full0 + 8 * s, ph);
+        const uint32_t sbase = smem0 + s * S::kStageBytes;
+        uint32_t w[S::kSegWords + S::kExtra];
+#pragma unroll
+        for (int k = 0; k < S::kSegChunks; ++k) {
+            const uint4 v = lds128(sbase + row * kRowBytes + (((cbase + k) ^ swz) << 4));
+            w[4 * k + 0] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w;
+        }
+        {
+            const uint32_t a = nb_halo ? (halo0 + 16 * s) : (sbase + nb_off);
+            if (S::k64) {
+                const uint2 v = lds64(a);
+                w[S::kSegWords] = v.x;
+                w[S::kSegWords + 1] = v.y;
+            } else {
+                w[S::kSegWords] = lds32(a);
+            }
+        }
+
+        if (!S::k64) {
+            uint32_t tw[17];
+#pragma unroll
+            for (int i = 0; i < 17; ++i) tw[i] = xform_word<KIND, XFORM>(w[i]);
+            uint32_t a[16], ab[16];
+            if (!MASKED) {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    a[i] = tw[i];
+                    ab[i] = tw[i] & successor_word<BYTES>(tw[i], tw[i + 1]);
+                }
+                A[0].add16(a, it);
+                AB[0].add16(ab, it);
+            } else {
+                uint32_t keep[17], b[16];
+#pragma unroll
+                for (int i = 0; i < 17; ++i) keep[i] = keep_fields<KIND, MASK>(w[i], mask_lo);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t v = keep[i] & successor_word<BYTES>(keep[i], keep[i + 1]);
+                    a[i] = tw[i] & v;
+                    b[i] = successor_word<BYTES>(tw[i], tw[i + 1]) & v;
+                    ab[i] = a[i] & b[i];
+                    nvalid += count_fields<BYTES>(v);
+                }
+                A[0].add16(a, it);
+                B[0].add16(b, it);
+                AB[0].add16(ab, it);
+            }
+        } else {
+            // 64-bit elements: even words = low halves, odd words = high halves (transform there)
+            uint32_t lo[17], hi[17];
+#pragma unroll
+            for (int e = 0; e < 17; ++e) {
+                lo[e] = w[2 * e];
+                hi[e] = (XFORM && KIND == kF64) ? sexp_f64_hi(w[2 * e + 1]) : w[2 * e + 1];
+            }
+            uint32_t x0[16], x1[16];
+            if (!MASKED) {
+                {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { x0[e] = lo[e]; x1[e] = lo[e] & lo[e + 1]; }
+                    A[0].add16(x0, it);
+                    AB[0].add16(x1, it);
+                }
+                {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) { x0[e] = hi[e]; x1[e] = hi[e] & hi[e + 1]; }
+                    A[NL - 1].add16(x0, it);
+                    AB[NL - 1].add16(x1, it);
+                }
+            } else {
+                uint32_t keep[17];
+#pragma unroll
+                for (int e = 0; e < 17; ++e) {
+                    const uint32_t rl = w[2 * e], rh = w[2 * e + 1];
+                    bool masked;
+                    if (MASK == kMaskNaN) {
+                        const uint32_t m = rh & 0x7FFFFFFFu;
+                        masked = m > 0x7FF00000u || (m == 0x7FF00000u && rl != 0u);
+                    } else {
+                        masked = (rl == mask_lo) && (rh == mask_hi);
+                    }
+                    keep[e] = masked ? 0u : 0xFFFFFFFFu;
+                }
+                uint32_t v[16], x2[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { v[e] = keep[e] & keep[e + 1]; nvalid += v[e] & 1u; }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { x0[e] = lo[e] & v[e]; x1[e] = lo[e + 1] & v[e]; x2[e] = x0[e] & x1[e]; }
+                A[0].add16(x0, it); B[0].add16(x1, it); AB[0].add16(x2, it);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { x0[e] = hi[e] & v[e]; x1[e] = hi[e + 1] & v[e]; x2[e] = x0[e] & x1[e]; }
+                A[NL - 1].add16(x0, it); B[MASKED ? NL - 1 : 0].add16(x1, it); AB[NL - 1].add16(x2, it);
+            }
+        }
+        // the stage's words are in registers and consumed: hand the buffer back
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty0 + 8 * s);
+        ++it;
+        if (it == L::kFlushChunks) flush();
+    }
+    flush();
+
+    // ---- block reduction over the 16 counting warps (named barrier 1, producer not involved)
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_n;
+    for (int i = t; i < 3 * 64; i += kCountThreads) (&s_sum[0][0])[i] = 0;
+    if (t == 0) s_n = 0;
+    asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        const int j = S::k64 ? (i * 32 + (int)lane) : ((int)lane % S::kBits);
+        if (accA[i]) atomicAdd(&s_sum[S_A][j], accA[i]);
+        if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
+        if (MASKED) {
+            if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
+        } else {
+            if (accA[i]) atomicAdd(&s_sum[S_B][j], accA[i]);  // corrected below (block 0)
+        }
+    }
+    if (MASKED && nvalid_total) atomicAdd(&s_n, nvalid_total);
+    asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
+    for (int i = t; i < 3 * 64; i += kCountThreads) {
+        const unsigned long long v = (&s_sum[0][0])[i];
+        if (v) atomicAdd(&dst->sums[0][0] + i, v);
+    }
+    if (MASKED && t == 0 && s_n) atomicAdd(&dst->npairs, s_n);
+
+    if (!MASKED && blockIdx.x == 0 && t < 64) {
+        // b-stream = a-stream shifted by one element: + bits(element after the region) - bits(first element)
+        using E = Elem<KIND>;
+        const long long last = nstages * (long long)S::kElemsPerStage;
+        uint32_t first_w[E::kWords], last_w[E::kWords];
+        E::load(region, 0, first_w);
+        E::load(region, last, last_w);
+        if (XFORM) { E::transform(first_w); E::transform(last_w); }
+        if ((int)t < S::kBits) {
+            const uint32_t wsel = t >> 5, bsel = t & 31u;
+            const unsigned long long up = (last_w[E::kWords == 2 ? wsel : 0] >> bsel) & 1u;
+            const unsigned long long down = (first_w[E::kWords == 2 ? wsel : 0] >> bsel) & 1u;
+            if (up != down) atomicAdd(&dst->sums[S_B][t], up - down);
+        }
+        if (t == 0) atomicAdd(&dst->npairs, (unsigned long long)last);
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode_fn() {
+    static EncodeFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+        else
+            cudaGetLastError();
+    });
+    return fn;
+}
+
+template <int KIND, int MASK, bool XFORM>
+cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream, int64_t* done_lo,
+                        int64_t* done_hi) {
+    using S = Seg<KIND>;
+    const int bytes = S::kBytes;
+    const uintptr_t addr = reinterpret_cast<uintptr_t>(job.x);
+    const int64_t head = (int64_t)(((16 - (addr & 15)) & 15) / bytes);
+    const int64_t numel = job.outer * job.n * job.inner;
+    if (npairs_flat <= head) return cudaSuccess;
+    int64_t nstages = (npairs_flat - head) / S::kElemsPerStage;
+    // the 16-byte halo copy after the last stage must stay inside the array
+    while (nstages > 0 && (head + nstages * S::kElemsPerStage) * bytes + 16 > numel * bytes) --nstages;
+    if (nstages < 1) return cudaSuccess;
+    const uint64_t nrows = (uint64_t)nstages * S::kRowsPerStage;
+    if (nrows >= (1ull << 31)) return cudaSuccess;  // TMA coordinates are 32-bit: leave it to the caller's slabs
+    EncodeFn encode = get_encode_fn();
+    if (!encode) return cudaSuccess;
+
+    const char* region = static_cast<const char*>(job.x) + head * bytes;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {32, nrows};
+    const cuuint64_t gstride[1] = {kRowBytes};
+    const cuuint32_t box[2] = {32, kBoxRows};
+    const cuuint32_t estride[2] = {1, 1};
+    const CUresult r = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<char*>(region), gdim, gstride, box,
+                              estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
+
+    auto kern = k_pairs_rows_tma<KIND, MASK, XFORM>;
+    static bool attr_set = false;  // per instantiation
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<KIND>());
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned grid = (unsigned)(nstages < sms ? nstages : sms);
+    kern<<<grid, kThreads, smem_bytes<KIND>(), stream>>>(tmap, region, (long long)nstages, (uint32_t)job.mask_bits,
+                                                          (uint32_t)(job.mask_bits >> 32), dst);
+    note_launch();
+    *done_lo = head;
+    *done_hi = head + nstages * S::kElemsPerStage;
+    return cudaGetLastError();
+}
+
+template <int KIND>
+cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream, int64_t* lo,
+                          int64_t* hi) {
+    constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
+    if (job.transform) {
+        if constexpr (isf) {
+            switch (job.mask_mode) {
+                case kMaskNone: return launch_rows<KIND, kMaskNone, true>(job, npairs_flat, dst, stream, lo, hi);
+                case kMaskNaN: return launch_rows<KIND, kMaskNaN, true>(job, npairs_flat, dst, stream, lo, hi);
+                default: return launch_rows<KIND, kMaskValue, true>(job, npairs_flat, dst, stream, lo, hi);
+            }
+        }
+        return cudaSuccess;
+    }
+    // untransformed data of any type is counted as the unsigned integer of its width; a NaN
+    // mask without the transform is rare enough to stay on the generic kernel
+    if (job.mask_mode == kMaskNaN) return cudaSuccess;
+    constexpr int UK = (KIND == kF16) ? kU16 : (KIND == kF32) ? kU32 : (KIND == kF64) ? kU64 : KIND;
+    if (job.mask_mode == kMaskNone) return launch_rows<UK, kMaskNone, false>(job, npairs_flat, dst, stream, lo, hi);
+    return launch_rows<UK, kMaskValue, false>(job, npairs_flat, dst, stream, lo, hi);
+}
+
+}  // namespace
+
+cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream,
+                             int64_t* done_lo, int64_t* done_hi) {
     *done_lo = 0;
     *done_hi = 0;
-    return cudaSuccess;
+    if (job.inner != 1) return cudaSuccess;  // strided adjacency: see xbi_count_cols.cu
+    switch (job.dtype) {
+        case XBI_U8: return dispatch_rows<kU8>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        case XBI_U16: return dispatch_rows<kU16>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        case XBI_U32: return dispatch_rows<kU32>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        case XBI_U64: return dispatch_rows<kU64>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        case XBI_F16: return dispatch_rows<kF16>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        case XBI_F32: return dispatch_rows<kF32>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        case XBI_F64: return dispatch_rows<kF64>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        default: return cudaErrorInvalidValue;
+    }
 }
+
 }  // namespace xbi

@@ -1,0 +1,116 @@
+"""Device-level plumbing: torch tensors in HBM <-> the C ABI.
+
+torch is used only for what it is good at here -- owning device memory, streams and the
+NCCL process group.  Every kernel is ours and is reached through ``_native.lib()``.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+
+from . import _native as nat
+
+_TORCH_CODES = {
+    torch.uint8: nat.U8, torch.int8: nat.U8,
+    torch.int16: nat.U16, torch.int32: nat.U32, torch.int64: nat.U64,
+    torch.float16: nat.F16, torch.float32: nat.F32, torch.float64: nat.F64,
+}
+for _name, _code in (("uint16", nat.U16), ("uint32", nat.U32), ("uint64", nat.U64)):
+    if hasattr(torch, _name):
+        _TORCH_CODES[getattr(torch, _name)] = _code
+
+_NP_OF_TORCH = {
+    torch.uint8: "uint8", torch.int8: "int8", torch.int16: "int16", torch.int32: "int32",
+    torch.int64: "int64", torch.float16: "float16", torch.float32: "float32", torch.float64: "float64",
+}
+for _name in ("uint16", "uint32", "uint64"):
+    if hasattr(torch, _name):
+        _NP_OF_TORCH[getattr(torch, _name)] = _name
+
+
+def numpy_dtype_of(t: torch.Tensor) -> np.dtype:
+    return np.dtype(_NP_OF_TORCH[t.dtype])
+
+
+def torch_dtype_code(dtype: torch.dtype) -> int:
+    try:
+        return _TORCH_CODES[dtype]
+    except KeyError:
+        raise ValueError(f"dtype {dtype} neither known nor implemented.") from None
+
+
+def require_cuda_tensor(x: torch.Tensor) -> None:
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise TypeError("expected a CUDA torch.Tensor (xbitinfo_b200 has no CPU path)")
+    if not x.is_contiguous():
+        raise ValueError("the device array must be C-contiguous")
+
+
+def split_axis(shape, axis: int):
+    """(outer, n, inner) view of a C-contiguous array for adjacency along ``axis``."""
+    ndim = len(shape)
+    if not -ndim <= axis < ndim:
+        raise ValueError(f"axis {axis} out of range for {ndim}-d array")
+    axis %= ndim
+    return math.prod(shape[:axis]), int(shape[axis]), math.prod(shape[axis + 1:])
+
+
+def _stream_ptr(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class PairCounter:
+    """Reusable device state for one (dtype) counting job: the accumulate-only
+    ``counts`` buffer (nbits x 2 x 2, int64) and the scratch workspace of K1."""
+
+    def __init__(self, dtype: torch.dtype, device):
+        self.code = torch_dtype_code(dtype)
+        self.nbits = 8 * torch.empty((), dtype=dtype).element_size()
+        self.device = torch.device(device)
+        self.counts = torch.zeros((self.nbits, 2, 2), dtype=torch.int64, device=self.device)
+        self.workspace = torch.empty(nat.lib().xbi_workspace_bytes(), dtype=torch.uint8, device=self.device)
+        self.mi = torch.empty(self.nbits, dtype=torch.float64, device=self.device)
+
+    def reset(self) -> None:
+        self.counts.zero_()
+
+    def add(self, x: torch.Tensor, axis: int = -1, *, transform: bool = True, masked_value=None,
+            force_generic: bool = False, dims=None) -> None:
+        """counts += pair histogram of ``x`` along ``axis`` (K1).  ``dims`` overrides the
+        (outer, n, inner) split, e.g. to describe a slab with a halo row."""
+        require_cuda_tensor(x)
+        if torch_dtype_code(x.dtype) != self.code:
+            raise ValueError("dtype differs from the counter's dtype")
+        outer, n, inner = dims if dims is not None else split_axis(tuple(x.shape), axis)
+        np_dtype = numpy_dtype_of(x)
+        flags, bits = nat.mask_spec(np_dtype, masked_value)
+        if np_dtype.kind == "f" and transform:
+            flags |= nat.SIGNED_EXPONENT
+        if force_generic:
+            flags |= nat.FORCE_GENERIC
+        with torch.cuda.device(x.device):
+            rc = nat.lib().xbi_count_pairs(
+                x.data_ptr(), self.code, outer, n, inner, flags, bits, self.counts.data_ptr(),
+                self.workspace.data_ptr(), self.workspace.numel(), _stream_ptr(x.device))
+        nat.check(rc)
+
+    def information(self, set_zero_insignificant: bool = False, confidence: float = 0.99) -> torch.Tensor:
+        """K2 on the current counts -> float64[nbits] on the device."""
+        with torch.cuda.device(self.device):
+            rc = nat.lib().xbi_mutual_information(
+                self.counts.data_ptr(), self.nbits, int(bool(set_zero_insignificant)), float(confidence),
+                self.mi.data_ptr(), _stream_ptr(self.device))
+        nat.check(rc)
+        return self.mi
+
+
+def bitround_(x: torch.Tensor, keepbits: int) -> torch.Tensor:
+    """K3 in place on a CUDA tensor."""
+    require_cuda_tensor(x)
+    code = torch_dtype_code(x.dtype)
+    with torch.cuda.device(x.device):
+        rc = nat.lib().xbi_bitround_inplace(x.data_ptr(), code, x.numel(), int(keepbits), _stream_ptr(x.device))
+    nat.check(rc)
+    return x
