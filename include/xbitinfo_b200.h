@@ -67,6 +67,8 @@ int xbi_abi_version(void);
 const char* xbi_last_error(void);
 /* number of kernels this library has launched so far in this process (all threads) */
 unsigned long long xbi_kernel_launches(void);
+/* how many of those were fast-path counting kernels (TMA rows / column walkers) */
+unsigned long long xbi_fast_path_launches(void);
 
 /* bytes of device scratch xbi_count_pairs needs (contents are overwritten) */
 size_t xbi_workspace_bytes(void);

@@ -111,3 +111,63 @@ def test_errors():
         run_host(x, 1, masked_value=float("nan"), transform=False) if False else nat.check(
             nat.lib().xbi_bitinformation_host(x.ctypes.data_as(C.c_void_p), nat.U32, 4, 4, 1, nat.MASK_NAN, 0, 0, 0.99,
                                               np.empty(32).ctypes.data_as(C.c_void_p), None, 0))
+
+
+STRIDED_DTYPES = ["float32", "float64", "float16", "uint8", "int16", "int32", "int64"]
+
+
+@pytest.mark.parametrize("dtype", STRIDED_DTYPES)
+@pytest.mark.parametrize("mask", [None, "nan", "value"])
+def test_strided_fast_path(dtype, mask):
+    """Adjacency along non-last axes with 16-byte aligned rows: the column-walker kernel
+    (must actually be taken) vs the oracle."""
+    isfloat = np.dtype(dtype).kind == "f"
+    if mask == "nan" and not isfloat:
+        pytest.skip("NaN mask needs floats")
+    rng = np.random.default_rng(3)
+    shape = (3, 301, 7, 64)  # rows of 64 elements: 16-byte aligned for every dtype
+    if isfloat:
+        x = smooth_field(rng, shape, dtype, axis=1, scale=0.2, base=3.0)
+    else:
+        info = np.iinfo(dtype)
+        x = rng.integers(info.min, info.max, size=shape, dtype=dtype, endpoint=True)
+    masked_value = None
+    if mask is not None:
+        masked_value = float("nan") if mask == "nan" else (-999.0 if isfloat else 7)
+        land = rng.random(shape[2:]) < 0.3
+        x[:, :, land] = masked_value
+        x[1, 5:9] = masked_value  # whole rows masked
+    for axis in (0, 1, 2):
+        before = nat.fast_path_launches()
+        counts, mi = run_host(x, axis, masked_value=masked_value)
+        assert nat.fast_path_launches() > before, "fast path was not taken"
+        ref_counts, npairs, ref_mi = bo.bitinformation(x, axis, masked_value=masked_value)
+        assert np.array_equal(counts, ref_counts), (dtype, axis, mask)
+        assert counts[0].sum() == npairs
+        assert_mi_close(mi, ref_mi)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "float16", "uint8", "uint16"])
+@pytest.mark.parametrize("mask", [None, "nan", "value"])
+def test_last_axis_fast_path(dtype, mask):
+    isfloat = np.dtype(dtype).kind == "f"
+    if mask == "nan" and not isfloat:
+        pytest.skip("NaN mask needs floats")
+    rng = np.random.default_rng(5)
+    shape = (37, 11, 1441)  # odd row length: rows are not vector aligned
+    if isfloat:
+        x = smooth_field(rng, shape, dtype, axis=-1, scale=0.2, base=3.0)
+    else:
+        info = np.iinfo(dtype)
+        x = rng.integers(info.min, info.max, size=shape, dtype=dtype, endpoint=True)
+    masked_value = None
+    if mask is not None:
+        masked_value = float("nan") if mask == "nan" else (-999.0 if isfloat else 7)
+        x[rng.random(shape) < 0.2] = masked_value
+    before = nat.fast_path_launches()
+    counts, mi = run_host(x, 2, masked_value=masked_value)
+    assert nat.fast_path_launches() > before, "fast path was not taken"
+    ref_counts, npairs, ref_mi = bo.bitinformation(x, 2, masked_value=masked_value)
+    assert np.array_equal(counts, ref_counts), (dtype, mask)
+    assert counts[0].sum() == npairs
+    assert_mi_close(mi, ref_mi)

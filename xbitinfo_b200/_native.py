@@ -63,6 +63,8 @@ def lib() -> C.CDLL:
     L.xbi_last_error.argtypes = []
     L.xbi_kernel_launches.restype = C.c_ulonglong
     L.xbi_kernel_launches.argtypes = []
+    L.xbi_fast_path_launches.restype = C.c_ulonglong
+    L.xbi_fast_path_launches.argtypes = []
     L.xbi_workspace_bytes.restype = C.c_size_t
     L.xbi_workspace_bytes.argtypes = []
     L.xbi_count_pairs.restype = i32
@@ -84,7 +86,8 @@ def lib() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = (
-    "xbi_abi_version", "xbi_last_error", "xbi_kernel_launches", "xbi_workspace_bytes",
+    "xbi_abi_version", "xbi_last_error", "xbi_kernel_launches", "xbi_fast_path_launches",
+    "xbi_workspace_bytes",
     "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace",
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
 )
@@ -104,6 +107,10 @@ def check(rc: int) -> None:
 
 def kernel_launches() -> int:
     return int(lib().xbi_kernel_launches())
+
+
+def fast_path_launches() -> int:
+    return int(lib().xbi_fast_path_launches())
 
 
 def mask_spec(dtype, masked_value):

@@ -12,8 +12,13 @@ namespace xbi {
 
 static thread_local std::string g_last_error;
 static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<unsigned long long> g_fast_launches{0};
 
 void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+void note_fast_launch() {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    g_fast_launches.fetch_add(1, std::memory_order_relaxed);
+}
 
 static int fail(int code, const std::string& msg) {
     g_last_error = msg;
@@ -58,8 +63,12 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
     XBI_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), stream), "cudaMemsetAsync(workspace)");
     const int64_t npairs_flat = numel - job.inner;
     int64_t dlo = 0, dhi = 0;
-    if (!(flags & XBI_FORCE_GENERIC))
-        XBI_CUDA(launch_pairs_tma(job, npairs_flat, &ws->plus, stream, &dlo, &dhi), "pair counting (TMA path)");
+    if (!(flags & XBI_FORCE_GENERIC)) {
+        if (job.inner == 1)
+            XBI_CUDA(launch_pairs_tma(job, npairs_flat, &ws->plus, stream, &dlo, &dhi), "pair counting (TMA rows)");
+        else
+            XBI_CUDA(launch_pairs_cols(job, ws, stream, &dlo, &dhi), "pair counting (column walkers)");
+    }
     if (dhi <= dlo) { dlo = 0; dhi = 0; }
     XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
     XBI_CUDA(launch_pairs_generic_flat(job, dhi, npairs_flat, &ws->plus, stream), "pair counting (generic, tail)");
@@ -134,6 +143,7 @@ extern "C" {
 int xbi_abi_version(void) { return XBI_ABI_VERSION; }
 const char* xbi_last_error(void) { return g_last_error.c_str(); }
 unsigned long long xbi_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
+unsigned long long xbi_fast_path_launches(void) { return g_fast_launches.load(std::memory_order_relaxed); }
 size_t xbi_workspace_bytes(void) { return sizeof(Workspace); }
 
 int xbi_count_pairs(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner, unsigned flags,

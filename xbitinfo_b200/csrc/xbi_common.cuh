@@ -54,50 +54,96 @@ __device__ __forceinline__ void csa(uint32_t& hi, uint32_t& lo, uint32_t a, uint
 }
 
 // ---------------------------------------------------------------------------------
-// Vertical counter.  DYN deferred carry-save levels (each holds a plane and a pending
-// carry), UP ripple planes on top.  One "chunk" = 16 words.  Capacity between flushes:
-// kFlushChunks chunks (chosen so that no digit can overflow).
+// flush helpers (out of line on purpose, see Ladder::warp_totals)
 // ---------------------------------------------------------------------------------
-template <int DYN, int UP>
+// n[from..to) += carry, as a ripple of half adders on bit planes
+static __device__ __noinline__ void ripple_add(uint32_t* n, int from, int to, uint32_t carry) {
+    for (int j = from; j < to; ++j) {
+        const uint32_t t = n[j] & carry;
+        n[j] ^= carry;
+        carry = t;
+    }
+}
+// n[0..planes) are the binary digits (as bit planes) of 32 per-lane counters per bit
+// position.  5-step butterfly: at distance d a lane keeps the bit positions whose bit
+// log2(d) equals its own, receives the partner's digits for those positions and adds.
+// Afterwards lane L holds the warp-wide count of bit position L; n needs planes+5 slots.
+static __device__ __noinline__ uint32_t butterfly_totals(uint32_t* n, int planes, uint32_t lane) {
+    for (int step = 0; step < 5; ++step) {
+        const int d = 16 >> step;
+        const uint32_t hi_sel = (d == 16) ? 0xFFFF0000u : (d == 8) ? 0xFF00FF00u : (d == 4) ? 0xF0F0F0F0u
+                               : (d == 2) ? 0xCCCCCCCCu : 0xAAAAAAAAu;
+        const uint32_t keep = (lane & d) ? hi_sel : ~hi_sel;
+        uint32_t carry = 0;
+        const int np = planes + step;
+        for (int j = 0; j < np; ++j) {
+            const uint32_t mine = n[j] & keep;
+            const uint32_t give = n[j] & ~keep;
+            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, give, d);
+            uint32_t hi, lo;
+            csa(hi, lo, mine, got, carry);
+            n[j] = lo;
+            carry = hi;
+        }
+        n[np] = carry;
+    }
+    uint32_t total = 0;
+    for (int j = 0; j < planes + 5; ++j) total |= ((n[j] >> lane) & 1u) << j;
+    return total;
+}
+
+// ---------------------------------------------------------------------------------
+// Vertical counter.  A "chunk" of 2^LOGC words is folded in with a static tree of
+// carry-save adders (digits 0..LOGC-1); its carry enters DYN deferred carry-save levels
+// (each holds a plane and a pending carry) and finally UP ripple planes.  Capacity between
+// flushes: kFlushChunks chunks (chosen so that no digit can overflow).
+// ---------------------------------------------------------------------------------
+template <int DYN, int UP, int LOGC = 4>
 struct Ladder {
-    static constexpr int kPlanes = 4 + DYN + UP;
+    static constexpr int kChunk = 1 << LOGC;
+    static constexpr int kPlanes = LOGC + DYN + UP;
     static constexpr uint32_t kFlushChunks = 1u << (DYN + UP - 1);
 
-    uint32_t p[4];            // digits 0..3 (weights 1,2,4,8)
-    uint32_t P[DYN], Q[DYN];  // digit 4+l and its pending carry of the same weight
-    uint32_t U[UP];           // digits 4+DYN ...
+    uint32_t p[LOGC];         // digits 0..LOGC-1
+    uint32_t P[DYN], Q[DYN];  // digit LOGC+l and its pending carry of the same weight
+    uint32_t U[UP];           // digits LOGC+DYN ...
 
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) p[i] = 0;
+        for (int i = 0; i < LOGC; ++i) p[i] = 0;
 #pragma unroll
         for (int i = 0; i < DYN; ++i) { P[i] = 0; Q[i] = 0; }
 #pragma unroll
         for (int i = 0; i < UP; ++i) U[i] = 0;
     }
 
-    // fold 16 words in; `it` is the number of chunks folded in since the last clear()
-    __device__ __forceinline__ void add16(const uint32_t (&w)[16], uint32_t it) {
-        uint32_t t0, t1, f0, f1, e0, e1, s;
-        csa(t0, p[0], p[0], w[0], w[1]);
-        csa(t1, p[0], p[0], w[2], w[3]);
-        csa(f0, p[1], p[1], t0, t1);
-        csa(t0, p[0], p[0], w[4], w[5]);
-        csa(t1, p[0], p[0], w[6], w[7]);
-        csa(f1, p[1], p[1], t0, t1);
-        csa(e0, p[2], p[2], f0, f1);
-        csa(t0, p[0], p[0], w[8], w[9]);
-        csa(t1, p[0], p[0], w[10], w[11]);
-        csa(f0, p[1], p[1], t0, t1);
-        csa(t0, p[0], p[0], w[12], w[13]);
-        csa(t1, p[0], p[0], w[14], w[15]);
-        csa(f1, p[1], p[1], t0, t1);
-        csa(e1, p[2], p[2], f0, f1);
-        csa(s, p[3], p[3], e0, e1);
-        push16(s, it);
+    // fold N = 2^k words into digits 0..k-1, return the carry of weight N
+    template <int N>
+    __device__ __forceinline__ uint32_t reduce(const uint32_t* w) {
+        if constexpr (N == 2) {
+            uint32_t c;
+            csa(c, p[0], p[0], w[0], w[1]);
+            return c;
+        } else {
+            constexpr int D = (N == 4) ? 1 : (N == 8) ? 2 : (N == 16) ? 3 : 4;
+            const uint32_t a = reduce<N / 2>(w);
+            const uint32_t b = reduce<N / 2>(w + N / 2);
+            uint32_t c;
+            csa(c, p[D], p[D], a, b);
+            return c;
+        }
     }
 
-    // a carry word of weight 16 enters the deferred levels; which levels fire depends
+    // fold one chunk in; `it` is the number of chunks folded in since the last clear()
+    __device__ __forceinline__ void add_chunk(const uint32_t (&w)[kChunk], uint32_t it) {
+        push_level<0>(reduce<kChunk>(w), it);
+    }
+    __device__ __forceinline__ void add16(const uint32_t (&w)[16], uint32_t it) {
+        static_assert(LOGC == 4, "add16 needs a 16-word chunk");
+        add_chunk(w, it);
+    }
+
+    // the chunk's carry word enters the deferred levels; which levels fire depends
     // only on `it`, so the branches are uniform across the whole grid.  Level l holds a
     // pending carry in Q[l] exactly when bit l of the number of chunks pushed so far is set.
     template <int LVL>
@@ -119,13 +165,11 @@ struct Ladder {
             }
         }
     }
-    __device__ __forceinline__ void push16(uint32_t carry, uint32_t it) { push_level<0>(carry, it); }
-
     // add a single word of weight 1 (rare events only: costs 2 ops per plane)
     __device__ __forceinline__ void add1_slow(uint32_t w) {
         uint32_t carry = w;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { uint32_t t = p[j] & carry; p[j] ^= carry; carry = t; }
+        for (int j = 0; j < LOGC; ++j) { uint32_t t = p[j] & carry; p[j] ^= carry; carry = t; }
 #pragma unroll
         for (int j = 0; j < DYN; ++j) { uint32_t t = P[j] & carry; P[j] ^= carry; carry = t; }
 #pragma unroll
@@ -136,48 +180,24 @@ struct Ladder {
     // count of bit position L.  `it` = chunks pushed since clear().  Must be called by all
     // 32 lanes.  Does not clear.
     __device__ __forceinline__ uint32_t warp_totals(uint32_t lane, uint32_t it) const {
+        // The digits go through a small local-memory array and two out-of-line helpers:
+        // flushes are rare, and keeping ~600 unrolled instructions per call site out of
+        // the kernels keeps their hot loops compact in the instruction cache.
         constexpr int W = kPlanes + 6;
         uint32_t n[W];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) n[i] = p[i];
+        for (int i = 0; i < LOGC; ++i) n[i] = p[i];
 #pragma unroll
-        for (int i = 0; i < DYN; ++i) n[4 + i] = P[i];
+        for (int i = 0; i < DYN; ++i) n[LOGC + i] = P[i];
 #pragma unroll
-        for (int i = 0; i < UP; ++i) n[4 + DYN + i] = U[i];
+        for (int i = 0; i < UP; ++i) n[LOGC + DYN + i] = U[i];
 #pragma unroll
         for (int i = kPlanes; i < W; ++i) n[i] = 0;
         // pending carries have the weight of their level
 #pragma unroll
-        for (int l = 0; l < DYN; ++l) {
-            uint32_t carry = ((it >> l) & 1u) ? Q[l] : 0u;
-#pragma unroll
-            for (int j = 4 + l; j < kPlanes + 1; ++j) { uint32_t t = n[j] & carry; n[j] ^= carry; carry = t; }
-        }
-        // butterfly: at distance d the lane keeps the bit positions whose bit log2(d)
-        // equals its own, receives the partner's values for those positions and adds
-#pragma unroll
-        for (int step = 0; step < 5; ++step) {
-            const int d = 16 >> step;
-            // positions with bit log2(d) set: 16 -> 0xFFFF0000, 8 -> 0xFF00FF00, ...
-            const uint32_t hi_sel = (d == 16) ? 0xFFFF0000u : (d == 8) ? 0xFF00FF00u : (d == 4) ? 0xF0F0F0F0u
-                                   : (d == 2) ? 0xCCCCCCCCu : 0xAAAAAAAAu;
-            const uint32_t keep = (lane & d) ? hi_sel : ~hi_sel;
-            uint32_t carry = 0;
-#pragma unroll
-            for (int j = 0; j < kPlanes + 1 + step; ++j) {
-                uint32_t mine = n[j] & keep;
-                uint32_t give = n[j] & ~keep;
-                uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, give, d);
-                uint32_t hi;
-                csa(hi, n[j], mine, got, carry);
-                carry = hi;
-            }
-            n[kPlanes + 1 + step] = carry;
-        }
-        uint32_t total = 0;
-#pragma unroll
-        for (int j = 0; j < W; ++j) total |= ((n[j] >> lane) & 1u) << j;
-        return total;
+        for (int l = 0; l < DYN; ++l)
+            if ((it >> l) & 1u) ripple_add(n, LOGC + l, kPlanes + 1, Q[l]);
+        return butterfly_totals(n, kPlanes + 1, lane);
     }
 };
 

@@ -18,7 +18,8 @@ namespace {
 constexpr int kThreads = 256;
 constexpr int kPairsPerTile = 16 * kThreads;
 
-template <int KIND, int MASK, bool XFORM, bool EDGE>
+// MODE 0: flat pairs (lo+t, lo+t+inner); 1: edge pairs; 2: single elements lo+t (a-stream only)
+template <int KIND, int MASK, bool XFORM, int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long long n, long long inner,
                 uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst) {
@@ -60,7 +61,7 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
             for (int w = 0; w < NW; ++w) { a[w] = 0; b[w] = 0; }
             if (t < count) {
                 long long f;
-                if (EDGE) {
+                if (MODE == 1) {
                     if (inner == 1) {
                         f = t * n + (n - 1);
                     } else {
@@ -71,16 +72,16 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
                     f = lo + t;
                 }
                 E::load(x, f, a);
-                E::load(x, f + inner, b);
+                if (MODE != 2) E::load(x, f + inner, b);
                 bool ok = true;
                 if (MASK == kMaskNaN) ok = !(E::is_nan(a) || E::is_nan(b));
                 if (MASK == kMaskValue) ok = !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
-                if (XFORM) { E::transform(a); E::transform(b); }
+                if (XFORM) { E::transform(a); if (MODE != 2) E::transform(b); }
                 if (!ok) {
 #pragma unroll
                     for (int w = 0; w < NW; ++w) { a[w] = 0; b[w] = 0; }
                 }
-                nvalid += ok ? 1u : 0u;
+                nvalid += (ok && MODE != 2) ? 1u : 0u;
             }
 #pragma unroll
             for (int w = 0; w < NW; ++w) { wa[w][u] = a[w]; wb[w][u] = b[w]; }
@@ -121,7 +122,7 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
     if (threadIdx.x == 0 && s_n) atomicAdd(&dst->npairs, s_n);
 }
 
-template <int KIND, int MASK, bool XFORM, bool EDGE>
+template <int KIND, int MASK, bool XFORM, int MODE>
 cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
     if (count <= 0) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -130,46 +131,46 @@ cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSu
     const long long tiles = (count + kPairsPerTile - 1) / kPairsPerTile;
     long long grid = (long long)sms * 4;
     if (grid > tiles) grid = tiles;
-    k_pairs_generic<KIND, MASK, XFORM, EDGE><<<(unsigned)grid, kThreads, 0, stream>>>(
+    k_pairs_generic<KIND, MASK, XFORM, MODE><<<(unsigned)grid, kThreads, 0, stream>>>(
         job.x, lo, count, job.n, job.inner, (uint32_t)(job.mask_bits & 0xFFFFFFFFu),
         (uint32_t)(job.mask_bits >> 32), dst);
     note_launch();
     return cudaGetLastError();
 }
 
-template <int KIND, bool EDGE>
+template <int KIND, int MODE>
 cudaError_t dispatch_mask(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (job.transform) {
         if constexpr (isf) {
             switch (job.mask_mode) {
-                case kMaskNone: return launch_one<KIND, kMaskNone, true, EDGE>(job, lo, count, dst, stream);
-                case kMaskNaN: return launch_one<KIND, kMaskNaN, true, EDGE>(job, lo, count, dst, stream);
-                default: return launch_one<KIND, kMaskValue, true, EDGE>(job, lo, count, dst, stream);
+                case kMaskNone: return launch_one<KIND, kMaskNone, true, MODE>(job, lo, count, dst, stream);
+                case kMaskNaN: return launch_one<KIND, kMaskNaN, true, MODE>(job, lo, count, dst, stream);
+                default: return launch_one<KIND, kMaskValue, true, MODE>(job, lo, count, dst, stream);
             }
         } else {
             return cudaErrorInvalidValue;
         }
     }
     switch (job.mask_mode) {
-        case kMaskNone: return launch_one<KIND, kMaskNone, false, EDGE>(job, lo, count, dst, stream);
+        case kMaskNone: return launch_one<KIND, kMaskNone, false, MODE>(job, lo, count, dst, stream);
         case kMaskNaN:
-            if constexpr (isf) return launch_one<KIND, kMaskNaN, false, EDGE>(job, lo, count, dst, stream);
+            if constexpr (isf) return launch_one<KIND, kMaskNaN, false, MODE>(job, lo, count, dst, stream);
             return cudaErrorInvalidValue;
-        default: return launch_one<KIND, kMaskValue, false, EDGE>(job, lo, count, dst, stream);
+        default: return launch_one<KIND, kMaskValue, false, MODE>(job, lo, count, dst, stream);
     }
 }
 
-template <bool EDGE>
+template <int MODE>
 cudaError_t dispatch_kind(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
     switch (job.dtype) {
-        case XBI_U8: return dispatch_mask<kU8, EDGE>(job, lo, count, dst, stream);
-        case XBI_U16: return dispatch_mask<kU16, EDGE>(job, lo, count, dst, stream);
-        case XBI_U32: return dispatch_mask<kU32, EDGE>(job, lo, count, dst, stream);
-        case XBI_U64: return dispatch_mask<kU64, EDGE>(job, lo, count, dst, stream);
-        case XBI_F16: return dispatch_mask<kF16, EDGE>(job, lo, count, dst, stream);
-        case XBI_F32: return dispatch_mask<kF32, EDGE>(job, lo, count, dst, stream);
-        case XBI_F64: return dispatch_mask<kF64, EDGE>(job, lo, count, dst, stream);
+        case XBI_U8: return dispatch_mask<kU8, MODE>(job, lo, count, dst, stream);
+        case XBI_U16: return dispatch_mask<kU16, MODE>(job, lo, count, dst, stream);
+        case XBI_U32: return dispatch_mask<kU32, MODE>(job, lo, count, dst, stream);
+        case XBI_U64: return dispatch_mask<kU64, MODE>(job, lo, count, dst, stream);
+        case XBI_F16: return dispatch_mask<kF16, MODE>(job, lo, count, dst, stream);
+        case XBI_F32: return dispatch_mask<kF32, MODE>(job, lo, count, dst, stream);
+        case XBI_F64: return dispatch_mask<kF64, MODE>(job, lo, count, dst, stream);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -178,12 +179,18 @@ cudaError_t dispatch_kind(const CountJob& job, long long lo, long long count, Ra
 
 cudaError_t launch_pairs_generic_flat(const CountJob& job, int64_t lo, int64_t hi, RawSums* dst,
                                       cudaStream_t stream) {
-    return dispatch_kind<false>(job, lo, hi - lo, dst, stream);
+    return dispatch_kind<0>(job, lo, hi - lo, dst, stream);
 }
 
 cudaError_t launch_pairs_generic_edges(const CountJob& job, RawSums* dst, cudaStream_t stream) {
     if (job.outer <= 1) return cudaSuccess;
-    return dispatch_kind<true>(job, 0, (job.outer - 1) * job.inner, dst, stream);
+    return dispatch_kind<1>(job, 0, (job.outer - 1) * job.inner, dst, stream);
+}
+
+cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream) {
+    CountJob j = job;
+    j.mask_mode = kMaskNone;
+    return dispatch_kind<2>(j, lo, count, dst, stream);
 }
 
 }  // namespace xbi

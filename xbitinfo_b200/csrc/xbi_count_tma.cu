@@ -400,7 +400,7 @@ cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst, 
     const unsigned grid = (unsigned)(nstages < sms ? nstages : sms);
     kern<<<grid, kThreads, smem_bytes<KIND>(), stream>>>(tmap, region, (long long)nstages, (uint32_t)job.mask_bits,
                                                           (uint32_t)(job.mask_bits >> 32), dst);
-    note_launch();
+    note_fast_launch();
     *done_lo = head;
     *done_hi = head + nstages * S::kElemsPerStage;
     return cudaGetLastError();

@@ -39,7 +39,8 @@ struct CountJob {
     int64_t outer, n, inner;
 };
 
-void note_launch();  // bumps the process-wide launch counter
+void note_launch();       // bumps the process-wide launch counter
+void note_fast_launch();  // ... and the fast-path counter
 
 // Flat pairs (f, f+inner) for f in [lo, hi) accumulated into `dst` -- any alignment.
 cudaError_t launch_pairs_generic_flat(const CountJob& job, int64_t lo, int64_t hi, RawSums* dst,
@@ -48,11 +49,19 @@ cudaError_t launch_pairs_generic_flat(const CountJob& job, int64_t lo, int64_t h
 // f = (o*n + n-1)*inner + i for o in [0, outer-1), i in [0, inner).
 cudaError_t launch_pairs_generic_edges(const CountJob& job, RawSums* dst, cudaStream_t stream);
 
+// Bit planes of the single elements f in [lo, lo+count) added to dst->sums[S_A] (transform
+// applied, no mask): the a-stream correction of the column walkers.
+cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream);
+
 // TMA fast paths.  Each consumes as much of [0, numel-inner) as its alignment rules
 // allow, reports the flat range it covered in [*done_lo, *done_hi) (empty if none), and
 // leaves the rest to the generic kernel.
 cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream,
                              int64_t* done_lo, int64_t* done_hi);
+
+// Column walkers for inner > 1 (16-byte aligned rows); covers flat pairs [*done_lo, *done_hi).
+cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
+                              int64_t* done_hi);
 
 cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* counts, cudaStream_t stream);
 cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, int set_zero,
