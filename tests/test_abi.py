@@ -1,0 +1,80 @@
+"""The C-ABI shared library: loads, exports every declared symbol, fails loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from xbitinfo_b200 import _native as nat
+from conftest import ROOT, _have_gpu
+
+
+def declared_functions():
+    text = open(os.path.join(ROOT, "include", "xbitinfo_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(xbi_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_is_built_in_tree():
+    assert os.path.exists(nat.LIB_PATH), "run `python -m xbitinfo_b200.csrc.build`"
+    assert nat.lib().xbi_abi_version() == 1
+
+
+def test_every_declared_symbol_is_exported():
+    lib = C.CDLL(nat.LIB_PATH)
+    names = declared_functions()
+    assert len(names) >= 10
+    for name in names:
+        assert hasattr(lib, name), f"{name} declared in include/xbitinfo_b200.h but not exported"
+    assert set(names) == set(nat.EXPORTED_SYMBOLS)
+
+
+def test_workspace_size_and_counters():
+    assert 1024 <= nat.lib().xbi_workspace_bytes() <= 1 << 16
+    assert nat.kernel_launches() >= 0
+    assert nat.fast_path_launches() <= nat.kernel_launches()
+
+
+def test_argument_errors_do_not_need_a_gpu():
+    x = np.zeros(16, dtype="float32")
+    lib = nat.lib()
+    rc = lib.xbi_bitround_host(x.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), nat.F32, 16, 24, 0)
+    assert rc == nat.ERR_ARG and b"keepbits too large" in lib.xbi_last_error()
+    rc = lib.xbi_bitround_host(x.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), nat.U32, 16, 3, 0)
+    assert rc == nat.ERR_ARG
+    with pytest.raises(ValueError):
+        nat.check(rc)
+    mi = np.empty(32)
+    rc = lib.xbi_bitinformation_host(x.ctypes.data_as(C.c_void_p), 99, 1, 16, 1, 0, 0, 0, 0.99,
+                                     mi.ctypes.data_as(C.c_void_p), None, 0)
+    assert rc == nat.ERR_ARG
+    rc = lib.xbi_bitinformation_host(x.ctypes.data_as(C.c_void_p), nat.U32, 1, 16, 1, nat.MASK_NAN, 0, 0, 0.99,
+                                     mi.ctypes.data_as(C.c_void_p), None, 0)
+    assert rc == nat.ERR_ARG
+
+
+@pytest.mark.skipif(_have_gpu(), reason="only meaningful on a box without a GPU")
+def test_product_path_fails_loudly_without_a_gpu():
+    from xbitinfo_b200 import engine
+
+    x = np.zeros((4, 8), dtype="float32")
+    with pytest.raises(nat.XbiError, match="no CUDA device"):
+        engine.bitinformation(x, 1)
+    with pytest.raises(nat.XbiError, match="no CUDA device"):
+        engine.bitround(x, 3)
+
+
+def test_product_package_does_not_import_the_oracle():
+    import importlib
+    import sys
+
+    for m in list(sys.modules):
+        if m.startswith("xbitinfo_b200"):
+            importlib.import_module(m)
+    pkg = os.path.join(ROOT, "xbitinfo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,231 @@
+"""The public API with implementation="cuda" against the CPU oracle -- written after the
+reference's own tests (tests/test_get_bitinformation.py, test_get_keepbits.py,
+test_bitround.py), on synthetic stand-ins for the tutorial datasets (no network here)."""
+import numpy as np
+import pytest
+import torch
+
+import xbitinfo_b200 as xb
+from oracle import bitinfo_oracle as bo
+from oracle import bitround_oracle as bro
+from oracle import keepbits_oracle as ko
+from xbitinfo_b200 import _native as nat
+from xbitinfo_b200 import engine
+from xbitinfo_b200.device import PairCounter, bitround_
+
+from conftest import smooth_field
+from test_counts_gpu import assert_mi_close
+
+pytestmark = pytest.mark.gpu
+
+
+def rasm_like(dtype="float64"):
+    rng = np.random.default_rng(0)
+    t = smooth_field(rng, (12, 40, 56), "float64", axis=0, scale=2.0, base=5.0)
+    t[:, rng.random((40, 56)) < 0.3] = np.nan
+    return xb.Dataset({"Tair": xb.DataArray(t.astype(dtype), dims=("time", "y", "x"), name="Tair", attrs={"units": "C"})})
+
+
+def eraint_like():
+    """BASELINE.json configs[0]: float32 z/u/v of shape (2, 3, 241, 480)."""
+    out = xb.Dataset()
+    for i, (name, base, scale) in enumerate([("z", 5.0e4, 30.0), ("u", 3.0, 0.8), ("v", -1.0, 0.6)]):
+        rng = np.random.default_rng(i)
+        x = smooth_field(rng, (2, 3, 241, 480), "float32", axis=-1, scale=scale, base=base)
+        out[name] = xb.DataArray(x, dims=("time", "level", "latitude", "longitude"), name=name)
+    return out
+
+
+def test_returns_dataset_and_is_sensitive_to_dim():
+    ds = rasm_like()
+    b0 = xb.get_bitinformation(ds, axis=0, implementation="cuda")
+    b2 = xb.get_bitinformation(ds, axis=2, implementation="cuda")
+    assert isinstance(b0, xb.Dataset)
+    assert not np.array_equal(b0["Tair"].values, b2["Tair"].values)
+    bx = xb.get_bitinformation(ds, dim="x")
+    assert np.array_equal(bx["Tair"].values, b2["Tair"].values)
+
+
+@pytest.mark.parametrize("dtype", ["float64", "float32", "float16", "int16"])
+def test_dtype_gives_number_of_bits(dtype):
+    ds = rasm_like()
+    if dtype == "int16":
+        ds = xb.Dataset({"Tair": xb.DataArray(np.nan_to_num(ds["Tair"].values).astype(dtype), dims=("time", "y", "x"))})
+    else:
+        ds = ds.astype(dtype)
+    bi = xb.get_bitinformation(ds, dim="x")
+    assert len(bi.coords["bit" + dtype].values) == np.dtype(dtype).itemsize * 8
+
+
+def test_masked_value_semantics():
+    ds = rasm_like()
+    x = ds["Tair"].values
+    default = xb.get_bitinformation(ds, dim="x", set_zero_insignificant=False)
+    nomask = xb.get_bitinformation(ds, dim="x", masked_value="nothing", set_zero_insignificant=False)
+    nomask2 = xb.get_bitinformation(ds, dim="x", masked_value=None, set_zero_insignificant=False)
+    filled = xb.Dataset({"Tair": xb.DataArray(np.where(np.isnan(x), -999.0, x), dims=("time", "y", "x"))})
+    fill = xb.get_bitinformation(filled, dim="x", masked_value=-999.0, set_zero_insignificant=False)
+    assert np.array_equal(nomask["Tair"].values, nomask2["Tair"].values)
+    # the default masks NaN on the raw values (documented deviation from reference quirk B3)
+    assert not np.array_equal(default["Tair"].values, nomask["Tair"].values)
+    # masking NaN or masking the fill value removes the same pairs: identical sign/mantissa information
+    assert_mi_close(default["Tair"].values, fill["Tair"].values)
+    _, _, ref = bo.bitinformation(x, 2, masked_value=float("nan"))
+    assert_mi_close(default["Tair"].values, ref)
+
+
+def test_set_zero_insignificant_and_confidence():
+    ds = eraint_like()
+    on = xb.get_bitinformation(ds, dim="longitude")  # default True, 0.99
+    off = xb.get_bitinformation(ds, dim="longitude", set_zero_insignificant=False)
+    c99 = xb.get_bitinformation(ds, dim="longitude", confidence=0.99)
+    c50 = xb.get_bitinformation(ds, dim="longitude", confidence=0.5)
+    assert np.array_equal(on["u"].values, c99["u"].values)
+    assert not np.array_equal(on["u"].values, off["u"].values)
+    assert not np.array_equal(c99["u"].values, c50["u"].values)
+    assert ((on["u"].values == 0) | (on["u"].values == off["u"].values)).all()
+
+
+def test_config0_implementations_agree_and_pipeline_is_exact():
+    """configs[0]: get_bitinformation(dim='longitude') + get_keepbits(0.99) + xr_bitround,
+    cuda vs the oracle of the reference's python path: information within 1e-12 (same
+    settings as the reference's own cross-implementation test), keepbits and rounded
+    arrays identical."""
+    ds = eraint_like()
+    bi = xb.get_bitinformation(ds, dim="longitude", implementation="cuda", set_zero_insignificant=False,
+                               masked_value=None)
+    keep = xb.get_keepbits(bi, 0.99)
+    rounded = xb.xr_bitround(ds, keep)
+    for v in ds.data_vars:
+        x = ds[v].values
+        _, _, ref = bo.bitinformation(x, 3, route="unpackbits")
+        assert_mi_close(bi[v].values, ref)
+        kref = ko.keepbits_from_info(ref, "float32", 0.99)
+        assert int(keep[v].values[0]) == kref
+        assert rounded[v].attrs["_QuantizeBitRoundNumberOfSignificantDigits"] == kref
+        assert np.array_equal(rounded[v].values.view("u4"), bro.bitround(x, kref).view("u4"))
+        assert not np.shares_memory(rounded[v].values, x)
+        assert (rounded[v].values != x).any()
+
+
+def test_all_dims_mixed_variables():
+    ds = rasm_like()
+    ds["Tair_mean"] = xb.DataArray(np.nanmean(ds["Tair"].values, axis=0), dims=("y", "x"))
+    ds["Tair32"] = ds["Tair"].astype("float32")
+    ds["Tair16"] = ds["Tair"].astype("float16")
+    bi = xb.get_bitinformation(ds, set_zero_insignificant=False)
+    assert list(bi.coords["dim"].values) == ["time", "x", "y"]
+    for bitdim in ("bitfloat16", "bitfloat32", "bitfloat64"):
+        assert bitdim in bi.dims
+    assert np.isnan(bi["Tair_mean"].sel(dim="time").values).all()
+    for d, axis in (("time", 0), ("y", 1), ("x", 2)):
+        _, _, ref = bo.bitinformation(ds["Tair16"].values, axis, masked_value=float("nan"))
+        assert_mi_close(bi["Tair16"].sel(dim=d).values, ref)
+
+
+@pytest.mark.parametrize("dtype,keeps", [("float16", range(0, 11)), ("float32", range(0, 24)), ("float64", range(0, 53, 3))])
+def test_bitround_bit_exact(dtype, keeps):
+    rng = np.random.default_rng(2)
+    x = (rng.standard_normal(100003) * np.exp(rng.uniform(-6, 6, 100003))).astype(dtype)
+    x[:7] = [0.0, -0.0, np.inf, -np.inf, np.nan, np.finfo(dtype).max, np.finfo(dtype).tiny]
+    ut = f"u{np.dtype(dtype).itemsize}"
+    for k in keeps:
+        got = engine.bitround(x, k)
+        assert np.array_equal(got.view(ut), bro.bitround(x, k).view(ut)), (dtype, k)
+    # every float16 bit pattern
+    if dtype == "float16":
+        allp = np.arange(1 << 16, dtype="uint16").view("float16")
+        for k in (0, 3, 9):
+            assert np.array_equal(engine.bitround(allp, k).view("u2"), bro.bitround(allp, k).view("u2"))
+
+
+def test_xr_bitround_interface():
+    ds = eraint_like().astype("float32")
+    for keepbits in (6, dict.fromkeys(ds.data_vars, 6)):
+        out = xb.xr_bitround(ds, keepbits)
+        for v in ds.data_vars:
+            np.testing.assert_allclose(out[v].values, ds[v].values, atol=0.01, rtol=0.01)
+            assert out[v].attrs["_QuantizeBitRoundNumberOfSignificantDigits"] == 6
+            assert (out[v].values != ds[v].values).any()
+    da = xb.xr_bitround(ds["u"], 6)
+    assert isinstance(da, xb.DataArray)
+    with pytest.raises(ValueError):
+        xb.xr_bitround(ds["u"], 24)
+    with pytest.raises(ValueError):
+        xb.xr_bitround(ds["u"], -1)
+    with pytest.raises(TypeError):
+        xb.xr_bitround(xb.DataArray(np.arange(5), dims=("x",), name="i"), 3)
+
+
+def test_device_tensors_unaligned_and_slab_accumulation():
+    rng = np.random.default_rng(8)
+    x = smooth_field(rng, (64, 96, 200), "float32", axis=-1, scale=0.2)
+    ref = {ax: bo.bitinformation(x, ax)[0] for ax in range(3)}
+    xt = torch.from_numpy(x).cuda()
+    pc = PairCounter(xt.dtype, xt.device)
+    for ax in range(3):
+        pc.reset(); pc.add(xt, ax)
+        assert np.array_equal(pc.counts.cpu().numpy(), ref[ax])
+    # unaligned base pointers: flat views starting 1..3 elements into the buffer
+    flat = torch.from_numpy(x.reshape(-1)).cuda()
+    for off in (1, 2, 3):
+        v = flat[off: off + 300000]
+        pc.reset(); pc.add(v, 0)
+        assert np.array_equal(pc.counts.cpu().numpy(), bo.bitinformation(x.reshape(-1)[off: off + 300000], 0)[0])
+    # slabs along a non-analysed axis add up; slabs along the analysed axis need the halo row
+    pc.reset()
+    for lo in range(0, 64, 16):
+        pc.add(xt[lo: lo + 16], 2)
+    assert np.array_equal(pc.counts.cpu().numpy(), ref[2])
+    pc.reset()
+    for lo in range(0, 64, 16):
+        hi = min(lo + 16 + 1, 64)  # halo: first row of the next slab
+        pc.add(xt[lo:hi], 0)
+    assert np.array_equal(pc.counts.cpu().numpy(), ref[0])
+    mi = pc.information().cpu().numpy()
+    assert_mi_close(mi, bo.mutual_information_from_counts(ref[0], int(ref[0][0].sum())))
+    # torch tensors through the public API stay on the device
+    ds = xb.Dataset({"t": xb.DataArray(xt, dims=("a", "b", "c"), name="t")})
+    bi = xb.get_bitinformation(ds, dim="c", masked_value=None, set_zero_insignificant=False)
+    assert_mi_close(bi["t"].values, bo.bitinformation(x, 2)[2])
+    y = bitround_(xt.clone(), 9)
+    assert np.array_equal(y.cpu().numpy().view("u4"), bro.bitround(x, 9).view("u4"))
+
+
+def test_host_path_streams_large_arrays_in_slabs(monkeypatch):
+    """Force tiny staging buffers so every slab plan of xbi_bitinformation_host runs:
+    whole blocks, column strips and row strips with halo."""
+    import os
+    import subprocess
+    import sys
+
+    code = r'''
+import sys, numpy as np
+sys.path.insert(0, ".")
+sys.path.insert(0, "tests")
+from conftest import smooth_field
+from oracle import bitinfo_oracle as bo
+from xbitinfo_b200 import engine
+rng = np.random.default_rng(5)
+x = smooth_field(rng, (6, 700, 384), "float32", axis=1, scale=0.3)     # 6.4 MB, staging is 1 MB
+for ax in range(3):
+    mi, c = engine.bitinformation(x, ax, return_counts=True)
+    assert np.array_equal(c, bo.bitinformation(x, ax)[0]), ax
+y = smooth_field(rng, (3000000,), "float32", axis=0, scale=0.3)          # 12 MB 1-D: row strips with halo
+mi, c = engine.bitinformation(y, 0, return_counts=True)
+assert np.array_equal(c, bo.bitinformation(y, 0)[0])
+z = engine.bitround(y, 5)
+from oracle import bitround_oracle as bro
+assert np.array_equal(z.view("u4"), bro.bitround(y, 5).view("u4"))
+print("ok")
+'''
+    env = dict(os.environ, XBI_STAGING_MB="1")
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_launch_counters_move():
+    before = nat.kernel_launches()
+    engine.bitinformation(np.zeros((8, 64), dtype="float32"), 1)
+    assert nat.kernel_launches() > before

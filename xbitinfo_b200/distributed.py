@@ -1,0 +1,96 @@
+"""Multi-GPU: shard planning and the one collective of the path.
+
+Pairs only couple neighbours along the analysed axis and the pair histogram is a plain sum
+over pairs (``xbitinfo/_py_bitinfo.py:124, 155-160``), so the pair set partitions along any
+other axis and integer counts add.  One process per GPU (``torch.distributed``, NCCL over
+NVLink/NVSwitch): every rank counts its slab locally with K1, then a single
+``all_reduce(SUM)`` of the ``int64[nbits,2,2]`` table (<= 2 KiB, latency-bound) gives every
+rank the global counts; K2 runs redundantly on each rank.  No data-path collective.
+
+When the array can only be split along the analysed axis itself, each shard but the last
+additionally reads one halo row (the first row of the next shard) so that the pair across
+the cut is counted exactly once.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+def shard_bounds(n_units: int, world_size: int, rank: int):
+    """Contiguous split of ``n_units`` into ``world_size`` parts; the first ``n_units %
+    world_size`` parts are one unit longer.  Returns (lo, hi)."""
+    base, extra = divmod(n_units, world_size)
+    lo = rank * base + min(rank, extra)
+    hi = lo + base + (1 if rank < extra else 0)
+    return lo, hi
+
+
+@dataclass(frozen=True)
+class ShardPlan:
+    split_axis: int   # axis of the global array that is cut
+    lo: int           # first index of this rank's slab along split_axis
+    hi: int           # one past the last index it owns
+    halo: int         # extra trailing rows it must also hold (0 or 1; only when split_axis == axis)
+
+    @property
+    def read_slice(self):
+        return slice(self.lo, self.hi + self.halo)
+
+
+def plan_shard(shape, axis: int, world_size: int, rank: int) -> ShardPlan:
+    """Which slab of a C-contiguous array of ``shape`` rank ``rank`` analyses for adjacency
+    along ``axis``.  Prefers the outermost non-analysed axis that is long enough to give
+    every rank work; falls back to cutting the analysed axis with a one-row halo."""
+    ndim = len(shape)
+    axis %= ndim
+    for ax in range(ndim):
+        if ax != axis and shape[ax] >= world_size:
+            lo, hi = shard_bounds(shape[ax], world_size, rank)
+            return ShardPlan(ax, lo, hi, 0)
+    # cut the analysed axis: pairs (j, j+1) with lo <= j < hi belong to this rank, so it
+    # reads rows lo .. hi (the halo) unless it owns the end of the axis
+    n = shape[axis]
+    lo, hi = shard_bounds(n, world_size, rank)
+    halo = 1 if (hi < n and hi > lo) else 0
+    return ShardPlan(axis, lo, hi, halo)
+
+
+def is_initialized() -> bool:
+    try:
+        import torch.distributed as dist
+
+        return dist.is_available() and dist.is_initialized()
+    except Exception:
+        return False
+
+
+def world():
+    """(rank, world_size) of the default process group, (0, 1) when not initialised."""
+    if not is_initialized():
+        return 0, 1
+    import torch.distributed as dist
+
+    return dist.get_rank(), dist.get_world_size()
+
+
+def allreduce_counts(counts, group=None):
+    """In-place SUM all-reduce of a counts tensor (int64).  NCCL for CUDA tensors, gloo for
+    CPU tensors (tests).  A no-op without an initialised process group."""
+    if not is_initialized():
+        return counts
+    import torch.distributed as dist
+
+    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+    return counts
+
+
+def sharded_bitinformation(local_slab, axis: int, masked_value=None, set_zero_insignificant: bool = False,
+                           confidence: float = 0.99, return_counts: bool = False):
+    """Information per bit of the GLOBAL array whose rank-local slab (as cut by
+    :func:`plan_shard`, halo row included) is ``local_slab`` (a CUDA tensor).  Every rank
+    returns the same numpy result."""
+    from .engine import bitinformation
+
+    return bitinformation(local_slab, axis, masked_value=masked_value,
+                          set_zero_insignificant=set_zero_insignificant, confidence=confidence,
+                          return_counts=return_counts, sharded=True)

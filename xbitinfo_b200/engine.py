@@ -1,0 +1,117 @@
+"""One variable, one axis: raw array in, information per bit out (K1 -> K2).
+
+This is the function behind the ``implementation="cuda"`` branch; it is the B200
+counterpart of ``pb.bitinformation(X, axis).compute()`` at ``xbitinfo/xbitinfo.py:366``
+together with the transform/cast that precedes it (``349-355``).
+
+* numpy (host) arrays go through the C ABI's host-buffer entry point
+  (``xbi_bitinformation_host``): slabs are staged host->device, counted, and only the
+  ``nbits`` doubles come back.
+* torch CUDA tensors are counted in place in HBM (``xbi_count_pairs`` +
+  ``xbi_mutual_information``); with an initialised ``torch.distributed`` NCCL group and
+  ``sharded=True`` the per-rank counts are summed with one all-reduce first.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as nat
+
+
+def _is_torch_tensor(x) -> bool:
+    return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
+
+
+def _native_contiguous(x: np.ndarray) -> np.ndarray:
+    if not x.dtype.isnative:
+        x = x.astype(x.dtype.newbyteorder("="))
+    return np.ascontiguousarray(x)
+
+
+def bitinformation(data, axis: int, masked_value=None, set_zero_insignificant: bool = False,
+                   confidence: float = 0.99, device: int | None = None, return_counts: bool = False,
+                   sharded: bool = False):
+    """float64[nbits] information per bit (most significant bit first) of ``data`` along
+    ``axis``; with ``return_counts`` also the (nbits,2,2) int64 pair counts."""
+    if _is_torch_tensor(data):
+        return _bitinformation_device(data, axis, masked_value, set_zero_insignificant, confidence,
+                                      return_counts, sharded)
+    if sharded:
+        raise ValueError("sharded=True needs per-rank CUDA tensors")
+    x = np.asarray(data)
+    code = nat.dtype_code(x.dtype)  # raises ValueError for unsupported dtypes
+    x = _native_contiguous(x)
+    if x.ndim == 0:
+        raise ValueError("cannot analyse a 0-d array")
+    axis = axis % x.ndim
+    outer = int(np.prod(x.shape[:axis], dtype=np.int64))
+    n = int(x.shape[axis])
+    inner = int(np.prod(x.shape[axis + 1:], dtype=np.int64))
+    nbits = 8 * x.dtype.itemsize
+    flags, bits = nat.mask_spec(x.dtype, masked_value)
+    if x.dtype.kind == "f":
+        flags |= nat.SIGNED_EXPONENT
+    mi = np.empty(nbits, dtype=np.float64)
+    counts = np.empty(nbits * 4, dtype=np.uint64)
+    if device is None:
+        device = _current_device()
+    rc = nat.lib().xbi_bitinformation_host(
+        x.ctypes.data_as(C.c_void_p), code, outer, n, inner, flags, bits, int(bool(set_zero_insignificant)),
+        float(confidence), mi.ctypes.data_as(C.c_void_p), counts.ctypes.data_as(C.c_void_p), int(device))
+    nat.check(rc)
+    if return_counts:
+        return mi, counts.reshape(nbits, 2, 2).astype(np.int64)
+    return mi
+
+
+def _current_device() -> int:
+    try:
+        import torch
+
+        if torch.cuda.is_available():
+            return torch.cuda.current_device()
+    except Exception:  # torch is plumbing, not a requirement of the host path
+        pass
+    return 0
+
+
+def _bitinformation_device(x, axis, masked_value, set_zero, confidence, return_counts, sharded):
+    from .device import PairCounter
+
+    if x.dim() == 0:
+        raise ValueError("cannot analyse a 0-d array")
+    if not x.is_contiguous():
+        x = x.contiguous()
+    pc = PairCounter(x.dtype, x.device)
+    pc.add(x, axis, masked_value=masked_value)
+    if sharded:
+        from .distributed import allreduce_counts
+
+        allreduce_counts(pc.counts)
+    mi = pc.information(set_zero, confidence).cpu().numpy()
+    if return_counts:
+        return mi, pc.counts.cpu().numpy()
+    return mi
+
+
+def bitround(data, keepbits: int, device: int | None = None):
+    """New array rounded to ``keepbits`` mantissa bits (K3); the input is not modified
+    (``xbitinfo/bitround.py:10``).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out."""
+    if _is_torch_tensor(data):
+        from .device import bitround_
+
+        return bitround_(data.contiguous().clone(), keepbits)
+    x = np.asarray(data)
+    if x.dtype.kind != "f" or x.dtype.itemsize > 8:
+        raise TypeError("Only float arrays (16-64bit) can be bit-rounded")
+    code = nat.dtype_code(x.dtype)
+    src = _native_contiguous(x)
+    out = np.empty_like(src)
+    if device is None:
+        device = _current_device()
+    rc = nat.lib().xbi_bitround_host(src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), code,
+                                     src.size, int(keepbits), int(device))
+    nat.check(rc)
+    return out
