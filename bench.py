@@ -1,0 +1,423 @@
+#!/usr/bin/env python
+"""bench.py -- the judged measurement of the bit-information hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): one ERA5-like float32 variable of shape
+(8760, 721, 1440) (36.4 GB), get_bitinformation along ``longitude`` (the last axis).
+One *step* = one pass of the hot path over that array, resident in HBM:
+K1 pair counting (TMA fast path + edge/tail passes + combine), the NCCL all-reduce of the
+int64[32,2,2] counts when N > 1, and the K2 mutual-information epilogue.  ``value`` is GB/s
+of input for the whole job.  With N > 1 every rank holds its own (8760, 721, 1440) time slab
+of a global (N*8760, 721, 1440) array ("weak"; ``--scaling strong`` splits the one array).
+
+``--impl reference`` times the reference's CPU algorithm (the numpy restatement in
+oracle/, the reference package itself cannot be imported in this image) on a bounded
+sample of the same workload with the thread-level parallelism its dask graph has (one
+task per byte plane).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "get_bitinformation_input_throughput"
+UNIT = "GB/s"
+FULL_SHAPE = (8760, 721, 1440)
+HBM_NOMINAL_GBS = 8000.0  # north star: "~8 TB/s peak"
+HBM_FALLBACK_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--time-steps", type=int, default=FULL_SHAPE[0], help="override the length of the time axis (debug)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------
+# synthetic data: base + cumulative sum of noise along longitude
+# --------------------------------------------------------------------------------------
+def synth_device(shape, seed, device):
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.empty(shape, dtype=torch.float32, device=device)
+    step = max(1, (256 << 20) // (shape[1] * shape[2] * 4))
+    for lo in range(0, shape[0], step):
+        blk = x[lo: lo + step]
+        blk.normal_(0.0, 0.35, generator=g)
+        torch.cumsum(blk, dim=-1, out=blk)
+        blk += 287.0
+    return x
+
+
+def synth_host(shape, seed):
+    import numpy as np
+
+    rng = np.random.default_rng(seed)
+    return (287.0 + np.cumsum(rng.standard_normal(shape, dtype=np.float32) * np.float32(0.35), axis=-1)).astype(np.float32)
+
+
+# --------------------------------------------------------------------------------------
+# clocks during the timed region
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {
+        0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+        0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x10: "sync_boost",
+    }
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                getter = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+                mask = int(getter(self.h))
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# --------------------------------------------------------------------------------------
+# the reference's CPU algorithm (oracle port) -- only the checker/baseline legs use it
+# --------------------------------------------------------------------------------------
+def reference_step(x, threads):
+    """One pass of the reference python path over ``x`` along the last axis with the
+    parallelism of its dask graph: one task per byte plane (xbitinfo/_py_bitinfo.py:128-140)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    import numpy as np
+
+    from oracle import bitinfo_oracle as bo
+
+    X = bo.to_analysis_words(x)
+    a, b = bo.adjacent_views(X, x.ndim - 1)
+    nbytes = X.dtype.itemsize
+    a, b = np.broadcast_arrays(a, b)
+
+    def plane(i):
+        s = (nbytes - 1 - i) * 8
+        return bo._paircount_byteplane((a >> s).astype("u1"), (b >> s).astype("u1"))
+
+    if threads > 1:
+        with ThreadPoolExecutor(max_workers=threads) as ex:
+            planes = list(ex.map(plane, range(nbytes)))
+    else:
+        planes = [plane(i) for i in range(nbytes)]
+    counts = np.concatenate(planes, axis=0).astype(np.int64)
+    return bo.mutual_information_from_counts(counts, a.size)
+
+
+def cpu_sample_rows(budget_s, per_step_steps, threads):
+    """How many time steps of the workload one CPU step may cover so that
+    ``per_step_steps`` steps fit in ``budget_s`` (calibrated on one time step)."""
+    x = synth_host((1,) + FULL_SHAPE[1:], 99)
+    t0 = time.perf_counter()
+    reference_step(x, threads)
+    t1 = time.perf_counter() - t0
+    rows = int(budget_s / max(per_step_steps, 1) / max(t1, 1e-3))
+    return max(1, min(rows, 16))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    threads = min(4, cores)  # float32: four byte planes = four independent dask task chains
+    steps, warm = args.steps, args.warmup
+    rows = cpu_sample_rows(150.0, steps + warm, threads)
+    x = synth_host((rows,) + FULL_SHAPE[1:], 1234)
+    for _ in range(warm):
+        reference_step(x, threads)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        reference_step(x, threads)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    gbs = x.nbytes / dt / 1e9
+    sample = f"({rows},{FULL_SHAPE[1]},{FULL_SHAPE[2]}) float32 time-slab of the workload per step, dim=longitude"
+    line = {
+        "impl": "reference", "metric": METRIC, "value": gbs, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+        "config": workload_config(args, 1),
+        "cpu_baseline": {"value": gbs, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "host_cores_available": cores,
+                         "note": "numpy restatement of xbitinfo/_py_bitinfo.py (oracle/); the reference package needs xarray/dask/numcodecs, absent here"},
+        "e2e": {"value": gbs, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, world):
+    shape = (args.time_steps,) + FULL_SHAPE[1:]
+    return {
+        "workload": "configs[1]: ERA5-like float32 (8760,721,1440), get_bitinformation dim='longitude' "
+                    "(masked_value=None, set_zero_insignificant=False: the reference python path's semantics)",
+        "per_gpu_shape": list(shape if args.scaling == "weak" else (shape[0] // world,) + shape[1:]),
+        "global_shape": [shape[0] * world if args.scaling == "weak" else shape[0], shape[1], shape[2]],
+        "sharding": "time axis, one slab per GPU, one all-reduce of int64[32,2,2] counts" if world > 1 else "none",
+        "l2": "input per GPU is far larger than the 126 MB L2 (no flush needed)",
+    }
+
+
+# --------------------------------------------------------------------------------------
+# our arm
+# --------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from xbitinfo_b200 import _native as nat
+    from xbitinfo_b200 import distributed as xdist
+    from xbitinfo_b200.device import PairCounter
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    shape = (args.time_steps,) + FULL_SHAPE[1:]
+    if args.scaling == "strong" and world > 1:
+        lo, hi = xdist.shard_bounds(shape[0], world, rank)
+        shape = (hi - lo,) + shape[1:]
+    x = synth_device(shape, 1234 + rank, dev)
+    nbytes_local = x.numel() * 4
+    pc = PairCounter(x.dtype, dev)
+    sync_all = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
+
+    def step():
+        pc.reset()
+        pc.add(x, -1, masked_value=None)  # K1
+        if world > 1:
+            xdist.allreduce_counts(pc.counts)  # the path's one collective
+        return pc.information(False)  # K2
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    sync_all()
+    launches0 = nat.kernel_launches()
+    nat.profile_enable(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clocks:
+        sync_all()
+        e0.record()
+        for _ in range(args.steps):
+            mi_dev = step()
+        e1.record()
+        sync_all()
+    elapsed_ms = e0.elapsed_time(e1)
+    kern_ms, kern_n, kern_bytes = nat.profile_collect()
+    nat.profile_enable(False)
+    launches = nat.kernel_launches() - launches0
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    total_bytes = nbytes_local * world
+    value = total_bytes / (ms_per_step * 1e-3) / 1e9
+    mi = mi_dev.cpu().numpy()
+
+    # roofline of the dominant kernel (TMA row kernel), timed with events on its own stream
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", HBM_FALLBACK_GBS))
+    achieved = (kern_bytes / kern_n) / (kern_ms / kern_n * 1e-3) / 1e9 if kern_n else None
+    roofline = {
+        "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": (achieved / peak) if achieved else None,
+        "peak_source": "MEASURED_PEAKS.json hbm_gbs (copy, of measured)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (of fallback)",
+        "frac_of_nominal_8TBs": (achieved / HBM_NOMINAL_GBS) if achieved else None,
+        "kernel": "k_pairs_rows_tma<f32,unmasked>", "launches_timed": kern_n,
+        "algorithmic_bytes_per_launch": (kern_bytes / kern_n) if kern_n else None,
+        "kernel_ms_avg": (kern_ms / kern_n) if kern_n else None,
+        "kernel_share_of_step": (kern_ms / elapsed_ms) if kern_n else None,
+        "traffic": None,  # dram__bytes per launch from ncu --set full: see profiles/
+    }
+    traffic_file = os.path.join(ROOT, "profiles", "k1_rows_f32_dram_bytes.json")
+    if os.path.exists(traffic_file):
+        try:
+            tr = json.load(open(traffic_file))
+            roofline["traffic"] = tr.get("dram_bytes_per_input_byte", 0) * roofline["algorithmic_bytes_per_launch"]
+            roofline["traffic_source"] = tr.get("source")
+        except Exception:
+            pass
+
+    # K3 on the same array (second half of the headline metric)
+    bitround_gbs = None
+    if rank == 0:
+        from xbitinfo_b200.device import bitround_
+
+        y = x[: min(shape[0], 2048)].clone()
+        for _ in range(3):
+            bitround_(y, 7)
+        torch.cuda.synchronize()
+        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        b0.record()
+        for _ in range(10):
+            bitround_(y, 7)
+        b1.record()
+        torch.cuda.synchronize()
+        bitround_gbs = y.numel() * 4 / (b0.elapsed_time(b1) / 10 * 1e-3) / 1e9
+        del y
+
+    # end to end through the public API with host buffers (H2D inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(args, x, rank, world, dev, sync_all)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rows = cpu_sample_rows(20.0, 1, 1)
+        xs = synth_host((rows,) + FULL_SHAPE[1:], 1234)
+        t0 = time.perf_counter()
+        reference_step(xs, 1)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {
+            "value": xs.nbytes / dt / 1e9, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"({rows},{FULL_SHAPE[1]},{FULL_SHAPE[2]}) float32 time-slab of the workload, one pass, dim=longitude",
+            "host_cores_available": os.cpu_count(),
+        }
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": args.scaling, "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+            "config": workload_config(args, world),
+            "pct_hbm_peak_nominal": 100.0 * value / (HBM_NOMINAL_GBS * world),
+            "pct_hbm_peak_measured": 100.0 * value / (peak * world),
+            "xr_bitround_input_GBps": bitround_gbs,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "gpu_launches": int(launches), "clocks": clocks.summary(),
+            "info_bits_preview": [float(v) for v in mi[:12]],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, x_dev, rank, world, dev, sync_all):
+    """Same metric through the public host-buffer API: numpy array in pinned host memory ->
+    sharded_bitinformation (xbi_bitinformation_host: slabs H2D + K1, then all-reduce + K2)
+    -> 32 doubles back.  The host array is the largest time-slab of the workload that fits
+    comfortably in host RAM."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from xbitinfo_b200 import distributed as xdist
+
+    try:
+        import psutil
+
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 64 << 30
+    full = x_dev.numel() * 4
+    budget = int(avail * 0.35 / max(world, 1))
+    rows = x_dev.shape[0] if full <= budget else max(1, int(x_dev.shape[0] * budget / full))
+    rows = min(rows, x_dev.shape[0])
+    try:
+        host = torch.empty((rows,) + tuple(x_dev.shape[1:]), dtype=torch.float32, pin_memory=True)
+        pinned = True
+    except Exception:
+        host = torch.empty((rows,) + tuple(x_dev.shape[1:]), dtype=torch.float32)
+        pinned = False
+    host.copy_(x_dev[:rows])
+    torch.cuda.synchronize()
+    xh = host.numpy()
+    steps = max(1, min(args.e2e_steps, args.steps))
+    xdist.sharded_bitinformation(xh, -1, masked_value=None, device=dev.index)  # warm (staging buffers)
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        mi = xdist.sharded_bitinformation(xh, -1, masked_value=None, device=dev.index)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / steps
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    return {
+        "value": xh.nbytes * world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes),
+        "d2h_bytes_per_step": int(32 * 8 + 32 * 4 * 8), "steps": steps, "pinned": pinned,
+        "sample": f"({rows},{x_dev.shape[1]},{x_dev.shape[2]}) float32 per GPU"
+                  + ("" if rows == x_dev.shape[0] else " (host RAM bound: time-slab of the workload)"),
+        "api": "xbitinfo_b200.distributed.sharded_bitinformation(numpy) -> xbi_bitinformation_host (C ABI)",
+    }
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

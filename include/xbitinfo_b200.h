@@ -70,6 +70,15 @@ unsigned long long xbi_kernel_launches(void);
 /* how many of those were fast-path counting kernels (TMA rows / column walkers) */
 unsigned long long xbi_fast_path_launches(void);
 
+/*
+ * Measurement aid (per host thread): while enabled, xbi_count_pairs brackets its fast-path
+ * counting kernel with CUDA events on the caller's stream.  xbi_profile_collect waits for
+ * them and returns the summed kernel time, the number of timed launches and the input
+ * bytes those launches covered.  Enabling resets the tallies.
+ */
+void xbi_profile_enable(int on);
+int xbi_profile_collect(double* total_ms, unsigned long long* launches, unsigned long long* bytes);
+
 /* bytes of device scratch xbi_count_pairs needs (contents are overwritten) */
 size_t xbi_workspace_bytes(void);
 

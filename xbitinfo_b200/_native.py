@@ -65,6 +65,10 @@ def lib() -> C.CDLL:
     L.xbi_kernel_launches.argtypes = []
     L.xbi_fast_path_launches.restype = C.c_ulonglong
     L.xbi_fast_path_launches.argtypes = []
+    L.xbi_profile_enable.restype = None
+    L.xbi_profile_enable.argtypes = [i32]
+    L.xbi_profile_collect.restype = i32
+    L.xbi_profile_collect.argtypes = [vp, vp, vp]
     L.xbi_workspace_bytes.restype = C.c_size_t
     L.xbi_workspace_bytes.argtypes = []
     L.xbi_count_pairs.restype = i32
@@ -87,7 +91,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = (
     "xbi_abi_version", "xbi_last_error", "xbi_kernel_launches", "xbi_fast_path_launches",
-    "xbi_workspace_bytes",
+    "xbi_workspace_bytes", "xbi_profile_enable", "xbi_profile_collect",
     "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace",
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
 )
@@ -111,6 +115,17 @@ def kernel_launches() -> int:
 
 def fast_path_launches() -> int:
     return int(lib().xbi_fast_path_launches())
+
+
+def profile_enable(on: bool) -> None:
+    lib().xbi_profile_enable(int(bool(on)))
+
+
+def profile_collect():
+    """(total kernel ms, timed launches, input bytes covered) since profile_enable(True)."""
+    ms, n, b = C.c_double(0.0), C.c_ulonglong(0), C.c_ulonglong(0)
+    check(lib().xbi_profile_collect(C.byref(ms), C.byref(n), C.byref(b)))
+    return ms.value, int(n.value), int(b.value)
 
 
 def mask_spec(dtype, masked_value):

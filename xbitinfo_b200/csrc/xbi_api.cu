@@ -55,6 +55,27 @@ static int make_job(CountJob& job, const void* x, int dtype, int64_t outer, int6
     return XBI_OK;
 }
 
+// ---------------------------------------------------------------------------------
+// optional timing of the dominant (fast-path) kernel: event pairs around its launch
+// ---------------------------------------------------------------------------------
+struct Profile {
+    static constexpr int kMax = 4096;
+    bool enabled = false;
+    int used = 0;
+    cudaEvent_t ev[2 * kMax];
+    int made = 0;
+    unsigned long long bytes = 0;  // algorithmic bytes covered by the timed launches
+};
+static thread_local Profile g_prof;
+
+static cudaEvent_t prof_event(int idx) {
+    while (g_prof.made <= idx) {
+        cudaEventCreate(&g_prof.ev[g_prof.made]);
+        ++g_prof.made;
+    }
+    return g_prof.ev[idx];
+}
+
 static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long long* counts_dev, Workspace* ws,
                             cudaStream_t stream) {
     const int nbits = 8 * dtype_bytes(job.dtype);
@@ -64,10 +85,19 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
     const int64_t npairs_flat = numel - job.inner;
     int64_t dlo = 0, dhi = 0;
     if (!(flags & XBI_FORCE_GENERIC)) {
+        const bool timed = g_prof.enabled && g_prof.used < Profile::kMax;
+        if (timed) XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used), stream), "cudaEventRecord");
         if (job.inner == 1)
             XBI_CUDA(launch_pairs_tma(job, npairs_flat, &ws->plus, stream, &dlo, &dhi), "pair counting (TMA rows)");
         else
             XBI_CUDA(launch_pairs_cols(job, ws, stream, &dlo, &dhi), "pair counting (column walkers)");
+        if (timed) {
+            XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used + 1), stream), "cudaEventRecord");
+            if (dhi > dlo) {
+                g_prof.bytes += (unsigned long long)(dhi - dlo) * dtype_bytes(job.dtype);
+                ++g_prof.used;
+            }
+        }
     }
     if (dhi <= dlo) { dlo = 0; dhi = 0; }
     XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
@@ -145,6 +175,26 @@ const char* xbi_last_error(void) { return g_last_error.c_str(); }
 unsigned long long xbi_kernel_launches(void) { return g_launches.load(std::memory_order_relaxed); }
 unsigned long long xbi_fast_path_launches(void) { return g_fast_launches.load(std::memory_order_relaxed); }
 size_t xbi_workspace_bytes(void) { return sizeof(Workspace); }
+
+void xbi_profile_enable(int on) {
+    g_prof.enabled = on != 0;
+    g_prof.used = 0;
+    g_prof.bytes = 0;
+}
+
+int xbi_profile_collect(double* total_ms, unsigned long long* launches, unsigned long long* bytes) {
+    double sum = 0.0;
+    for (int i = 0; i < g_prof.used; ++i) {
+        XBI_CUDA(cudaEventSynchronize(g_prof.ev[2 * i + 1]), "cudaEventSynchronize");
+        float ms = 0.f;
+        XBI_CUDA(cudaEventElapsedTime(&ms, g_prof.ev[2 * i], g_prof.ev[2 * i + 1]), "cudaEventElapsedTime");
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = (unsigned long long)g_prof.used;
+    if (bytes) *bytes = g_prof.bytes;
+    return XBI_OK;
+}
 
 int xbi_count_pairs(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner, unsigned flags,
                     uint64_t mask_bits, unsigned long long* counts_dev, void* workspace_dev, size_t workspace_bytes,

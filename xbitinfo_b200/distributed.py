@@ -85,12 +85,32 @@ def allreduce_counts(counts, group=None):
 
 
 def sharded_bitinformation(local_slab, axis: int, masked_value=None, set_zero_insignificant: bool = False,
-                           confidence: float = 0.99, return_counts: bool = False):
+                           confidence: float = 0.99, return_counts: bool = False, device=None):
     """Information per bit of the GLOBAL array whose rank-local slab (as cut by
-    :func:`plan_shard`, halo row included) is ``local_slab`` (a CUDA tensor).  Every rank
-    returns the same numpy result."""
-    from .engine import bitinformation
+    :func:`plan_shard`, halo row included) is ``local_slab``.  A CUDA tensor is counted in
+    place; a numpy array is streamed through the host-buffer entry point of the C ABI.
+    The per-rank ``int64[nbits,2,2]`` counts are summed with one all-reduce and K2 runs on
+    every rank, so every rank returns the same numpy result."""
+    import numpy as np
+    import torch
 
-    return bitinformation(local_slab, axis, masked_value=masked_value,
-                          set_zero_insignificant=set_zero_insignificant, confidence=confidence,
-                          return_counts=return_counts, sharded=True)
+    from . import engine
+    from .device import PairCounter
+
+    if type(local_slab).__module__.startswith("torch"):
+        return engine.bitinformation(local_slab, axis, masked_value=masked_value,
+                                     set_zero_insignificant=set_zero_insignificant, confidence=confidence,
+                                     return_counts=return_counts, sharded=True)
+    x = np.asarray(local_slab)
+    _, counts = engine.bitinformation(x, axis, masked_value=masked_value, return_counts=True, device=device)
+    dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+    tdtype = getattr(torch, {"int8": "uint8"}.get(x.dtype.name, x.dtype.name), None)
+    if tdtype is None:  # unsigned types torch lacks: same width signed
+        tdtype = getattr(torch, x.dtype.name.replace("uint", "int"))
+    pc = PairCounter(tdtype, dev)
+    pc.counts.copy_(torch.from_numpy(counts))
+    allreduce_counts(pc.counts)
+    mi = pc.information(set_zero_insignificant, confidence).cpu().numpy()
+    if return_counts:
+        return mi, pc.counts.cpu().numpy()
+    return mi
