@@ -84,11 +84,12 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
     XBI_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), stream), "cudaMemsetAsync(workspace)");
     const int64_t npairs_flat = numel - job.inner;
     int64_t dlo = 0, dhi = 0;
+    bool edges_done = false;
     if (!(flags & XBI_FORCE_GENERIC)) {
         const bool timed = g_prof.enabled && g_prof.used < Profile::kMax;
         if (timed) XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used), stream), "cudaEventRecord");
         if (job.inner == 1)
-            XBI_CUDA(launch_pairs_tma(job, npairs_flat, &ws->plus, stream, &dlo, &dhi), "pair counting (TMA rows)");
+            XBI_CUDA(launch_pairs_tma(job, npairs_flat, ws, stream, &dlo, &dhi, &edges_done), "pair counting (TMA rows)");
         else
             XBI_CUDA(launch_pairs_cols(job, ws, stream, &dlo, &dhi), "pair counting (column walkers)");
         if (timed) {
@@ -99,10 +100,17 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
             }
         }
     }
-    if (dhi <= dlo) { dlo = 0; dhi = 0; }
+    if (dhi <= dlo) { dlo = 0; dhi = 0; edges_done = false; }
     XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
     XBI_CUDA(launch_pairs_generic_flat(job, dhi, npairs_flat, &ws->plus, stream), "pair counting (generic, tail)");
-    XBI_CUDA(launch_pairs_generic_edges(job, &ws->minus, stream), "pair counting (edge pairs)");
+    const int64_t nedges = (job.outer - 1) * job.inner;
+    if (edges_done) {
+        // inner == 1: edge t sits at flat index t*n + n-1; those inside [dlo, dhi) are done
+        XBI_CUDA(launch_pairs_generic_edges(job, 0, dlo / job.n, &ws->minus, stream), "pair counting (edge pairs, head)");
+        XBI_CUDA(launch_pairs_generic_edges(job, dhi / job.n, nedges, &ws->minus, stream), "pair counting (edge pairs, tail)");
+    } else {
+        XBI_CUDA(launch_pairs_generic_edges(job, 0, nedges, &ws->minus, stream), "pair counting (edge pairs)");
+    }
     XBI_CUDA(launch_combine(ws, nbits, counts_dev, stream), "combine");
     return XBI_OK;
 }

@@ -62,11 +62,12 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
             if (t < count) {
                 long long f;
                 if (MODE == 1) {
+                    const long long te = lo + t;  // edge index
                     if (inner == 1) {
-                        f = t * n + (n - 1);
+                        f = te * n + (n - 1);
                     } else {
-                        const long long o = t / inner;
-                        f = (o * n + (n - 1)) * inner + (t - o * inner);
+                        const long long o = te / inner;
+                        f = (o * n + (n - 1)) * inner + (te - o * inner);
                     }
                 } else {
                     f = lo + t;
@@ -182,9 +183,13 @@ cudaError_t launch_pairs_generic_flat(const CountJob& job, int64_t lo, int64_t h
     return dispatch_kind<0>(job, lo, hi - lo, dst, stream);
 }
 
-cudaError_t launch_pairs_generic_edges(const CountJob& job, RawSums* dst, cudaStream_t stream) {
-    if (job.outer <= 1) return cudaSuccess;
-    return dispatch_kind<1>(job, 0, (job.outer - 1) * job.inner, dst, stream);
+cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int64_t t_end, RawSums* dst,
+                                       cudaStream_t stream) {
+    const int64_t total = (job.outer - 1) * job.inner;
+    if (t_begin < 0) t_begin = 0;
+    if (t_end > total) t_end = total;
+    if (t_end <= t_begin) return cudaSuccess;
+    return dispatch_kind<1>(job, t_begin, t_end - t_begin, dst, stream);
 }
 
 cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream) {

@@ -51,7 +51,7 @@ struct Seg {
 template <int KIND>
 constexpr size_t smem_bytes() {
     return 1024 + (size_t)Seg<KIND>::kStages * Seg<KIND>::kStageBytes + Seg<KIND>::kStages * 16 +
-           2 * Seg<KIND>::kStages * 8 + 64;
+           2 * Seg<KIND>::kStages * 8 + 64 + 16 * 32 * 2 * (Seg<KIND>::k64 ? 2 : 1) * 4;
 }
 
 // ---- per-word helpers for types that fit one word -------------------------------------
@@ -98,10 +98,31 @@ __device__ __forceinline__ uint32_t count_fields(uint32_t v) {
     return __popc(v & 0x01010101u);
 }
 
+// one element of BYTES bytes from shared memory, zero-extended into 32-bit words
+template <int BYTES>
+__device__ __forceinline__ void lds_elem(uint32_t addr, uint32_t (&w)[BYTES == 8 ? 2 : 1]) {
+    if constexpr (BYTES == 8) {
+        const uint2 v = lds64(addr);
+        w[0] = v.x;
+        w[1] = v.y;
+    } else if constexpr (BYTES == 4) {
+        w[0] = lds32(addr);
+    } else if constexpr (BYTES == 2) {
+        uint16_t v;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr));
+        w[0] = v;
+    } else {
+        uint32_t v;
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+        w[0] = v;
+    }
+}
+
 template <int KIND, int MASK, bool XFORM>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restrict__ region, long long nstages,
-                 uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst) {
+                 uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst, RawSums* __restrict__ dst_minus,
+                 long long row_len, long long region_phase) {
     using S = Seg<KIND>;
     constexpr int BYTES = S::kBytes;
     constexpr int NL = S::kLaddersPerStream;
@@ -114,6 +135,7 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     const uint32_t halo0 = smem0 + S::kStages * S::kStageBytes;
     const uint32_t full0 = halo0 + S::kStages * 16;
     const uint32_t empty0 = full0 + S::kStages * 8;
+    const uint32_t ebuf0 = (empty0 + S::kStages * 8 + 15u) & ~15u;  // [16 stages][32 lanes][a,b words]
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31u;
@@ -121,18 +143,125 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     if (threadIdx.x == 0) {
         for (int s = 0; s < S::kStages; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, kCountWarps);
+            mbar_init(empty0 + 8 * s, kCountWarps + ((!S::k64 && row_len > 0) ? 1 : 0));
         }
         mbar_fence_init();
         tma_prefetch_descriptor(&tmap);
     }
     __syncthreads();
 
-    if (warp == 0) {
-        // ================= producer =================
-        if (lane == 0) {
-            uint32_t iter = 0;
-            for (long long g = blockIdx.x; g < nstages; g += gridDim.x, ++iter) {
+    // the producer is the LAST warp: the scheduler favours higher warp ids, so its few
+    // instructions (TMA issue, row edges) are never starved by the 15 counting warps
+    if (warp == kCountWarps) {
+        // ================= producer (+ row edges) =================
+        // Lane 0 keeps the ring full.  When row_len > 0 the whole warp additionally removes,
+        // for every landed stage, the flat pairs that straddle two rows of the analysed
+        // axis (last element of a row, first of the next): the reference never forms them
+        // (xbitinfo/_py_bitinfo.py:155-160).  They are read from shared memory -- no extra
+        // HBM traffic -- and accumulated into the `minus` sums.
+        using E = Elem<KIND>;
+        constexpr int NW = E::kWords;
+        constexpr int LAG = S::kStages - 1;
+        constexpr long long EPS = S::kElemsPerStage;
+        // (64-bit types keep the separate edge pass: the extra state costs them more than it saves)
+        const bool edges = (NW == 1) && row_len > 0;  // fewer than 32 row ends per stage: lane L takes the L-th
+        // Lane L parks the raw (last, first) words of its row end in a private shared-memory
+        // slot; every 16 stages the parked words are transformed and folded 16 at a time.
+        using EL = Ladder<2, 4>;
+        EL eA[NW], eB[NW], eAB[NW];
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { eA[w].clear(); eB[w].clear(); eAB[w].clear(); }
+        unsigned long long accA[NW], accB[NW], accAB[NW], acc_n = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { accA[w] = 0; accB[w] = 0; accAB[w] = 0; }
+        uint32_t nedge = 0, eit = 0, okmask = 0, gcount = 0;
+        const uint32_t my_slots = ebuf0 + lane * (2 * NW * 4);  // + k * 32 * (2*NW*4)
+        auto eflush = [&]() {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                accA[w] += eA[w].warp_totals(lane, eit);
+                accB[w] += eB[w].warp_totals(lane, eit);
+                accAB[w] += eAB[w].warp_totals(lane, eit);
+                eA[w].clear(); eB[w].clear(); eAB[w].clear();
+            }
+            acc_n += nedge;
+            nedge = 0;
+            eit = 0;
+        };
+        auto fold_group = [&]() {
+            uint32_t wa[NW][16], wb[NW][16];
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                uint32_t a[NW], b[NW];
+                const uint32_t slot = my_slots + k * (32 * 2 * NW * 4);
+                if constexpr (NW == 2) {
+                    const uint4 v = lds128(slot);
+                    a[0] = v.x; a[1] = v.y; b[0] = v.z; b[1] = v.w;
+                } else {
+                    const uint2 v = lds64(slot);
+                    a[0] = v.x; b[0] = v.y;
+                }
+                bool ok = (okmask >> k) & 1u;
+                if (MASK == kMaskNaN) ok = ok && !(E::is_nan(a) || E::is_nan(b));
+                if (MASK == kMaskValue) ok = ok && !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
+                if (XFORM) { E::transform(a); E::transform(b); }
+#pragma unroll
+                for (int w = 0; w < NW; ++w) { wa[w][k] = ok ? a[w] : 0u; wb[w][k] = ok ? b[w] : 0u; }
+                nedge += ok ? 1u : 0u;
+            }
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                uint32_t wab[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k) wab[k] = wa[w][k] & wb[w][k];
+                eA[w].add16(wa[w], eit);
+                eB[w].add16(wb[w], eit);
+                eAB[w].add16(wab, eit);
+            }
+            ++eit;
+            if (eit == EL::kFlushChunks) eflush();
+            okmask = 0;
+            gcount = 0;
+        };
+        // position of the stage's first element inside its row, tracked without divisions
+        long long phase = 0, phase_step = 0;
+        if (edges) {
+            phase = (region_phase + (long long)blockIdx.x * EPS) % row_len;
+            phase_step = ((long long)gridDim.x * EPS) % row_len;
+        }
+        auto stage_edges = [&](uint32_t j) {
+            const uint32_t s = j % S::kStages;
+            mbar_wait(full0 + 8 * s, (j / S::kStages) & 1u);
+            const uint32_t sbase = smem0 + s * S::kStageBytes;
+            const long long d = (row_len - 1 - phase) + (long long)lane * row_len;  // this lane's row end
+            if (d < EPS) {
+                uint32_t a[NW], b[NW];
+                const uint32_t oa = (uint32_t)d * BYTES, ob = oa + BYTES;
+                const uint32_t ra = oa >> 7, rb = ob >> 7;
+                const uint32_t pa = sbase + (ra << 7) + (((((oa >> 4) & 7u) ^ (ra & 7u)) << 4) | (oa & 15u));
+                const uint32_t pb = (ob == (uint32_t)S::kStageBytes)
+                                        ? (halo0 + 16 * s)
+                                        : sbase + (rb << 7) + (((((ob >> 4) & 7u) ^ (rb & 7u)) << 4) | (ob & 15u));
+                lds_elem<BYTES>(pa, a);
+                lds_elem<BYTES>(pb, b);
+                const uint32_t slot = my_slots + gcount * (32 * 2 * NW * 4);
+                if constexpr (NW == 2) {
+                    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(slot), "r"(a[0]), "r"(a[1]), "r"(b[0]), "r"(b[1]) : "memory");
+                } else {
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(slot), "r"(a[0]), "r"(b[0]) : "memory");
+                }
+                okmask |= 1u << gcount;
+            }
+            phase += phase_step;
+            if (phase >= row_len) phase -= row_len;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty0 + 8 * s);
+            if (++gcount == 16) fold_group();
+        };
+
+        uint32_t iter = 0;
+        for (long long g = blockIdx.x; g < nstages; g += gridDim.x, ++iter) {
+            if (lane == 0) {
                 const uint32_t s = iter % S::kStages;
                 const uint32_t ph = (iter / S::kStages) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
@@ -144,12 +273,31 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                                 full0 + 8 * s);
                 bulk_load_1d(halo0 + 16 * s, region + (row0 + S::kRowsPerStage) * kRowBytes, 16, full0 + 8 * s);
             }
+            __syncwarp();
+            if (edges && iter >= (uint32_t)LAG) stage_edges(iter - LAG);
+        }
+        if (edges) {
+            for (uint32_t j = (iter > (uint32_t)LAG ? iter - LAG : 0); j < iter; ++j) stage_edges(j);
+            if (gcount > 0) fold_group();
+            eflush();
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const int jbit = w * 32 + (int)lane;
+                if (accA[w]) atomicAdd(&dst_minus->sums[S_A][jbit], accA[w]);
+                if (accB[w]) atomicAdd(&dst_minus->sums[S_B][jbit], accB[w]);
+                if (accAB[w]) atomicAdd(&dst_minus->sums[S_AB][jbit], accAB[w]);
+            }
+            // acc_n is per lane: reduce over the warp
+            unsigned long long nsum = acc_n;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) nsum += __shfl_xor_sync(0xFFFFFFFFu, nsum, o);
+            if (lane == 0 && nsum) atomicAdd(&dst_minus->npairs, nsum);
         }
         return;
     }
 
     // ================= counting warps =================
-    const uint32_t t = threadIdx.x - 32u;
+    const uint32_t t = threadIdx.x;
     const uint32_t row = t / S::kThreadsPerRow;
     const uint32_t cbase = (t % S::kThreadsPerRow) * S::kSegChunks;
     const uint32_t swz = row & 7u;
@@ -359,8 +507,8 @@ EncodeFn get_encode_fn() {
 }
 
 template <int KIND, int MASK, bool XFORM>
-cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream, int64_t* done_lo,
-                        int64_t* done_hi) {
+cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
+                        int64_t* done_hi, bool* edges_done) {
     using S = Seg<KIND>;
     const int bytes = S::kBytes;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(job.x);
@@ -388,18 +536,24 @@ cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst, 
     if (r != CUDA_SUCCESS) return cudaErrorInvalidValue;
 
     auto kern = k_pairs_rows_tma<KIND, MASK, XFORM>;
-    static bool attr_set = false;  // per instantiation
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<KIND>());
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
+    static bool attr_set[64] = {};  // per instantiation and device (the opt-in is per device)
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<KIND>());
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(nstages < sms ? nstages : sms);
+    // rows long enough that a stage holds fewer than 32 row ends: the producer warp removes the
+    // row-straddling pairs in shared memory (one per lane); shorter rows go to the edge pass
+    const bool in_kernel_edges = !S::k64 && job.n > S::kElemsPerStage / 32 && job.outer > 1;
     kern<<<grid, kThreads, smem_bytes<KIND>(), stream>>>(tmap, region, (long long)nstages, (uint32_t)job.mask_bits,
-                                                          (uint32_t)(job.mask_bits >> 32), dst);
+                                                          (uint32_t)(job.mask_bits >> 32), &ws->plus, &ws->minus,
+                                                          in_kernel_edges ? (long long)job.n : 0ll,
+                                                          (long long)(head % job.n));
+    *edges_done = in_kernel_edges;
     note_fast_launch();
     *done_lo = head;
     *done_hi = head + nstages * S::kElemsPerStage;
@@ -407,15 +561,15 @@ cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst, 
 }
 
 template <int KIND>
-cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream, int64_t* lo,
-                          int64_t* hi) {
+cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, Workspace* dst, cudaStream_t stream, int64_t* lo,
+                          int64_t* hi, bool* ed) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (job.transform) {
         if constexpr (isf) {
             switch (job.mask_mode) {
-                case kMaskNone: return launch_rows<KIND, kMaskNone, true>(job, npairs_flat, dst, stream, lo, hi);
-                case kMaskNaN: return launch_rows<KIND, kMaskNaN, true>(job, npairs_flat, dst, stream, lo, hi);
-                default: return launch_rows<KIND, kMaskValue, true>(job, npairs_flat, dst, stream, lo, hi);
+                case kMaskNone: return launch_rows<KIND, kMaskNone, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                case kMaskNaN: return launch_rows<KIND, kMaskNaN, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                default: return launch_rows<KIND, kMaskValue, true>(job, npairs_flat, dst, stream, lo, hi, ed);
             }
         }
         return cudaSuccess;
@@ -424,25 +578,26 @@ cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, RawSums* dst
     // mask without the transform is rare enough to stay on the generic kernel
     if (job.mask_mode == kMaskNaN) return cudaSuccess;
     constexpr int UK = (KIND == kF16) ? kU16 : (KIND == kF32) ? kU32 : (KIND == kF64) ? kU64 : KIND;
-    if (job.mask_mode == kMaskNone) return launch_rows<UK, kMaskNone, false>(job, npairs_flat, dst, stream, lo, hi);
-    return launch_rows<UK, kMaskValue, false>(job, npairs_flat, dst, stream, lo, hi);
+    if (job.mask_mode == kMaskNone) return launch_rows<UK, kMaskNone, false>(job, npairs_flat, dst, stream, lo, hi, ed);
+    return launch_rows<UK, kMaskValue, false>(job, npairs_flat, dst, stream, lo, hi, ed);
 }
 
 }  // namespace
 
-cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream,
-                             int64_t* done_lo, int64_t* done_hi) {
+cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, Workspace* dst, cudaStream_t stream,
+                             int64_t* done_lo, int64_t* done_hi, bool* edges_done) {
     *done_lo = 0;
     *done_hi = 0;
+    *edges_done = false;
     if (job.inner != 1) return cudaSuccess;  // strided adjacency: see xbi_count_cols.cu
     switch (job.dtype) {
-        case XBI_U8: return dispatch_rows<kU8>(job, npairs_flat, dst, stream, done_lo, done_hi);
-        case XBI_U16: return dispatch_rows<kU16>(job, npairs_flat, dst, stream, done_lo, done_hi);
-        case XBI_U32: return dispatch_rows<kU32>(job, npairs_flat, dst, stream, done_lo, done_hi);
-        case XBI_U64: return dispatch_rows<kU64>(job, npairs_flat, dst, stream, done_lo, done_hi);
-        case XBI_F16: return dispatch_rows<kF16>(job, npairs_flat, dst, stream, done_lo, done_hi);
-        case XBI_F32: return dispatch_rows<kF32>(job, npairs_flat, dst, stream, done_lo, done_hi);
-        case XBI_F64: return dispatch_rows<kF64>(job, npairs_flat, dst, stream, done_lo, done_hi);
+        case XBI_U8: return dispatch_rows<kU8>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
+        case XBI_U16: return dispatch_rows<kU16>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
+        case XBI_U32: return dispatch_rows<kU32>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
+        case XBI_U64: return dispatch_rows<kU64>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
+        case XBI_F16: return dispatch_rows<kF16>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
+        case XBI_F32: return dispatch_rows<kF32>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
+        case XBI_F64: return dispatch_rows<kF64>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
         default: return cudaErrorInvalidValue;
     }
 }

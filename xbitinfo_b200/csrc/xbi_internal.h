@@ -47,7 +47,9 @@ cudaError_t launch_pairs_generic_flat(const CountJob& job, int64_t lo, int64_t h
                                       cudaStream_t stream);
 // The flat pairs that straddle two consecutive blocks of the analysed axis:
 // f = (o*n + n-1)*inner + i for o in [0, outer-1), i in [0, inner).
-cudaError_t launch_pairs_generic_edges(const CountJob& job, RawSums* dst, cudaStream_t stream);
+// restricted to edge indices t = o*inner + i in [t_begin, t_end)
+cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int64_t t_end, RawSums* dst,
+                                       cudaStream_t stream);
 
 // Bit planes of the single elements f in [lo, lo+count) added to dst->sums[S_A] (transform
 // applied, no mask): the a-stream correction of the column walkers.
@@ -56,8 +58,9 @@ cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, R
 // TMA fast paths.  Each consumes as much of [0, numel-inner) as its alignment rules
 // allow, reports the flat range it covered in [*done_lo, *done_hi) (empty if none), and
 // leaves the rest to the generic kernel.
-cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, RawSums* dst, cudaStream_t stream,
-                             int64_t* done_lo, int64_t* done_hi);
+// *edges_done: the kernel also removed the row-straddling pairs inside [*done_lo, *done_hi).
+cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream,
+                             int64_t* done_lo, int64_t* done_hi, bool* edges_done);
 
 // Column walkers for inner > 1 (16-byte aligned rows); covers flat pairs [*done_lo, *done_hi).
 cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
