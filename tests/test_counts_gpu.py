@@ -171,3 +171,32 @@ def test_last_axis_fast_path(dtype, mask):
     assert np.array_equal(counts, ref_counts), (dtype, mask)
     assert counts[0].sum() == npairs
     assert_mi_close(mi, ref_mi)
+
+
+@pytest.mark.parametrize("dtype,mask", [("float64", "nan"), ("float64", None), ("float32", "nan"), ("float16", None)])
+def test_long_segments_and_ragged_strips_fast_equals_generic(dtype, mask):
+    """Column walkers on a tall, narrow matrix: rows are not a multiple of the 512-byte strip
+    (idle lanes) and segments are longer than a flush period.  At this size the checker is
+    the generic kernel (itself checked against the oracle above)."""
+    import torch
+
+    from xbitinfo_b200.device import PairCounter
+
+    rows, cols = 700_000, (40 if dtype == "float16" else 36)  # 16-byte aligned rows, not a multiple of 512 bytes
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.empty((rows, cols), dtype=torch.float32, device="cuda").normal_(0.0, 0.3, generator=g)
+    x = (torch.cumsum(x, dim=0) + 3.0).to(getattr(torch, dtype))
+    mv = None
+    if mask == "nan":
+        mv = float("nan")
+        x[torch.rand((rows, cols), device="cuda", generator=g) < 0.1] = float("nan")
+    pc = PairCounter(x.dtype, x.device)
+    before = nat.fast_path_launches()
+    pc.add(x, 0, masked_value=mv)
+    assert nat.fast_path_launches() > before
+    fast = pc.counts.clone()
+    pc.reset()
+    pc.add(x, 0, masked_value=mv, force_generic=True)
+    assert torch.equal(fast, pc.counts)
+    if mask is None:
+        assert int(fast[0].sum()) == (rows - 1) * cols

@@ -13,9 +13,13 @@
 // row); two small row-plane passes (xbi_count_generic.cu) add those to the plus / minus sums.
 // Pairs that straddle two blocks of the analysed axis are subtracted by the edge pass
 // (xbi_count_generic.cu).
+#include <cstdlib>
+
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
+#include "xbi_tma.cuh"
+#include "xbi_tmap.h"
 
 namespace xbi {
 
@@ -144,8 +148,14 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
     uint32_t nvalid = 0;
     unsigned long long nvalid_total = 0;
     uint32_t it = 0;
+    bool lane_live = true;  // false while this lane shadows an item beyond the end (last warp item)
 
     auto flush = [&]() {
+        if (!lane_live) {
+#pragma unroll
+            for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); if (MASKED) Al[i].clear(); }
+            nvalid = 0;
+        }
 #pragma unroll
         for (int i = 0; i < NL; ++i) {
             accB[i] += Bl[i].warp_totals(lane, it);
@@ -165,6 +175,7 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
         // handles.  Idle lanes shadow a valid item; what they add is discarded below.
         const bool ragged = __any_sync(0xFFFFFFFFu, !active);
         if (ragged) flush();
+        lane_live = active;
         if (!active) item = total - 1;
         long long seg = 0, chunk = item;
         if (nseg > 1) { seg = item / chunks_per_row; chunk = item - seg * chunks_per_row; }
@@ -287,12 +298,8 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
             process(bufA, tail_rows);
         }
         if (ragged) {
-            if (!active) {
-#pragma unroll
-                for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); if (MASKED) Al[i].clear(); }
-                nvalid = 0;
-            }
             flush();
+            lane_live = true;
         }
     }
     flush();
@@ -325,6 +332,286 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
     }
 }
 
+// ---------------------------------------------------------------------------------
+// TMA variant of the column walkers.  Same work split (a warp item = one row segment x one
+// 512-byte column strip, lane = 16-byte column chunk, previous row carried in registers),
+// but the rows arrive through a per-warp ring of 6 shared-memory tiles of 4 rows x 512 B
+// filled by 2-D TMA loads that the warp's own lane 0 issues five tiles ahead.  No producer
+// warp and no block-wide barrier: each warp is its own software pipeline, and the loads in
+// flight (16 warps x 5 tiles x 2 KB = 160 KB per SM) no longer live in registers.
+// ---------------------------------------------------------------------------------
+constexpr int kTmaThreads = 512;
+constexpr int kTmaWarps = kTmaThreads / 32;
+constexpr int kRing = 6;
+constexpr int kTileRows = 4;
+constexpr int kStripBytes = 512;
+constexpr int kTileBytes = kTileRows * kStripBytes;
+constexpr size_t kColsSmem = 128 + (size_t)kTmaWarps * kRing * kTileBytes + kTmaWarps * kRing * 8;
+
+template <int KIND, int MASK, bool XFORM>
+__global__ void __launch_bounds__(kTmaThreads, 1)
+k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ x, long long chunks_per_row,
+                 long long strips, long long nseg, long long seg_min, long long seg_extra, uint32_t mask_lo,
+                 uint32_t mask_hi, Workspace* __restrict__ ws) {
+    constexpr int BYTES = Elem<KIND>::kBytes;
+    constexpr bool K64 = (BYTES == 8);
+    constexpr bool MASKED = (MASK != kMaskNone);
+    constexpr int NL = K64 ? 2 : 1;
+    constexpr int LOGC = K64 ? 3 : 4;
+    constexpr int CH = 1 << LOGC;
+    constexpr int kNumLadders = NL * (MASKED ? 3 : 2);
+    using L = Ladder<3, (kNumLadders >= 6 ? 4 : kNumLadders >= 4 ? 5 : 8), LOGC>;
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t ring0 = smem0 + warp * (kRing * kTileBytes);
+    const uint32_t bar0 = smem0 + kTmaWarps * kRing * kTileBytes + warp * (kRing * 8);
+    if (lane == 0) {
+        for (int i = 0; i < kRing; ++i) mbar_init(bar0 + 8 * i, 1);
+        mbar_fence_init();
+    }
+    if (threadIdx.x == 0) tma_prefetch_descriptor(&tmap);
+    __syncthreads();
+
+    const long long n_witems = strips * nseg;
+    const long long warps_total = (long long)gridDim.x * kTmaWarps;
+
+    L Bl[NL], ABl[NL], Al[MASKED ? NL : 1];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); }
+    if (MASKED) {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) Al[i].clear();
+    }
+    unsigned long long accA[NL], accB[NL], accAB[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { accA[i] = 0; accB[i] = 0; accAB[i] = 0; }
+    uint32_t nvalid = 0;
+    unsigned long long nvalid_total = 0;
+    uint32_t it = 0;
+    uint32_t t_issued = 0, t_consumed = 0;  // tiles of this warp since kernel start (ring position / phase)
+    bool lane_live = true;  // false while this lane shadows a column chunk beyond the row (ragged strip)
+
+    auto flush = [&]() {
+        if (!lane_live) {  // whatever an idle lane gathered since the last flush is discarded
+#pragma unroll
+            for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); if (MASKED) Al[i].clear(); }
+            nvalid = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            accB[i] += Bl[i].warp_totals(lane, it);
+            accAB[i] += ABl[i].warp_totals(lane, it);
+            Bl[i].clear(); ABl[i].clear();
+            if (MASKED) { accA[i] += Al[i].warp_totals(lane, it); Al[i].clear(); }
+        }
+        nvalid_total += nvalid;
+        nvalid = 0;
+        it = 0;
+    };
+
+    for (long long wi = (long long)blockIdx.x * kTmaWarps + warp; wi < n_witems; wi += warps_total) {
+        const long long seg = wi / strips;
+        const long long strip = wi - seg * strips;
+        const long long chunk = strip * 32 + lane;
+        const bool active = chunk < chunks_per_row;
+        const bool ragged = __any_sync(0xFFFFFFFFu, !active);  // last strip of a row only
+        if (ragged) flush();  // bank what the previous items gathered before lanes go idle
+        lane_live = active;
+        const long long row_begin = seg * seg_min + (seg < seg_extra ? seg : seg_extra);
+        const long long seg_len = seg_min + (seg < seg_extra ? 1 : 0);
+        const long long ntiles = (seg_len + kTileRows - 1) / kTileRows;
+
+        uint32_t prev[4] = {0u, 0u, 0u, 0u}, prev_keep[4] = {0u, 0u, 0u, 0u};
+        if (active) {
+            const uint4 v = ldg_stream(x + row_begin * chunks_per_row + chunk);
+            prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w;
+            if (MASKED) keep_chunk<KIND, MASK>(prev, mask_lo, mask_hi, prev_keep);
+            xform_chunk<KIND, XFORM>(prev);
+        }
+
+        auto issue_tile = [&](long long k) {
+            if (lane == 0) {
+                const uint32_t slot = t_issued % kRing;
+                // the slot was last read through the generic proxy by this warp (before the
+                // __syncwarp that ended that iteration); order those reads before the async write
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                mbar_arrive_expect_tx(bar0 + 8 * slot, kTileBytes);
+                tma_load_2d(ring0 + slot * kTileBytes, &tmap, (int32_t)(strip * (kStripBytes / 4)),
+                            (int32_t)(row_begin + 1 + k * kTileRows), bar0 + 8 * slot);
+            }
+            ++t_issued;
+        };
+
+        auto process = [&](const uint4 (&buf)[4], int nrows) {
+            uint32_t wb[4][4], wab[4][4], wa[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                uint32_t cur[4] = {buf[r].x, buf[r].y, buf[r].z, buf[r].w};
+                uint32_t keep[4];
+                if (MASKED) keep_chunk<KIND, MASK>(cur, mask_lo, mask_hi, keep);
+                xform_chunk<KIND, XFORM>(cur);
+                const bool present = r < nrows;
+                if (!MASKED) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        wb[r][i] = present ? cur[i] : 0u;
+                        wab[r][i] = wb[r][i] & prev[i];
+                    }
+                } else {
+                    uint32_t v[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        v[i] = present ? (keep[i] & prev_keep[i]) : 0u;
+                        wa[r][i] = prev[i] & v[i];
+                        wb[r][i] = cur[i] & v[i];
+                        wab[r][i] = wa[r][i] & wb[r][i];
+                        if (present) prev_keep[i] = keep[i];
+                    }
+                    nvalid += count_chunk<BYTES>(v);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (present) prev[i] = cur[i];
+            }
+            if constexpr (!K64) {
+                uint32_t f[16];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wb[r][i];
+                Bl[0].add_chunk(f, it);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wab[r][i];
+                ABl[0].add_chunk(f, it);
+                if constexpr (MASKED) {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) f[4 * r + i] = wa[r][i];
+                    Al[0].add_chunk(f, it);
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t f[CH];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { f[2 * r] = wb[r][h]; f[2 * r + 1] = wb[r][h + 2]; }
+                    Bl[h % NL].add_chunk(f, it);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { f[2 * r] = wab[r][h]; f[2 * r + 1] = wab[r][h + 2]; }
+                    ABl[h % NL].add_chunk(f, it);
+                    if constexpr (MASKED) {
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) { f[2 * r] = wa[r][h]; f[2 * r + 1] = wa[r][h + 2]; }
+                        Al[h % NL].add_chunk(f, it);
+                    }
+                }
+            }
+            ++it;
+            if (it == L::kFlushChunks) flush();
+        };
+
+        const long long pre = ntiles < (kRing - 1) ? ntiles : (kRing - 1);
+        for (long long k = 0; k < pre; ++k) issue_tile(k);
+        for (long long k = 0; k < ntiles; ++k) {
+            if (k + (kRing - 1) < ntiles) issue_tile(k + (kRing - 1));
+            const uint32_t slot = t_consumed % kRing;
+            mbar_wait(bar0 + 8 * slot, (t_consumed / kRing) & 1u);
+            const uint32_t base = ring0 + slot * kTileBytes + lane * 16;
+            uint4 buf[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) buf[r] = lds128(base + r * kStripBytes);
+            if (k + 1 < ntiles) {
+                process(buf, 4);
+            } else {
+                process(buf, (int)(seg_len - k * kTileRows));
+            }
+            ++t_consumed;
+            __syncwarp();
+        }
+        if (ragged) {
+            flush();
+            lane_live = true;
+        }
+    }
+    flush();
+
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_n;
+    for (int i = threadIdx.x; i < 3 * 64; i += kTmaThreads) (&s_sum[0][0])[i] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        const int j = K64 ? (i * 32 + (int)lane) : ((int)lane % (8 * BYTES));
+        const unsigned long long a = MASKED ? accA[i] : accB[i];  // unmasked: corrected by the row-plane passes
+        if (a) atomicAdd(&s_sum[S_A][j], a);
+        if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
+        if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
+    }
+    if (MASKED && nvalid_total) atomicAdd(&s_n, nvalid_total);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 64; i += kTmaThreads) {
+        const unsigned long long v = (&s_sum[0][0])[i];
+        if (v) atomicAdd(&ws->plus.sums[0][0] + i, v);
+    }
+    if (MASKED && threadIdx.x == 0 && s_n) atomicAdd(&ws->plus.npairs, s_n);
+    if (!MASKED && blockIdx.x == 0 && threadIdx.x == 0) {
+        constexpr long long kElemsPerChunk = 16 / BYTES;
+        atomicAdd(&ws->plus.npairs, (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * kElemsPerChunk));
+    }
+}
+
+// returns false when the TMA variant cannot be used (no encoder, extents beyond 32-bit coordinates)
+template <int KIND, int MASK, bool XFORM>
+bool try_launch_cols_tma(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t chunks, int64_t rows,
+                         int64_t pair_rows, int sms, cudaError_t* err) {
+    *err = cudaSuccess;
+    EncodeFn encode = get_encode_fn();
+    const int64_t row_words = chunks * 4;
+    if (!encode || rows >= (1ll << 31) || row_words >= (1ll << 31)) return false;
+    CUtensorMap tmap;
+    const cuuint64_t gdim[2] = {(cuuint64_t)row_words, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)row_words * 4};
+    const cuuint32_t box[2] = {kStripBytes / 4, kTileRows};
+    const cuuint32_t estride[2] = {1, 1};
+    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(job.x), gdim, gstride, box, estride,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return false;
+    auto kern = k_pairs_cols_tma<KIND, MASK, XFORM>;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_set[64] = {};
+    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+        *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColsSmem);
+        if (*err != cudaSuccess) return true;
+        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+    }
+    const int64_t strips = (chunks + 31) / 32;
+    // a few items per warp for balance, segments of at least 64 rows
+    const int64_t want_items = (int64_t)sms * kTmaWarps * 4;
+    int64_t nseg = (want_items + strips - 1) / strips;
+    const int64_t max_seg = pair_rows / 64 > 0 ? pair_rows / 64 : 1;
+    if (nseg > max_seg) nseg = max_seg;
+    if (nseg < 1) nseg = 1;
+    const int64_t seg_min = pair_rows / nseg;
+    const int64_t seg_extra = pair_rows - seg_min * nseg;
+    int64_t blocks = (strips * nseg + kTmaWarps - 1) / kTmaWarps;
+    if (blocks > sms) blocks = sms;
+    kern<<<(unsigned)blocks, kTmaThreads, kColsSmem, stream>>>(tmap, static_cast<const uint4*>(job.x), (long long)chunks,
+                                                                (long long)strips, (long long)nseg, (long long)seg_min,
+                                                                (long long)seg_extra, (uint32_t)job.mask_bits,
+                                                                (uint32_t)(job.mask_bits >> 32), ws);
+    *err = cudaGetLastError();
+    return true;
+}
+
 template <int KIND, int MASK, bool XFORM>
 cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo, int64_t* done_hi) {
     constexpr int BYTES = Elem<KIND>::kBytes;
@@ -337,6 +624,11 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t terr = cudaSuccess;
+    const bool use_ldg = std::getenv("XBI_COLS_LDG") != nullptr;  // development switch: register-staged variant
+    if (!use_ldg && try_launch_cols_tma<KIND, MASK, XFORM>(job, ws, stream, chunks, rows, pair_rows, sms, &terr)) {
+        if (terr != cudaSuccess) return terr;
+    } else {
     // enough threads to fill the machine about twice, but segments of at least 64 rows
     const int64_t want_threads = (int64_t)sms * 2048 * 2;
     int64_t nseg = (want_threads + chunks - 1) / chunks;
@@ -352,6 +644,7 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
     k_pairs_cols<KIND, MASK, XFORM><<<(unsigned)blocks, kThreads, 0, stream>>>(
         static_cast<const uint4*>(job.x), (long long)chunks, (long long)nseg, (long long)seg_min, (long long)seg_extra,
         (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), ws);
+    }
     if (MASK == kMaskNone) {
         // a-stream correction: + planes(first row) - planes(row after the last pair row)
         cudaError_t e = launch_elem_planes(job, 0, job.inner, &ws->plus, stream);

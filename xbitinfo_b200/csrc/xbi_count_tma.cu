@@ -14,12 +14,11 @@
 // Unmasked pairs need only two word streams: a (every element) and a&b.  The b-stream
 // total equals the a-stream total shifted by one element, i.e. A - bits(first element)
 // + bits(halo element of the last stage); block 0 applies that correction.
-#include <mutex>
-
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
 #include "xbi_tma.cuh"
+#include "xbi_tmap.h"
 
 namespace xbi {
 
@@ -487,25 +486,6 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
 // ---------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------
-using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                              const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                              CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeFn get_encode_fn() {
-    static EncodeFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, []() {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeFn>(p);
-        else
-            cudaGetLastError();
-    });
-    return fn;
-}
-
 template <int KIND, int MASK, bool XFORM>
 cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
                         int64_t* done_hi, bool* edges_done) {
