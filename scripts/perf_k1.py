@@ -1,5 +1,6 @@
 """Quick K1/K3 timing on one GPU (development aid; bench.py is the judged harness)."""
 import argparse
+import os
 import sys
 import time
 
@@ -19,7 +20,7 @@ def synth(shape, dtype, axis=-1, seed=1234):
     return x.to(dtype)
 
 
-def timeit(fn, iters=5, warm=2):
+def timeit(fn, iters=10, warm=3):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
@@ -31,6 +32,8 @@ def timeit(fn, iters=5, warm=2):
         e1.record()
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1) * 1e-3)
+    if os.environ.get('XBI_PERF_VERBOSE'):
+        print('   iters ms:', ' '.join(f'{t*1e3:.3f}' for t in ts))
     return min(ts), sorted(ts)[len(ts) // 2]
 
 
@@ -57,6 +60,13 @@ def main():
     torch.cuda.synchronize()
     print("launches per call:", nat.kernel_launches() - l0)
     best, med = timeit(lambda: pc.add(x, a.axis, masked_value=mv))
+    nat.profile_enable(True)
+    for _ in range(10):
+        pc.add(x, a.axis, masked_value=mv)
+    kms, kn, kb = nat.profile_collect()
+    nat.profile_enable(False)
+    if kn:
+        print(f"   fast-path kernel alone: {kms/kn:.3f} ms avg over {kn} launches = {kb/kn/(kms/kn)/1e6:.0f} GB/s")
     print(f"K1 {a.dtype} {shape} axis={a.axis} mask={a.mask}: best {best*1e3:.3f} ms  median {med*1e3:.3f} ms  "
           f"{nbytes/best/1e9:.1f} GB/s best, {nbytes/med/1e9:.1f} GB/s median ({nbytes/1e9:.2f} GB)")
     if a.check:

@@ -364,7 +364,9 @@ k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restri
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
-    const uint32_t warp = threadIdx.x >> 5;
+    // broadcast from lane 0: tells the compiler the value is warp-uniform (uniform branches, no
+    // reconvergence bookkeeping around the ladder pushes)
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t ring0 = smem0 + warp * (kRing * kTileBytes);
     const uint32_t bar0 = smem0 + kTmaWarps * kRing * kTileBytes + warp * (kRing * 8);
@@ -435,9 +437,8 @@ k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restri
         auto issue_tile = [&](long long k) {
             if (lane == 0) {
                 const uint32_t slot = t_issued % kRing;
-                // the slot was last read through the generic proxy by this warp (before the
-                // __syncwarp that ended that iteration); order those reads before the async write
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                // the slot was last read (LDS) by this warp before the __syncwarp that ended that
+                // iteration, and those values have been consumed: safe to overwrite
                 mbar_arrive_expect_tx(bar0 + 8 * slot, kTileBytes);
                 tma_load_2d(ring0 + slot * kTileBytes, &tmap, (int32_t)(strip * (kStripBytes / 4)),
                             (int32_t)(row_begin + 1 + k * kTileRows), bar0 + 8 * slot);
@@ -625,7 +626,11 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t terr = cudaSuccess;
-    const bool use_ldg = std::getenv("XBI_COLS_LDG") != nullptr;  // development switch: register-staged variant
+    // Measured on B200 (same box, kernel alone): with a power-of-two row pitch the TMA ring
+    // runs at 3.7-3.9 TB/s where the register-staged variant reaches 5.4-5.5 TB/s; with other
+    // pitches the TMA ring wins (5.5-5.8 vs 4.9-5.1 TB/s).  XBI_COLS_LDG / XBI_COLS_TMA force one.
+    const bool pow2_pitch = (row_bytes & (row_bytes - 1)) == 0;
+    const bool use_ldg = std::getenv("XBI_COLS_LDG") != nullptr || (pow2_pitch && std::getenv("XBI_COLS_TMA") == nullptr);
     if (!use_ldg && try_launch_cols_tma<KIND, MASK, XFORM>(job, ws, stream, chunks, rows, pair_rows, sms, &terr)) {
         if (terr != cudaSuccess) return terr;
     } else {

@@ -53,6 +53,13 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
     const long long tiles = (count + kPairsPerTile - 1) / kPairsPerTile;
     for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
         uint32_t wa[NW][16], wb[NW][16];
+        // edge mode: (block o, column i) of this thread's first edge, then advanced without divisions
+        long long eo = 0, ei = 0;
+        if (MODE == 1 && inner != 1) {
+            const long long te0 = lo + tile * kPairsPerTile + threadIdx.x;
+            eo = te0 / inner;
+            ei = te0 - eo * inner;
+        }
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
             const long long t = tile * kPairsPerTile + (long long)u * kThreads + threadIdx.x;
@@ -62,12 +69,12 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
             if (t < count) {
                 long long f;
                 if (MODE == 1) {
-                    const long long te = lo + t;  // edge index
                     if (inner == 1) {
-                        f = te * n + (n - 1);
+                        f = (lo + t) * n + (n - 1);
                     } else {
-                        const long long o = te / inner;
-                        f = (o * n + (n - 1)) * inner + (te - o * inner);
+                        f = (eo * n + (n - 1)) * inner + ei;
+                        ei += kThreads;
+                        while (ei >= inner) { ei -= inner; ++eo; }
                     }
                 } else {
                     f = lo + t;
