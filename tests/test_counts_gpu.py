@@ -200,3 +200,19 @@ def test_long_segments_and_ragged_strips_fast_equals_generic(dtype, mask):
     assert torch.equal(fast, pc.counts)
     if mask is None:
         assert int(fast[0].sum()) == (rows - 1) * cols
+
+
+def test_all_float16_patterns_through_the_packed_paths():
+    """Every float16 bit pattern (incl. NaN payloads, infinities, subnormals) in random order,
+    along the last axis (TMA row kernel, two halves per word) and along axis 0 (column
+    walkers): the packed signed-exponent transform must match the reference bit for bit."""
+    rng = np.random.default_rng(12)
+    pats = np.arange(1 << 16, dtype="uint16")
+    x = np.concatenate([rng.permutation(pats) for _ in range(6)]).view("float16").reshape(768, 512)
+    for axis in (1, 0):
+        before = nat.fast_path_launches()
+        counts, _ = run_host(x, axis)
+        assert nat.fast_path_launches() > before
+        assert np.array_equal(counts, bo.bitinformation(x, axis)[0]), axis
+    counts, _ = run_host(x, 1, masked_value=float("nan"))
+    assert np.array_equal(counts, bo.bitinformation(x, 1, masked_value=float("nan"))[0])

@@ -17,6 +17,7 @@
 // 5-step butterfly across the warp that leaves lane L holding the count of bit position L.
 #pragma once
 #include <cstdint>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 
 namespace xbi {
@@ -221,13 +222,13 @@ __device__ __forceinline__ uint32_t sexp_f16_single(uint32_t w) {  // one half i
     return ((w & 0x7C00u) >= 0x3C00u) ? (w - 0x3C00u) : (w ^ 0x7C00u);
 }
 __device__ __forceinline__ uint32_t sexp_f16x2(uint32_t w) {  // two halves packed in one word
-    // per-half 0xFFFF where field >= 15: compare the 15-bit magnitudes without carries
-    const uint32_t mag = w & 0x7FFF7FFFu;
-    // (mag + (0x8000 - 0x3C00)) sets bit 15 of a half iff its magnitude >= 0x3C00; no carry
-    // leaves the half because mag <= 0x7FFF
-    const uint32_t ge = ((mag + 0x44004400u) >> 15) & 0x00010001u;
-    const uint32_t m = ge * 0xFFFFu;  // 0xFFFF per selected half
-    return ((w - (m & 0x3C003C00u)) & m) | ((w ^ 0x7C007C00u) & ~m);
+    // per-half 0xFFFF where |x| >= 1 or x is NaN, i.e. exponent field >= 15: one packed
+    // half-precision compare (unordered >=) on |w|
+    const __half2 h = *reinterpret_cast<const __half2*>(&w);
+    const uint32_t m = __hgeu2_mask(__habs2(h), __half2half2(__ushort_as_half((unsigned short)0x3C00)));
+    // selected halves: subtract the bias (no borrow leaves a selected half: its magnitude is
+    // >= 0x3C00); the others: flip the exponent field
+    return (w ^ (0x7C007C00u & ~m)) - (m & 0x3C003C00u);
 }
 
 }  // namespace xbi
