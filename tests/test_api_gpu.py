@@ -229,3 +229,44 @@ def test_launch_counters_move():
     before = nat.kernel_launches()
     engine.bitinformation(np.zeros((8, 64), dtype="float32"), 1)
     assert nat.kernel_launches() > before
+
+
+def test_streamed_from_memmap_equals_in_memory(tmp_path):
+    """Row f1: slab streaming from a file-backed array (np.memmap), incl. the halo row when
+    the sliced axis is the analysed one, equals the in-memory result exactly."""
+    from xbitinfo_b200.streaming import bitinformation_streamed, slab_plan
+
+    rng = np.random.default_rng(17)
+    x = smooth_field(rng, (301, 48, 64), "float32", axis=0, scale=0.4)
+    x[rng.random(x.shape) < 0.05] = np.nan
+    path = tmp_path / "field.dat"
+    x.tofile(path)
+    mm = np.memmap(path, dtype="float32", mode="r", shape=x.shape)
+    assert len(slab_plan(x.shape, 0, 4, 200_000)) > 10
+    for axis in (0, 1, 2):
+        for mv in (None, float("nan")):
+            mi_ref, c_ref = engine.bitinformation(x, axis, masked_value=mv, return_counts=True)
+            mi, c = bitinformation_streamed(mm, axis, slab_bytes=200_000, masked_value=mv, return_counts=True)
+            assert np.array_equal(c, c_ref), (axis, mv)
+            assert_mi_close(mi, mi_ref)
+    y = x[:, 0, 0].copy()  # 1-D
+    _, c = bitinformation_streamed(y, 0, slab_bytes=64, return_counts=True)
+    assert np.array_equal(c, bo.bitinformation(y, 0)[0])
+
+
+def test_bitround_along_dim():
+    from xbitinfo_b200.bitround import bitround_along_dim
+
+    ds = eraint_like()
+    info = xb.get_bitinformation(ds, dim="longitude")
+    out = bitround_along_dim(ds, info, dim="longitude", inflevels=[1.0, 0.9999, 0.99, 0.975])
+    assert out["u"].shape == ds["u"].shape and out["u"].dtype == ds["u"].dtype
+    assert np.array_equal(out["u"].values[..., :120], ds["u"].values[..., :120])  # inflevel 1: untouched
+    assert (out["u"].values[..., 120:] != ds["u"].values[..., 120:]).any()
+    assert abs(float(np.mean(ds["u"].values - out["u"].values))) < 0.05
+    out2 = bitround_along_dim(ds, info, dim="longitude", inflevels=None, keepbits=2)
+    assert out2["u"].shape == ds["u"].shape
+    with pytest.raises(ValueError):
+        bitround_along_dim(ds, info, dim="latitude", keepbits=2, inflevels=[1.0, 0.99])
+    with pytest.raises(ValueError):
+        bitround_along_dim(ds, info, dim="latitude", inflevels=None)

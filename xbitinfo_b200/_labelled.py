@@ -224,8 +224,33 @@ class Dataset:
             out[k] = v.sel(**use) if use else v
         return out
 
+    def isel(self, indexers=None, **kw):
+        indexers = dict(indexers or {}, **kw)
+        out = Dataset(attrs=self.attrs)
+        for k, v in self._vars.items():
+            use = {d: i for d, i in indexers.items() if d in v.dims}
+            out[k] = v.isel(**use) if use else v
+        return out
+
     def __repr__(self):
         lines = [f"<xbitinfo_b200.Dataset dims={dict(self.dims)}>"]
         for k, v in self._vars.items():
             lines.append(f"    {k} {v.dims} {v.dtype}")
         return "\n".join(lines)
+
+
+def concat(objs, dim):
+    """Concatenate DataArrays or Datasets along an existing dimension (numpy data only)."""
+    first = objs[0]
+    if isinstance(first, Dataset):
+        out = Dataset(attrs=first.attrs)
+        for k in first.data_vars:
+            out[k] = concat([o[k] for o in objs], dim)
+        return out
+    ax = first.get_axis_num(dim)
+    data = np.concatenate([np.asarray(o.values) for o in objs], axis=ax)
+    coords = OrderedDict(first.coords)
+    if dim in coords:
+        cv = np.concatenate([np.atleast_1d(o.coords[dim].values) for o in objs])
+        coords[dim] = DataArray(cv, dims=(dim,), name=dim, attrs=first.coords[dim].attrs)
+    return first._replace(data, coords=coords)

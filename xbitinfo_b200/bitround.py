@@ -95,3 +95,29 @@ def xr_bitround(da, keepbits):
         out = da._replace(_cuda_bitround(da.data, keep))
     out.attrs["_QuantizeBitRoundNumberOfSignificantDigits"] = keep
     return out
+
+
+def bitround_along_dim(ds, info_per_bit, dim, inflevels=[1.0, 0.9999, 0.99, 0.975, 0.95], keepbits=None):
+    """Apply bitrounding on slices along ``dim`` based on ``inflevels`` (figure helper,
+    [bitround.py:138-207]): the axis is cut into ``len(inflevels)`` slices (the last one takes
+    the remainder), slice i is rounded to ``get_keepbits(info_per_bit, inflevels[i])`` (left
+    untouched for inflevel 1), and the slices are concatenated again."""
+    from .keepbits import get_keepbits
+
+    new_ds = []
+    if inflevels is not None and keepbits is not None:
+        raise ValueError("Either inflevel or keepbits should be None")
+    elif inflevels is not None:
+        size = ds[dim].size if _xr.is_xarray(ds) else ds.sizes[dim]
+        stride = size // len(inflevels)
+        for i, inf in enumerate(inflevels):  # last slice might be a bit larger
+            ds_slice = ds.isel({dim: slice(stride * i, stride * (i + 1) if i != len(inflevels) - 1 else None)})
+            keepbits_slice = get_keepbits(info_per_bit, inf)
+            new_ds.append(xr_bitround(ds_slice, keepbits_slice) if inf != 1 else ds_slice)
+    elif keepbits is not None:
+        new_ds = [xr_bitround(ds, keepbits)]
+    else:
+        raise ValueError("Either inflevel or keepbits should NOT be None")
+    if _xr.is_xarray(ds):  # pragma: no cover - xarray is absent from the build image
+        return _xr.xarray_module().concat(new_ds, dim)
+    return _labelled.concat(new_ds, dim)
