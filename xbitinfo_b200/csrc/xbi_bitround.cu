@@ -4,6 +4,8 @@
 //     b += ((b >> drop) & 1) + (2^(drop-1) - 1);   b &= ~(2^drop - 1)
 // (wrapping add).  Pure streaming kernel: one 128-bit load and one 128-bit store per
 // 16 bytes, 2 x numel x itemsize bytes of HBM traffic.
+#include <cstdlib>
+
 #include "xbi_common.cuh"
 #include "xbi_internal.h"
 
@@ -65,27 +67,41 @@ __device__ __forceinline__ void round_scalar(void* x, long long i, uint32_t drop
 }
 
 constexpr int kThreads = 256;
-constexpr int kVecPerThread = 4;  // 4 independent 128-bit loads in flight per thread
 
-// head: elements before the first 16-byte boundary; nvec: number of whole 16-byte vectors
-template <int BYTES>
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) {
+    asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+// head: elements before the first 16-byte boundary; nvec: number of whole 16-byte vectors.
+// VPT independent 128-bit loads are in flight per thread before the first store.
+template <int BYTES, int VPT, bool HINT>
 __global__ void __launch_bounds__(kThreads)
 k_bitround(void* __restrict__ x, long long numel, long long head, long long nvec, uint32_t drop,
            unsigned long long half_m1, unsigned long long keep) {
     constexpr int EPV = 16 / BYTES;
     uint4* vbase = reinterpret_cast<uint4*>(static_cast<char*>(x) + head * BYTES);
-    const long long stride = (long long)gridDim.x * kThreads * kVecPerThread;
-    for (long long base = (long long)blockIdx.x * kThreads * kVecPerThread; base < nvec; base += stride) {
-        uint4 v[kVecPerThread];
+    const long long stride = (long long)gridDim.x * kThreads * VPT;
+    for (long long base = (long long)blockIdx.x * kThreads * VPT; base < nvec; base += stride) {
+        uint4 v[VPT];
 #pragma unroll
-        for (int u = 0; u < kVecPerThread; ++u) {
+        for (int u = 0; u < VPT; ++u) {
             const long long i = base + (long long)u * kThreads + threadIdx.x;
-            if (i < nvec) v[u] = vbase[i];
+            if (i < nvec) v[u] = HINT ? ld_stream(vbase + i) : vbase[i];
         }
 #pragma unroll
-        for (int u = 0; u < kVecPerThread; ++u) {
+        for (int u = 0; u < VPT; ++u) {
             const long long i = base + (long long)u * kThreads + threadIdx.x;
-            if (i < nvec) vbase[i] = round_vec<BYTES>(v[u], drop, half_m1, keep);
+            if (i < nvec) {
+                const uint4 r = round_vec<BYTES>(v[u], drop, half_m1, keep);
+                if (HINT) st_stream(vbase + i, r); else vbase[i] = r;
+            }
         }
     }
     // ragged ends (fewer than 2 vectors' worth of elements in total)
@@ -93,6 +109,35 @@ k_bitround(void* __restrict__ x, long long numel, long long head, long long nvec
         const long long tail0 = head + nvec * EPV;
         for (long long i = threadIdx.x; i < head; i += kThreads) round_scalar<BYTES>(x, i, drop, half_m1, keep);
         for (long long i = tail0 + threadIdx.x; i < numel; i += kThreads) round_scalar<BYTES>(x, i, drop, half_m1, keep);
+    }
+}
+
+template <int BYTES, int VPT, bool HINT>
+void launch_variant(void* x, long long numel, long long head, long long nvec, uint32_t drop, unsigned long long half_m1,
+                    unsigned long long keep, int sms, int waves, cudaStream_t stream) {
+    long long blocks = (nvec + (long long)kThreads * VPT - 1) / ((long long)kThreads * VPT);
+    const long long cap = (long long)sms * waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    k_bitround<BYTES, VPT, HINT><<<(unsigned)blocks, kThreads, 0, stream>>>(x, numel, head, nvec, drop, half_m1, keep);
+}
+
+template <int BYTES>
+void launch_bytes(void* x, long long numel, long long head, long long nvec, uint32_t drop, unsigned long long half_m1,
+                  unsigned long long keep, int sms, cudaStream_t stream) {
+    // development switches (defaults are the measured best)
+    static const int vpt = std::getenv("XBI_BR_VPT") ? std::atoi(std::getenv("XBI_BR_VPT")) : 8;
+    static const int hint = std::getenv("XBI_BR_HINT") ? std::atoi(std::getenv("XBI_BR_HINT")) : 0;
+    static const int waves = std::getenv("XBI_BR_WAVES") ? std::atoi(std::getenv("XBI_BR_WAVES")) : 64;
+    if (vpt == 8) {
+        if (hint) launch_variant<BYTES, 8, true>(x, numel, head, nvec, drop, half_m1, keep, sms, waves, stream);
+        else launch_variant<BYTES, 8, false>(x, numel, head, nvec, drop, half_m1, keep, sms, waves, stream);
+    } else if (vpt == 2) {
+        if (hint) launch_variant<BYTES, 2, true>(x, numel, head, nvec, drop, half_m1, keep, sms, waves, stream);
+        else launch_variant<BYTES, 2, false>(x, numel, head, nvec, drop, half_m1, keep, sms, waves, stream);
+    } else {
+        if (hint) launch_variant<BYTES, 4, true>(x, numel, head, nvec, drop, half_m1, keep, sms, waves, stream);
+        else launch_variant<BYTES, 4, false>(x, numel, head, nvec, drop, half_m1, keep, sms, waves, stream);
     }
 }
 
@@ -117,14 +162,10 @@ cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cud
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    long long blocks = (nvec + (long long)kThreads * kVecPerThread - 1) / ((long long)kThreads * kVecPerThread);
-    const long long cap = (long long)sms * 16;
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
     switch (bytes) {
-        case 2: k_bitround<2><<<(unsigned)blocks, kThreads, 0, stream>>>(x, numel, head, nvec, drop, half_m1, keep); break;
-        case 4: k_bitround<4><<<(unsigned)blocks, kThreads, 0, stream>>>(x, numel, head, nvec, drop, half_m1, keep); break;
-        case 8: k_bitround<8><<<(unsigned)blocks, kThreads, 0, stream>>>(x, numel, head, nvec, drop, half_m1, keep); break;
+        case 2: launch_bytes<2>(x, numel, head, nvec, drop, half_m1, keep, sms, stream); break;
+        case 4: launch_bytes<4>(x, numel, head, nvec, drop, half_m1, keep, sms, stream); break;
+        case 8: launch_bytes<8>(x, numel, head, nvec, drop, half_m1, keep, sms, stream); break;
         default: return cudaErrorInvalidValue;
     }
     note_launch();
