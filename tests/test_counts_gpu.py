@@ -216,3 +216,22 @@ def test_all_float16_patterns_through_the_packed_paths():
         assert np.array_equal(counts, bo.bitinformation(x, axis)[0]), axis
     counts, _ = run_host(x, 1, masked_value=float("nan"))
     assert np.array_equal(counts, bo.bitinformation(x, 1, masked_value=float("nan"))[0])
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float16", "uint8", "float64"])
+@pytest.mark.parametrize("n", [1920, 3840, 7680, 481, 250])
+def test_row_ends_on_stage_boundaries(dtype, n):
+    """Row lengths that put row ends exactly on TMA stage boundaries (the partner of the last
+    element is the halo word), just above the in-kernel threshold, and below it."""
+    rng = np.random.default_rng(n)
+    rows = 70 if n >= 1920 else 300
+    if np.dtype(dtype).kind == "f":
+        x = smooth_field(rng, (rows, n), dtype, axis=1, scale=0.3, base=2.0)
+    else:
+        x = rng.integers(0, 255, size=(rows, n), dtype=dtype, endpoint=True)
+    before = nat.fast_path_launches()
+    counts, _ = run_host(x, 1)
+    assert nat.fast_path_launches() > before
+    ref, npairs, _ = bo.bitinformation(x, 1)
+    assert np.array_equal(counts, ref)
+    assert counts[0].sum() == npairs == rows * (n - 1)

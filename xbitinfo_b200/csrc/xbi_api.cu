@@ -91,7 +91,7 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
         if (job.inner == 1)
             XBI_CUDA(launch_pairs_tma(job, npairs_flat, ws, stream, &dlo, &dhi, &edges_done), "pair counting (TMA rows)");
         else
-            XBI_CUDA(launch_pairs_cols(job, ws, stream, &dlo, &dhi), "pair counting (column walkers)");
+            XBI_CUDA(launch_pairs_cols(job, ws, stream, &dlo, &dhi, &edges_done), "pair counting (column walkers)");
         if (timed) {
             XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used + 1), stream), "cudaEventRecord");
             if (dhi > dlo) {
@@ -104,7 +104,9 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
     XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
     XBI_CUDA(launch_pairs_generic_flat(job, dhi, npairs_flat, &ws->plus, stream), "pair counting (generic, tail)");
     const int64_t nedges = (job.outer - 1) * job.inner;
-    if (edges_done) {
+    if (edges_done && job.inner != 1) {
+        // column walkers: every block-boundary pair has been subtracted by k_block_edges
+    } else if (edges_done) {
         // inner == 1: edge t sits at flat index t*n + n-1; those inside [dlo, dhi) are done
         XBI_CUDA(launch_pairs_generic_edges(job, 0, dlo / job.n, &ws->minus, stream), "pair counting (edge pairs, head)");
         XBI_CUDA(launch_pairs_generic_edges(job, dhi / job.n, nedges, &ws->minus, stream), "pair counting (edge pairs, tail)");

@@ -613,8 +613,158 @@ bool try_launch_cols_tma(const CountJob& job, Workspace* ws, cudaStream_t stream
     return true;
 }
 
+// ---------------------------------------------------------------------------------
+// Block-boundary pairs for inner > 1: (last row of block o, first row of block o+1) for
+// o < outer-1.  The flat formulation counts them, the reference does not; they are two
+// adjacent rows in memory, read here with the same 128-bit column chunks and subtracted
+// through the `minus` sums.  A work item is (group of 4 boundaries, column chunk); all three
+// streams are formed explicitly, so absent boundaries / idle lanes simply contribute zeros.
+// ---------------------------------------------------------------------------------
 template <int KIND, int MASK, bool XFORM>
-cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo, int64_t* done_hi) {
+__global__ void __launch_bounds__(kThreads)
+k_block_edges(const uint4* __restrict__ x, long long chunks_per_row, long long n, long long nbound, uint32_t mask_lo,
+              uint32_t mask_hi, RawSums* __restrict__ dst) {
+    constexpr int BYTES = Elem<KIND>::kBytes;
+    constexpr bool K64 = (BYTES == 8);
+    constexpr bool MASKED = (MASK != kMaskNone);
+    constexpr int NL = K64 ? 2 : 1;
+    constexpr int LOGC = K64 ? 3 : 4;
+    constexpr int CH = 1 << LOGC;
+    using L = Ladder<3, 4, LOGC>;
+    const uint32_t lane = threadIdx.x & 31u;
+    const long long groups = (nbound + 3) >> 2;
+    const long long total = groups * chunks_per_row;
+    const long long n_witems = (total + 31) >> 5;
+    const long long warps_total = (long long)gridDim.x * (kThreads / 32);
+
+    L Al[NL], Bl[NL], ABl[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { Al[i].clear(); Bl[i].clear(); ABl[i].clear(); }
+    unsigned long long accA[NL], accB[NL], accAB[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { accA[i] = 0; accB[i] = 0; accAB[i] = 0; }
+    uint32_t nvalid = 0, it = 0;
+    unsigned long long nvalid_total = 0;
+    auto flush = [&]() {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            accA[i] += Al[i].warp_totals(lane, it);
+            accB[i] += Bl[i].warp_totals(lane, it);
+            accAB[i] += ABl[i].warp_totals(lane, it);
+            Al[i].clear(); Bl[i].clear(); ABl[i].clear();
+        }
+        nvalid_total += nvalid;
+        nvalid = 0;
+        it = 0;
+    };
+
+    for (long long wi = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); wi < n_witems; wi += warps_total) {
+        const long long item = (wi << 5) + lane;
+        const bool live = item < total;
+        const long long g = live ? item / chunks_per_row : 0;
+        const long long chunk = live ? item - g * chunks_per_row : 0;
+        uint4 va[4], vb[4];
+        bool present[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long o = 4 * g + q;
+            present[q] = live && o < nbound;
+            const long long row = ((present[q] ? o : 0) + 1) * n - 1;  // last row of block o
+            const uint4* pa = x + row * chunks_per_row + chunk;
+            va[q] = ldg_stream(pa);
+            vb[q] = ldg_stream(pa + chunks_per_row);
+        }
+        uint32_t wa[4][4], wb[4][4], wab[4][4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint32_t a[4] = {va[q].x, va[q].y, va[q].z, va[q].w};
+            uint32_t b[4] = {vb[q].x, vb[q].y, vb[q].z, vb[q].w};
+            uint32_t v[4];
+            if (MASKED) {
+                uint32_t ka[4], kb[4];
+                keep_chunk<KIND, MASK>(a, mask_lo, mask_hi, ka);
+                keep_chunk<KIND, MASK>(b, mask_lo, mask_hi, kb);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = present[q] ? (ka[i] & kb[i]) : 0u;
+                nvalid += count_chunk<BYTES>(v);
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) v[i] = present[q] ? 0xFFFFFFFFu : 0u;
+            }
+            xform_chunk<KIND, XFORM>(a);
+            xform_chunk<KIND, XFORM>(b);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                wa[q][i] = a[i] & v[i];
+                wb[q][i] = b[i] & v[i];
+                wab[q][i] = wa[q][i] & wb[q][i];
+            }
+        }
+        if constexpr (!K64) {
+            uint32_t f[16];
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[4 * q + i] = wa[q][i];
+            Al[0].add_chunk(f, it);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[4 * q + i] = wb[q][i];
+            Bl[0].add_chunk(f, it);
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[4 * q + i] = wab[q][i];
+            ABl[0].add_chunk(f, it);
+        } else {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t f[CH];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { f[2 * q] = wa[q][h]; f[2 * q + 1] = wa[q][h + 2]; }
+                Al[h % NL].add_chunk(f, it);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { f[2 * q] = wb[q][h]; f[2 * q + 1] = wb[q][h + 2]; }
+                Bl[h % NL].add_chunk(f, it);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) { f[2 * q] = wab[q][h]; f[2 * q + 1] = wab[q][h + 2]; }
+                ABl[h % NL].add_chunk(f, it);
+            }
+        }
+        ++it;
+        if (it == L::kFlushChunks) flush();
+    }
+    flush();
+
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_n;
+    for (int i = threadIdx.x; i < 3 * 64; i += kThreads) (&s_sum[0][0])[i] = 0;
+    if (threadIdx.x == 0) s_n = 0;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NL; ++i) {
+        const int j = K64 ? (i * 32 + (int)lane) : ((int)lane % (8 * BYTES));
+        if (accA[i]) atomicAdd(&s_sum[S_A][j], accA[i]);
+        if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
+        if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
+    }
+    if (MASKED && nvalid_total) atomicAdd(&s_n, nvalid_total);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 3 * 64; i += kThreads) {
+        const unsigned long long v = (&s_sum[0][0])[i];
+        if (v) atomicAdd(&dst->sums[0][0] + i, v);
+    }
+    if (MASKED && threadIdx.x == 0 && s_n) atomicAdd(&dst->npairs, s_n);
+    if (!MASKED && blockIdx.x == 0 && threadIdx.x == 0) {
+        constexpr long long kElemsPerChunk = 16 / BYTES;
+        atomicAdd(&dst->npairs, (unsigned long long)(nbound * chunks_per_row * kElemsPerChunk));
+    }
+}
+
+template <int KIND, int MASK, bool XFORM>
+cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo, int64_t* done_hi,
+                        bool* edges_done) {
     constexpr int BYTES = Elem<KIND>::kBytes;
     const int64_t row_bytes = job.inner * BYTES;
     if (row_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(job.x) % 16 != 0) return cudaSuccess;
@@ -657,6 +807,20 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
         e = launch_elem_planes(job, pair_rows * job.inner, job.inner, &ws->minus, stream);
         if (e != cudaSuccess) return e;
     }
+    if (job.outer > 1) {
+        const int64_t nbound = job.outer - 1;
+        const int64_t items = ((nbound + 3) / 4) * chunks;
+        // the end-of-kernel flush costs a warp ~10 items' worth of instructions: give every
+        // warp at least 16 items before adding more blocks
+        int64_t eblocks = (items + (int64_t)kThreads * 16 - 1) / ((int64_t)kThreads * 16);
+        if (eblocks > (int64_t)sms * 8) eblocks = (int64_t)sms * 8;
+        if (eblocks < 1) eblocks = 1;
+        k_block_edges<KIND, MASK, XFORM><<<(unsigned)eblocks, kThreads, 0, stream>>>(
+            static_cast<const uint4*>(job.x), (long long)chunks, (long long)job.n, (long long)nbound,
+            (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), &ws->minus);
+        note_launch();
+    }
+    *edges_done = true;
     note_fast_launch();
     *done_lo = 0;
     *done_hi = pair_rows * job.inner;  // every flat pair
@@ -664,38 +828,39 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
 }
 
 template <int KIND>
-cudaError_t dispatch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* lo, int64_t* hi) {
+cudaError_t dispatch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* lo, int64_t* hi, bool* ed) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (job.transform) {
         if constexpr (isf) {
             switch (job.mask_mode) {
-                case kMaskNone: return launch_cols<KIND, kMaskNone, true>(job, ws, stream, lo, hi);
-                case kMaskNaN: return launch_cols<KIND, kMaskNaN, true>(job, ws, stream, lo, hi);
-                default: return launch_cols<KIND, kMaskValue, true>(job, ws, stream, lo, hi);
+                case kMaskNone: return launch_cols<KIND, kMaskNone, true>(job, ws, stream, lo, hi, ed);
+                case kMaskNaN: return launch_cols<KIND, kMaskNaN, true>(job, ws, stream, lo, hi, ed);
+                default: return launch_cols<KIND, kMaskValue, true>(job, ws, stream, lo, hi, ed);
             }
         }
         return cudaSuccess;
     }
     if (job.mask_mode == kMaskNaN) return cudaSuccess;  // stays on the generic kernel
     constexpr int UK = (KIND == kF16) ? kU16 : (KIND == kF32) ? kU32 : (KIND == kF64) ? kU64 : KIND;
-    if (job.mask_mode == kMaskNone) return launch_cols<UK, kMaskNone, false>(job, ws, stream, lo, hi);
-    return launch_cols<UK, kMaskValue, false>(job, ws, stream, lo, hi);
+    if (job.mask_mode == kMaskNone) return launch_cols<UK, kMaskNone, false>(job, ws, stream, lo, hi, ed);
+    return launch_cols<UK, kMaskValue, false>(job, ws, stream, lo, hi, ed);
 }
 
 }  // namespace
 
 cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
-                              int64_t* done_hi) {
+                              int64_t* done_hi, bool* edges_done) {
     *done_lo = 0;
     *done_hi = 0;
+    *edges_done = false;
     switch (job.dtype) {
-        case XBI_U8: return dispatch_cols<kU8>(job, ws, stream, done_lo, done_hi);
-        case XBI_U16: return dispatch_cols<kU16>(job, ws, stream, done_lo, done_hi);
-        case XBI_U32: return dispatch_cols<kU32>(job, ws, stream, done_lo, done_hi);
-        case XBI_U64: return dispatch_cols<kU64>(job, ws, stream, done_lo, done_hi);
-        case XBI_F16: return dispatch_cols<kF16>(job, ws, stream, done_lo, done_hi);
-        case XBI_F32: return dispatch_cols<kF32>(job, ws, stream, done_lo, done_hi);
-        case XBI_F64: return dispatch_cols<kF64>(job, ws, stream, done_lo, done_hi);
+        case XBI_U8: return dispatch_cols<kU8>(job, ws, stream, done_lo, done_hi, edges_done);
+        case XBI_U16: return dispatch_cols<kU16>(job, ws, stream, done_lo, done_hi, edges_done);
+        case XBI_U32: return dispatch_cols<kU32>(job, ws, stream, done_lo, done_hi, edges_done);
+        case XBI_U64: return dispatch_cols<kU64>(job, ws, stream, done_lo, done_hi, edges_done);
+        case XBI_F16: return dispatch_cols<kF16>(job, ws, stream, done_lo, done_hi, edges_done);
+        case XBI_F32: return dispatch_cols<kF32>(job, ws, stream, done_lo, done_hi, edges_done);
+        case XBI_F64: return dispatch_cols<kF64>(job, ws, stream, done_lo, done_hi, edges_done);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -63,8 +63,9 @@ cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, Workspace
                              int64_t* done_lo, int64_t* done_hi, bool* edges_done);
 
 // Column walkers for inner > 1 (16-byte aligned rows); covers flat pairs [*done_lo, *done_hi).
+// *edges_done: the block-boundary pairs have been subtracted as well (all of them).
 cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
-                              int64_t* done_hi);
+                              int64_t* done_hi, bool* edges_done);
 
 cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* counts, cudaStream_t stream);
 cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, int set_zero,
