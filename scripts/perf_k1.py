@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--dtype", default="float32")
     ap.add_argument("--axis", type=int, default=-1)
     ap.add_argument("--mask", default="none")
+    ap.add_argument("--land", type=float, default=0.0, help="fraction of the last two dims set to the masked value (a rectangle)")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--bitround", action="store_true")
     a = ap.parse_args()
@@ -53,6 +54,10 @@ def main():
     else:
         x = torch.randint(-2**30, 2**30, shape, device="cuda", dtype=torch.int64).to(dtype)
     mv = None if a.mask == "none" else float(a.mask)
+    if a.land > 0 and mv is not None:
+        h, w = x.shape[-2], x.shape[-1]
+        x[..., int(0.2 * h): int(0.7 * h), : int(min(1.0, a.land / 0.5) * w)] = mv
+        print(f"masked fraction: {float((x != x).float().mean() if mv != mv else (x == mv).float().mean()):.3f}")
     nbytes = x.numel() * x.element_size()
     pc = PairCounter(x.dtype, x.device)
     l0 = nat.kernel_launches()

@@ -235,3 +235,121 @@ def test_row_ends_on_stage_boundaries(dtype, n):
     ref, npairs, _ = bo.bitinformation(x, 1)
     assert np.array_equal(counts, ref)
     assert counts[0].sum() == npairs == rows * (n - 1)
+
+
+# ---------------------------------------------------------------------------------------
+# masked counting through the fast kernels: clean warps, fully masked warps, validity
+# boundaries (the rare-event corrections of csrc/xbi_mask.cuh), probe false positives
+# ---------------------------------------------------------------------------------------
+def _mask_pattern(x, pattern, rng, mv):
+    """Write the masked value into x (in place) following a named pattern."""
+    flat = x.reshape(-1)
+    if pattern == "none":
+        pass
+    elif pattern == "blocks":  # long contiguous runs: whole warps see only masked elements
+        n = flat.size
+        for lo in (0, n // 5, n // 2 + 13):
+            flat[lo: lo + n // 8 + 7] = mv
+    elif pattern == "alternating":  # every pair straddles a validity boundary
+        flat[::2] = mv
+    elif pattern == "sparse":  # isolated masked elements
+        flat[rng.integers(0, flat.size, size=max(4, flat.size // 3000))] = mv
+    elif pattern == "ends":  # first / last elements of the array and of rows
+        flat[0] = mv
+        flat[-1] = mv
+        x[..., 0] = mv
+        x[..., -1] = mv
+    elif pattern == "all":
+        flat[:] = mv
+    elif pattern == "slabs":  # masked along every axis: slabs, rows and columns
+        x[x.shape[0] // 3: x.shape[0] // 3 + max(1, x.shape[0] // 4)] = mv
+        x[:, ..., 1::5] = mv
+    else:
+        raise AssertionError(pattern)
+
+
+MASK_PATTERNS = ["none", "blocks", "alternating", "sparse", "ends", "all", "slabs"]
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "float16"])
+@pytest.mark.parametrize("pattern", MASK_PATTERNS)
+@pytest.mark.parametrize("mv", [float("nan"), -999.0])
+def test_mask_patterns_rows_kernel(dtype, pattern, mv):
+    rng = np.random.default_rng(21)
+    x = smooth_field(rng, (48, 4099), dtype, axis=1, scale=0.3, base=2.0)
+    x[3, 7] = np.inf  # probe false positive in the NaN variants; an ordinary value otherwise
+    x[5, 100:140] = -np.inf
+    _mask_pattern(x, pattern, rng, mv)
+    before = nat.fast_path_launches()
+    counts, mi = run_host(x, 1, masked_value=mv)
+    assert nat.fast_path_launches() > before
+    ref_counts, npairs, ref_mi = bo.bitinformation(x, 1, masked_value=mv)
+    assert np.array_equal(counts, ref_counts), (dtype, pattern, mv)
+    assert counts[0].sum() == npairs
+    assert_mi_close(mi, ref_mi)
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "float16"])
+@pytest.mark.parametrize("pattern", MASK_PATTERNS)
+@pytest.mark.parametrize("shape", [(1300, 4, 128), (900, 5, 72)])  # power-of-two pitch / other pitch (TMA ring)
+def test_mask_patterns_column_walkers(dtype, pattern, shape):
+    rng = np.random.default_rng(22)
+    mv = float("nan") if shape[2] == 128 else -999.0
+    x = smooth_field(rng, shape, dtype, axis=0, scale=0.3, base=2.0)
+    x[7, 1, 3] = np.inf
+    _mask_pattern(x, pattern, rng, mv)
+    before = nat.fast_path_launches()
+    counts, mi = run_host(x, 0, masked_value=mv)
+    assert nat.fast_path_launches() > before
+    ref_counts, npairs, ref_mi = bo.bitinformation(x, 0, masked_value=mv)
+    assert np.array_equal(counts, ref_counts), (dtype, pattern, shape)
+    assert counts[0].sum() == npairs
+    assert_mi_close(mi, ref_mi)
+
+
+@pytest.mark.parametrize("dtype,mv", [("uint8", 7), ("int16", -3), ("uint32", 0), ("int64", 2**40 + 5)])
+@pytest.mark.parametrize("pattern", ["blocks", "alternating", "sparse", "ends"])
+def test_mask_patterns_integers(dtype, mv, pattern):
+    rng = np.random.default_rng(23)
+    info = np.iinfo(dtype)
+    for shape, axis in (((40, 8200), 1), ((1100, 3, 64), 0)):
+        x = rng.integers(info.min, info.max, size=shape, dtype=dtype, endpoint=True)
+        _mask_pattern(x, pattern, rng, mv)
+        before = nat.fast_path_launches()
+        counts, _ = run_host(x, axis, masked_value=mv)
+        assert nat.fast_path_launches() > before
+        ref_counts, npairs, _ = bo.bitinformation(x, axis, masked_value=mv)
+        assert np.array_equal(counts, ref_counts), (dtype, pattern, shape)
+        assert counts[0].sum() == npairs
+
+
+def test_mask_probe_false_positives_float64():
+    """Doubles >= 2^1017 and infinities look like NaN to the high-word probe; a masked value
+    whose high word collides with ordinary data looks masked to the value probe.  Both must
+    only cost time, never change the counts."""
+    rng = np.random.default_rng(24)
+    x = smooth_field(rng, (30, 4100), "float64", axis=1, scale=0.3, base=2.0)
+    x[2, 50:90] = 1.5e306
+    x[4, 10] = np.inf
+    x[9, 1000:1100] = np.nan
+    for mv in (float("nan"), 2.0):
+        y = x.copy()
+        if mv == 2.0:
+            y[11, 5:50] = 2.0
+            y[12, 5:50] = np.nextafter(2.0, 3.0)  # same high word as the masked value, not masked
+        counts, _ = run_host(y, 1, masked_value=mv)
+        ref_counts, npairs, _ = bo.bitinformation(y, 1, masked_value=mv)
+        assert np.array_equal(counts, ref_counts)
+        assert counts[0].sum() == npairs
+
+
+def test_masked_zero_matches_bit_pattern_only():
+    """masked_value=0.0 masks +0.0 but not -0.0 (bit identity)."""
+    rng = np.random.default_rng(25)
+    x = smooth_field(rng, (20, 8000), "float32", axis=1, scale=0.3, base=0.0)
+    x[3, 100:200] = 0.0
+    x[4, 100:200] = -0.0
+    counts, _ = run_host(x, 1, masked_value=0.0)
+    ref_counts, npairs, _ = bo.bitinformation(x, 1, masked_value=0.0)
+    assert np.array_equal(counts, ref_counts)
+    assert counts[0].sum() == npairs == 20 * 7999 - 101

@@ -8,9 +8,10 @@
 // (16 words) are folded per step into the bit-sliced counters of xbi_common.cuh, with the
 // next four rows already in flight.
 //
-// Unmasked, only two word streams are needed: b (every row below the first) and a&b.
-// The a-stream total is the b-stream total + bits(first row of the matrix) - bits(its last
-// row); two small row-plane passes (xbi_count_generic.cu) add those to the plus / minus sums.
+// Only two word streams are needed: b (every row below the first; masked elements zeroed)
+// and a&b.  The a-stream total is the b-stream total + bits(first row of the matrix) -
+// bits(its last row); two small row-plane passes (xbi_count_generic.cu) add those to the
+// plus / minus sums.  Masked modes add the boundary corrections of xbi_mask.cuh.
 // Pairs that straddle two blocks of the analysed axis are subtracted by the edge pass
 // (xbi_count_generic.cu).
 #include <cstdlib>
@@ -18,6 +19,7 @@
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
+#include "xbi_mask.cuh"
 #include "xbi_tma.cuh"
 #include "xbi_tmap.h"
 
@@ -33,17 +35,6 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
                  : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
                  : "l"(p));
     return v;
-}
-
-// lane L gets the number of lanes whose word has bit L set (rare use: once per thread)
-__device__ __forceinline__ uint32_t warp_bit_totals(uint32_t w, uint32_t lane) {
-    uint32_t mine = 0;
-#pragma unroll 4
-    for (uint32_t k = 0; k < 32; ++k) {
-        const uint32_t b = __ballot_sync(0xFFFFFFFFu, (w >> k) & 1u);
-        if (lane == k) mine = __popc(b);
-    }
-    return mine;
 }
 
 // transform the four words of a 16-byte chunk in place
@@ -65,40 +56,12 @@ __device__ __forceinline__ void xform_chunk(uint32_t (&w)[4]) {
 // all-ones in the field of every element of the chunk that is NOT masked (raw words)
 template <int KIND, int MASK>
 __device__ __forceinline__ void keep_chunk(const uint32_t (&w)[4], uint32_t mlo, uint32_t mhi, uint32_t (&k)[4]) {
-    constexpr int BYTES = Elem<KIND>::kBytes;
-    if (BYTES == 8) {
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            const uint32_t lo = w[2 * e], hi = w[2 * e + 1];
-            bool masked;
-            if (MASK == kMaskNaN) {
-                const uint32_t m = hi & 0x7FFFFFFFu;
-                masked = m > 0x7FF00000u || (m == 0x7FF00000u && lo != 0u);
-            } else {
-                masked = (lo == mlo) && (hi == mhi);
-            }
-            k[2 * e] = k[2 * e + 1] = masked ? 0u : 0xFFFFFFFFu;
-        }
+    if (Elem<KIND>::kBytes == 8) {
+        k[0] = k[1] = keep_elem64<KIND, MASK>(w[0], w[1], mlo, mhi);
+        k[2] = k[3] = keep_elem64<KIND, MASK>(w[2], w[3], mlo, mhi);
     } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const uint32_t x = w[i];
-            if (BYTES == 4) {
-                if (MASK == kMaskNaN) k[i] = ((x & 0x7FFFFFFFu) > 0x7F800000u) ? 0u : 0xFFFFFFFFu;
-                else k[i] = (x == mlo) ? 0u : 0xFFFFFFFFu;
-            } else if (BYTES == 2) {
-                if (MASK == kMaskNaN) {
-                    const uint32_t nan = (((x & 0x7FFF7FFFu) + 0x03FF03FFu) >> 15) & 0x00010001u;
-                    k[i] = ~(nan * 0xFFFFu);
-                } else {
-                    const uint32_t d = x ^ (mlo * 0x00010001u);
-                    k[i] = (((((d & 0x7FFF7FFFu) + 0x7FFF7FFFu) | d) >> 15) & 0x00010001u) * 0xFFFFu;
-                }
-            } else {
-                const uint32_t d = x ^ (mlo * 0x01010101u);
-                k[i] = (((((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) >> 7) & 0x01010101u) * 0xFFu;
-            }
-        }
+        for (int i = 0; i < 4; ++i) k[i] = keep_word<KIND, MASK>(w[i], mlo);
     }
 }
 template <int BYTES>
@@ -109,6 +72,320 @@ __device__ __forceinline__ uint32_t count_chunk(const uint32_t (&v)[4]) {
     return __popc(v[0] & m) + __popc(v[1] & m) + __popc(v[2] & m) + __popc(v[3] & m);
 }
 
+// ---------------------------------------------------------------------------------
+// Per-thread state of a column walker: the counters, the previous row of its 16-byte
+// column chunk (x': transformed, masked elements zeroed) and, in masked modes, that row's
+// keep-mask.  Shared by the register-staged and the TMA-ring kernels.
+// ---------------------------------------------------------------------------------
+template <int KIND, int MASK, bool XFORM>
+struct ColWalker {
+    static constexpr int BYTES = Elem<KIND>::kBytes;
+    static constexpr bool K64 = (BYTES == 8);
+    static constexpr bool MASKED = (MASK != kMaskNone);
+    static constexpr int NL = K64 ? 2 : 1;    // ladders per stream (low / high words)
+    static constexpr int LOGC = K64 ? 3 : 4;  // 4 rows give 8 low + 8 high words, or 16 words
+    static constexpr bool WHOLE = (BYTES >= 4);  // an element is one or two whole words
+    static constexpr int WPE = K64 ? 2 : 1;      // words per element (whole-word types)
+    static constexpr int EPC = 16 / BYTES;       // elements per 16-byte chunk
+    using L = Ladder<3, (NL * 2 >= 4 ? 5 : 8), LOGC>;
+
+    L Bl[NL], ABl[NL];
+    unsigned long long accB[NL], accAB[NL];
+    uint32_t prev[4];
+    uint32_t pm;            // masked modes, whole-word types: bit e = element e of prev is masked
+    uint32_t prev_keep[4];  // masked modes, packed types: keep-mask of prev ...
+    bool prev_clean;        // ... which may be stale while prev_clean (no masked element in prev)
+    bool lane_live;     // false while this lane shadows a chunk that does not exist (ragged warp item)
+    uint32_t it;
+    uint32_t ninvalid;  // pairs with a masked element since the last flush
+    unsigned long long ninvalid_total;
+    // the boundary-event planes live in local memory and their address is handed to
+    // out-of-line helpers: they are a separate object of the kernel so that this struct
+    // stays in registers
+    using Events = BoundaryEvents<MASKED ? Elem<KIND>::kWords : 1>;
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); accB[i] = 0; accAB[i] = 0; }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { prev[i] = 0u; prev_keep[i] = 0u; }
+        prev_clean = true;
+        pm = 0u;
+        lane_live = true;
+        it = 0;
+        ninvalid = 0;
+        ninvalid_total = 0;
+    }
+
+    __device__ __forceinline__ void flush(uint32_t lane) {
+        if (!lane_live) {  // whatever an idle lane gathered since the last flush is discarded
+#pragma unroll
+            for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); }
+            ninvalid = 0;
+        }
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            accB[i] += Bl[i].warp_totals(lane, it);
+            accAB[i] += ABl[i].warp_totals(lane, it);
+            Bl[i].clear(); ABl[i].clear();
+        }
+        ninvalid_total += ninvalid;
+        ninvalid = 0;
+        it = 0;
+    }
+
+    // first row of a work item (raw words; `live` = the chunk exists)
+    __device__ __forceinline__ void start(const uint4& v, bool live, uint32_t mlo, uint32_t mhi) {
+        prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w;
+        if constexpr (MASKED && WHOLE) {
+            pm = 0u;
+#pragma unroll
+            for (int e = 0; e < EPC; ++e)
+                if (masked_elem<KIND, MASK>(prev[WPE * e], prev[WPE * e + WPE - 1], mlo, mhi)) pm |= 1u << e;
+        } else if constexpr (MASKED) {
+            keep_chunk<KIND, MASK>(prev, mlo, mhi, prev_keep);
+        }
+        xform_chunk<KIND, XFORM>(prev);
+        if constexpr (MASKED && WHOLE) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if ((pm >> (i / WPE)) & 1u) prev[i] = 0u;
+        } else if constexpr (MASKED) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) prev[i] &= prev_keep[i];
+            prev_clean = (prev_keep[0] & prev_keep[1] & prev_keep[2] & prev_keep[3]) == 0xFFFFFFFFu;
+        }
+        if (!live) {  // a lane without a chunk: behaves like a fully masked column
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { prev[i] = 0u; prev_keep[i] = 0u; }
+            prev_clean = false;
+            pm = (1u << EPC) - 1u;
+        }
+    }
+
+    // fold 4 rows; rows >= nrows are absent (tail group only)
+    __device__ __forceinline__ void process(const uint4 (&buf)[4], int nrows, uint32_t mlo, uint32_t mhi, uint32_t lane,
+                                            Events& ev) {
+        uint32_t cur[4][4];
+        bool skip = false;  // warp-uniform: nothing in this group (nor the row above it) is valid
+        if constexpr (MASKED && WHOLE) {
+            // ---- whole-word elements: per-thread bit masks, only the dirty threads pay ----
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { cur[r][0] = buf[r].x; cur[r][1] = buf[r].y; cur[r][2] = buf[r].z; cur[r][3] = buf[r].w; }
+            constexpr uint32_t kRowMask = (1u << EPC) - 1u;
+            uint32_t m = 0u;  // bit EPC*r + e: element e of row r is masked
+            {
+                uint32_t raw[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) raw[j] = cur[j >> 2][j & 3];
+                const bool tdirty = (pm != 0u) || may_contain_masked<KIND, MASK>(raw, mlo, mhi);
+                if (__any_sync(0xFFFFFFFFu, tdirty)) {
+                    const bool allm = (pm == kRowMask) && all_masked_quick<KIND, MASK>(raw, mlo, mhi);
+                    if (__all_sync(0xFFFFFFFFu, allm)) {
+                        ninvalid += (uint32_t)nrows * EPC;
+                        return;  // nothing valid in the whole warp: prev stays zero, pm stays all-masked
+                    }
+                    if (tdirty) {
+#pragma unroll
+                        for (int j = 0; j < 4 * EPC; ++j)
+                            if (masked_elem<KIND, MASK>(raw[WPE * j], raw[WPE * j + WPE - 1], mlo, mhi)) m |= 1u << j;
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) xform_chunk<KIND, XFORM>(cur[r]);
+            if (m | pm) {  // this thread's chunk has masked elements (or sits under one)
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    if ((m >> (j / WPE)) & 1u) cur[j >> 2][j & 3] = 0u;
+                const uint32_t present = (nrows >= 4) ? (0xFFFFu >> (16 - 4 * EPC)) : ((1u << (EPC * nrows)) - 1u);
+                const uint32_t above = (m << EPC) | pm;  // the element over each element
+                ninvalid += __popc((m | above) & present);
+                const uint32_t bnd = (m ^ above) & present;
+                if (bnd && lane_live) {  // validity changes between two rows of this chunk: rare
+                    ev.touch();
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e) {
+                            if ((bnd >> (EPC * r + e)) & 1u) {
+                                if ((m >> (EPC * r + e)) & 1u) {  // a valid, b masked
+#pragma unroll
+                                    for (int k = 0; k < WPE; ++k)
+                                        ev.add_a(k, (r == 0) ? prev[WPE * e + k] : cur[r > 0 ? r - 1 : 0][WPE * e + k]);
+                                } else {  // a masked, b valid
+#pragma unroll
+                                    for (int k = 0; k < WPE; ++k) ev.add_b(k, cur[r][WPE * e + k]);
+                                }
+                            }
+                        }
+                    }
+                }
+                if (nrows > 0) pm = (m >> (EPC * (nrows - 1))) & kRowMask;
+            }
+        } else if constexpr (MASKED) {
+            // ---- packed 8/16-bit elements: warp-uniform general path on keep-masks ----
+            uint32_t raw[16];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) { raw[4 * r] = buf[r].x; raw[4 * r + 1] = buf[r].y; raw[4 * r + 2] = buf[r].z; raw[4 * r + 3] = buf[r].w; }
+            const bool dirty = __any_sync(0xFFFFFFFFu, !prev_clean || may_contain_masked<KIND, MASK>(raw, mlo, mhi));
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) cur[r][i] = raw[4 * r + i];
+                xform_chunk<KIND, XFORM>(cur[r]);
+            }
+            if (dirty) {
+                if (prev_clean) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) prev_keep[i] = 0xFFFFFFFFu;
+                }
+                uint32_t keep[4][4];
+                uint32_t anyk = prev_keep[0] | prev_keep[1] | prev_keep[2] | prev_keep[3];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const uint32_t rw[4] = {raw[4 * r], raw[4 * r + 1], raw[4 * r + 2], raw[4 * r + 3]};
+                    keep_chunk<KIND, MASK>(rw, mlo, mhi, keep[r]);
+                    if (r < nrows) anyk |= keep[r][0] | keep[r][1] | keep[r][2] | keep[r][3];
+                }
+                if (__all_sync(0xFFFFFFFFu, anyk == 0u)) {
+                    ninvalid += (uint32_t)nrows * (16u / BYTES);
+                    skip = true;  // prev stays zero, prev_keep stays zero
+                } else {
+                    uint32_t bnd = 0u;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) cur[r][i] &= keep[r][i];
+                        if (r < nrows) {
+                            uint32_t inval[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const uint32_t pk = (r == 0) ? prev_keep[i] : keep[r > 0 ? r - 1 : 0][i];
+                                inval[i] = ~(pk & keep[r][i]);
+                                bnd |= pk ^ keep[r][i];
+                            }
+                            ninvalid += count_chunk<BYTES>(inval);
+                        }
+                    }
+                    if (bnd && lane_live) {  // validity changes between two rows of this chunk: rare
+                        ev.touch();
+#pragma unroll
+                        for (int r = 0; r < 4; ++r) {
+                            if (r < nrows) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) {
+                                    const uint32_t pk = (r == 0) ? prev_keep[i] : keep[r > 0 ? r - 1 : 0][i];
+                                    const uint32_t pa = (r == 0) ? prev[i] : cur[r > 0 ? r - 1 : 0][i];
+                                    const uint32_t va = pk & ~keep[r][i], vb = ~pk & keep[r][i];
+                                    if (va) ev.add_a(0, pa & va);
+                                    if (vb) ev.add_b(0, cur[r][i] & vb);
+                                }
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (r < nrows) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) prev_keep[i] = keep[r][i];
+                        }
+                    }
+                    prev_clean = (prev_keep[0] & prev_keep[1] & prev_keep[2] & prev_keep[3]) == 0xFFFFFFFFu;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                cur[r][0] = buf[r].x; cur[r][1] = buf[r].y; cur[r][2] = buf[r].z; cur[r][3] = buf[r].w;
+                xform_chunk<KIND, XFORM>(cur[r]);
+            }
+        }
+        if (skip) return;
+
+        uint32_t wb[4][4], wab[4][4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const bool present = r < nrows;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                wb[r][i] = present ? cur[r][i] : 0u;
+                wab[r][i] = wb[r][i] & prev[i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (present) prev[i] = cur[r][i];
+        }
+        if constexpr (!K64) {
+            uint32_t f[16];
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[4 * r + i] = wb[r][i];
+            Bl[0].add_chunk(f, it);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) f[4 * r + i] = wab[r][i];
+            ABl[0].add_chunk(f, it);
+        } else {
+            // words 0,2 of a chunk are low halves, words 1,3 high halves
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                uint32_t f[1 << LOGC];
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { f[2 * r] = wb[r][h]; f[2 * r + 1] = wb[r][h + 2]; }
+                Bl[h % NL].add_chunk(f, it);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) { f[2 * r] = wab[r][h]; f[2 * r + 1] = wab[r][h + 2]; }
+                ABl[h % NL].add_chunk(f, it);
+            }
+        }
+        ++it;
+        if (it == L::kFlushChunks) flush(lane);
+    }
+
+    // end of kernel: block reduction, one atomic per non-zero counter and block.  s_sum /
+    // s_minus / s_n are shared scratch of the calling kernel; all threads of the block call.
+    __device__ __forceinline__ void finish(uint32_t lane, int nthreads, unsigned long long (*s_sum)[64],
+                                           unsigned long long (*s_minus)[64], unsigned long long* s_n, Workspace* ws,
+                                           unsigned long long flat_pairs, Events& ev) {
+        flush(lane);
+        for (int i = threadIdx.x; i < 3 * 64; i += nthreads) (&s_sum[0][0])[i] = 0;
+        if (MASKED) {
+            for (int i = threadIdx.x; i < 2 * 64; i += nthreads) (&s_minus[0][0])[i] = 0;
+            if (threadIdx.x == 0) *s_n = 0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NL; ++i) {
+            const int j = K64 ? (i * 32 + (int)lane) : ((int)lane % (8 * BYTES));
+            // the a-stream is the b-stream shifted up one row; the launcher adds the first row of
+            // the matrix and subtracts the last one (row-plane passes)
+            if (accB[i]) atomicAdd(&s_sum[S_A][j], accB[i]);
+            if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
+            if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
+        }
+        if (MASKED) {
+            if (ninvalid_total) atomicAdd(s_n, ninvalid_total);
+            ev.drain(s_minus, 8 * BYTES);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 3 * 64; i += nthreads) {
+            const unsigned long long v = (&s_sum[0][0])[i];
+            if (v) atomicAdd(&ws->plus.sums[0][0] + i, v);
+        }
+        if (MASKED) {
+            for (int i = threadIdx.x; i < 2 * 64; i += nthreads) {
+                const unsigned long long v = (&s_minus[0][0])[i];
+                if (v) atomicAdd(&ws->minus.sums[0][0] + i, v);  // [S_A], [S_B] are the first two rows
+            }
+            if (threadIdx.x == 0 && *s_n) atomicAdd(&ws->minus.npairs, *s_n);
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ws->plus.npairs, flat_pairs);
+    }
+};
+
 // Work item = (segment, chunk) = divmod(item, chunks_per_row): one 16-byte column chunk
 // walked down one segment of rows.  The pair rows [0, nseg*seg_min + seg_extra) are split
 // into nseg segments; the first seg_extra segments are one row longer.  A warp takes 32
@@ -116,17 +393,11 @@ __device__ __forceinline__ uint32_t count_chunk(const uint32_t (&v)[4]) {
 // same number of full 4-row groups -- the flush shuffles rely on that -- plus one
 // predicated tail group for the remaining 0..4 rows of each lane's segment.
 template <int KIND, int MASK, bool XFORM>
-__global__ void __launch_bounds__(kThreads, (MASK == kMaskNone) ? 2 : 1)
+__global__ void __launch_bounds__(kThreads, 2)
 k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long nseg, long long seg_min,
              long long seg_extra, uint32_t mask_lo, uint32_t mask_hi, Workspace* __restrict__ ws) {
-    constexpr int BYTES = Elem<KIND>::kBytes;
-    constexpr bool K64 = (BYTES == 8);
-    constexpr bool MASKED = (MASK != kMaskNone);
-    constexpr int NL = K64 ? 2 : 1;             // ladders per stream (low / high words)
-    constexpr int LOGC = K64 ? 3 : 4;           // 4 rows give 8 low + 8 high words, or 16 words
-    constexpr int CH = 1 << LOGC;
-    constexpr int kNumLadders = NL * (MASKED ? 3 : 2);
-    using L = Ladder<3, (kNumLadders >= 6 ? 4 : kNumLadders >= 4 ? 5 : 8), LOGC>;
+    using W = ColWalker<KIND, MASK, XFORM>;
+    constexpr int BYTES = W::BYTES;
 
     const uint32_t lane = threadIdx.x & 31u;
     const long long total = chunks_per_row * nseg;
@@ -135,47 +406,19 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
     const long long groups = seg_min >> 2;  // full 4-row groups, the same for every item
     const long long stride = chunks_per_row * 16;  // bytes between rows
 
-    L Bl[NL], ABl[NL], Al[MASKED ? NL : 1];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); }
-    if (MASKED) {
-#pragma unroll
-        for (int i = 0; i < NL; ++i) Al[i].clear();
-    }
-    unsigned long long accA[NL], accB[NL], accAB[NL];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) { accA[i] = 0; accB[i] = 0; accAB[i] = 0; }
-    uint32_t nvalid = 0;
-    unsigned long long nvalid_total = 0;
-    uint32_t it = 0;
-    bool lane_live = true;  // false while this lane shadows an item beyond the end (last warp item)
-
-    auto flush = [&]() {
-        if (!lane_live) {
-#pragma unroll
-            for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); if (MASKED) Al[i].clear(); }
-            nvalid = 0;
-        }
-#pragma unroll
-        for (int i = 0; i < NL; ++i) {
-            accB[i] += Bl[i].warp_totals(lane, it);
-            accAB[i] += ABl[i].warp_totals(lane, it);
-            Bl[i].clear(); ABl[i].clear();
-            if (MASKED) { accA[i] += Al[i].warp_totals(lane, it); Al[i].clear(); }
-        }
-        nvalid_total += nvalid;
-        nvalid = 0;
-        it = 0;
-    };
+    W cw;
+    cw.init();
+    typename W::Events ev;
+    ev.init();
 
     for (long long wi = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); wi < n_witems; wi += warps_total) {
         long long item = (wi << 5) + lane;
         const bool active = item < total;
         // only the very last warp item can have idle lanes; it is the last one its warp
-        // handles.  Idle lanes shadow a valid item; what they add is discarded below.
+        // handles.  Idle lanes shadow a valid item; what they add is discarded at the flush.
         const bool ragged = __any_sync(0xFFFFFFFFu, !active);
-        if (ragged) flush();
-        lane_live = active;
+        if (ragged) cw.flush(lane);
+        cw.lane_live = active;
         if (!active) item = total - 1;
         long long seg = 0, chunk = item;
         if (nseg > 1) { seg = item / chunks_per_row; chunk = item - seg * chunks_per_row; }
@@ -183,13 +426,7 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
         const int tail_rows = (int)(seg_min + (seg < seg_extra ? 1 : 0) - (groups << 2));  // 0..4
 
         const char* q = reinterpret_cast<const char*>(x + row_begin * chunks_per_row + chunk);
-        uint32_t prev[4], prev_keep[4];
-        {
-            const uint4 v = ldg_stream(reinterpret_cast<const uint4*>(q));
-            prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w;
-            if (MASKED) keep_chunk<KIND, MASK>(prev, mask_lo, mask_hi, prev_keep);
-            xform_chunk<KIND, XFORM>(prev);
-        }
+        cw.start(ldg_stream(reinterpret_cast<const uint4*>(q)), true, mask_lo, mask_hi);
         q += stride;  // first b-row
 
         auto load_group = [&](uint4 (&buf)[4]) {
@@ -203,91 +440,18 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
             q = q3 + stride;
         };
 
-        // fold 4 rows; rows >= nrows are absent (tail group only)
-        auto process = [&](const uint4 (&buf)[4], int nrows) {
-            uint32_t wb[4][4], wab[4][4], wa[4][4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                uint32_t cur[4] = {buf[r].x, buf[r].y, buf[r].z, buf[r].w};
-                uint32_t keep[4];
-                if (MASKED) keep_chunk<KIND, MASK>(cur, mask_lo, mask_hi, keep);
-                xform_chunk<KIND, XFORM>(cur);
-                const bool present = r < nrows;
-                if (!MASKED) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        wb[r][i] = present ? cur[i] : 0u;
-                        wab[r][i] = wb[r][i] & prev[i];
-                    }
-                } else {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[i] = present ? (keep[i] & prev_keep[i]) : 0u;
-                        wa[r][i] = prev[i] & v[i];
-                        wb[r][i] = cur[i] & v[i];
-                        wab[r][i] = wa[r][i] & wb[r][i];
-                        if (present) prev_keep[i] = keep[i];
-                    }
-                    nvalid += count_chunk<BYTES>(v);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (present) prev[i] = cur[i];
-            }
-            if constexpr (!K64) {
-                uint32_t f[16];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wb[r][i];
-                Bl[0].add_chunk(f, it);
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wab[r][i];
-                ABl[0].add_chunk(f, it);
-                if constexpr (MASKED) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) f[4 * r + i] = wa[r][i];
-                    Al[0].add_chunk(f, it);
-                }
-            } else {
-                // words 0,2 of a chunk are low halves, words 1,3 high halves
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t f[CH];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { f[2 * r] = wb[r][h]; f[2 * r + 1] = wb[r][h + 2]; }
-                    Bl[h % NL].add_chunk(f, it);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { f[2 * r] = wab[r][h]; f[2 * r + 1] = wab[r][h + 2]; }
-                    ABl[h % NL].add_chunk(f, it);
-                    if constexpr (MASKED) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) { f[2 * r] = wa[r][h]; f[2 * r + 1] = wa[r][h + 2]; }
-                        Al[h % NL].add_chunk(f, it);
-                    }
-                }
-            }
-            ++it;
-            if (it == L::kFlushChunks) flush();
-        };
-
         // ping-pong: the next group's four loads are in flight while the current one is folded
         uint4 bufA[4], bufB[4];
         long long g = 0;
         if (groups > 0) load_group(bufA);
         while (g + 2 <= groups) {
             load_group(bufB);
-            process(bufA, 4);
+            cw.process(bufA, 4, mask_lo, mask_hi, lane, ev);
             if (g + 2 < groups) load_group(bufA);
-            process(bufB, 4);
+            cw.process(bufB, 4, mask_lo, mask_hi, lane, ev);
             g += 2;
         }
-        if (g < groups) process(bufA, 4);
+        if (g < groups) cw.process(bufA, 4, mask_lo, mask_hi, lane, ev);
         // tail: up to 4 remaining rows; absent rows re-read an in-bounds row and are zeroed
         if (__any_sync(0xFFFFFFFFu, tail_rows > 0)) {
 #pragma unroll
@@ -295,41 +459,19 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
                 const long long rr = (r < tail_rows) ? r : (long long)tail_rows - 1;  // -1: last full-group row
                 bufA[r] = ldg_stream(reinterpret_cast<const uint4*>(q + rr * stride));
             }
-            process(bufA, tail_rows);
+            cw.process(bufA, tail_rows, mask_lo, mask_hi, lane, ev);
         }
         if (ragged) {
-            flush();
-            lane_live = true;
+            cw.flush(lane);
+            cw.lane_live = true;
         }
     }
-    flush();
 
     __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_minus[2][64];
     __shared__ unsigned long long s_n;
-    for (int i = threadIdx.x; i < 3 * 64; i += kThreads) (&s_sum[0][0])[i] = 0;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-        const int j = K64 ? (i * 32 + (int)lane) : ((int)lane % (8 * BYTES));
-        // unmasked: the a-stream is the b-stream shifted up one row; the launcher adds the
-        // first row of the matrix and subtracts the last one (row-plane passes)
-        const unsigned long long a = MASKED ? accA[i] : accB[i];
-        if (a) atomicAdd(&s_sum[S_A][j], a);
-        if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
-        if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
-    }
-    if (MASKED && nvalid_total) atomicAdd(&s_n, nvalid_total);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 64; i += kThreads) {
-        const unsigned long long v = (&s_sum[0][0])[i];
-        if (v) atomicAdd(&ws->plus.sums[0][0] + i, v);
-    }
-    if (MASKED && threadIdx.x == 0 && s_n) atomicAdd(&ws->plus.npairs, s_n);
-    if (!MASKED && blockIdx.x == 0 && threadIdx.x == 0) {
-        constexpr long long kElemsPerChunk = 16 / BYTES;
-        atomicAdd(&ws->plus.npairs, (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * kElemsPerChunk));
-    }
+    cw.finish(lane, kThreads, s_sum, s_minus, &s_n, ws,
+              (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * (16 / BYTES)), ev);
 }
 
 // ---------------------------------------------------------------------------------
@@ -353,14 +495,8 @@ __global__ void __launch_bounds__(kTmaThreads, 1)
 k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ x, long long chunks_per_row,
                  long long strips, long long nseg, long long seg_min, long long seg_extra, uint32_t mask_lo,
                  uint32_t mask_hi, Workspace* __restrict__ ws) {
-    constexpr int BYTES = Elem<KIND>::kBytes;
-    constexpr bool K64 = (BYTES == 8);
-    constexpr bool MASKED = (MASK != kMaskNone);
-    constexpr int NL = K64 ? 2 : 1;
-    constexpr int LOGC = K64 ? 3 : 4;
-    constexpr int CH = 1 << LOGC;
-    constexpr int kNumLadders = NL * (MASKED ? 3 : 2);
-    using L = Ladder<3, (kNumLadders >= 6 ? 4 : kNumLadders >= 4 ? 5 : 8), LOGC>;
+    using W = ColWalker<KIND, MASK, XFORM>;
+    constexpr int BYTES = W::BYTES;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
@@ -380,39 +516,11 @@ k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restri
     const long long n_witems = strips * nseg;
     const long long warps_total = (long long)gridDim.x * kTmaWarps;
 
-    L Bl[NL], ABl[NL], Al[MASKED ? NL : 1];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); }
-    if (MASKED) {
-#pragma unroll
-        for (int i = 0; i < NL; ++i) Al[i].clear();
-    }
-    unsigned long long accA[NL], accB[NL], accAB[NL];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) { accA[i] = 0; accB[i] = 0; accAB[i] = 0; }
-    uint32_t nvalid = 0;
-    unsigned long long nvalid_total = 0;
-    uint32_t it = 0;
+    W cw;
+    cw.init();
+    typename W::Events ev;
+    ev.init();
     uint32_t t_issued = 0, t_consumed = 0;  // tiles of this warp since kernel start (ring position / phase)
-    bool lane_live = true;  // false while this lane shadows a column chunk beyond the row (ragged strip)
-
-    auto flush = [&]() {
-        if (!lane_live) {  // whatever an idle lane gathered since the last flush is discarded
-#pragma unroll
-            for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); if (MASKED) Al[i].clear(); }
-            nvalid = 0;
-        }
-#pragma unroll
-        for (int i = 0; i < NL; ++i) {
-            accB[i] += Bl[i].warp_totals(lane, it);
-            accAB[i] += ABl[i].warp_totals(lane, it);
-            Bl[i].clear(); ABl[i].clear();
-            if (MASKED) { accA[i] += Al[i].warp_totals(lane, it); Al[i].clear(); }
-        }
-        nvalid_total += nvalid;
-        nvalid = 0;
-        it = 0;
-    };
 
     for (long long wi = (long long)blockIdx.x * kTmaWarps + warp; wi < n_witems; wi += warps_total) {
         const long long seg = wi / strips;
@@ -420,18 +528,16 @@ k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restri
         const long long chunk = strip * 32 + lane;
         const bool active = chunk < chunks_per_row;
         const bool ragged = __any_sync(0xFFFFFFFFu, !active);  // last strip of a row only
-        if (ragged) flush();  // bank what the previous items gathered before lanes go idle
-        lane_live = active;
+        if (ragged) cw.flush(lane);  // bank what the previous items gathered before lanes go idle
+        cw.lane_live = active;
         const long long row_begin = seg * seg_min + (seg < seg_extra ? seg : seg_extra);
         const long long seg_len = seg_min + (seg < seg_extra ? 1 : 0);
         const long long ntiles = (seg_len + kTileRows - 1) / kTileRows;
 
-        uint32_t prev[4] = {0u, 0u, 0u, 0u}, prev_keep[4] = {0u, 0u, 0u, 0u};
-        if (active) {
-            const uint4 v = ldg_stream(x + row_begin * chunks_per_row + chunk);
-            prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w;
-            if (MASKED) keep_chunk<KIND, MASK>(prev, mask_lo, mask_hi, prev_keep);
-            xform_chunk<KIND, XFORM>(prev);
+        {
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (active) v = ldg_stream(x + row_begin * chunks_per_row + chunk);
+            cw.start(v, active, mask_lo, mask_hi);
         }
 
         auto issue_tile = [&](long long k) {
@@ -446,77 +552,6 @@ k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restri
             ++t_issued;
         };
 
-        auto process = [&](const uint4 (&buf)[4], int nrows) {
-            uint32_t wb[4][4], wab[4][4], wa[4][4];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                uint32_t cur[4] = {buf[r].x, buf[r].y, buf[r].z, buf[r].w};
-                uint32_t keep[4];
-                if (MASKED) keep_chunk<KIND, MASK>(cur, mask_lo, mask_hi, keep);
-                xform_chunk<KIND, XFORM>(cur);
-                const bool present = r < nrows;
-                if (!MASKED) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        wb[r][i] = present ? cur[i] : 0u;
-                        wab[r][i] = wb[r][i] & prev[i];
-                    }
-                } else {
-                    uint32_t v[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        v[i] = present ? (keep[i] & prev_keep[i]) : 0u;
-                        wa[r][i] = prev[i] & v[i];
-                        wb[r][i] = cur[i] & v[i];
-                        wab[r][i] = wa[r][i] & wb[r][i];
-                        if (present) prev_keep[i] = keep[i];
-                    }
-                    nvalid += count_chunk<BYTES>(v);
-                }
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    if (present) prev[i] = cur[i];
-            }
-            if constexpr (!K64) {
-                uint32_t f[16];
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wb[r][i];
-                Bl[0].add_chunk(f, it);
-#pragma unroll
-                for (int r = 0; r < 4; ++r)
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wab[r][i];
-                ABl[0].add_chunk(f, it);
-                if constexpr (MASKED) {
-#pragma unroll
-                    for (int r = 0; r < 4; ++r)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) f[4 * r + i] = wa[r][i];
-                    Al[0].add_chunk(f, it);
-                }
-            } else {
-#pragma unroll
-                for (int h = 0; h < 2; ++h) {
-                    uint32_t f[CH];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { f[2 * r] = wb[r][h]; f[2 * r + 1] = wb[r][h + 2]; }
-                    Bl[h % NL].add_chunk(f, it);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) { f[2 * r] = wab[r][h]; f[2 * r + 1] = wab[r][h + 2]; }
-                    ABl[h % NL].add_chunk(f, it);
-                    if constexpr (MASKED) {
-#pragma unroll
-                        for (int r = 0; r < 4; ++r) { f[2 * r] = wa[r][h]; f[2 * r + 1] = wa[r][h + 2]; }
-                        Al[h % NL].add_chunk(f, it);
-                    }
-                }
-            }
-            ++it;
-            if (it == L::kFlushChunks) flush();
-        };
-
         const long long pre = ntiles < (kRing - 1) ? ntiles : (kRing - 1);
         for (long long k = 0; k < pre; ++k) issue_tile(k);
         for (long long k = 0; k < ntiles; ++k) {
@@ -528,44 +563,24 @@ k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restri
 #pragma unroll
             for (int r = 0; r < 4; ++r) buf[r] = lds128(base + r * kStripBytes);
             if (k + 1 < ntiles) {
-                process(buf, 4);
+                cw.process(buf, 4, mask_lo, mask_hi, lane, ev);
             } else {
-                process(buf, (int)(seg_len - k * kTileRows));
+                cw.process(buf, (int)(seg_len - k * kTileRows), mask_lo, mask_hi, lane, ev);
             }
             ++t_consumed;
             __syncwarp();
         }
         if (ragged) {
-            flush();
-            lane_live = true;
+            cw.flush(lane);
+            cw.lane_live = true;
         }
     }
-    flush();
 
     __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_minus[2][64];
     __shared__ unsigned long long s_n;
-    for (int i = threadIdx.x; i < 3 * 64; i += kTmaThreads) (&s_sum[0][0])[i] = 0;
-    if (threadIdx.x == 0) s_n = 0;
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < NL; ++i) {
-        const int j = K64 ? (i * 32 + (int)lane) : ((int)lane % (8 * BYTES));
-        const unsigned long long a = MASKED ? accA[i] : accB[i];  // unmasked: corrected by the row-plane passes
-        if (a) atomicAdd(&s_sum[S_A][j], a);
-        if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
-        if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
-    }
-    if (MASKED && nvalid_total) atomicAdd(&s_n, nvalid_total);
-    __syncthreads();
-    for (int i = threadIdx.x; i < 3 * 64; i += kTmaThreads) {
-        const unsigned long long v = (&s_sum[0][0])[i];
-        if (v) atomicAdd(&ws->plus.sums[0][0] + i, v);
-    }
-    if (MASKED && threadIdx.x == 0 && s_n) atomicAdd(&ws->plus.npairs, s_n);
-    if (!MASKED && blockIdx.x == 0 && threadIdx.x == 0) {
-        constexpr long long kElemsPerChunk = 16 / BYTES;
-        atomicAdd(&ws->plus.npairs, (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * kElemsPerChunk));
-    }
+    cw.finish(lane, kTmaThreads, s_sum, s_minus, &s_n, ws,
+              (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * (16 / BYTES)), ev);
 }
 
 // returns false when the TMA variant cannot be used (no encoder, extents beyond 32-bit coordinates)
@@ -800,8 +815,9 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
         static_cast<const uint4*>(job.x), (long long)chunks, (long long)nseg, (long long)seg_min, (long long)seg_extra,
         (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), ws);
     }
-    if (MASK == kMaskNone) {
+    {
         // a-stream correction: + planes(first row) - planes(row after the last pair row)
+        // (masked elements contribute nothing, as in the walkers)
         cudaError_t e = launch_elem_planes(job, 0, job.inner, &ws->plus, stream);
         if (e != cudaSuccess) return e;
         e = launch_elem_planes(job, pair_rows * job.inner, job.inner, &ws->minus, stream);

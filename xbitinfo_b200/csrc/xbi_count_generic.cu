@@ -82,8 +82,9 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
                 E::load(x, f, a);
                 if (MODE != 2) E::load(x, f + inner, b);
                 bool ok = true;
-                if (MASK == kMaskNaN) ok = !(E::is_nan(a) || E::is_nan(b));
-                if (MASK == kMaskValue) ok = !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
+                if (MASK == kMaskNaN) ok = !(E::is_nan(a) || (MODE != 2 && E::is_nan(b)));
+                if (MASK == kMaskValue)
+                    ok = !(E::equals(a, mask_lo, mask_hi) || (MODE != 2 && E::equals(b, mask_lo, mask_hi)));
                 if (XFORM) { E::transform(a); if (MODE != 2) E::transform(b); }
                 if (!ok) {
 #pragma unroll
@@ -200,9 +201,7 @@ cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int
 }
 
 cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream) {
-    CountJob j = job;
-    j.mask_mode = kMaskNone;
-    return dispatch_kind<2>(j, lo, count, dst, stream);
+    return dispatch_kind<2>(job, lo, count, dst, stream);
 }
 
 }  // namespace xbi

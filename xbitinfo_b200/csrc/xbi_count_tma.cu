@@ -17,6 +17,7 @@
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
+#include "xbi_mask.cuh"
 #include "xbi_tma.cuh"
 #include "xbi_tmap.h"
 
@@ -67,36 +68,6 @@ __device__ __forceinline__ uint32_t successor_word(uint32_t cur, uint32_t next) 
     if (BYTES == 4) return next;
     return __funnelshift_r(cur, next, 8 * BYTES);
 }
-// all-ones in the field of every element that is NOT masked
-template <int KIND, int MASK>
-__device__ __forceinline__ uint32_t keep_fields(uint32_t w, uint32_t mask_lo) {
-    if (MASK == kMaskNone) return 0xFFFFFFFFu;
-    constexpr int BYTES = Elem<KIND>::kBytes;
-    if (BYTES == 4) {
-        if (MASK == kMaskNaN) return ((w & 0x7FFFFFFFu) > 0x7F800000u) ? 0u : 0xFFFFFFFFu;
-        return (w == mask_lo) ? 0u : 0xFFFFFFFFu;
-    } else if (BYTES == 2) {
-        if (MASK == kMaskNaN) {
-            const uint32_t mag = w & 0x7FFF7FFFu;  // NaN <=> magnitude > 0x7C00
-            const uint32_t nan = ((mag + 0x03FF03FFu) >> 15) & 0x00010001u;
-            return ~(nan * 0xFFFFu);
-        }
-        const uint32_t x = w ^ (mask_lo * 0x00010001u);
-        const uint32_t nz = ((((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) >> 15) & 0x00010001u;
-        return nz * 0xFFFFu;
-    } else {
-        const uint32_t x = w ^ (mask_lo * 0x01010101u);
-        const uint32_t nz = ((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u;
-        return nz * 0xFFu;
-    }
-}
-template <int BYTES>
-__device__ __forceinline__ uint32_t count_fields(uint32_t v) {
-    if (BYTES == 4) return v & 1u;
-    if (BYTES == 2) return __popc(v & 0x00010001u);
-    return __popc(v & 0x01010101u);
-}
-
 // one element of BYTES bytes from shared memory, zero-extended into 32-bit words
 template <int BYTES>
 __device__ __forceinline__ void lds_elem(uint32_t addr, uint32_t (&w)[BYTES == 8 ? 2 : 1]) {
@@ -126,8 +97,8 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     constexpr int BYTES = S::kBytes;
     constexpr int NL = S::kLaddersPerStream;
     constexpr bool MASKED = (MASK != kMaskNone);
-    constexpr int kNumLadders = NL * (MASKED ? 3 : 2);
-    using L = Ladder<3, (kNumLadders >= 6 ? 3 : kNumLadders >= 4 ? 5 : 8)>;
+    constexpr int kNumLadders = NL * 2;
+    using L = Ladder<3, (kNumLadders >= 4 ? 5 : 8)>;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
@@ -296,6 +267,8 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     }
 
     // ================= counting warps =================
+    // Two word streams in every mode: a (x', masked elements zeroed) and a&b.  Masked modes
+    // add the boundary corrections and the invalid-pair count of xbi_mask.cuh.
     const uint32_t t = threadIdx.x;
     const uint32_t row = t / S::kThreadsPerRow;
     const uint32_t cbase = (t % S::kThreadsPerRow) * S::kSegChunks;
@@ -306,18 +279,16 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     const uint32_t nb_off = nb_same_row ? (row * kRowBytes + (((cbase + S::kSegChunks) ^ swz) << 4))
                                         : ((row + 1) * kRowBytes + (((row + 1) & 7u) << 4));
 
-    L A[NL], AB[NL], B[MASKED ? NL : 1];
+    L A[NL], AB[NL];
 #pragma unroll
     for (int i = 0; i < NL; ++i) { A[i].clear(); AB[i].clear(); }
-    if (MASKED) {
+    unsigned long long accA[NL], accAB[NL];
 #pragma unroll
-        for (int i = 0; i < NL; ++i) B[i].clear();
-    }
-    unsigned long long accA[NL], accAB[NL], accB[NL];
-#pragma unroll
-    for (int i = 0; i < NL; ++i) { accA[i] = 0; accAB[i] = 0; accB[i] = 0; }
-    uint32_t nvalid = 0;
-    unsigned long long nvalid_total = 0;
+    for (int i = 0; i < NL; ++i) { accA[i] = 0; accAB[i] = 0; }
+    uint32_t ninvalid = 0;  // pairs with a masked element (this thread, since the last flush)
+    unsigned long long ninvalid_total = 0;
+    BoundaryEvents<MASKED ? Elem<KIND>::kWords : 1> ev;
+    ev.init();
     uint32_t it = 0;
 
     auto flush = [&]() {
@@ -326,10 +297,9 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
             accA[i] += A[i].warp_totals(lane, it);
             accAB[i] += AB[i].warp_totals(lane, it);
             A[i].clear(); AB[i].clear();
-            if (MASKED) { accB[i] += B[i].warp_totals(lane, it); B[i].clear(); }
         }
-        nvalid_total += nvalid;
-        nvalid = 0;
+        ninvalid_total += ninvalid;
+        ninvalid = 0;
         it = 0;
     };
 
@@ -355,13 +325,44 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                 w[S::kSegWords] = lds32(a);
             }
         }
+        bool skip = false;  // warp-uniform: every element this warp holds is masked
 
-        if (!S::k64) {
+        if constexpr (BYTES < 4) {
+            // ---- packed 8/16-bit elements (a NaN / value mask is decided on keep-masks) ----
             uint32_t tw[17];
 #pragma unroll
             for (int i = 0; i < 17; ++i) tw[i] = xform_word<KIND, XFORM>(w[i]);
-            uint32_t a[16], ab[16];
-            if (!MASKED) {
+            if (MASKED && __any_sync(0xFFFFFFFFu, may_contain_masked<KIND, MASK>(w, mask_lo, mask_hi))) {
+                uint32_t keep[17], anyk = 0u;
+#pragma unroll
+                for (int i = 0; i < 17; ++i) { keep[i] = keep_word<KIND, MASK>(w[i], mask_lo); anyk |= keep[i]; }
+                if (__all_sync(0xFFFFFFFFu, anyk == 0u)) {
+                    ninvalid += 16u * (4u / BYTES);
+                    skip = true;
+                } else {
+                    uint32_t bnd = 0u;
+#pragma unroll
+                    for (int i = 0; i < 17; ++i) tw[i] &= keep[i];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        const uint32_t ks = successor_word<BYTES>(keep[i], keep[i + 1]);
+                        ninvalid += count_fields<BYTES>(~(keep[i] & ks));
+                        bnd |= keep[i] ^ ks;
+                    }
+                    if (bnd) {  // validity changes inside this thread's words: rare
+                        ev.touch();
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const uint32_t ks = successor_word<BYTES>(keep[i], keep[i + 1]);
+                            const uint32_t va = keep[i] & ~ks, vb = ~keep[i] & ks;
+                            if (va) ev.add_a(0, tw[i] & va);
+                            if (vb) ev.add_b(0, successor_word<BYTES>(tw[i], tw[i + 1]) & vb);
+                        }
+                    }
+                }
+            }
+            if (!skip) {
+                uint32_t a[16], ab[16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     a[i] = tw[i];
@@ -369,114 +370,135 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                 }
                 A[0].add16(a, it);
                 AB[0].add16(ab, it);
-            } else {
-                uint32_t keep[17], b[16];
-#pragma unroll
-                for (int i = 0; i < 17; ++i) keep[i] = keep_fields<KIND, MASK>(w[i], mask_lo);
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const uint32_t v = keep[i] & successor_word<BYTES>(keep[i], keep[i + 1]);
-                    a[i] = tw[i] & v;
-                    b[i] = successor_word<BYTES>(tw[i], tw[i + 1]) & v;
-                    ab[i] = a[i] & b[i];
-                    nvalid += count_fields<BYTES>(v);
-                }
-                A[0].add16(a, it);
-                B[0].add16(b, it);
-                AB[0].add16(ab, it);
             }
         } else {
-            // 64-bit elements: even words = low halves, odd words = high halves (transform there)
-            uint32_t lo[17], hi[17];
+            // ---- whole-word elements (4 / 8 bytes): 17 elements, the last one is the neighbour.
+            // Masked modes: a per-thread bit mask of the masked elements; only the threads that
+            // hold one pay for the exact test, the zeroing and the corrections. ----
+            constexpr int WPE = S::k64 ? 2 : 1;
+            uint32_t m = 0u;  // bit e: element e (0..16) is masked
+            if (MASKED) {
+                const bool tdirty = may_contain_masked<KIND, MASK>(w, mask_lo, mask_hi);
+                if (__any_sync(0xFFFFFFFFu, tdirty)) {
+                    if (__all_sync(0xFFFFFFFFu, all_masked_quick<KIND, MASK>(w, mask_lo, mask_hi))) {
+                        ninvalid += 16u;
+                        skip = true;
+                    } else if (tdirty) {
 #pragma unroll
-            for (int e = 0; e < 17; ++e) {
-                lo[e] = w[2 * e];
-                hi[e] = (XFORM && KIND == kF64) ? sexp_f64_hi(w[2 * e + 1]) : w[2 * e + 1];
-            }
-            uint32_t x0[16], x1[16];
-            if (!MASKED) {
-                {
-#pragma unroll
-                    for (int e = 0; e < 16; ++e) { x0[e] = lo[e]; x1[e] = lo[e] & lo[e + 1]; }
-                    A[0].add16(x0, it);
-                    AB[0].add16(x1, it);
+                        for (int e = 0; e < 17; ++e)
+                            if (masked_elem<KIND, MASK>(w[WPE * e], w[WPE * e + WPE - 1], mask_lo, mask_hi)) m |= 1u << e;
+                    }
                 }
-                {
+            }
+            if (!skip) {
+                uint32_t lo[17], hi[S::k64 ? 17 : 1];
+#pragma unroll
+                for (int e = 0; e < 17; ++e) {
+                    if constexpr (S::k64) {
+                        lo[e] = w[2 * e];
+                        hi[e] = (XFORM && KIND == kF64) ? sexp_f64_hi(w[2 * e + 1]) : w[2 * e + 1];
+                    } else {
+                        lo[e] = xform_word<KIND, XFORM>(w[e]);
+                    }
+                }
+                if (MASKED && m != 0u) {
+#pragma unroll
+                    for (int e = 0; e < 17; ++e) {
+                        if ((m >> e) & 1u) {
+                            lo[e] = 0u;
+                            if constexpr (S::k64) hi[e] = 0u;
+                        }
+                    }
+                    ninvalid += __popc((m | (m >> 1)) & 0xFFFFu);
+                    const uint32_t bnd = (m ^ (m >> 1)) & 0xFFFFu;
+                    if (bnd) {  // validity changes inside this thread's elements: rare
+                        ev.touch();
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) {
+                            if ((bnd >> e) & 1u) {
+                                if ((m >> e) & 1u) {  // a masked, b valid
+                                    ev.add_b(0, lo[e + 1]);
+                                    if constexpr (S::k64) ev.add_b(1, hi[e + 1]);
+                                } else {  // a valid, b masked
+                                    ev.add_a(0, lo[e]);
+                                    if constexpr (S::k64) ev.add_a(1, hi[e]);
+                                }
+                            }
+                        }
+                    }
+                }
+                uint32_t x0[16], x1[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { x0[e] = lo[e]; x1[e] = lo[e] & lo[e + 1]; }
+                A[0].add16(x0, it);
+                AB[0].add16(x1, it);
+                if constexpr (S::k64) {
 #pragma unroll
                     for (int e = 0; e < 16; ++e) { x0[e] = hi[e]; x1[e] = hi[e] & hi[e + 1]; }
                     A[NL - 1].add16(x0, it);
                     AB[NL - 1].add16(x1, it);
                 }
-            } else {
-                uint32_t keep[17];
-#pragma unroll
-                for (int e = 0; e < 17; ++e) {
-                    const uint32_t rl = w[2 * e], rh = w[2 * e + 1];
-                    bool masked;
-                    if (MASK == kMaskNaN) {
-                        const uint32_t m = rh & 0x7FFFFFFFu;
-                        masked = m > 0x7FF00000u || (m == 0x7FF00000u && rl != 0u);
-                    } else {
-                        masked = (rl == mask_lo) && (rh == mask_hi);
-                    }
-                    keep[e] = masked ? 0u : 0xFFFFFFFFu;
-                }
-                uint32_t v[16], x2[16];
-#pragma unroll
-                for (int e = 0; e < 16; ++e) { v[e] = keep[e] & keep[e + 1]; nvalid += v[e] & 1u; }
-#pragma unroll
-                for (int e = 0; e < 16; ++e) { x0[e] = lo[e] & v[e]; x1[e] = lo[e + 1] & v[e]; x2[e] = x0[e] & x1[e]; }
-                A[0].add16(x0, it); B[0].add16(x1, it); AB[0].add16(x2, it);
-#pragma unroll
-                for (int e = 0; e < 16; ++e) { x0[e] = hi[e] & v[e]; x1[e] = hi[e + 1] & v[e]; x2[e] = x0[e] & x1[e]; }
-                A[NL - 1].add16(x0, it); B[MASKED ? NL - 1 : 0].add16(x1, it); AB[NL - 1].add16(x2, it);
             }
         }
         // the stage's words are in registers and consumed: hand the buffer back
         __syncwarp();
         if (lane == 0) mbar_arrive(empty0 + 8 * s);
-        ++it;
-        if (it == L::kFlushChunks) flush();
+        if (!skip) {
+            ++it;
+            if (it == L::kFlushChunks) flush();
+        }
     }
     flush();
 
-    // ---- block reduction over the 16 counting warps (named barrier 1, producer not involved)
+    // ---- block reduction over the 15 counting warps (named barrier 1, producer not involved)
     __shared__ unsigned long long s_sum[3][64];
-    __shared__ unsigned long long s_n;
+    __shared__ unsigned long long s_minus[2][64];  // boundary corrections of the a and b streams
+    __shared__ unsigned long long s_ninvalid;
     for (int i = t; i < 3 * 64; i += kCountThreads) (&s_sum[0][0])[i] = 0;
-    if (t == 0) s_n = 0;
+    if (MASKED) {
+        for (int i = t; i < 2 * 64; i += kCountThreads) (&s_minus[0][0])[i] = 0;
+        if (t == 0) s_ninvalid = 0;
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
         const int j = S::k64 ? (i * 32 + (int)lane) : ((int)lane % S::kBits);
         if (accA[i]) atomicAdd(&s_sum[S_A][j], accA[i]);
         if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
-        if (MASKED) {
-            if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
-        } else {
-            if (accA[i]) atomicAdd(&s_sum[S_B][j], accA[i]);  // corrected below (block 0)
-        }
+        if (accA[i]) atomicAdd(&s_sum[S_B][j], accA[i]);  // shifted by one element: corrected below (block 0)
     }
-    if (MASKED && nvalid_total) atomicAdd(&s_n, nvalid_total);
+    if (MASKED) {
+        if (ninvalid_total) atomicAdd(&s_ninvalid, ninvalid_total);
+        ev.drain(s_minus, S::kBits);
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
     for (int i = t; i < 3 * 64; i += kCountThreads) {
         const unsigned long long v = (&s_sum[0][0])[i];
         if (v) atomicAdd(&dst->sums[0][0] + i, v);
     }
-    if (MASKED && t == 0 && s_n) atomicAdd(&dst->npairs, s_n);
+    if (MASKED) {
+        for (int i = t; i < 2 * 64; i += kCountThreads) {
+            const unsigned long long v = (&s_minus[0][0])[i];
+            if (v) atomicAdd(&dst_minus->sums[0][0] + i, v);  // [S_A], [S_B] are the first two rows
+        }
+        if (t == 0 && s_ninvalid) atomicAdd(&dst_minus->npairs, s_ninvalid);
+    }
 
-    if (!MASKED && blockIdx.x == 0 && t < 64) {
+    if (blockIdx.x == 0 && t < 64) {
         // b-stream = a-stream shifted by one element: + bits(element after the region) - bits(first element)
         using E = Elem<KIND>;
         const long long last = nstages * (long long)S::kElemsPerStage;
         uint32_t first_w[E::kWords], last_w[E::kWords];
         E::load(region, 0, first_w);
         E::load(region, last, last_w);
+        bool first_ok = true, last_ok = true;
+        if (MASK == kMaskNaN) { first_ok = !E::is_nan(first_w); last_ok = !E::is_nan(last_w); }
+        if (MASK == kMaskValue) { first_ok = !E::equals(first_w, mask_lo, mask_hi); last_ok = !E::equals(last_w, mask_lo, mask_hi); }
         if (XFORM) { E::transform(first_w); E::transform(last_w); }
         if ((int)t < S::kBits) {
             const uint32_t wsel = t >> 5, bsel = t & 31u;
-            const unsigned long long up = (last_w[E::kWords == 2 ? wsel : 0] >> bsel) & 1u;
-            const unsigned long long down = (first_w[E::kWords == 2 ? wsel : 0] >> bsel) & 1u;
+            const unsigned long long up = last_ok ? ((last_w[E::kWords == 2 ? wsel : 0] >> bsel) & 1u) : 0u;
+            const unsigned long long down = first_ok ? ((first_w[E::kWords == 2 ? wsel : 0] >> bsel) & 1u) : 0u;
             if (up != down) atomicAdd(&dst->sums[S_B][t], up - down);
         }
         if (t == 0) atomicAdd(&dst->npairs, (unsigned long long)last);

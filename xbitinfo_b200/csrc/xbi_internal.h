@@ -52,7 +52,7 @@ cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int
                                        cudaStream_t stream);
 
 // Bit planes of the single elements f in [lo, lo+count) added to dst->sums[S_A] (transform
-// applied, no mask): the a-stream correction of the column walkers.
+// applied, masked elements skipped): the a-stream correction of the column walkers.
 cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream);
 
 // TMA fast paths.  Each consumes as much of [0, numel-inner) as its alignment rules

@@ -1,0 +1,232 @@
+// Masked counting (masked_value / NaN pair exclusion) -- device-side building blocks.
+//
+// A pair is dropped when either element is masked.  With k_f = 1 for
+// an unmasked element, x'_f = k_f ? T(x_f) : 0 (T = signed-exponent transform) and pairs
+// (f, g = f + inner), the three plane sums and the pair count of the valid pairs are
+//
+//     AB = sum x'_f & x'_g                                (no validity needed at all)
+//     A  = sum x'_f  -  sum_{k_f=1, k_g=0} x'_f           ("a valid, b masked" boundaries)
+//     B  = sum x'_g  -  sum_{k_f=0, k_g=1} x'_g           ("a masked, b valid" boundaries)
+//     N  = #flat pairs - #{pairs with k_f & k_g = 0}
+//
+// so a masked pass is the unmasked two-stream pass over x' plus corrections that are only
+// non-zero where validity CHANGES between neighbours.  The fast kernels therefore
+//   1. probe each thread's words for masked elements with instructions that stay off the
+//      ALU pipe where possible (x*0 accumulated with FFMA/HFMA2: NaN iff a NaN/Inf went in);
+//   2. take the plain unmasked code when a whole warp is clean;
+//   3. otherwise build the keep-masks, zero the masked elements, count the invalid pairs
+//      and, at validity boundaries only, ripple the correction words into a rare-event
+//      vertical counter kept in local memory (-> the `minus` sums of the workspace).
+// The probe may report false positives (Inf, doubles >= 2^1017, ...), never false negatives:
+// step 3 always uses the exact test.
+#pragma once
+#include "xbi_common.cuh"
+#include "xbi_elem.cuh"
+#include "xbi_internal.h"
+
+namespace xbi {
+
+// ---------------------------------------------------------------------------------
+// exact keep-masks: all-ones in the field of every element that is NOT masked
+// ---------------------------------------------------------------------------------
+template <int KIND, int MASK>
+__device__ __forceinline__ uint32_t keep_word(uint32_t w, uint32_t mask_lo) {  // types of <= 32 bits
+    if (MASK == kMaskNone) return 0xFFFFFFFFu;
+    constexpr int BYTES = Elem<KIND>::kBytes;
+    if (BYTES == 4) {
+        if (MASK == kMaskNaN) return ((w & 0x7FFFFFFFu) > 0x7F800000u) ? 0u : 0xFFFFFFFFu;
+        return (w == mask_lo) ? 0u : 0xFFFFFFFFu;
+    } else if (BYTES == 2) {
+        if (MASK == kMaskNaN) {
+            const uint32_t mag = w & 0x7FFF7FFFu;  // NaN <=> magnitude > 0x7C00
+            const uint32_t nan = ((mag + 0x03FF03FFu) >> 15) & 0x00010001u;
+            return ~(nan * 0xFFFFu);
+        }
+        const uint32_t x = w ^ (mask_lo * 0x00010001u);
+        const uint32_t nz = ((((x & 0x7FFF7FFFu) + 0x7FFF7FFFu) | x) >> 15) & 0x00010001u;
+        return nz * 0xFFFFu;
+    } else {
+        const uint32_t x = w ^ (mask_lo * 0x01010101u);
+        const uint32_t nz = ((((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x) >> 7) & 0x01010101u;
+        return nz * 0xFFu;
+    }
+}
+template <int KIND, int MASK>
+__device__ __forceinline__ uint32_t keep_elem64(uint32_t lo, uint32_t hi, uint32_t mask_lo, uint32_t mask_hi) {
+    if (MASK == kMaskNone) return 0xFFFFFFFFu;
+    bool masked;
+    if (MASK == kMaskNaN) {
+        const uint32_t m = hi & 0x7FFFFFFFu;
+        masked = m > 0x7FF00000u || (m == 0x7FF00000u && lo != 0u);
+    } else {
+        masked = (lo == mask_lo) && (hi == mask_hi);
+    }
+    return masked ? 0u : 0xFFFFFFFFu;
+}
+// number of elements whose field in v is all-ones (v holds whole fields of ones / zeros)
+template <int BYTES>
+__device__ __forceinline__ uint32_t count_fields(uint32_t v) {
+    if (BYTES >= 4) return v & 1u;
+    if (BYTES == 2) return __popc(v & 0x00010001u);
+    return __popc(v & 0x01010101u);
+}
+
+// ---------------------------------------------------------------------------------
+// probe: may these raw words contain a masked element?  (64-bit types: w = lo,hi,lo,hi,...)
+// ---------------------------------------------------------------------------------
+__device__ __forceinline__ float fma_zero(uint32_t w, float acc) {  // acc + w*0, IEEE (NaN/Inf -> NaN)
+    float r;
+    asm("fma.rn.f32 %0, %1, 0f00000000, %2;" : "=f"(r) : "f"(__uint_as_float(w)), "f"(acc));
+    return r;
+}
+__device__ __forceinline__ uint32_t hfma2_zero(uint32_t w, uint32_t acc) {  // per half: acc + w*0
+    uint32_t r;
+    asm("{.reg .b32 z; mov.b32 z, 0; fma.rn.f16x2 %0, %1, z, %2;}" : "=r"(r) : "r"(w), "r"(acc));
+    return r;
+}
+
+template <int KIND, int MASK, int N>
+__device__ __forceinline__ bool may_contain_masked(const uint32_t (&w)[N], uint32_t mask_lo, uint32_t mask_hi) {
+    constexpr int BYTES = Elem<KIND>::kBytes;
+    if (MASK == kMaskNone) return false;
+    if (MASK == kMaskNaN) {
+        if (BYTES == 4 || BYTES == 8) {
+            // float32: the word itself; float64: the high word read as a float32 is NaN/Inf
+            // exactly when the top eight exponent bits are ones (every double NaN/Inf, plus
+            // finite |x| >= 2^1017)
+            constexpr int STEP = (BYTES == 8) ? 2 : 1;
+            float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = STEP - 1, c = 0; i < N; i += STEP, ++c) s[c & 3] = fma_zero(w[i], s[c & 3]);
+            const float t = (s[0] + s[1]) + (s[2] + s[3]);
+            return !(t == t);
+        } else {
+            uint32_t s[2] = {0u, 0u};
+#pragma unroll
+            for (int i = 0; i < N; ++i) s[i & 1] = hfma2_zero(w[i], s[i & 1]);
+            return ((s[0] | s[1]) & 0x7FFF7FFFu) != 0u;  // sums are +-0 or NaN per half
+        }
+    } else {
+        if (BYTES == 4) {
+            bool hit = false;
+#pragma unroll
+            for (int i = 0; i < N; ++i) hit |= (w[i] == mask_lo);
+            return hit;
+        } else if (BYTES == 8) {
+            bool hit = false;
+#pragma unroll
+            for (int i = 1; i < N; i += 2) hit |= (w[i] == mask_hi);  // high words only: conservative
+            return hit;
+        } else {
+            // any zero field in w ^ pattern  ("haszero": exact for the any-question)
+            constexpr uint32_t ones = (BYTES == 2) ? 0x00010001u : 0x01010101u;
+            constexpr uint32_t highs = (BYTES == 2) ? 0x80008000u : 0x80808080u;
+            const uint32_t pat = mask_lo * ones;
+            uint32_t acc = 0u;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const uint32_t x = w[i] ^ pat;
+                acc |= (x - ones) & ~x;
+            }
+            return (acc & highs) != 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// whole-word element types (4 and 8 bytes): exact per-element test, and a cheap sufficient
+// test for "every element of these words is masked" (NaN: all quiet NaNs; value: all equal)
+// ---------------------------------------------------------------------------------
+template <int KIND, int MASK>
+__device__ __forceinline__ bool masked_elem(uint32_t lo, uint32_t hi, uint32_t mask_lo, uint32_t mask_hi) {
+    // 4-byte types: the element is `lo`, `hi` is ignored
+    if (MASK == kMaskNone) return false;
+    if (Elem<KIND>::kBytes == 8) {
+        if (MASK == kMaskNaN) {
+            const uint32_t m = hi & 0x7FFFFFFFu;
+            return m > 0x7FF00000u || (m == 0x7FF00000u && lo != 0u);
+        }
+        return lo == mask_lo && hi == mask_hi;
+    }
+    if (MASK == kMaskNaN) return (lo & 0x7FFFFFFFu) > 0x7F800000u;
+    return lo == mask_lo;
+}
+template <int KIND, int MASK, int N>
+__device__ __forceinline__ bool all_masked_quick(const uint32_t (&w)[N], uint32_t mask_lo, uint32_t mask_hi) {
+    constexpr int BYTES = Elem<KIND>::kBytes;
+    static_assert(BYTES >= 4, "whole-word element types only");
+    if (MASK == kMaskNaN) {
+        constexpr int STEP = (BYTES == 8) ? 2 : 1;
+        constexpr uint32_t quiet = (BYTES == 8) ? 0x7FF80000u : 0x7FC00000u;  // exponent ones + quiet bit
+        uint32_t acc = 0xFFFFFFFFu;
+#pragma unroll
+        for (int i = STEP - 1; i < N; i += STEP) acc &= w[i];
+        return (acc & quiet) == quiet;
+    } else {
+        uint32_t acc = 0u;
+        if (BYTES == 8) {
+#pragma unroll
+            for (int i = 0; i < N; i += 2) acc |= (w[i] ^ mask_lo) | (w[i + 1] ^ mask_hi);
+        } else {
+#pragma unroll
+            for (int i = 0; i < N; ++i) acc |= w[i] ^ mask_lo;
+        }
+        return acc == 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------------
+// rare-event vertical counter: 32 bit planes in local memory (one array per stream and
+// word), rippled with early exit; capacity 2^32-1 events per lane and bit -- more than a
+// thread can see in one launch.
+// ---------------------------------------------------------------------------------
+static __device__ __noinline__ void event_add(uint32_t* n, uint32_t w) {
+#pragma unroll 1
+    for (int j = 0; j < 32 && w != 0u; ++j) {
+        const uint32_t t = n[j] & w;
+        n[j] ^= w;
+        w = t;
+    }
+}
+static __device__ __noinline__ void event_clear(uint32_t* n, int words) {
+#pragma unroll 1
+    for (int j = 0; j < words; ++j) n[j] = 0u;
+}
+// add the counter of bit position p to dst[p % nbits] (dst: shared-memory totals)
+static __device__ __noinline__ void event_drain(const uint32_t* n, unsigned long long* dst, int nbits) {
+#pragma unroll 1
+    for (int p = 0; p < 32; ++p) {
+        unsigned long long c = 0;
+#pragma unroll 1
+        for (int j = 0; j < 32; ++j) c |= (unsigned long long)((n[j] >> p) & 1u) << j;
+        if (c) atomicAdd(&dst[p % nbits], c);
+    }
+}
+
+// Per-thread state of the boundary corrections: [stream a/b][word lo/hi][32 planes].
+template <int NW>
+struct BoundaryEvents {
+    uint32_t planes[2][NW][32];
+    bool used;
+    __device__ __forceinline__ void init() { used = false; }
+    __device__ __forceinline__ void touch() {
+        if (!used) {
+            event_clear(&planes[0][0][0], 2 * NW * 32);
+            used = true;
+        }
+    }
+    // a-stream correction ("a valid, b masked"): word `wi` of the a element, fields selected
+    __device__ __forceinline__ void add_a(int wi, uint32_t word) { event_add(planes[0][wi], word); }
+    __device__ __forceinline__ void add_b(int wi, uint32_t word) { event_add(planes[1][wi], word); }
+    // s_minus: shared [2][64] totals (stream a, stream b), bit number from the least significant bit
+    __device__ __forceinline__ void drain(unsigned long long (*s_minus)[64], int nbits) {
+        if (!used) return;
+#pragma unroll 1
+        for (int s = 0; s < 2; ++s)
+#pragma unroll 1
+            for (int wi = 0; wi < NW; ++wi)
+                event_drain(planes[s][wi], &s_minus[s][wi * 32], nbits < 32 ? nbits : 32);
+    }
+};
+
+}  // namespace xbi
