@@ -140,17 +140,18 @@ struct ColWalker {
         if constexpr (MASKED && WHOLE) {
             pm = 0u;
 #pragma unroll
-            for (int e = 0; e < EPC; ++e)
-                if (masked_elem<KIND, MASK>(prev[WPE * e], prev[WPE * e + WPE - 1], mlo, mhi)) pm |= 1u << e;
+            for (int e = 0; e < EPC; ++e) {
+                if (masked_elem<KIND, MASK>(prev[WPE * e], prev[WPE * e + WPE - 1], mlo, mhi)) {
+                    pm |= 1u << e;
+#pragma unroll
+                    for (int k = 0; k < WPE; ++k) prev[WPE * e + k] = neutral_word<KIND, XFORM>(k);
+                }
+            }
         } else if constexpr (MASKED) {
             keep_chunk<KIND, MASK>(prev, mlo, mhi, prev_keep);
         }
         xform_chunk<KIND, XFORM>(prev);
-        if constexpr (MASKED && WHOLE) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if ((pm >> (i / WPE)) & 1u) prev[i] = 0u;
-        } else if constexpr (MASKED) {
+        if constexpr (MASKED && !WHOLE) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) prev[i] &= prev_keep[i];
             prev_clean = (prev_keep[0] & prev_keep[1] & prev_keep[2] & prev_keep[3]) == 0xFFFFFFFFu;
@@ -187,17 +188,20 @@ struct ColWalker {
                     }
                     if (tdirty) {
 #pragma unroll
-                        for (int j = 0; j < 4 * EPC; ++j)
-                            if (masked_elem<KIND, MASK>(raw[WPE * j], raw[WPE * j + WPE - 1], mlo, mhi)) m |= 1u << j;
+                        for (int j = 0; j < 4 * EPC; ++j) {
+                            if (masked_elem<KIND, MASK>(raw[WPE * j], raw[WPE * j + WPE - 1], mlo, mhi)) {
+                                m |= 1u << j;
+                                // overwritten with the value whose transform is 0: drops out of every sum
+#pragma unroll
+                                for (int k = 0; k < WPE; ++k) cur[(WPE * j + k) >> 2][(WPE * j + k) & 3] = neutral_word<KIND, XFORM>(k);
+                            }
+                        }
                     }
                 }
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) xform_chunk<KIND, XFORM>(cur[r]);
             if (m | pm) {  // this thread's chunk has masked elements (or sits under one)
-#pragma unroll
-                for (int j = 0; j < 16; ++j)
-                    if ((m >> (j / WPE)) & 1u) cur[j >> 2][j & 3] = 0u;
                 const uint32_t present = (nrows >= 4) ? (0xFFFFu >> (16 - 4 * EPC)) : ((1u << (EPC * nrows)) - 1u);
                 const uint32_t above = (m << EPC) | pm;  // the element over each element
                 ninvalid += __popc((m | above) & present);
@@ -368,7 +372,7 @@ struct ColWalker {
         }
         if (MASKED) {
             if (ninvalid_total) atomicAdd(s_n, ninvalid_total);
-            ev.drain(s_minus, 8 * BYTES);
+            ev.drain(s_minus, 8 * BYTES, lane);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 3 * 64; i += nthreads) {

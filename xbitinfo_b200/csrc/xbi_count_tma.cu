@@ -376,7 +376,6 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
             // Masked modes: a per-thread bit mask of the masked elements; only the threads that
             // hold one pay for the exact test, the zeroing and the corrections. ----
             constexpr int WPE = S::k64 ? 2 : 1;
-            uint32_t m = 0u;  // bit e: element e (0..16) is masked
             if (MASKED) {
                 const bool tdirty = may_contain_masked<KIND, MASK>(w, mask_lo, mask_hi);
                 if (__any_sync(0xFFFFFFFFu, tdirty)) {
@@ -384,9 +383,46 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                         ninvalid += 16u;
                         skip = true;
                     } else if (tdirty) {
+                        uint32_t m = 0u;  // bit e: element e (0..16) is masked
 #pragma unroll
-                        for (int e = 0; e < 17; ++e)
-                            if (masked_elem<KIND, MASK>(w[WPE * e], w[WPE * e + WPE - 1], mask_lo, mask_hi)) m |= 1u << e;
+                        for (int e = 0; e < 17; ++e) {
+                            if (masked_elem<KIND, MASK>(w[WPE * e], w[WPE * e + WPE - 1], mask_lo, mask_hi)) {
+                                m |= 1u << e;
+                                // overwritten with the value whose transform is 0: drops out of every sum
+#pragma unroll
+                                for (int k = 0; k < WPE; ++k) w[WPE * e + k] = neutral_word<KIND, XFORM>(k);
+                            }
+                        }
+                        ninvalid += __popc((m | (m >> 1)) & 0xFFFFu);
+                        uint32_t bnd = (m ^ (m >> 1)) & 0xFFFFu;
+                        if (bnd) ev.touch();
+                        // validity changes between elements e and e+1: the valid one of the two is
+                        // re-read from the stage buffer (still ours) and rippled into the corrections
+#pragma unroll 1
+                        while (bnd) {
+                            const uint32_t e = (uint32_t)__ffs((int)bnd) - 1u;
+                            bnd &= bnd - 1u;
+                            const bool a_masked = (m >> e) & 1u;
+                            const uint32_t ve = a_masked ? e + 1u : e;
+                            const uint32_t wi = ve * WPE;  // word index inside the thread's segment
+                            const uint32_t addr = (ve == 16u)
+                                                      ? (nb_halo ? (halo0 + 16 * s) : (sbase + nb_off))
+                                                      : (sbase + row * kRowBytes + (((cbase + (wi >> 2)) ^ swz) << 4) + ((wi & 3u) << 2));
+                            uint32_t v[Elem<KIND>::kWords];
+                            if constexpr (S::k64) {
+                                const uint2 q = lds64(addr);
+                                v[0] = q.x;
+                                v[1] = q.y;
+                            } else {
+                                v[0] = lds32(addr);
+                            }
+                            if (XFORM) Elem<KIND>::transform(v);
+#pragma unroll
+                            for (int k = 0; k < WPE; ++k) {
+                                if (a_masked) ev.add_b(k, v[k]);
+                                else ev.add_a(k, v[k]);
+                            }
+                        }
                     }
                 }
             }
@@ -399,32 +435,6 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                         hi[e] = (XFORM && KIND == kF64) ? sexp_f64_hi(w[2 * e + 1]) : w[2 * e + 1];
                     } else {
                         lo[e] = xform_word<KIND, XFORM>(w[e]);
-                    }
-                }
-                if (MASKED && m != 0u) {
-#pragma unroll
-                    for (int e = 0; e < 17; ++e) {
-                        if ((m >> e) & 1u) {
-                            lo[e] = 0u;
-                            if constexpr (S::k64) hi[e] = 0u;
-                        }
-                    }
-                    ninvalid += __popc((m | (m >> 1)) & 0xFFFFu);
-                    const uint32_t bnd = (m ^ (m >> 1)) & 0xFFFFu;
-                    if (bnd) {  // validity changes inside this thread's elements: rare
-                        ev.touch();
-#pragma unroll
-                        for (int e = 0; e < 16; ++e) {
-                            if ((bnd >> e) & 1u) {
-                                if ((m >> e) & 1u) {  // a masked, b valid
-                                    ev.add_b(0, lo[e + 1]);
-                                    if constexpr (S::k64) ev.add_b(1, hi[e + 1]);
-                                } else {  // a valid, b masked
-                                    ev.add_a(0, lo[e]);
-                                    if constexpr (S::k64) ev.add_a(1, hi[e]);
-                                }
-                            }
-                        }
                     }
                 }
                 uint32_t x0[16], x1[16];
@@ -469,7 +479,7 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     }
     if (MASKED) {
         if (ninvalid_total) atomicAdd(&s_ninvalid, ninvalid_total);
-        ev.drain(s_minus, S::kBits);
+        ev.drain(s_minus, S::kBits, lane);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
     for (int i = t; i < 3 * 64; i += kCountThreads) {

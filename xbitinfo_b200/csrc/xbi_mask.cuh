@@ -143,13 +143,25 @@ __device__ __forceinline__ bool masked_elem(uint32_t lo, uint32_t hi, uint32_t m
     if (MASK == kMaskNone) return false;
     if (Elem<KIND>::kBytes == 8) {
         if (MASK == kMaskNaN) {
-            const uint32_t m = hi & 0x7FFFFFFFu;
-            return m > 0x7FF00000u || (m == 0x7FF00000u && lo != 0u);
+            const double d = __hiloint2double((int)hi, (int)lo);
+            return d != d;  // one DSETP; only dirty threads get here
         }
         return lo == mask_lo && hi == mask_hi;
     }
-    if (MASK == kMaskNaN) return (lo & 0x7FFFFFFFu) > 0x7F800000u;
+    if (MASK == kMaskNaN) {
+        const float f = __uint_as_float(lo);
+        return f != f;
+    }
     return lo == mask_lo;
+}
+// Raw word(s) whose transformed image is all-zero bits: masked elements are overwritten with
+// it so that they drop out of every plane sum (1.0 under the signed-exponent transform).
+template <int KIND, bool XFORM>
+__device__ __forceinline__ uint32_t neutral_word(int word_in_elem) {
+    if (!XFORM) return 0u;
+    if (KIND == kF32) return 0x3F800000u;
+    if (KIND == kF64) return word_in_elem == 1 ? 0x3FF00000u : 0u;
+    return 0u;
 }
 template <int KIND, int MASK, int N>
 __device__ __forceinline__ bool all_masked_quick(const uint32_t (&w)[N], uint32_t mask_lo, uint32_t mask_hi) {
@@ -192,15 +204,40 @@ static __device__ __noinline__ void event_clear(uint32_t* n, int words) {
 #pragma unroll 1
     for (int j = 0; j < words; ++j) n[j] = 0u;
 }
-// add the counter of bit position p to dst[p % nbits] (dst: shared-memory totals)
-static __device__ __noinline__ void event_drain(const uint32_t* n, unsigned long long* dst, int nbits) {
+// Warp-collective drain (all 32 lanes call): the 32 planes of every lane that used its
+// counter are summed over the warp with the butterfly of xbi_common.cuh; lane L ends up with
+// the warp's count of bit position L and adds it to dst[L % nbits] (shared-memory totals).
+static __device__ __noinline__ void event_drain_warp(const uint32_t* planes, bool used, uint32_t lane,
+                                                     unsigned long long* dst, int nbits) {
+    constexpr int P = 32;
+    uint32_t n[P + 6];
 #pragma unroll 1
-    for (int p = 0; p < 32; ++p) {
-        unsigned long long c = 0;
+    for (int j = 0; j < P; ++j) n[j] = used ? planes[j] : 0u;
 #pragma unroll 1
-        for (int j = 0; j < 32; ++j) c |= (unsigned long long)((n[j] >> p) & 1u) << j;
-        if (c) atomicAdd(&dst[p % nbits], c);
+    for (int j = P; j < P + 6; ++j) n[j] = 0u;
+    for (int step = 0; step < 5; ++step) {
+        const int d = 16 >> step;
+        const uint32_t hi_sel = (d == 16) ? 0xFFFF0000u : (d == 8) ? 0xFF00FF00u : (d == 4) ? 0xF0F0F0F0u
+                               : (d == 2) ? 0xCCCCCCCCu : 0xAAAAAAAAu;
+        const uint32_t keep = (lane & d) ? hi_sel : ~hi_sel;
+        uint32_t carry = 0;
+        const int np = P + step;
+#pragma unroll 1
+        for (int j = 0; j < np; ++j) {
+            const uint32_t mine = n[j] & keep;
+            const uint32_t give = n[j] & ~keep;
+            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, give, d);
+            uint32_t hi, lo;
+            csa(hi, lo, mine, got, carry);
+            n[j] = lo;
+            carry = hi;
+        }
+        n[np] = carry;
     }
+    unsigned long long total = 0;
+#pragma unroll 1
+    for (int j = 0; j < P + 5; ++j) total |= (unsigned long long)((n[j] >> lane) & 1u) << j;
+    if (total) atomicAdd(&dst[lane % nbits], total);
 }
 
 // Per-thread state of the boundary corrections: [stream a/b][word lo/hi][32 planes].
@@ -219,13 +256,14 @@ struct BoundaryEvents {
     __device__ __forceinline__ void add_a(int wi, uint32_t word) { event_add(planes[0][wi], word); }
     __device__ __forceinline__ void add_b(int wi, uint32_t word) { event_add(planes[1][wi], word); }
     // s_minus: shared [2][64] totals (stream a, stream b), bit number from the least significant bit
-    __device__ __forceinline__ void drain(unsigned long long (*s_minus)[64], int nbits) {
-        if (!used) return;
+    // warp-collective: every lane of the warp must call
+    __device__ __forceinline__ void drain(unsigned long long (*s_minus)[64], int nbits, uint32_t lane) {
+        if (!__any_sync(0xFFFFFFFFu, used)) return;
 #pragma unroll 1
         for (int s = 0; s < 2; ++s)
 #pragma unroll 1
             for (int wi = 0; wi < NW; ++wi)
-                event_drain(planes[s][wi], &s_minus[s][wi * 32], nbits < 32 ? nbits : 32);
+                event_drain_warp(planes[s][wi], used, lane, &s_minus[s][wi * 32], nbits < 32 ? nbits : 32);
     }
 };
 
