@@ -2,26 +2,25 @@
 //
 // The C-contiguous array is a matrix of R = outer*n rows of `inner` elements; the partner
 // of an element is the one directly below it.  A thread owns one 16-byte column chunk and
-// walks down a segment of rows with 128-bit coalesced, L1-bypassing loads (a warp reads
-// 512 contiguous bytes per row), keeping the previous row in registers -- every element
-// is read from HBM exactly once and needs no shared-memory staging or halo.  Four rows
-// (16 words) are folded per step into the bit-sliced counters of xbi_common.cuh, with the
-// next four rows already in flight.
+// walks down a segment of rows, keeping the previous row in registers -- every element is
+// read from HBM exactly once and needs no halo.  Rows reach the thread through a per-thread
+// cp.async pipeline in shared memory (a warp copies 512 contiguous bytes per row), five
+// 4-row groups ahead of the fold; four rows (16 words) are folded per step into the
+// bit-sliced counters of xbi_common.cuh.
 //
 // Only two word streams are needed: b (every row below the first; masked elements zeroed)
 // and a&b.  The a-stream total is the b-stream total + bits(first row of the matrix) -
 // bits(its last row); two small row-plane passes (xbi_count_generic.cu) add those to the
 // plus / minus sums.  Masked modes add the boundary corrections of xbi_mask.cuh.
-// Pairs that straddle two blocks of the analysed axis are subtracted by the edge pass
-// (xbi_count_generic.cu).
-#include <cstdlib>
-
+// Pairs that straddle two blocks of the analysed axis are subtracted by k_block_edges.
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
 #include "xbi_mask.cuh"
 #include "xbi_tma.cuh"
-#include "xbi_tmap.h"
+
+// (constexpr members that only some instantiations use)
+#pragma nv_diag_suppress 177
 
 namespace xbi {
 
@@ -75,7 +74,7 @@ __device__ __forceinline__ uint32_t count_chunk(const uint32_t (&v)[4]) {
 // ---------------------------------------------------------------------------------
 // Per-thread state of a column walker: the counters, the previous row of its 16-byte
 // column chunk (x': transformed, masked elements zeroed) and, in masked modes, that row's
-// keep-mask.  Shared by the register-staged and the TMA-ring kernels.
+// keep-mask.
 // ---------------------------------------------------------------------------------
 template <int KIND, int MASK, bool XFORM>
 struct ColWalker {
@@ -390,36 +389,64 @@ struct ColWalker {
     }
 };
 
-// Work item = (segment, chunk) = divmod(item, chunks_per_row): one 16-byte column chunk
-// walked down one segment of rows.  The pair rows [0, nseg*seg_min + seg_extra) are split
-// into nseg segments; the first seg_extra segments are one row longer.  A warp takes 32
-// consecutive items at a time (grid-stride over "warp items"), so all its lanes run the
-// same number of full 4-row groups -- the flush shuffles rely on that -- plus one
-// predicated tail group for the remaining 0..4 rows of each lane's segment.
+constexpr int kStripBytes = 512;               // a warp's slice of a row: 32 lanes x 16 bytes
+constexpr int kTileBytes = 4 * kStripBytes;     // one 4-row group of a warp
+
+// ---------------------------------------------------------------------------------
+// The column-walker kernel.  Work item = (segment, chunk) = divmod(item, chunks_per_row): one
+// 16-byte column chunk walked down one segment of rows.  The pair rows
+// [0, nseg*seg_min + seg_extra) are split into nseg segments; the first seg_extra segments are
+// one row longer.  A warp takes 32 consecutive items at a time (grid-stride over "warp items"),
+// so all its lanes run the same number of full 4-row groups -- the flush shuffles rely on that
+// -- plus one predicated tail group for the remaining 0..4 rows of each lane's segment.
+// A lane's rows travel through its own slice of a shared-memory ring with 16-byte cp.async
+// (LDGSTS, L1 bypass) kAhead 4-row groups ahead of the fold.  A lane only ever reads back the bytes it copied itself, so the pipeline is
+// per thread: cp.async.commit_group / wait_group, no mbarrier, no warp or block barrier and
+// no registers held by loads in flight.  160 KB per SM are in flight.
+// ---------------------------------------------------------------------------------
+constexpr int kAsyncThreads = 512;
+constexpr int kAsyncWarps = kAsyncThreads / 32;
+constexpr int kAsyncRing = 6;             // groups of 4 rows x 512 B per warp
+constexpr int kAhead = kAsyncRing - 1;    // groups in flight
+constexpr size_t kAsyncSmem = 128 + (size_t)kAsyncWarps * kAsyncRing * kTileBytes;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 template <int KIND, int MASK, bool XFORM>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kAsyncThreads, 1)
 k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long nseg, long long seg_min,
-             long long seg_extra, uint32_t mask_lo, uint32_t mask_hi, Workspace* __restrict__ ws) {
+                   long long seg_extra, uint32_t mask_lo, uint32_t mask_hi, Workspace* __restrict__ ws) {
     using W = ColWalker<KIND, MASK, XFORM>;
     constexpr int BYTES = W::BYTES;
 
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
     const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t my0 = smem0 + warp * (kAsyncRing * kTileBytes) + lane * 16;  // + slot * kTileBytes + r * 512
+
     const long long total = chunks_per_row * nseg;
     const long long n_witems = (total + 31) >> 5;
-    const long long warps_total = (long long)gridDim.x * (kThreads / 32);
-    const long long groups = seg_min >> 2;  // full 4-row groups, the same for every item
+    const long long warps_total = (long long)gridDim.x * kAsyncWarps;
+    const long long groups = seg_min >> 2;         // full 4-row groups, the same for every item
     const long long stride = chunks_per_row * 16;  // bytes between rows
 
     W cw;
     cw.init();
     typename W::Events ev;
     ev.init();
+    uint32_t slot_w = 0, slot_r = 0;  // ring positions (the same on every lane)
 
-    for (long long wi = (long long)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5); wi < n_witems; wi += warps_total) {
+    for (long long wi = (long long)blockIdx.x * kAsyncWarps + warp; wi < n_witems; wi += warps_total) {
         long long item = (wi << 5) + lane;
         const bool active = item < total;
-        // only the very last warp item can have idle lanes; it is the last one its warp
-        // handles.  Idle lanes shadow a valid item; what they add is discarded at the flush.
+        // only the very last warp item can have idle lanes.  Idle lanes shadow a valid item;
+        // what they add is discarded at the flush.
         const bool ragged = __any_sync(0xFFFFFFFFu, !active);
         if (ragged) cw.flush(lane);
         cw.lane_live = active;
@@ -428,208 +455,91 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
         if (nseg > 1) { seg = item / chunks_per_row; chunk = item - seg * chunks_per_row; }
         const long long row_begin = seg * seg_min + (seg < seg_extra ? seg : seg_extra);
         const int tail_rows = (int)(seg_min + (seg < seg_extra ? 1 : 0) - (groups << 2));  // 0..4
+        const bool any_tail = __any_sync(0xFFFFFFFFu, tail_rows > 0);
+        const long long ngroups = groups + (any_tail ? 1 : 0);
 
-        const char* q = reinterpret_cast<const char*>(x + row_begin * chunks_per_row + chunk);
-        cw.start(ldg_stream(reinterpret_cast<const uint4*>(q)), true, mask_lo, mask_hi);
-        q += stride;  // first b-row
-
-        auto load_group = [&](uint4 (&buf)[4]) {
-            const char* q1 = q + stride;
-            const char* q2 = q1 + stride;
-            const char* q3 = q2 + stride;
-            buf[0] = ldg_stream(reinterpret_cast<const uint4*>(q));
-            buf[1] = ldg_stream(reinterpret_cast<const uint4*>(q1));
-            buf[2] = ldg_stream(reinterpret_cast<const uint4*>(q2));
-            buf[3] = ldg_stream(reinterpret_cast<const uint4*>(q3));
-            q = q3 + stride;
-        };
-
-        // ping-pong: the next group's four loads are in flight while the current one is folded
-        uint4 bufA[4], bufB[4];
-        long long g = 0;
-        if (groups > 0) load_group(bufA);
-        while (g + 2 <= groups) {
-            load_group(bufB);
-            cw.process(bufA, 4, mask_lo, mask_hi, lane, ev);
-            if (g + 2 < groups) load_group(bufA);
-            cw.process(bufB, 4, mask_lo, mask_hi, lane, ev);
-            g += 2;
-        }
-        if (g < groups) cw.process(bufA, 4, mask_lo, mask_hi, lane, ev);
-        // tail: up to 4 remaining rows; absent rows re-read an in-bounds row and are zeroed
-        if (__any_sync(0xFFFFFFFFu, tail_rows > 0)) {
+        const char* q0 = reinterpret_cast<const char*>(x + row_begin * chunks_per_row + chunk);
+        const char* q = q0 + stride;  // first b-row; advanced by issue()
+        long long issued = 0;
+        // issue group `issued` (4 rows; the tail group re-reads an in-bounds row for absent rows)
+        auto issue = [&]() {
+            if (issued < ngroups) {
+                const uint32_t dst = my0 + slot_w * kTileBytes;
+                if (issued < groups) {
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const long long rr = (r < tail_rows) ? r : (long long)tail_rows - 1;  // -1: last full-group row
-                bufA[r] = ldg_stream(reinterpret_cast<const uint4*>(q + rr * stride));
+                    for (int r = 0; r < 4; ++r) cp_async16(dst + r * kStripBytes, q + r * stride);
+                    q += 4 * stride;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const long long rr = (r < tail_rows) ? r : (long long)tail_rows - 1;  // -1: last full-group row
+                        cp_async16(dst + r * kStripBytes, q + rr * stride);
+                    }
+                }
             }
-            cw.process(bufA, tail_rows, mask_lo, mask_hi, lane, ev);
-        }
-        if (ragged) {
-            cw.flush(lane);
-            cw.lane_live = true;
-        }
-    }
-
-    __shared__ unsigned long long s_sum[3][64];
-    __shared__ unsigned long long s_minus[2][64];
-    __shared__ unsigned long long s_n;
-    cw.finish(lane, kThreads, s_sum, s_minus, &s_n, ws,
-              (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * (16 / BYTES)), ev);
-}
-
-// ---------------------------------------------------------------------------------
-// TMA variant of the column walkers.  Same work split (a warp item = one row segment x one
-// 512-byte column strip, lane = 16-byte column chunk, previous row carried in registers),
-// but the rows arrive through a per-warp ring of 6 shared-memory tiles of 4 rows x 512 B
-// filled by 2-D TMA loads that the warp's own lane 0 issues five tiles ahead.  No producer
-// warp and no block-wide barrier: each warp is its own software pipeline, and the loads in
-// flight (16 warps x 5 tiles x 2 KB = 160 KB per SM) no longer live in registers.
-// ---------------------------------------------------------------------------------
-constexpr int kTmaThreads = 512;
-constexpr int kTmaWarps = kTmaThreads / 32;
-constexpr int kRing = 6;
-constexpr int kTileRows = 4;
-constexpr int kStripBytes = 512;
-constexpr int kTileBytes = kTileRows * kStripBytes;
-constexpr size_t kColsSmem = 128 + (size_t)kTmaWarps * kRing * kTileBytes + kTmaWarps * kRing * 8;
-
-template <int KIND, int MASK, bool XFORM>
-__global__ void __launch_bounds__(kTmaThreads, 1)
-k_pairs_cols_tma(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ x, long long chunks_per_row,
-                 long long strips, long long nseg, long long seg_min, long long seg_extra, uint32_t mask_lo,
-                 uint32_t mask_hi, Workspace* __restrict__ ws) {
-    using W = ColWalker<KIND, MASK, XFORM>;
-    constexpr int BYTES = W::BYTES;
-
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
-    // broadcast from lane 0: tells the compiler the value is warp-uniform (uniform branches, no
-    // reconvergence bookkeeping around the ladder pushes)
-    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t ring0 = smem0 + warp * (kRing * kTileBytes);
-    const uint32_t bar0 = smem0 + kTmaWarps * kRing * kTileBytes + warp * (kRing * 8);
-    if (lane == 0) {
-        for (int i = 0; i < kRing; ++i) mbar_init(bar0 + 8 * i, 1);
-        mbar_fence_init();
-    }
-    if (threadIdx.x == 0) tma_prefetch_descriptor(&tmap);
-    __syncthreads();
-
-    const long long n_witems = strips * nseg;
-    const long long warps_total = (long long)gridDim.x * kTmaWarps;
-
-    W cw;
-    cw.init();
-    typename W::Events ev;
-    ev.init();
-    uint32_t t_issued = 0, t_consumed = 0;  // tiles of this warp since kernel start (ring position / phase)
-
-    for (long long wi = (long long)blockIdx.x * kTmaWarps + warp; wi < n_witems; wi += warps_total) {
-        const long long seg = wi / strips;
-        const long long strip = wi - seg * strips;
-        const long long chunk = strip * 32 + lane;
-        const bool active = chunk < chunks_per_row;
-        const bool ragged = __any_sync(0xFFFFFFFFu, !active);  // last strip of a row only
-        if (ragged) cw.flush(lane);  // bank what the previous items gathered before lanes go idle
-        cw.lane_live = active;
-        const long long row_begin = seg * seg_min + (seg < seg_extra ? seg : seg_extra);
-        const long long seg_len = seg_min + (seg < seg_extra ? 1 : 0);
-        const long long ntiles = (seg_len + kTileRows - 1) / kTileRows;
-
-        {
-            uint4 v = make_uint4(0u, 0u, 0u, 0u);
-            if (active) v = ldg_stream(x + row_begin * chunks_per_row + chunk);
-            cw.start(v, active, mask_lo, mask_hi);
-        }
-
-        auto issue_tile = [&](long long k) {
-            if (lane == 0) {
-                const uint32_t slot = t_issued % kRing;
-                // the slot was last read (LDS) by this warp before the __syncwarp that ended that
-                // iteration, and those values have been consumed: safe to overwrite
-                mbar_arrive_expect_tx(bar0 + 8 * slot, kTileBytes);
-                tma_load_2d(ring0 + slot * kTileBytes, &tmap, (int32_t)(strip * (kStripBytes / 4)),
-                            (int32_t)(row_begin + 1 + k * kTileRows), bar0 + 8 * slot);
-            }
-            ++t_issued;
+            cp_async_commit();  // (possibly empty: keeps the group count uniform)
+            slot_w = (slot_w + 1 == kAsyncRing) ? 0 : slot_w + 1;
+            ++issued;
         };
-
-        const long long pre = ntiles < (kRing - 1) ? ntiles : (kRing - 1);
-        for (long long k = 0; k < pre; ++k) issue_tile(k);
-        for (long long k = 0; k < ntiles; ++k) {
-            if (k + (kRing - 1) < ntiles) issue_tile(k + (kRing - 1));
-            const uint32_t slot = t_consumed % kRing;
-            mbar_wait(bar0 + 8 * slot, (t_consumed / kRing) & 1u);
-            const uint32_t base = ring0 + slot * kTileBytes + lane * 16;
+#pragma unroll 1
+        for (int k = 0; k < kAhead; ++k) issue();
+        cw.start(ldg_stream(reinterpret_cast<const uint4*>(q0)), true, mask_lo, mask_hi);
+#pragma unroll 1
+        for (long long g = 0; g < ngroups; ++g) {
+            issue();
+            cp_async_wait<kAhead>();  // group g has landed (kAhead younger ones may be in flight)
+            const uint32_t src = my0 + slot_r * kTileBytes;
             uint4 buf[4];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) buf[r] = lds128(base + r * kStripBytes);
-            if (k + 1 < ntiles) {
-                cw.process(buf, 4, mask_lo, mask_hi, lane, ev);
-            } else {
-                cw.process(buf, (int)(seg_len - k * kTileRows), mask_lo, mask_hi, lane, ev);
-            }
-            ++t_consumed;
-            __syncwarp();
+            for (int r = 0; r < 4; ++r) buf[r] = lds128(src + r * kStripBytes);
+            slot_r = (slot_r + 1 == kAsyncRing) ? 0 : slot_r + 1;
+            if (g < groups) cw.process(buf, 4, mask_lo, mask_hi, lane, ev);
+            else cw.process(buf, tail_rows, mask_lo, mask_hi, lane, ev);
         }
+        // the kAhead groups committed past the end of the item are empty; the ring position
+        // moved with them, keep reader and writer aligned
+        slot_r = slot_w;
         if (ragged) {
             cw.flush(lane);
             cw.lane_live = true;
         }
     }
+    cp_async_wait<0>();
 
     __shared__ unsigned long long s_sum[3][64];
     __shared__ unsigned long long s_minus[2][64];
     __shared__ unsigned long long s_n;
-    cw.finish(lane, kTmaThreads, s_sum, s_minus, &s_n, ws,
+    cw.finish(lane, kAsyncThreads, s_sum, s_minus, &s_n, ws,
               (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * (16 / BYTES)), ev);
 }
 
-// returns false when the TMA variant cannot be used (no encoder, extents beyond 32-bit coordinates)
 template <int KIND, int MASK, bool XFORM>
-bool try_launch_cols_tma(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t chunks, int64_t rows,
-                         int64_t pair_rows, int sms, cudaError_t* err) {
-    *err = cudaSuccess;
-    EncodeFn encode = get_encode_fn();
-    const int64_t row_words = chunks * 4;
-    if (!encode || rows >= (1ll << 31) || row_words >= (1ll << 31)) return false;
-    CUtensorMap tmap;
-    const cuuint64_t gdim[2] = {(cuuint64_t)row_words, (cuuint64_t)rows};
-    const cuuint64_t gstride[1] = {(cuuint64_t)row_words * 4};
-    const cuuint32_t box[2] = {kStripBytes / 4, kTileRows};
-    const cuuint32_t estride[2] = {1, 1};
-    if (encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, const_cast<void*>(job.x), gdim, gstride, box, estride,
-               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
-        return false;
-    auto kern = k_pairs_cols_tma<KIND, MASK, XFORM>;
+cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t chunks, int64_t pair_rows,
+                              int sms) {
+    auto kern = k_pairs_cols<KIND, MASK, XFORM>;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};
     if (dev < 0 || dev >= 64 || !attr_set[dev]) {
-        *err = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kColsSmem);
-        if (*err != cudaSuccess) return true;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsyncSmem);
+        if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    const int64_t strips = (chunks + 31) / 32;
     // a few items per warp for balance, segments of at least 64 rows
-    const int64_t want_items = (int64_t)sms * kTmaWarps * 4;
-    int64_t nseg = (want_items + strips - 1) / strips;
+    const int64_t want_items = (int64_t)sms * kAsyncWarps * 4 * 32;  // in lanes (chunks x segments)
+    int64_t nseg = (want_items + chunks - 1) / chunks;
     const int64_t max_seg = pair_rows / 64 > 0 ? pair_rows / 64 : 1;
     if (nseg > max_seg) nseg = max_seg;
     if (nseg < 1) nseg = 1;
     const int64_t seg_min = pair_rows / nseg;
     const int64_t seg_extra = pair_rows - seg_min * nseg;
-    int64_t blocks = (strips * nseg + kTmaWarps - 1) / kTmaWarps;
+    const int64_t total = chunks * nseg;
+    int64_t blocks = (total + kAsyncThreads - 1) / kAsyncThreads;
     if (blocks > sms) blocks = sms;
-    kern<<<(unsigned)blocks, kTmaThreads, kColsSmem, stream>>>(tmap, static_cast<const uint4*>(job.x), (long long)chunks,
-                                                                (long long)strips, (long long)nseg, (long long)seg_min,
-                                                                (long long)seg_extra, (uint32_t)job.mask_bits,
-                                                                (uint32_t)(job.mask_bits >> 32), ws);
-    *err = cudaGetLastError();
-    return true;
+    kern<<<(unsigned)blocks, kAsyncThreads, kAsyncSmem, stream>>>(
+        static_cast<const uint4*>(job.x), (long long)chunks, (long long)nseg, (long long)seg_min, (long long)seg_extra,
+        (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), ws);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------
@@ -794,30 +704,9 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaError_t terr = cudaSuccess;
-    // Measured on B200 (same box, kernel alone): with a power-of-two row pitch the TMA ring
-    // runs at 3.7-3.9 TB/s where the register-staged variant reaches 5.4-5.5 TB/s; with other
-    // pitches the TMA ring wins (5.5-5.8 vs 4.9-5.1 TB/s).  XBI_COLS_LDG / XBI_COLS_TMA force one.
-    const bool pow2_pitch = (row_bytes & (row_bytes - 1)) == 0;
-    const bool use_ldg = std::getenv("XBI_COLS_LDG") != nullptr || (pow2_pitch && std::getenv("XBI_COLS_TMA") == nullptr);
-    if (!use_ldg && try_launch_cols_tma<KIND, MASK, XFORM>(job, ws, stream, chunks, rows, pair_rows, sms, &terr)) {
-        if (terr != cudaSuccess) return terr;
-    } else {
-    // enough threads to fill the machine about twice, but segments of at least 64 rows
-    const int64_t want_threads = (int64_t)sms * 2048 * 2;
-    int64_t nseg = (want_threads + chunks - 1) / chunks;
-    const int64_t max_seg = pair_rows / 64 > 0 ? pair_rows / 64 : 1;
-    if (nseg > max_seg) nseg = max_seg;
-    if (nseg < 1) nseg = 1;
-    const int64_t seg_min = pair_rows / nseg;
-    const int64_t seg_extra = pair_rows - seg_min * nseg;  // this many segments get one more row
-    const int64_t total = chunks * nseg;
-    int64_t blocks = (total + kThreads - 1) / kThreads;
-    const int64_t cap = (int64_t)sms * 16;  // a few waves; warps loop over the remaining items
-    if (blocks > cap) blocks = cap;
-    k_pairs_cols<KIND, MASK, XFORM><<<(unsigned)blocks, kThreads, 0, stream>>>(
-        static_cast<const uint4*>(job.x), (long long)chunks, (long long)nseg, (long long)seg_min, (long long)seg_extra,
-        (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), ws);
+    {
+        cudaError_t e = launch_cols_async<KIND, MASK, XFORM>(job, ws, stream, chunks, pair_rows, sms);
+        if (e != cudaSuccess) return e;
     }
     {
         // a-stream correction: + planes(first row) - planes(row after the last pair row)

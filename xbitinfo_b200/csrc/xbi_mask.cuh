@@ -85,6 +85,15 @@ __device__ __forceinline__ uint32_t hfma2_zero(uint32_t w, uint32_t acc) {  // p
     return r;
 }
 
+// two words at a time (sm_100 packed fp32 FMA): halves the issue slots the probe takes
+__device__ __forceinline__ unsigned long long fma2_zero(uint32_t w0, uint32_t w1, unsigned long long acc) {
+    unsigned long long r;
+    asm("{.reg .b64 t, z; mov.b64 t, {%1, %2}; mov.b64 z, 0; fma.rn.f32x2 %0, t, z, %3;}"
+        : "=l"(r)
+        : "r"(w0), "r"(w1), "l"(acc));
+    return r;
+}
+
 template <int KIND, int MASK, int N>
 __device__ __forceinline__ bool may_contain_masked(const uint32_t (&w)[N], uint32_t mask_lo, uint32_t mask_hi) {
     constexpr int BYTES = Elem<KIND>::kBytes;
@@ -94,10 +103,19 @@ __device__ __forceinline__ bool may_contain_masked(const uint32_t (&w)[N], uint3
             // float32: the word itself; float64: the high word read as a float32 is NaN/Inf
             // exactly when the top eight exponent bits are ones (every double NaN/Inf, plus
             // finite |x| >= 2^1017)
-            constexpr int STEP = (BYTES == 8) ? 2 : 1;
+            if (BYTES == 4) {
+                // words arrive in aligned register pairs (128-bit loads): FFMA2 on (w[2i], w[2i+1])
+                unsigned long long p[2] = {0ull, 0ull};
+#pragma unroll
+                for (int i = 0; i + 1 < N; i += 2) p[(i >> 1) & 1] = fma2_zero(w[i], w[i + 1], p[(i >> 1) & 1]);
+                float t = (__uint_as_float((uint32_t)p[0]) + __uint_as_float((uint32_t)(p[0] >> 32))) +
+                          (__uint_as_float((uint32_t)p[1]) + __uint_as_float((uint32_t)(p[1] >> 32)));
+                if (N & 1) t = fma_zero(w[N - 1], t);
+                return !(t == t);
+            }
             float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-            for (int i = STEP - 1, c = 0; i < N; i += STEP, ++c) s[c & 3] = fma_zero(w[i], s[c & 3]);
+            for (int i = 1, c = 0; i < N; i += 2, ++c) s[c & 3] = fma_zero(w[i], s[c & 3]);
             const float t = (s[0] + s[1]) + (s[2] + s[3]);
             return !(t == t);
         } else {
