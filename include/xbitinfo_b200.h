@@ -117,6 +117,22 @@ int xbi_mutual_information(const unsigned long long* counts_dev, int nbits,
 int xbi_bitround_inplace(void* x_dev, int dtype, int64_t numel, int keepbits, void* stream);
 
 /*
+ * K4: the lossless-compression pre-filters that follow bitround on the reference's save path
+ * (xbitinfo/save_compressed.py:44-80: netCDF `shuffle=True`, i.e. the HDF5 shuffle filter;
+ * :155-209: zarr Blosc with SHUFFLE / BITSHUFFLE), out of place on the device.
+ *   kind XBI_SHUFFLE_BYTES: dst[j*numel + i] = src[i*itemsize + j]
+ *   kind XBI_SHUFFLE_BITS:  bit (i%8) of dst[p*numel/8 + i/8] = bit p of element i, with
+ *                           p = 8*byte + bit counted from the least significant bit of the
+ *                           little-endian element; numel must be a multiple of 8
+ *   inverse != 0 undoes the transform.  itemsize in {2, 4, 8}; src and dst are numel*itemsize
+ *   bytes each and must not overlap.
+ */
+#define XBI_SHUFFLE_BYTES 0
+#define XBI_SHUFFLE_BITS 1
+int xbi_shuffle(const void* src_dev, void* dst_dev, int itemsize, int64_t numel, int kind, int inverse,
+                void* stream);
+
+/*
  * Host-buffer entry points: what the numpy-facing plugin functions call.  Data is
  * streamed host -> device in slabs through a double-buffered staging area on `device`
  * (allocated on first use per host thread, released by xbi_host_release), counted /

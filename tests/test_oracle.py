@@ -137,3 +137,26 @@ def test_bitround_contract():
     assert not np.shares_memory(x, y)
     np.testing.assert_allclose(y, x, rtol=2 ** -8, atol=0)
     assert (y.view("u4") & ((1 << 16) - 1) == 0).all()
+
+
+def test_shuffle_oracle_layouts_and_round_trips():
+    """The byte / bit shuffle restatements: documented layouts on hand-made vectors,
+    inverses, and the relation between the two (a bit plane of the bit shuffle is the packed
+    bit of the matching byte plane of the byte shuffle)."""
+    from oracle import shuffle_oracle as so
+
+    x = np.array([0x04030201, 0x08070605, 0x0C0B0A09, 0x100F0E0D, 0, 0, 0, 0x80000000], dtype="<u4")
+    b = so.byte_shuffle(x)
+    assert b.size == 32 and list(b[:4]) == [1, 5, 9, 13] and list(b[24:28]) == [4, 8, 12, 16] and b[31] == 0x80
+    s = so.bit_shuffle(x)
+    assert s.size == 32 and s[0] == 0b00000111 and s[31] == 0b10000000  # bit 0 of elements 0,1,2; sign of element 7
+    rng = np.random.default_rng(0)
+    for dt in ("float16", "float32", "float64", "int16", "int64"):
+        y = rng.integers(0, 255, size=8 * 37 * np.dtype(dt).itemsize, dtype="u1").view(dt)
+        assert np.array_equal(so.byte_unshuffle(so.byte_shuffle(y), dt).view("u1"), y.view("u1"))
+        assert np.array_equal(so.bit_unshuffle(so.bit_shuffle(y), dt).view("u1"), y.view("u1"))
+        planes = so.byte_shuffle(y).reshape(y.dtype.itemsize, -1)
+        bits = so.bit_shuffle(y).reshape(8 * y.dtype.itemsize, -1)
+        for j in range(y.dtype.itemsize):
+            for k in range(8):
+                assert np.array_equal(bits[8 * j + k], np.packbits((planes[j] >> k) & 1, bitorder="little"))

@@ -18,6 +18,8 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libxbitinfo_b200.so")
 U8, U16, U32, U64, F16, F32, F64 = range(7)
 # flags
 SIGNED_EXPONENT, MASK_NAN, MASK_VALUE, FORCE_GENERIC = 1, 2, 4, 8
+# xbi_shuffle kinds
+SHUFFLE_BYTES, SHUFFLE_BITS = 0, 1
 # error codes
 ERR_ARG, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA_BASE = 1, 2, 3, 1000
 
@@ -77,6 +79,8 @@ def lib() -> C.CDLL:
     L.xbi_mutual_information.argtypes = [vp, i32, i32, dbl, vp, vp]
     L.xbi_bitround_inplace.restype = i32
     L.xbi_bitround_inplace.argtypes = [vp, i32, i64, i32, vp]
+    L.xbi_shuffle.restype = i32
+    L.xbi_shuffle.argtypes = [vp, vp, i32, i64, i32, i32, vp]
     L.xbi_bitinformation_host.restype = i32
     L.xbi_bitinformation_host.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, i32]
     L.xbi_bitround_host.restype = i32
@@ -92,7 +96,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "xbi_abi_version", "xbi_last_error", "xbi_kernel_launches", "xbi_fast_path_launches",
     "xbi_workspace_bytes", "xbi_profile_enable", "xbi_profile_collect",
-    "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace",
+    "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace", "xbi_shuffle",
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
 )
 

@@ -253,6 +253,23 @@ int xbi_bitround_inplace(void* x_dev, int dtype, int64_t numel, int keepbits, vo
     return XBI_OK;
 }
 
+int xbi_shuffle(const void* src_dev, void* dst_dev, int itemsize, int64_t numel, int kind, int inverse, void* stream) {
+    if (itemsize != 2 && itemsize != 4 && itemsize != 8) return fail(XBI_ERR_ARG, "itemsize must be 2, 4 or 8");
+    if (kind != XBI_SHUFFLE_BYTES && kind != XBI_SHUFFLE_BITS) return fail(XBI_ERR_ARG, "unknown shuffle kind");
+    if (numel < 0) return fail(XBI_ERR_ARG, "negative numel");
+    if (numel == 0) return XBI_OK;
+    if (!src_dev || !dst_dev) return fail(XBI_ERR_ARG, "null data pointer");
+    if (kind == XBI_SHUFFLE_BITS && numel % 8 != 0)
+        return fail(XBI_ERR_ARG, "bit shuffle needs a number of elements that is a multiple of 8");
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src_dev), b = reinterpret_cast<uintptr_t>(dst_dev);
+    const uint64_t bytes = (uint64_t)numel * (uint64_t)itemsize;
+    if (a < b + bytes && b < a + bytes) return fail(XBI_ERR_ARG, "source and destination overlap");
+    XBI_CUDA(launch_shuffle(src_dev, dst_dev, itemsize, numel, kind == XBI_SHUFFLE_BITS, inverse == 0,
+                            static_cast<cudaStream_t>(stream)),
+             "shuffle");
+    return XBI_OK;
+}
+
 // Slab plan for streaming a host (outer, n, inner) array through a staging buffer.
 //   mode 0: whole blocks   -- `blocks` consecutive outer indices per slab (1-D copy)
 //   mode 1: column strips  -- all n rows x `cols` columns of one outer index (2-D copy)

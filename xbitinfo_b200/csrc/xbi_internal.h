@@ -71,6 +71,10 @@ cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* c
 cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, int set_zero,
                                       double z_quantile, double* mi, cudaStream_t stream);
 cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cudaStream_t stream);
+// K4: byte (bits == false) or bit (bits == true) shuffle of numel elements of itemsize bytes,
+// forward or inverse; src and dst must not overlap
+cudaError_t launch_shuffle(const void* src, void* dst, int itemsize, int64_t numel, bool bits, bool forward,
+                           cudaStream_t stream);
 
 double normal_quantile(double p);  // AS241, host
 
