@@ -353,3 +353,43 @@ def test_masked_zero_matches_bit_pattern_only():
     ref_counts, npairs, _ = bo.bitinformation(x, 1, masked_value=0.0)
     assert np.array_equal(counts, ref_counts)
     assert counts[0].sum() == npairs == 20 * 7999 - 101
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "int32", "uint64"])
+@pytest.mark.parametrize("mask", [None, "nan", "value", "neutral"])
+def test_strided_rows_that_are_only_element_aligned(dtype, mask):
+    """Adjacency along non-last axes when a row is not a multiple of 16 bytes (and the base
+    is not 16-byte aligned either): whole-word element types still take the column walkers,
+    with short copies and a last chunk per row that is padded with the neutral value.
+    'neutral' masks exactly that padding value (1.0 / 0)."""
+    import torch
+
+    from xbitinfo_b200.device import PairCounter
+
+    isfloat = np.dtype(dtype).kind == "f"
+    if mask == "nan" and not isfloat:
+        pytest.skip("NaN mask needs floats")
+    rng = np.random.default_rng(31)
+    shape = (3, 257, 5, 13)  # rows of 13 and of 65 elements
+    n = int(np.prod(shape))
+    if isfloat:
+        flat = smooth_field(rng, (n + 3,), dtype, axis=0, scale=0.2, base=1.0)
+    else:
+        flat = rng.integers(0, 5, size=n + 3, dtype=dtype)
+    masked_value = None
+    if mask is not None:
+        masked_value = {"nan": float("nan"), "value": (-999.0 if isfloat else 3), "neutral": (1.0 if isfloat else 0)}[mask]
+        sel = rng.random(n + 3) < 0.25
+        sel[1000:1400] = True
+        flat[sel] = masked_value
+    for off in (0, 1, 3):  # base address 0, 1 and 3 elements past a 16-byte boundary
+        x = flat[off: off + n].reshape(shape)
+        t = torch.from_numpy(flat).cuda()[off: off + n].view(shape)
+        for axis in (0, 1, 2):
+            pc = PairCounter(t.dtype, t.device)
+            before = nat.fast_path_launches()
+            pc.add(t, axis, masked_value=masked_value)
+            assert nat.fast_path_launches() > before, "fast path was not taken"
+            ref_counts, npairs, _ = bo.bitinformation(x, axis, masked_value=masked_value)
+            assert np.array_equal(pc.counts.cpu().numpy(), ref_counts), (dtype, mask, off, axis)
+            assert int(pc.counts[0].sum()) == npairs

@@ -95,6 +95,8 @@ struct ColWalker {
     uint32_t prev_keep[4];  // masked modes, packed types: keep-mask of prev ...
     bool prev_clean;        // ... which may be stale while prev_clean (no masked element in prev)
     bool lane_live;     // false while this lane shadows a chunk that does not exist (ragged warp item)
+    uint32_t vrep;      // whole-word types: bit EPC*r + e set = element e of the chunk exists (last chunk
+                        // of a row whose length is not a multiple of 16 bytes), replicated for 4 rows
     uint32_t it;
     uint32_t ninvalid;  // pairs with a masked element since the last flush
     unsigned long long ninvalid_total;
@@ -110,6 +112,7 @@ struct ColWalker {
         for (int i = 0; i < 4; ++i) { prev[i] = 0u; prev_keep[i] = 0u; }
         prev_clean = true;
         pm = 0u;
+        vrep = 0xFFFFu;
         lane_live = true;
         it = 0;
         ninvalid = 0;
@@ -182,7 +185,7 @@ struct ColWalker {
                 if (__any_sync(0xFFFFFFFFu, tdirty)) {
                     const bool allm = (pm == kRowMask) && all_masked_quick<KIND, MASK>(raw, mlo, mhi);
                     if (__all_sync(0xFFFFFFFFu, allm)) {
-                        ninvalid += (uint32_t)nrows * EPC;
+                        ninvalid += (uint32_t)nrows * (uint32_t)__popc(vrep & kRowMask);
                         return;  // nothing valid in the whole warp: prev stays zero, pm stays all-masked
                     }
                     if (tdirty) {
@@ -201,7 +204,7 @@ struct ColWalker {
 #pragma unroll
             for (int r = 0; r < 4; ++r) xform_chunk<KIND, XFORM>(cur[r]);
             if (m | pm) {  // this thread's chunk has masked elements (or sits under one)
-                const uint32_t present = (nrows >= 4) ? (0xFFFFu >> (16 - 4 * EPC)) : ((1u << (EPC * nrows)) - 1u);
+                const uint32_t present = ((nrows >= 4) ? (0xFFFFu >> (16 - 4 * EPC)) : ((1u << (EPC * nrows)) - 1u)) & vrep;
                 const uint32_t above = (m << EPC) | pm;  // the element over each element
                 ninvalid += __popc((m | above) & present);
                 const uint32_t bnd = (m ^ above) & present;
@@ -417,12 +420,39 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int KIND, int MASK, bool XFORM>
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
+}
+// one 16-byte column chunk of which the first `vb` bytes exist, copied in pieces of G bytes
+template <int G>
+__device__ __forceinline__ void copy_chunk(uint32_t dst, const char* src, int vb) {
+    if constexpr (G == 16) {
+        cp_async16(dst, src);
+    } else if constexpr (G == 8) {
+        cp_async8(dst, src);
+        if (vb > 8) cp_async8(dst + 8, src + 8);
+    } else {
+        cp_async4(dst, src);
+        if (vb > 4) cp_async4(dst + 4, src + 4);
+        if (vb > 8) cp_async4(dst + 8, src + 8);
+        if (vb > 12) cp_async4(dst + 12, src + 12);
+    }
+}
+
+// G = 16: rows are 16-byte aligned and a multiple of 16 bytes long.  G = 8 / 4 (element types of
+// that size): rows are only element aligned; chunks are still 16 bytes of a row, the last one
+// of a row may be short, and what does not exist is filled with the value whose transform is 0.
+template <int KIND, int MASK, bool XFORM, int G>
 __global__ void __launch_bounds__(kAsyncThreads, 1)
-k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long nseg, long long seg_min,
-                   long long seg_extra, uint32_t mask_lo, uint32_t mask_hi, Workspace* __restrict__ ws) {
+k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_per_row, long long nseg,
+             long long seg_min, long long seg_extra, uint32_t mask_lo, uint32_t mask_hi,
+             unsigned long long flat_pairs, Workspace* __restrict__ ws) {
     using W = ColWalker<KIND, MASK, XFORM>;
     constexpr int BYTES = W::BYTES;
+    static_assert(G == 16 || G == BYTES, "short copies are element sized");
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
@@ -433,8 +463,8 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
     const long long total = chunks_per_row * nseg;
     const long long n_witems = (total + 31) >> 5;
     const long long warps_total = (long long)gridDim.x * kAsyncWarps;
-    const long long groups = seg_min >> 2;         // full 4-row groups, the same for every item
-    const long long stride = chunks_per_row * 16;  // bytes between rows
+    const long long groups = seg_min >> 2;  // full 4-row groups, the same for every item
+    const long long stride = row_bytes;     // bytes between rows
 
     W cw;
     cw.init();
@@ -458,7 +488,27 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
         const bool any_tail = __any_sync(0xFFFFFFFFu, tail_rows > 0);
         const long long ngroups = groups + (any_tail ? 1 : 0);
 
-        const char* q0 = reinterpret_cast<const char*>(x + row_begin * chunks_per_row + chunk);
+        const char* q0 = x + row_begin * row_bytes + chunk * 16;
+        int vb = 16;  // bytes of this chunk that exist
+        if constexpr (G != 16) {
+            const long long left = row_bytes - chunk * 16;
+            vb = left < 16 ? (int)left : 16;
+            const uint32_t ve = (uint32_t)vb / BYTES;  // elements that exist
+            constexpr uint32_t kRep = ((1u << (4 * W::EPC)) - 1u) / ((1u << W::EPC) - 1u);  // 1 + 2^EPC + 2^2EPC + 2^3EPC
+            cw.vrep = ((1u << ve) - 1u) * kRep;
+            if (vb < 16) {
+                // nothing of the previous item is in flight any more: fill what the copies will
+                // never write with the neutral value, in every slot of this lane's ring
+#pragma unroll 1
+                for (int c = 0; c < kAsyncRing * 4; ++c) {
+                    const uint32_t cell = my0 + (c >> 2) * kTileBytes + (c & 3) * kStripBytes;
+                    for (int wdx = vb >> 2; wdx < 4; ++wdx) {
+                        const uint32_t nv = neutral_word<KIND, XFORM>(BYTES == 8 ? (wdx & 1) : 0);
+                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cell + 4 * wdx), "r"(nv) : "memory");
+                    }
+                }
+            }
+        }
         const char* q = q0 + stride;  // first b-row; advanced by issue()
         long long issued = 0;
         // issue group `issued` (4 rows; the tail group re-reads an in-bounds row for absent rows)
@@ -467,13 +517,13 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
                 const uint32_t dst = my0 + slot_w * kTileBytes;
                 if (issued < groups) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) cp_async16(dst + r * kStripBytes, q + r * stride);
+                    for (int r = 0; r < 4; ++r) copy_chunk<G>(dst + r * kStripBytes, q + r * stride, vb);
                     q += 4 * stride;
                 } else {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const long long rr = (r < tail_rows) ? r : (long long)tail_rows - 1;  // -1: last full-group row
-                        cp_async16(dst + r * kStripBytes, q + rr * stride);
+                        copy_chunk<G>(dst + r * kStripBytes, q + rr * stride, vb);
                     }
                 }
             }
@@ -483,7 +533,21 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
         };
 #pragma unroll 1
         for (int k = 0; k < kAhead; ++k) issue();
-        cw.start(ldg_stream(reinterpret_cast<const uint4*>(q0)), true, mask_lo, mask_hi);
+        {
+            uint4 first;
+            if constexpr (G == 16) {
+                first = ldg_stream(reinterpret_cast<const uint4*>(q0));
+            } else {
+                uint32_t fw[4];
+#pragma unroll
+                for (int wdx = 0; wdx < 4; ++wdx) {
+                    fw[wdx] = neutral_word<KIND, XFORM>(BYTES == 8 ? (wdx & 1) : 0);
+                    if (4 * wdx < vb) fw[wdx] = __ldg(reinterpret_cast<const uint32_t*>(q0) + wdx);
+                }
+                first = make_uint4(fw[0], fw[1], fw[2], fw[3]);
+            }
+            cw.start(first, true, mask_lo, mask_hi);
+        }
 #pragma unroll 1
         for (long long g = 0; g < ngroups; ++g) {
             issue();
@@ -509,14 +573,13 @@ k_pairs_cols(const uint4* __restrict__ x, long long chunks_per_row, long long ns
     __shared__ unsigned long long s_sum[3][64];
     __shared__ unsigned long long s_minus[2][64];
     __shared__ unsigned long long s_n;
-    cw.finish(lane, kAsyncThreads, s_sum, s_minus, &s_n, ws,
-              (unsigned long long)((nseg * seg_min + seg_extra) * chunks_per_row * (16 / BYTES)), ev);
+    cw.finish(lane, kAsyncThreads, s_sum, s_minus, &s_n, ws, flat_pairs, ev);
 }
 
-template <int KIND, int MASK, bool XFORM>
-cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t chunks, int64_t pair_rows,
-                              int sms) {
-    auto kern = k_pairs_cols<KIND, MASK, XFORM>;
+template <int KIND, int MASK, bool XFORM, int G>
+cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t row_bytes, int64_t chunks,
+                              int64_t pair_rows, int sms) {
+    auto kern = k_pairs_cols<KIND, MASK, XFORM, G>;
     int dev = 0;
     cudaGetDevice(&dev);
     static bool attr_set[64] = {};
@@ -537,8 +600,9 @@ cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t s
     int64_t blocks = (total + kAsyncThreads - 1) / kAsyncThreads;
     if (blocks > sms) blocks = sms;
     kern<<<(unsigned)blocks, kAsyncThreads, kAsyncSmem, stream>>>(
-        static_cast<const uint4*>(job.x), (long long)chunks, (long long)nseg, (long long)seg_min, (long long)seg_extra,
-        (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), ws);
+        static_cast<const char*>(job.x), (long long)row_bytes, (long long)chunks, (long long)nseg, (long long)seg_min,
+        (long long)seg_extra, (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32),
+        (unsigned long long)(pair_rows * job.inner), ws);
     return cudaGetLastError();
 }
 
@@ -696,16 +760,25 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
                         bool* edges_done) {
     constexpr int BYTES = Elem<KIND>::kBytes;
     const int64_t row_bytes = job.inner * BYTES;
-    if (row_bytes % 16 != 0 || reinterpret_cast<uintptr_t>(job.x) % 16 != 0) return cudaSuccess;
+    const bool aligned = row_bytes % 16 == 0 && reinterpret_cast<uintptr_t>(job.x) % 16 == 0;
+    // rows that are only element aligned: whole-word element types take the short-copy variant,
+    // packed 8/16-bit types stay on the generic kernel
+    if (!aligned && BYTES < 4) return cudaSuccess;
     const int64_t rows = job.outer * job.n;
     const int64_t pair_rows = rows - 1;
     if (pair_rows < 1) return cudaSuccess;
-    const int64_t chunks = row_bytes / 16;
+    const int64_t chunks = (row_bytes + 15) / 16;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     {
-        cudaError_t e = launch_cols_async<KIND, MASK, XFORM>(job, ws, stream, chunks, pair_rows, sms);
+        cudaError_t e;
+        if (aligned) {
+            e = launch_cols_async<KIND, MASK, XFORM, 16>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
+        } else {
+            if constexpr (BYTES >= 4) e = launch_cols_async<KIND, MASK, XFORM, BYTES>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
+            else e = cudaErrorInvalidValue;
+        }
         if (e != cudaSuccess) return e;
     }
     {
@@ -716,7 +789,7 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
         e = launch_elem_planes(job, pair_rows * job.inner, job.inner, &ws->minus, stream);
         if (e != cudaSuccess) return e;
     }
-    if (job.outer > 1) {
+    if (job.outer > 1 && aligned) {
         const int64_t nbound = job.outer - 1;
         const int64_t items = ((nbound + 3) / 4) * chunks;
         // the end-of-kernel flush costs a warp ~10 items' worth of instructions: give every
@@ -729,7 +802,7 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
             (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), &ws->minus);
         note_launch();
     }
-    *edges_done = true;
+    *edges_done = aligned;  // otherwise the caller runs the generic edge pass
     note_fast_launch();
     *done_lo = 0;
     *done_hi = pair_rows * job.inner;  // every flat pair
