@@ -270,3 +270,70 @@ def test_bitround_along_dim():
         bitround_along_dim(ds, info, dim="latitude", keepbits=2, inflevels=[1.0, 0.99])
     with pytest.raises(ValueError):
         bitround_along_dim(ds, info, dim="latitude", inflevels=None)
+
+
+class _LazyChunked:
+    """A stand-in for a dask / zarr array: sliceable, has ``chunks``, counts what is read."""
+
+    def __init__(self, arr, chunk_rows):
+        self._a = arr
+        self.shape, self.dtype = arr.shape, arr.dtype
+        self.chunks = (chunk_rows,) + arr.shape[1:]
+        self.rows_read = 0
+        self.reads = []
+
+    def __getitem__(self, key):
+        out = self._a[key]
+        if isinstance(key, slice):
+            self.rows_read += out.shape[0]
+            self.reads.append((key.start, key.stop))
+        return out
+
+
+def test_lazy_arrays_are_streamed_on_chunk_boundaries(monkeypatch):
+    """f1: a lazy variable goes through get_bitinformation without being materialised: slabs
+    along the first axis, cut on the source's chunk boundaries, each row read once (plus one
+    halo row per slab when the first axis is the analysed one)."""
+    from xbitinfo_b200 import streaming
+
+    rng = np.random.default_rng(8)
+    x = smooth_field(rng, (50, 24, 36), "float32", axis=2, scale=0.4, base=280.0)
+    x[:, rng.random((24, 36)) < 0.2] = np.nan
+    orig = streaming.bitinformation_streamed
+    monkeypatch.setattr(streaming, "bitinformation_streamed",
+                        lambda src, axis, **kw: orig(src, axis, slab_bytes=13 * 24 * 36 * 4, **kw))
+    for dim, axis in (("x", 2), ("time", 0)):
+        lazy = _LazyChunked(x, chunk_rows=6)
+        ds = xb.Dataset({"T": xb.DataArray(lazy, dims=("time", "y", "x"), name="T")})
+        got = xb.get_bitinformation(ds, dim=dim, implementation="cuda")
+        ref = xb.get_bitinformation(xb.Dataset({"T": xb.DataArray(x, dims=("time", "y", "x"), name="T")}), dim=dim)
+        assert np.array_equal(got["T"].values, ref["T"].values)
+        if axis != 0:
+            assert lazy.rows_read == 50
+            assert all(lo % 6 == 0 for lo, _ in lazy.reads)  # 12-row slabs: two whole chunks each
+        else:
+            assert lazy.rows_read == 50 + len(lazy.reads) - 1  # one halo row per slab but the last
+
+
+def test_bitround_by_chunks_equals_the_per_block_loop_of_the_chunking_notebook():
+    from xbitinfo_b200.chunked import bitround_by_chunks, slices_from_chunks, normalize_chunks
+
+    rng = np.random.default_rng(9)
+    x = smooth_field(rng, (120, 25, 53), "float32", axis=1, scale=0.3, base=280.0)
+    x[:, :10] *= 1e-3  # a region with a different bit spectrum
+    chunks = {1: 5, 2: 10}
+    rounded, keep = bitround_by_chunks(x, chunks, axis=1, inflevel=0.99, masked_value=None, set_zero_insignificant=False)
+    grid = normalize_chunks(x.shape, chunks)
+    assert keep.shape == (1, 5, 6) and grid[2][-1] == 3
+    want = np.empty_like(x)
+    for idx, sl in zip(np.ndindex(*keep.shape), slices_from_chunks(grid)):
+        _, _, mi = bo.bitinformation(x[sl], 1)
+        k = max(0, ko.keepbits_from_info(mi, "float32", 0.99))
+        assert keep[idx] == k, idx
+        want[sl] = bro.bitround(np.ascontiguousarray(x[sl]), k)
+    assert np.array_equal(rounded.view("u4"), want.view("u4"))
+    assert len(np.unique(keep)) > 1
+    # device tensors stay on the device
+    t = torch.from_numpy(x).cuda()
+    r2, k2 = bitround_by_chunks(t, chunks, axis=1, inflevel=0.99, masked_value=None, set_zero_insignificant=False)
+    assert r2.is_cuda and np.array_equal(r2.cpu().numpy().view("u4"), want.view("u4")) and np.array_equal(k2, keep)

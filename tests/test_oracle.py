@@ -149,7 +149,7 @@ def test_shuffle_oracle_layouts_and_round_trips():
     b = so.byte_shuffle(x)
     assert b.size == 32 and list(b[:4]) == [1, 5, 9, 13] and list(b[24:28]) == [4, 8, 12, 16] and b[31] == 0x80
     s = so.bit_shuffle(x)
-    assert s.size == 32 and s[0] == 0b00000111 and s[31] == 0b10000000  # bit 0 of elements 0,1,2; sign of element 7
+    assert s.size == 32 and s[0] == 0b00001111 and s[31] == 0b10000000  # bit 0 of elements 0..3; sign of element 7
     rng = np.random.default_rng(0)
     for dt in ("float16", "float32", "float64", "int16", "int64"):
         y = rng.integers(0, 255, size=8 * 37 * np.dtype(dt).itemsize, dtype="u1").view(dt)

@@ -19,9 +19,15 @@ def _is_torch_tensor(x) -> bool:
     return type(x).__module__.startswith("torch") and hasattr(x, "data_ptr")
 
 
+def _is_lazy(data) -> bool:
+    from .streaming import is_lazy_array
+
+    return is_lazy_array(data)
+
+
 class DataArray:
     def __init__(self, data, dims=None, coords=None, name=None, attrs=None, encoding=None):
-        if not _is_torch_tensor(data) and not isinstance(data, np.ndarray):
+        if not _is_torch_tensor(data) and not isinstance(data, np.ndarray) and not _is_lazy(data):
             data = np.asarray(data)
         self.data = data
         ndim = len(data.shape)
@@ -45,6 +51,8 @@ class DataArray:
     def values(self):
         if _is_torch_tensor(self.data):
             return self.data.detach().cpu().numpy()
+        if _is_lazy(self.data):
+            return np.asarray(self.data[...])
         return self.data
 
     @property

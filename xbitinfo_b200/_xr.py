@@ -38,10 +38,13 @@ def namespace_for(obj):
 
 def raw_data(da):
     """The array behind a DataArray without forcing it to the host: a torch tensor stays a
-    torch tensor, anything else becomes a numpy array (dask arrays are computed)."""
+    torch tensor, a lazy array (dask, zarr, h5py ...) stays lazy and is streamed slab by slab
+    (``streaming.py``), anything else becomes a numpy array."""
+    from .streaming import is_lazy_array
+
     if isinstance(da, _labelled.DataArray):
         return da.data
     data = getattr(da, "data", None)
-    if data is not None and type(data).__module__.startswith("torch"):
+    if data is not None and (type(data).__module__.startswith("torch") or is_lazy_array(data)):
         return data
     return da.values

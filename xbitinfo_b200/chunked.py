@@ -1,0 +1,93 @@
+"""Per-chunk bit information, keepbits and bitround: the workflow of the reference's
+``docs/chunking.ipynb`` (cells 8-10: for every dask block run ``get_bitinformation`` ->
+``get_keepbits`` -> ``xr_bitround`` on that block alone and write it to its region), with the
+blocks cut and processed on the device.
+
+Every block is an independent K1 -> K2 -> (host: keepbits) -> K3 job; the array stays in HBM,
+only ``nbits`` doubles per block come back to the host for the keepbits decision.
+"""
+from __future__ import annotations
+
+from itertools import product
+
+import numpy as np
+import torch
+
+from .device import PairCounter, bitround_
+from .keepbits import _cdf_from_info_per_bit
+from .bitinfo import bit_partitioning
+
+_MANT = {torch.float16: 10, torch.float32: 23, torch.float64: 52}
+
+
+def slices_from_chunks(chunks):
+    """Chunks tuple -> slices in product order (``docs/chunking.ipynb`` cell 8).
+
+    >>> slices_from_chunks(((2, 2), (3, 3, 3)))[1]
+    (slice(0, 2, None), slice(3, 6, None))
+    """
+    cumdims = []
+    for bds in chunks:
+        out = np.empty(len(bds) + 1, dtype=int)
+        out[0] = 0
+        np.cumsum(bds, out=out[1:])
+        cumdims.append(out)
+    slices = [[slice(int(s), int(s + d)) for s, d in zip(starts, shapes)] for starts, shapes in zip(cumdims, chunks)]
+    return list(product(*slices))
+
+
+def normalize_chunks(shape, chunks):
+    """``{axis: size}`` / per-axis sizes / explicit tuples -> tuple of per-axis chunk-length tuples."""
+    out = []
+    for ax, n in enumerate(shape):
+        c = chunks.get(ax, n) if isinstance(chunks, dict) else chunks[ax]
+        if isinstance(c, (tuple, list)):
+            if sum(c) != n:
+                raise ValueError(f"chunks along axis {ax} do not add up to {n}")
+            out.append(tuple(int(v) for v in c))
+        else:
+            c = int(n if c in (None, -1) else c)
+            out.append(tuple([c] * (n // c) + ([n % c] if n % c else [])))
+    return tuple(out)
+
+
+def keepbits_of_information(info, np_dtype, inflevel=0.99) -> int:
+    """``get_keepbits`` on one information vector (``xbitinfo/xbitinfo.py:686-717``)."""
+    n_bits, _, _, n_mant = bit_partitioning(np_dtype)
+    if inflevel == 1.0:
+        return n_mant
+    cdf = _cdf_from_info_per_bit(np.asarray(info, dtype="float64"))
+    with np.errstate(invalid="ignore"):
+        return int((cdf > inflevel).argmax() + 1 - (n_bits - n_mant))
+
+
+def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_value=float("nan"),
+                       set_zero_insignificant: bool = True, confidence: float = 0.99):
+    """Round every chunk of ``x`` to its own keepbits.
+
+    ``x``: numpy array or CUDA tensor (floats); ``chunks``: ``{axis: size}``, per-axis sizes or
+    explicit per-axis tuples (dask's ``.chunks``); ``axis``: the dimension analysed inside each
+    chunk.  Returns ``(rounded, keepbits)`` with ``rounded`` of the type of ``x`` (a new array)
+    and ``keepbits`` an int64 array with one entry per chunk (shape = chunks per axis).
+    Negative keepbits (not even all exponent bits carry information) are clamped to 0, as the
+    reference's multi-file flow does (``xbitinfo/xbitinfo.py:867-868``).
+    """
+    is_np = isinstance(x, np.ndarray)
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda() if is_np else x.contiguous().clone()
+    if t.dtype not in _MANT:
+        raise TypeError("Only float arrays (16-64bit) can be bit-rounded")
+    np_dtype = np.dtype(str(t.dtype).replace("torch.", ""))
+    grid = normalize_chunks(tuple(t.shape), chunks)
+    keep = np.zeros([len(c) for c in grid], dtype="int64")
+    pc = PairCounter(t.dtype, t.device)
+    axis %= t.dim()
+    for idx, sl in zip(np.ndindex(*keep.shape), slices_from_chunks(grid)):
+        blk = t[sl].contiguous()
+        pc.reset()
+        pc.add(blk, axis, masked_value=masked_value)
+        info = pc.information(set_zero_insignificant, confidence).cpu().numpy()
+        k = max(0, min(keepbits_of_information(info, np_dtype, inflevel), _MANT[t.dtype]))
+        keep[idx] = k
+        bitround_(blk, k)
+        t[sl] = blk
+    return (t.cpu().numpy() if is_np else t), keep

@@ -40,6 +40,13 @@ def bitinformation(data, axis: int, masked_value=None, set_zero_insignificant: b
                                       return_counts, sharded)
     if sharded:
         raise ValueError("sharded=True needs per-rank CUDA tensors")
+    from .streaming import bitinformation_streamed, is_lazy_array
+
+    if is_lazy_array(data):
+        # dask / zarr / h5py ...: never materialised on the host; slabs along the first axis
+        return bitinformation_streamed(data, axis, masked_value=masked_value,
+                                       set_zero_insignificant=set_zero_insignificant, confidence=confidence,
+                                       device=device, return_counts=return_counts)
     x = np.asarray(data)
     code = nat.dtype_code(x.dtype)  # raises ValueError for unsupported dtypes
     x = _native_contiguous(x)

@@ -25,12 +25,51 @@ _TORCH_OF_NP = {
 }
 
 
-def slab_plan(shape, axis: int, itemsize: int, slab_bytes: int):
-    """[(lo, hi, halo)] rows of axis 0 per slab; ``halo`` (0/1) extra trailing rows to read."""
+def is_lazy_array(obj) -> bool:
+    """A sliceable array-like that is neither a numpy array nor a torch tensor: np.memmap is
+    a numpy array and stays on the in-memory path unless the caller streams it explicitly;
+    dask / zarr / h5py / netCDF4 variables (``shape``, ``dtype``, ``__getitem__``) are lazy."""
+    if isinstance(obj, np.ndarray) or type(obj).__module__.startswith("torch"):
+        return False
+    return all(hasattr(obj, a) for a in ("shape", "dtype", "__getitem__")) and not np.isscalar(obj)
+
+
+def _chunk_edges_axis0(source):
+    """Boundaries of the source's own chunks along axis 0 (dask ``.chunks`` tuples, zarr / h5py
+    ``.chunks`` chunk shape), or None."""
+    ch = getattr(source, "chunks", None)
+    if not ch:
+        return None
+    first = ch[0]
+    n0 = int(source.shape[0])
+    if isinstance(first, (tuple, list)):
+        edges = np.concatenate([[0], np.cumsum(first)])
+    else:
+        step = int(first)
+        if step <= 0:
+            return None
+        edges = np.arange(0, n0 + step, step)
+        edges[-1] = n0
+    return [int(e) for e in edges if e <= n0]
+
+
+def slab_plan(shape, axis: int, itemsize: int, slab_bytes: int, chunk_edges=None):
+    """[(lo, hi, halo)] rows of axis 0 per slab; ``halo`` (0/1) extra trailing rows to read.
+    With ``chunk_edges`` (the source's own chunk boundaries along axis 0) slabs end on chunk
+    boundaries whenever a whole chunk fits, so that no stored chunk is decoded twice."""
     n0 = int(shape[0])
     row_bytes = int(np.prod(shape[1:], dtype=np.int64)) * itemsize
     rows = max(1 if axis != 0 else 2, int(slab_bytes // max(row_bytes, 1)))
     plan = []
+    if axis != 0 and chunk_edges and len(chunk_edges) > 1:
+        lo = 0
+        while lo < n0:
+            limit = min(lo + rows, n0)
+            fit = [e for e in chunk_edges if lo < e <= limit]
+            hi = fit[-1] if fit else limit  # a chunk larger than a slab is cut
+            plan.append((lo, hi, 0))
+            lo = hi
+        return plan
     if axis != 0:
         for lo in range(0, n0, rows):
             plan.append((lo, min(lo + rows, n0), 0))
@@ -57,7 +96,7 @@ def bitinformation_streamed(source, axis: int, slab_bytes: int = 1 << 30, masked
     nat.dtype_code(dtype)  # ValueError for unsupported dtypes
     tdtype = _TORCH_OF_NP[dtype.name]
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-    plan = slab_plan(shape, axis, dtype.itemsize, slab_bytes)
+    plan = slab_plan(shape, axis, dtype.itemsize, slab_bytes, _chunk_edges_axis0(source))
     inner_elems = int(np.prod(shape[1:], dtype=np.int64))
     max_rows = max((hi - lo + halo for lo, hi, halo in plan), default=0)
     counters = [PairCounter(tdtype, dev) for _ in range(2)]
