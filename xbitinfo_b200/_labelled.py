@@ -136,6 +136,21 @@ class DataArray:
                 dims.pop(ax)
         return self._replace(data, dims=dims, coords=coords)
 
+    def _reduce(self, fn, dim):
+        """Reduce over one named dimension (``kb.max(dim="dim")`` of the reference's pipeline test)."""
+        if dim is None:
+            return self._replace(np.asarray(fn(self.values)), dims=(), coords={})
+        ax = self.get_axis_num(dim)
+        dims = [d for d in self.dims if d != dim]
+        coords = OrderedDict((k, c) for k, c in self.coords.items() if dim not in getattr(c, "dims", ()) and k != dim)
+        return self._replace(fn(self.values, axis=ax), dims=dims, coords=coords)
+
+    def max(self, dim=None):
+        return self._reduce(np.max, dim)
+
+    def min(self, dim=None):
+        return self._reduce(np.min, dim)
+
     def sel(self, **indexers):
         pos = {}
         for d, label in indexers.items():
@@ -230,6 +245,18 @@ class Dataset:
         for k, v in self._vars.items():
             use = {d: i for d, i in indexers.items() if d in v.dims}
             out[k] = v.sel(**use) if use else v
+        return out
+
+    def max(self, dim=None):
+        out = Dataset(attrs=self.attrs)
+        for k, v in self._vars.items():
+            out[k] = v.max(dim=dim) if (dim is None or dim in v.dims) else v
+        return out
+
+    def min(self, dim=None):
+        out = Dataset(attrs=self.attrs)
+        for k, v in self._vars.items():
+            out[k] = v.min(dim=dim) if (dim is None or dim in v.dims) else v
         return out
 
     def isel(self, indexers=None, **kw):
