@@ -171,6 +171,9 @@ def test_k3_k4_never_touch_memory_outside_their_buffers(dtype, n, where):
         dst.close()
 
 
+@pytest.mark.skipif(not __import__("os").environ.get("XBI_RUN_GUARD_CANARY"),
+                    reason="provokes a GPU page fault on purpose; opt in with XBI_RUN_GUARD_CANARY=1 "
+                           "(verified on a B200 box: the overrun faults, see profiles/README.md)")
 def test_the_guard_bites():
     """The harness itself: a call that is told the array is longer than it is must fault (run in
     a child process, an illegal address poisons the CUDA context)."""
