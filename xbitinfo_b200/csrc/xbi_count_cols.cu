@@ -588,12 +588,27 @@ cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t s
         if (e != cudaSuccess) return e;
         if (dev >= 0 && dev < 64) attr_set[dev] = true;
     }
-    // a few items per warp for balance, segments of at least 64 rows
-    const int64_t want_items = (int64_t)sms * kAsyncWarps * 4 * 32;  // in lanes (chunks x segments)
-    int64_t nseg = (want_items + chunks - 1) / chunks;
+    // Work split: warp items = 32-chunk strips x row segments, dealt round-robin to the
+    // sms*16 warps.  All items cost the same (segments differ by one row at most), so the
+    // kernel ends when the warps with one item more than the others finish: pick the number
+    // of segments (4 to 8 rounds of items per warp, segments of at least 64 rows) that wastes
+    // the least of the last round.  (With 4.3 items per warp 13 % of the SM time was idle.)
+    const int64_t warps = (int64_t)sms * kAsyncWarps;
     const int64_t max_seg = pair_rows / 64 > 0 ? pair_rows / 64 : 1;
-    if (nseg > max_seg) nseg = max_seg;
-    if (nseg < 1) nseg = 1;
+    auto witems = [&](int64_t ns) { return (chunks * ns + 31) / 32; };
+    int64_t lo_seg = (4 * warps * 32 + chunks - 1) / chunks, hi_seg = (8 * warps * 32) / chunks;
+    if (lo_seg < 1) lo_seg = 1;
+    if (hi_seg < lo_seg) hi_seg = lo_seg;
+    if (lo_seg > max_seg) lo_seg = max_seg;
+    if (hi_seg > max_seg) hi_seg = max_seg;
+    if (hi_seg - lo_seg > 4096) hi_seg = lo_seg + 4096;  // (narrow rows: bound the search)
+    int64_t nseg = lo_seg;
+    double best = -1.0;
+    for (int64_t ns = lo_seg; ns <= hi_seg; ++ns) {
+        const int64_t it = witems(ns), rounds = (it + warps - 1) / warps;
+        const double eff = (double)it / (double)(rounds * warps);
+        if (eff > best + 1e-9) { best = eff; nseg = ns; }
+    }
     const int64_t seg_min = pair_rows / nseg;
     const int64_t seg_extra = pair_rows - seg_min * nseg;
     const int64_t total = chunks * nseg;
