@@ -131,6 +131,14 @@ int xbi_bitround_inplace(void* x_dev, int dtype, int64_t numel, int keepbits, vo
 #define XBI_SHUFFLE_BITS 1
 int xbi_shuffle(const void* src_dev, void* dst_dev, int itemsize, int64_t numel, int kind, int inverse,
                 void* stream);
+/*
+ * K3 + K4 fused: dst = shuffle(bitround(src, keepbits)) in ONE pass over HBM (read once, write
+ * once) -- xr_bitround (xbitinfo/bitround.py:69-101) followed by the save path's shuffle
+ * (xbitinfo/save_compressed.py:44-80, 155-209).  src is not modified.  dtype XBI_F16/F32/F64,
+ * keepbits as for xbi_bitround_inplace, kind as for xbi_shuffle.
+ */
+int xbi_bitround_shuffle(const void* src_dev, void* dst_dev, int dtype, int64_t numel, int keepbits, int kind,
+                         void* stream);
 
 /*
  * Host-buffer entry points: what the numpy-facing plugin functions call.  Data is

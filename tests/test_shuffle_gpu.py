@@ -113,3 +113,25 @@ def test_large_round_trip_float32():
     sign_plane = b[31 * (n // 8): 31 * (n // 8) + 512]  # plane 31 = the sign bit
     assert int(sign_plane.count_nonzero()) == 0  # all values positive
     assert torch.equal(xs.bit_unshuffle(b, torch.float32), t)
+
+
+@pytest.mark.parametrize("dtype,keeps", [("float16", (0, 3, 9, 10)), ("float32", (0, 7, 22, 23)), ("float64", (0, 11, 51, 52))])
+@pytest.mark.parametrize("n", [8, 1000, 2048, 4096 + 64, (1 << 16) + 8, 262_144 + 1032])
+@pytest.mark.parametrize("bits", [False, True])
+def test_fused_bitround_shuffle_equals_round_then_shuffle(dtype, keeps, n, bits):
+    """K3 fused into K4: one pass, same bytes as bitround followed by the shuffle (oracle for both)."""
+    x = _data(dtype, n, seed=4)
+    x[::97] = -x[::97]
+    if n > 100:
+        x[5], x[6], x[7] = np.inf, -np.inf, np.nan  # the integer arithmetic treats them like numcodecs does
+    t = torch.from_numpy(x).cuda()
+    for keep in keeps:
+        got = xs.bitround_shuffle(t, keep, bits=bits).cpu().numpy()
+        rounded = bro.bitround(x, keep)
+        want = so.bit_shuffle(rounded) if bits else so.byte_shuffle(rounded)
+        assert np.array_equal(got, want), (dtype, keep, n, bits)
+    assert np.array_equal(t.cpu().numpy().view(f"u{x.dtype.itemsize}"), x.view(f"u{x.dtype.itemsize}"))  # input untouched
+    with pytest.raises(ValueError):
+        xs.bitround_shuffle(t, -1)
+    with pytest.raises(ValueError):
+        xs.bitround_shuffle(t, keeps[-1] + 1)

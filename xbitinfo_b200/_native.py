@@ -81,6 +81,8 @@ def lib() -> C.CDLL:
     L.xbi_bitround_inplace.argtypes = [vp, i32, i64, i32, vp]
     L.xbi_shuffle.restype = i32
     L.xbi_shuffle.argtypes = [vp, vp, i32, i64, i32, i32, vp]
+    L.xbi_bitround_shuffle.restype = i32
+    L.xbi_bitround_shuffle.argtypes = [vp, vp, i32, i64, i32, i32, vp]
     L.xbi_bitinformation_host.restype = i32
     L.xbi_bitinformation_host.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, i32]
     L.xbi_bitround_host.restype = i32
@@ -96,7 +98,7 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = (
     "xbi_abi_version", "xbi_last_error", "xbi_kernel_launches", "xbi_fast_path_launches",
     "xbi_workspace_bytes", "xbi_profile_enable", "xbi_profile_collect",
-    "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace", "xbi_shuffle",
+    "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace", "xbi_shuffle", "xbi_bitround_shuffle",
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
 )
 

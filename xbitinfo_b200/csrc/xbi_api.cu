@@ -264,9 +264,28 @@ int xbi_shuffle(const void* src_dev, void* dst_dev, int itemsize, int64_t numel,
     const uintptr_t a = reinterpret_cast<uintptr_t>(src_dev), b = reinterpret_cast<uintptr_t>(dst_dev);
     const uint64_t bytes = (uint64_t)numel * (uint64_t)itemsize;
     if (a < b + bytes && b < a + bytes) return fail(XBI_ERR_ARG, "source and destination overlap");
-    XBI_CUDA(launch_shuffle(src_dev, dst_dev, itemsize, numel, kind == XBI_SHUFFLE_BITS, inverse == 0,
+    XBI_CUDA(launch_shuffle(src_dev, dst_dev, itemsize, numel, kind == XBI_SHUFFLE_BITS, inverse == 0, 0,
                             static_cast<cudaStream_t>(stream)),
              "shuffle");
+    return XBI_OK;
+}
+
+int xbi_bitround_shuffle(const void* src_dev, void* dst_dev, int dtype, int64_t numel, int keepbits, int kind,
+                         void* stream) {
+    if (int rc = check_bitround_args(dtype, numel, keepbits)) return rc;
+    if (kind != XBI_SHUFFLE_BYTES && kind != XBI_SHUFFLE_BITS) return fail(XBI_ERR_ARG, "unknown shuffle kind");
+    if (numel == 0) return XBI_OK;
+    if (!src_dev || !dst_dev) return fail(XBI_ERR_ARG, "null data pointer");
+    if (kind == XBI_SHUFFLE_BITS && numel % 8 != 0)
+        return fail(XBI_ERR_ARG, "bit shuffle needs a number of elements that is a multiple of 8");
+    const int itemsize = dtype_bytes(dtype);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src_dev), b = reinterpret_cast<uintptr_t>(dst_dev);
+    const uint64_t bytes = (uint64_t)numel * (uint64_t)itemsize;
+    if (a < b + bytes && b < a + bytes) return fail(XBI_ERR_ARG, "source and destination overlap");
+    const int mant = dtype == XBI_F16 ? 10 : dtype == XBI_F32 ? 23 : 52;
+    XBI_CUDA(launch_shuffle(src_dev, dst_dev, itemsize, numel, kind == XBI_SHUFFLE_BITS, true, mant - keepbits,
+                            static_cast<cudaStream_t>(stream)),
+             "bitround + shuffle");
     return XBI_OK;
 }
 

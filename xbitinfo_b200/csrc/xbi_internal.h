@@ -72,9 +72,10 @@ cudaError_t launch_mutual_information(const unsigned long long* counts, int nbit
                                       double z_quantile, double* mi, cudaStream_t stream);
 cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cudaStream_t stream);
 // K4: byte (bits == false) or bit (bits == true) shuffle of numel elements of itemsize bytes,
-// forward or inverse; src and dst must not overlap
+// forward or inverse; src and dst must not overlap.  drop_bits > 0 (forward only): the elements are
+// bitrounded (K3's arithmetic, that many trailing mantissa bits dropped) on their way through.
 cudaError_t launch_shuffle(const void* src, void* dst, int itemsize, int64_t numel, bool bits, bool forward,
-                           cudaStream_t stream);
+                           int drop_bits, cudaStream_t stream);
 
 double normal_quantile(double p);  // AS241, host
 

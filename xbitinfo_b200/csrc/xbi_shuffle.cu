@@ -26,6 +26,50 @@ namespace {
 constexpr int kThreads = 256;
 
 // ---------------------------------------------------------------------------------
+// optional fused bitround (K3's arithmetic, xbi_bitround.cu) applied to the words as they are
+// loaded by the forward kernels: round-then-shuffle in one pass over HBM instead of two
+// ---------------------------------------------------------------------------------
+struct RoundSpec {
+    uint32_t drop;                // mantissa bits to drop; 0 = no rounding
+    unsigned long long half_m1;   // 2^(drop-1) - 1
+    unsigned long long keep;      // ~(2^drop - 1) within the element width
+};
+template <int S>
+__device__ __forceinline__ void round_words(uint32_t* w, int nwords, const RoundSpec& r) {
+    // w: consecutive little-endian words of whole elements of S bytes
+    if (S == 4) {
+#pragma unroll
+        for (int i = 0; i < nwords; ++i) w[i] = (w[i] + ((w[i] >> r.drop) & 1u) + (uint32_t)r.half_m1) & (uint32_t)r.keep;
+    } else if (S == 2) {
+#pragma unroll
+        for (int i = 0; i < nwords; ++i) {
+            const uint32_t lo = w[i] & 0xFFFFu, hi = w[i] >> 16;
+            const uint32_t rl = (lo + ((lo >> r.drop) & 1u) + (uint32_t)r.half_m1) & (uint32_t)r.keep;
+            const uint32_t rh = (hi + ((hi >> r.drop) & 1u) + (uint32_t)r.half_m1) & (uint32_t)r.keep;
+            w[i] = (rl & 0xFFFFu) | (rh << 16);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i + 1 < nwords; i += 2) {
+            unsigned long long b = ((unsigned long long)w[i + 1] << 32) | w[i];
+            b = (b + ((b >> r.drop) & 1ull) + r.half_m1) & r.keep;
+            w[i] = (uint32_t)b;
+            w[i + 1] = (uint32_t)(b >> 32);
+        }
+    }
+}
+// one element given as S bytes (byte-wise tails)
+template <int S>
+__device__ __forceinline__ void round_bytes(uint8_t (&e)[S], const RoundSpec& r) {
+    unsigned long long b = 0;
+#pragma unroll
+    for (int j = 0; j < S; ++j) b |= (unsigned long long)e[j] << (8 * j);
+    b = (b + ((b >> r.drop) & 1ull) + r.half_m1) & r.keep;
+#pragma unroll
+    for (int j = 0; j < S; ++j) e[j] = (uint8_t)(b >> (8 * j));
+}
+
+// ---------------------------------------------------------------------------------
 // byte shuffle / unshuffle
 // ---------------------------------------------------------------------------------
 // 16 elements of S bytes held as 4*S words  <->  S planes of 16 bytes (4 words each)
@@ -112,7 +156,7 @@ __device__ __forceinline__ void planes_to_bytes(const uint32_t (&in)[S][4], uint
 // groups of 16 elements; N = 16*ngroups + tail, the tail is moved byte by byte
 template <int S, bool FORWARD>
 __global__ void __launch_bounds__(kThreads)
-k_byte_shuffle(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long n, long long ngroups) {
+k_byte_shuffle(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long n, long long ngroups, RoundSpec rs) {
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long g = (long long)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
         if (FORWARD) {
@@ -122,6 +166,10 @@ k_byte_shuffle(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long 
             for (int k = 0; k < S; ++k) {
                 const uint4 v = __ldg(p + k);
                 in[4 * k] = v.x; in[4 * k + 1] = v.y; in[4 * k + 2] = v.z; in[4 * k + 3] = v.w;
+            }
+            if (rs.drop) {
+#pragma unroll
+                for (int k = 0; k < 4 * S; k += 2) round_words<S>(in + k, 2, rs);
             }
             bytes_to_planes<S>(in, out);
 #pragma unroll
@@ -142,10 +190,16 @@ k_byte_shuffle(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long 
     }
     // elements outside the 16-element groups (unaligned buffers take this path entirely)
     for (long long i = 16 * ngroups + (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += stride) {
+        if (FORWARD) {
+            uint8_t e[S];
 #pragma unroll
-        for (int j = 0; j < S; ++j) {
-            if (FORWARD) dst[j * n + i] = src[i * S + j];
-            else dst[i * S + j] = src[j * n + i];
+            for (int j = 0; j < S; ++j) e[j] = src[i * S + j];
+            if (rs.drop) round_bytes<S>(e, rs);
+#pragma unroll
+            for (int j = 0; j < S; ++j) dst[j * n + i] = e[j];
+        } else {
+#pragma unroll
+            for (int j = 0; j < S; ++j) dst[i * S + j] = src[j * n + i];
         }
     }
 }
@@ -181,7 +235,7 @@ constexpr int kPitch = 36;  // words per staged row of 32 words: 128-bit accesse
 //   S == 2: tile = 2048 elements; lane t holds elements 64t..64t+63 -> words 2t, 2t+1 of 16 planes
 template <int S, bool FORWARD>
 __global__ void __launch_bounds__(kThreads)
-k_bit_shuffle(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long long n, long long ntiles) {
+k_bit_shuffle(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long long n, long long ntiles, RoundSpec rs) {
     constexpr int EPT = (S == 2) ? 2048 : 1024;    // elements per warp tile
     constexpr int WPT = EPT * S / 4;               // words per warp tile (1024 or 2048)
     constexpr int NSUB = WPT / 1024;               // 32x32-word sub-tiles per warp tile
@@ -201,7 +255,8 @@ k_bit_shuffle(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long
                     const uint4* p = reinterpret_cast<const uint4*>(src + tile * WPT);
 #pragma unroll
                     for (int k = 0; k < 16; ++k) {
-                        const uint4 v = __ldg(p + lane + 32 * k);  // elements 2*(lane+32k), 2*(lane+32k)+1
+                        uint4 v = __ldg(p + lane + 32 * k);  // elements 2*(lane+32k), 2*(lane+32k)+1
+                        if (rs.drop) round_words<S>(&v.x, 4, rs);
                         const uint32_t e = 2 * (lane + 32 * k);    // element index in the tile
                         const uint32_t w0 = sub == 0 ? v.x : v.y, w1 = sub == 0 ? v.z : v.w;
                         // element e lives in staged row e/32, column e%32
@@ -211,7 +266,8 @@ k_bit_shuffle(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long
                     const uint4* p = reinterpret_cast<const uint4*>(src + tile * WPT + sub * 1024);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const uint4 v = __ldg(p + lane + 32 * k);
+                        uint4 v = __ldg(p + lane + 32 * k);
+                        if (rs.drop) round_words<S>(&v.x, 4, rs);
                         const uint32_t w = 4 * (lane + 32 * k);  // word index in the sub-tile
                         *reinterpret_cast<uint4*>(&st[(w >> 5) * kPitch + (w & 31u)]) = v;
                     }
@@ -301,7 +357,7 @@ k_bit_shuffle(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long
 // elements [lo, n) of a bit shuffle that do not fill a warp tile: one thread per 8 elements
 template <int S, bool FORWARD>
 __global__ void __launch_bounds__(kThreads)
-k_bit_shuffle_tail(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long n, long long lo) {
+k_bit_shuffle_tail(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long n, long long lo, RoundSpec rs) {
     const long long nb = n / 8;  // bytes per bit plane
     const long long stride = (long long)gridDim.x * kThreads;
     for (long long g = lo / 8 + (long long)blockIdx.x * kThreads + threadIdx.x; g < nb; g += stride) {
@@ -311,6 +367,10 @@ k_bit_shuffle_tail(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, l
             for (int i = 0; i < 8; ++i)
 #pragma unroll
                 for (int j = 0; j < S; ++j) e[i][j] = src[(8 * g + i) * S + j];
+            if (rs.drop) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) round_bytes<S>(e[i], rs);
+            }
 #pragma unroll
             for (int j = 0; j < S; ++j)
 #pragma unroll
@@ -343,7 +403,7 @@ k_bit_shuffle_tail(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, l
 }
 
 template <int S, bool FORWARD>
-cudaError_t launch_byte(const void* src, void* dst, int64_t n, int sms, cudaStream_t stream) {
+cudaError_t launch_byte(const void* src, void* dst, int64_t n, int sms, cudaStream_t stream, RoundSpec rs) {
     // the 128-bit accesses need 16-byte aligned planes: n % 16 == 0 and aligned bases,
     // otherwise everything goes through the byte-wise tail loop
     const bool aligned = (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (reinterpret_cast<uintptr_t>(dst) % 16 == 0) && (n % 16 == 0);
@@ -352,13 +412,13 @@ cudaError_t launch_byte(const void* src, void* dst, int64_t n, int sms, cudaStre
     if (blocks > (long long)sms * 32) blocks = (long long)sms * 32;
     if (blocks < 1) blocks = 1;
     k_byte_shuffle<S, FORWARD><<<(unsigned)blocks, kThreads, 0, stream>>>(static_cast<const uint8_t*>(src),
-                                                                          static_cast<uint8_t*>(dst), n, ngroups);
+                                                                          static_cast<uint8_t*>(dst), n, ngroups, rs);
     note_launch();
     return cudaGetLastError();
 }
 
 template <int S, bool FORWARD>
-cudaError_t launch_bit(const void* src, void* dst, int64_t n, int sms, cudaStream_t stream) {
+cudaError_t launch_bit(const void* src, void* dst, int64_t n, int sms, cudaStream_t stream, RoundSpec rs) {
     constexpr int EPT = (S == 2) ? 2048 : 1024;
     // plane rows must be word aligned for the tile kernel: n % 32 == 0 (and 16-byte aligned
     // bases; S == 2 writes 8-byte pairs: n % 64 == 0)
@@ -369,7 +429,7 @@ cudaError_t launch_bit(const void* src, void* dst, int64_t n, int sms, cudaStrea
         long long blocks = (ntiles + kBsWarps - 1) / kBsWarps;
         if (blocks > (long long)sms * 16) blocks = (long long)sms * 16;
         k_bit_shuffle<S, FORWARD><<<(unsigned)blocks, kThreads, 0, stream>>>(static_cast<const uint32_t*>(src),
-                                                                             static_cast<uint32_t*>(dst), n, ntiles);
+                                                                             static_cast<uint32_t*>(dst), n, ntiles, rs);
         note_launch();
     }
     const long long lo = ntiles * EPT;
@@ -378,7 +438,7 @@ cudaError_t launch_bit(const void* src, void* dst, int64_t n, int sms, cudaStrea
         if (blocks > (long long)sms * 8) blocks = (long long)sms * 8;
         if (blocks < 1) blocks = 1;
         k_bit_shuffle_tail<S, FORWARD><<<(unsigned)blocks, kThreads, 0, stream>>>(static_cast<const uint8_t*>(src),
-                                                                                   static_cast<uint8_t*>(dst), n, lo);
+                                                                                   static_cast<uint8_t*>(dst), n, lo, rs);
         note_launch();
     }
     return cudaGetLastError();
@@ -387,14 +447,22 @@ cudaError_t launch_bit(const void* src, void* dst, int64_t n, int sms, cudaStrea
 }  // namespace
 
 cudaError_t launch_shuffle(const void* src, void* dst, int itemsize, int64_t numel, bool bits, bool forward,
-                           cudaStream_t stream) {
+                           int drop_bits, cudaStream_t stream) {
     if (numel <= 0) return cudaSuccess;
+    RoundSpec rs{0u, 0ull, ~0ull};
+    if (drop_bits > 0 && forward) {
+        const int width = 8 * itemsize;
+        const unsigned long long full = width == 64 ? ~0ull : ((1ull << width) - 1ull);
+        rs.drop = (uint32_t)drop_bits;
+        rs.keep = (full >> drop_bits) << drop_bits;
+        rs.half_m1 = (1ull << (drop_bits - 1)) - 1ull;
+    }
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 #define XBI_SHUF(S)                                                                                       \
-    (bits ? (forward ? launch_bit<S, true>(src, dst, numel, sms, stream) : launch_bit<S, false>(src, dst, numel, sms, stream)) \
-          : (forward ? launch_byte<S, true>(src, dst, numel, sms, stream) : launch_byte<S, false>(src, dst, numel, sms, stream)))
+    (bits ? (forward ? launch_bit<S, true>(src, dst, numel, sms, stream, rs) : launch_bit<S, false>(src, dst, numel, sms, stream, rs)) \
+          : (forward ? launch_byte<S, true>(src, dst, numel, sms, stream, rs) : launch_byte<S, false>(src, dst, numel, sms, stream, rs)))
     switch (itemsize) {
         case 2: return XBI_SHUF(2);
         case 4: return XBI_SHUF(4);

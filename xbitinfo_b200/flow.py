@@ -55,18 +55,27 @@ def save_npz(ds, path):
     np.savez(path, **arrays)
 
 
-def save_compressed(ds, path, complevel=7, shuffle=True):
+def save_compressed(ds, path, complevel=7, shuffle=True, keepbits=None):
     """One file: a JSON header line, then per variable the zlib stream of the (byte-shuffled on
     the device) array.  Mirrors the zlib + shuffle encoding of ``get_compress_encoding_nc``
-    (``xbitinfo/save_compressed.py:44-80``) for single-chunk variables."""
+    (``xbitinfo/save_compressed.py:44-80``) for single-chunk variables.  With ``keepbits``
+    (``{variable: int}``) float variables are bitrounded on their way through the shuffle kernel
+    (``xbi_bitround_shuffle``: one pass over HBM) -- the result is the file ``xr_bitround``
+    followed by this function would write."""
     import torch
 
-    from .shuffle import byte_shuffle
+    from .shuffle import bitround_shuffle, byte_shuffle
 
     header, blobs = {"vars": []}, []
     for v in ds.data_vars:
         a = np.ascontiguousarray(ds[v].values)
-        if shuffle and a.dtype.itemsize in (2, 4, 8):
+        attrs = dict(ds[v].attrs)
+        keep = None if keepbits is None else keepbits.get(v)
+        if keep is not None and a.dtype.kind == "f" and shuffle:
+            raw = bitround_shuffle(torch.from_numpy(a.reshape(-1)).cuda(), int(keep)).cpu().numpy().tobytes()
+            attrs["_QuantizeBitRoundNumberOfSignificantDigits"] = int(keep)
+            shuffled = True
+        elif shuffle and a.dtype.itemsize in (2, 4, 8):
             raw = byte_shuffle(torch.from_numpy(a.reshape(-1)).cuda()).cpu().numpy().tobytes()
             shuffled = True
         else:
@@ -74,7 +83,7 @@ def save_compressed(ds, path, complevel=7, shuffle=True):
         blob = zlib.compress(raw, complevel)
         header["vars"].append({"name": v, "dtype": a.dtype.str, "shape": list(a.shape), "dims": list(ds[v].dims),
                                "attrs": {k: (int(x) if isinstance(x, (int, np.integer)) else str(x))
-                                         for k, x in ds[v].attrs.items()},
+                                         for k, x in attrs.items()},
                                "shuffle": shuffled, "nbytes": len(blob)})
         blobs.append(blob)
     with open(path, "wb") as f:
@@ -160,8 +169,13 @@ def bitround_and_save(path, keepbits, complevel=4, rename=(".npz", "_bitrounded_
     ds = opener(path)
     if enforce_dtype:
         ds = ds.astype(enforce_dtype)
-    ds_bitround = xr_bitround(ds, keepbits)
-    saver(ds_bitround, new_path, complevel)
+    if saver is save_compressed:
+        # round and shuffle in one pass over the device copy (same bytes as the two-step sequence)
+        save_compressed(ds, new_path, complevel, keepbits={v: keepbits[v] for v in ds.data_vars if v in keepbits
+                                                            and np.dtype(ds[v].dtype).kind == "f"})
+    else:
+        ds_bitround = xr_bitround(ds, keepbits)
+        saver(ds_bitround, new_path, complevel)
     return new_path
 
 

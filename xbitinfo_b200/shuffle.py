@@ -54,6 +54,22 @@ def bit_unshuffle(buf: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     return _run(buf.contiguous(), torch.empty((), dtype=dtype).element_size(), nat.SHUFFLE_BITS, True, dtype)
 
 
+def bitround_shuffle(x: torch.Tensor, keepbits: int, bits: bool = False) -> torch.Tensor:
+    """``shuffle(bitround(x, keepbits))`` in one pass over HBM (K3 fused into K4): the uint8
+    planes of the rounded array, ``x`` itself untouched.  ``bits`` selects the bit shuffle."""
+    from .device import torch_dtype_code
+
+    x = x.contiguous()
+    require_cuda_tensor(x)
+    out = torch.empty(x.numel() * x.element_size(), dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = nat.lib().xbi_bitround_shuffle(x.data_ptr(), out.data_ptr(), torch_dtype_code(x.dtype), x.numel(),
+                                            int(keepbits), nat.SHUFFLE_BITS if bits else nat.SHUFFLE_BYTES,
+                                            _stream_ptr(x.device))
+    nat.check(rc)
+    return out
+
+
 class _DeviceFilter:
     """numcodecs-style codec whose permutation runs on the GPU (host buffer in, host buffer out)."""
 
