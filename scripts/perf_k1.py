@@ -44,6 +44,7 @@ def main():
     ap.add_argument("--axis", type=int, default=-1)
     ap.add_argument("--mask", default="none")
     ap.add_argument("--land", type=float, default=0.0, help="fraction of the last two dims set to the masked value (a rectangle)")
+    ap.add_argument("--randmask", type=float, default=0.0, help="fraction of elements masked at random positions")
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--bitround", action="store_true")
     a = ap.parse_args()
@@ -58,6 +59,11 @@ def main():
         h, w = x.shape[-2], x.shape[-1]
         x[..., int(0.2 * h): int(0.7 * h), : int(min(1.0, a.land / 0.5) * w)] = mv
         print(f"masked fraction: {float((x != x).float().mean() if mv != mv else (x == mv).float().mean()):.3f}")
+    if a.randmask > 0 and mv is not None:
+        g = torch.Generator(device="cuda").manual_seed(7)
+        sel = torch.rand(x.shape, device="cuda", generator=g) < a.randmask
+        x[sel] = mv
+        del sel
     nbytes = x.numel() * x.element_size()
     pc = PairCounter(x.dtype, x.device)
     l0 = nat.kernel_launches()

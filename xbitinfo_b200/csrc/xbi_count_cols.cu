@@ -100,12 +100,13 @@ struct ColWalker {
     uint32_t it;
     uint32_t ninvalid;  // pairs with a masked element since the last flush
     unsigned long long ninvalid_total;
-    // the boundary-event planes live in local memory and their address is handed to
-    // out-of-line helpers: they are a separate object of the kernel so that this struct
-    // stays in registers
-    using Events = BoundaryEvents<MASKED ? Elem<KIND>::kWords : 1>;
+    static constexpr int kEvWords = MASKED ? Elem<KIND>::kWords : 1;
+    static constexpr int kEvPlanes = K64 ? 3 : 5;  // 64-bit types (two words per element): 3 planes, one row per reserve
+    EventPlanes<kEvWords, kEvPlanes> er;            // boundary corrections of the masked modes
+    unsigned long long (*s_minus)[64];              // the block's shared correction totals (flush target)
 
-    __device__ __forceinline__ void init() {
+    __device__ __forceinline__ void init(unsigned long long (*shared_minus)[64]) {
+        s_minus = shared_minus;
 #pragma unroll
         for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); accB[i] = 0; accAB[i] = 0; }
 #pragma unroll
@@ -117,6 +118,7 @@ struct ColWalker {
         it = 0;
         ninvalid = 0;
         ninvalid_total = 0;
+        if (MASKED) er.init();
     }
 
     __device__ __forceinline__ void flush(uint32_t lane) {
@@ -167,8 +169,7 @@ struct ColWalker {
     }
 
     // fold 4 rows; rows >= nrows are absent (tail group only)
-    __device__ __forceinline__ void process(const uint4 (&buf)[4], int nrows, uint32_t mlo, uint32_t mhi, uint32_t lane,
-                                            Events& ev) {
+    __device__ __forceinline__ void process(const uint4 (&buf)[4], int nrows, uint32_t mlo, uint32_t mhi, uint32_t lane) {
         uint32_t cur[4][4];
         bool skip = false;  // warp-uniform: nothing in this group (nor the row above it) is valid
         if constexpr (MASKED && WHOLE) {
@@ -177,12 +178,14 @@ struct ColWalker {
             for (int r = 0; r < 4; ++r) { cur[r][0] = buf[r].x; cur[r][1] = buf[r].y; cur[r][2] = buf[r].z; cur[r][3] = buf[r].w; }
             constexpr uint32_t kRowMask = (1u << EPC) - 1u;
             uint32_t m = 0u;  // bit EPC*r + e: element e of row r is masked
+            bool warp_dirty = false;  // warp-uniform
             {
                 uint32_t raw[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) raw[j] = cur[j >> 2][j & 3];
                 const bool tdirty = (pm != 0u) || may_contain_masked<KIND, MASK>(raw, mlo, mhi);
                 if (__any_sync(0xFFFFFFFFu, tdirty)) {
+                    warp_dirty = true;
                     const bool allm = (pm == kRowMask) && all_masked_quick<KIND, MASK>(raw, mlo, mhi);
                     if (__all_sync(0xFFFFFFFFu, allm)) {
                         ninvalid += (uint32_t)nrows * (uint32_t)__popc(vrep & kRowMask);
@@ -203,31 +206,42 @@ struct ColWalker {
             }
 #pragma unroll
             for (int r = 0; r < 4; ++r) xform_chunk<KIND, XFORM>(cur[r]);
-            if (m | pm) {  // this thread's chunk has masked elements (or sits under one)
-                const uint32_t present = ((nrows >= 4) ? (0xFFFFu >> (16 - 4 * EPC)) : ((1u << (EPC * nrows)) - 1u)) & vrep;
-                const uint32_t above = (m << EPC) | pm;  // the element over each element
-                ninvalid += __popc((m | above) & present);
-                const uint32_t bnd = (m ^ above) & present;
-                if (bnd && lane_live) {  // validity changes between two rows of this chunk: rare
-                    ev.touch();
+            if (warp_dirty) {
+                uint32_t bnd = 0u;
+                if (m | pm) {  // this thread's chunk has masked elements (or sits under one)
+                    const uint32_t present = ((nrows >= 4) ? (0xFFFFu >> (16 - 4 * EPC)) : ((1u << (EPC * nrows)) - 1u)) & vrep;
+                    const uint32_t above = (m << EPC) | pm;  // the element over each element
+                    ninvalid += __popc((m | above) & present);
+                    if (lane_live) bnd = (m ^ above) & present;
+                }
+                // validity changes between two rows of this chunk: the valid element of the pair goes
+                // into the correction planes
+                constexpr int kHalves = K64 ? 4 : 1, kRowsPer = 4 / kHalves;
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) {
+                for (int h = 0; h < kHalves; ++h) {
+                    er.reserve((uint32_t)(kRowsPer * EPC), lane, s_minus, 8 * BYTES);
+                    const uint32_t hb = (bnd >> (EPC * kRowsPer * h)) & ((1u << (EPC * kRowsPer)) - 1u);
+                    if (hb) {
 #pragma unroll
-                        for (int e = 0; e < EPC; ++e) {
-                            if ((bnd >> (EPC * r + e)) & 1u) {
-                                if ((m >> (EPC * r + e)) & 1u) {  // a valid, b masked
+                        for (int r = kRowsPer * h; r < kRowsPer * (h + 1); ++r) {
 #pragma unroll
-                                    for (int k = 0; k < WPE; ++k)
-                                        ev.add_a(k, (r == 0) ? prev[WPE * e + k] : cur[r > 0 ? r - 1 : 0][WPE * e + k]);
-                                } else {  // a masked, b valid
-#pragma unroll
-                                    for (int k = 0; k < WPE; ++k) ev.add_b(k, cur[r][WPE * e + k]);
+                            for (int e = 0; e < EPC; ++e) {
+                                if ((bnd >> (EPC * r + e)) & 1u) {
+                                    if ((m >> (EPC * r + e)) & 1u) {  // a valid, b masked
+                                        er.template add<0, 0>((r == 0) ? prev[WPE * e] : cur[r > 0 ? r - 1 : 0][WPE * e]);
+                                        if constexpr (K64)
+                                            er.template add<0, kEvWords - 1>((r == 0) ? prev[WPE * e + 1] : cur[r > 0 ? r - 1 : 0][WPE * e + 1]);
+                                    } else {  // a masked, b valid
+                                        er.template add<1, 0>(cur[r][WPE * e]);
+                                        if constexpr (K64) er.template add<1, kEvWords - 1>(cur[r][WPE * e + 1]);
+                                    }
                                 }
                             }
                         }
+                        er.ecnt += (uint32_t)__popc(hb);
                     }
                 }
-                if (nrows > 0) pm = (m >> (EPC * (nrows - 1))) & kRowMask;
+                if ((m | pm) && nrows > 0) pm = (m >> (EPC * (nrows - 1))) & kRowMask;
             }
         } else if constexpr (MASKED) {
             // ---- packed 8/16-bit elements: warp-uniform general path on keep-masks ----
@@ -274,8 +288,8 @@ struct ColWalker {
                             ninvalid += count_chunk<BYTES>(inval);
                         }
                     }
-                    if (bnd && lane_live) {  // validity changes between two rows of this chunk: rare
-                        ev.touch();
+                    er.reserve(16u, lane, s_minus, 8 * BYTES);
+                    if (bnd && lane_live) {  // validity changes between two rows of this chunk
 #pragma unroll
                         for (int r = 0; r < 4; ++r) {
                             if (r < nrows) {
@@ -284,8 +298,9 @@ struct ColWalker {
                                     const uint32_t pk = (r == 0) ? prev_keep[i] : keep[r > 0 ? r - 1 : 0][i];
                                     const uint32_t pa = (r == 0) ? prev[i] : cur[r > 0 ? r - 1 : 0][i];
                                     const uint32_t va = pk & ~keep[r][i], vb = ~pk & keep[r][i];
-                                    if (va) ev.add_a(0, pa & va);
-                                    if (vb) ev.add_b(0, cur[r][i] & vb);
+                                    if (va) er.template add<0, 0>(pa & va);
+                                    if (vb) er.template add<1, 0>(cur[r][i] & vb);
+                                    er.ecnt += (va | vb) ? 1u : 0u;
                                 }
                             }
                         }
@@ -351,15 +366,13 @@ struct ColWalker {
         if (it == L::kFlushChunks) flush(lane);
     }
 
-    // end of kernel: block reduction, one atomic per non-zero counter and block.  s_sum /
-    // s_minus / s_n are shared scratch of the calling kernel; all threads of the block call.
+    // end of kernel: block reduction, one atomic per non-zero counter and block.  s_sum / s_n are
+    // shared scratch of the calling kernel (s_minus was handed to init()); all threads of the block call.
     __device__ __forceinline__ void finish(uint32_t lane, int nthreads, unsigned long long (*s_sum)[64],
-                                           unsigned long long (*s_minus)[64], unsigned long long* s_n, Workspace* ws,
-                                           unsigned long long flat_pairs, Events& ev) {
+                                           unsigned long long* s_n, Workspace* ws, unsigned long long flat_pairs) {
         flush(lane);
         for (int i = threadIdx.x; i < 3 * 64; i += nthreads) (&s_sum[0][0])[i] = 0;
         if (MASKED) {
-            for (int i = threadIdx.x; i < 2 * 64; i += nthreads) (&s_minus[0][0])[i] = 0;
             if (threadIdx.x == 0) *s_n = 0;
         }
         __syncthreads();
@@ -374,7 +387,7 @@ struct ColWalker {
         }
         if (MASKED) {
             if (ninvalid_total) atomicAdd(s_n, ninvalid_total);
-            ev.drain(s_minus, 8 * BYTES, lane);
+            er.flush(lane, s_minus, 8 * BYTES);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 3 * 64; i += nthreads) {
@@ -466,10 +479,14 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
     const long long groups = seg_min >> 2;  // full 4-row groups, the same for every item
     const long long stride = row_bytes;     // bytes between rows
 
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_minus[2][64];
+    __shared__ unsigned long long s_n;
+    for (int i = threadIdx.x; i < 2 * 64; i += kAsyncThreads) (&s_minus[0][0])[i] = 0;
+    __syncthreads();
+
     W cw;
-    cw.init();
-    typename W::Events ev;
-    ev.init();
+    cw.init(s_minus);
     uint32_t slot_w = 0, slot_r = 0;  // ring positions (the same on every lane)
 
     for (long long wi = (long long)blockIdx.x * kAsyncWarps + warp; wi < n_witems; wi += warps_total) {
@@ -557,8 +574,8 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
 #pragma unroll
             for (int r = 0; r < 4; ++r) buf[r] = lds128(src + r * kStripBytes);
             slot_r = (slot_r + 1 == kAsyncRing) ? 0 : slot_r + 1;
-            if (g < groups) cw.process(buf, 4, mask_lo, mask_hi, lane, ev);
-            else cw.process(buf, tail_rows, mask_lo, mask_hi, lane, ev);
+            if (g < groups) cw.process(buf, 4, mask_lo, mask_hi, lane);
+            else cw.process(buf, tail_rows, mask_lo, mask_hi, lane);
         }
         // the kAhead groups committed past the end of the item are empty; the ring position
         // moved with them, keep reader and writer aligned
@@ -570,10 +587,7 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
     }
     cp_async_wait<0>();
 
-    __shared__ unsigned long long s_sum[3][64];
-    __shared__ unsigned long long s_minus[2][64];
-    __shared__ unsigned long long s_n;
-    cw.finish(lane, kAsyncThreads, s_sum, s_minus, &s_n, ws, flat_pairs, ev);
+    cw.finish(lane, kAsyncThreads, s_sum, &s_n, ws, flat_pairs);
 }
 
 template <int KIND, int MASK, bool XFORM, int G>

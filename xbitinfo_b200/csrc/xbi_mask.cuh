@@ -285,4 +285,61 @@ struct BoundaryEvents {
     }
 };
 
+// ---------------------------------------------------------------------------------
+// Boundary-correction counters: P bit planes per stream and element word, in registers.  A
+// correction word is added with 2P logic operations.  Before a warp adds up to `upcoming`
+// more events per lane it calls reserve(): if some lane could overflow, the whole warp
+// flushes -- the planes are summed over the warp with the butterfly of xbi_common.cuh (lane L
+// ends up with the count of bit position L) and added to the block's shared `minus` totals.
+// No local memory, no per-event memory traffic; the cost of a flush (~400 instructions per
+// stream) is paid once per 2^P - 1 - upcoming events of the busiest lane.
+// ---------------------------------------------------------------------------------
+template <int NW, int P>
+struct EventPlanes {
+    static constexpr uint32_t kCap = (1u << P) - 1u;
+    uint32_t r[2][NW][P];
+    uint32_t ecnt;  // events added by this lane since the last flush (bounds every bit position's count)
+
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int w = 0; w < NW; ++w)
+#pragma unroll
+                for (int j = 0; j < P; ++j) r[s][w][j] = 0u;
+        ecnt = 0u;
+    }
+    // stream 0: a-stream correction ("a valid, b masked"), stream 1: b-stream correction
+    template <int STREAM, int WI>
+    __device__ __forceinline__ void add(uint32_t word) {
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const uint32_t t = r[STREAM][WI][j] & word;
+            r[STREAM][WI][j] ^= word;
+            word = t;
+        }
+    }
+    // warp-collective (all 32 lanes, converged): s_minus = shared [2][64] totals, bit number from the LSB
+    __device__ __forceinline__ void flush(uint32_t lane, unsigned long long (*s_minus)[64], int nbits) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                uint32_t n[P + 6];
+#pragma unroll
+                for (int j = 0; j < P; ++j) { n[j] = r[s][w][j]; r[s][w][j] = 0u; }
+#pragma unroll
+                for (int j = P; j < P + 6; ++j) n[j] = 0u;
+                const uint32_t total = butterfly_totals(n, P, lane);
+                if (total) atomicAdd(&s_minus[s][w * 32 + (int)(lane % (uint32_t)(nbits < 32 ? nbits : 32))], (unsigned long long)total);
+            }
+        }
+        ecnt = 0u;
+    }
+    // warp-collective: make room for `upcoming` more events in every lane
+    __device__ __forceinline__ void reserve(uint32_t upcoming, uint32_t lane, unsigned long long (*s_minus)[64], int nbits) {
+        if (__any_sync(0xFFFFFFFFu, ecnt + upcoming > kCap)) flush(lane, s_minus, nbits);
+    }
+};
+
 }  // namespace xbi
