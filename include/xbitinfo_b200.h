@@ -55,6 +55,8 @@ enum xbi_dtype {
 #define XBI_MASK_NAN 2u        /* floats: a pair with a NaN element (any payload) is not counted   */
 #define XBI_MASK_VALUE 4u      /* a pair with an element bit-identical to mask_bits is not counted */
 #define XBI_FORCE_GENERIC 8u   /* testing: skip the TMA fast paths                                  */
+#define XBI_FORCE_SPARSE 16u   /* testing: masked fast kernels in their boundary-correction flavour */
+#define XBI_FORCE_DENSE 32u    /* testing: ... in their three-stream flavour (default: sampled)     */
 
 /* error codes */
 #define XBI_OK 0

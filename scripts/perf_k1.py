@@ -45,6 +45,7 @@ def main():
     ap.add_argument("--mask", default="none")
     ap.add_argument("--land", type=float, default=0.0, help="fraction of the last two dims set to the masked value (a rectangle)")
     ap.add_argument("--randmask", type=float, default=0.0, help="fraction of elements masked at random positions")
+    ap.add_argument("--flavour", default=None, choices=[None, "sparse", "dense"])
     ap.add_argument("--check", action="store_true")
     ap.add_argument("--bitround", action="store_true")
     a = ap.parse_args()
@@ -67,13 +68,13 @@ def main():
     nbytes = x.numel() * x.element_size()
     pc = PairCounter(x.dtype, x.device)
     l0 = nat.kernel_launches()
-    pc.add(x, a.axis, masked_value=mv)
+    pc.add(x, a.axis, masked_value=mv, flavour=a.flavour)
     torch.cuda.synchronize()
     print("launches per call:", nat.kernel_launches() - l0)
-    best, med = timeit(lambda: pc.add(x, a.axis, masked_value=mv))
+    best, med = timeit(lambda: pc.add(x, a.axis, masked_value=mv, flavour=a.flavour))
     nat.profile_enable(True)
     for _ in range(10):
-        pc.add(x, a.axis, masked_value=mv)
+        pc.add(x, a.axis, masked_value=mv, flavour=a.flavour)
     kms, kn, kb = nat.profile_collect()
     nat.profile_enable(False)
     if kn:
@@ -81,7 +82,7 @@ def main():
     print(f"K1 {a.dtype} {shape} axis={a.axis} mask={a.mask}: best {best*1e3:.3f} ms  median {med*1e3:.3f} ms  "
           f"{nbytes/best/1e9:.1f} GB/s best, {nbytes/med/1e9:.1f} GB/s median ({nbytes/1e9:.2f} GB)")
     if a.check:
-        pc.reset(); pc.add(x, a.axis, masked_value=mv); fast = pc.counts.clone()
+        pc.reset(); pc.add(x, a.axis, masked_value=mv, flavour=a.flavour); fast = pc.counts.clone()
         pc.reset(); pc.add(x, a.axis, masked_value=mv, force_generic=True); gen = pc.counts.clone()
         bg, _ = timeit(lambda: pc.add(x, a.axis, masked_value=mv, force_generic=True), iters=2, warm=1)
         print("fast == generic:", bool(torch.equal(fast, gen)), f"(generic {nbytes/bg/1e9:.1f} GB/s)")

@@ -393,3 +393,34 @@ def test_strided_rows_that_are_only_element_aligned(dtype, mask):
             ref_counts, npairs, _ = bo.bitinformation(x, axis, masked_value=masked_value)
             assert np.array_equal(pc.counts.cpu().numpy(), ref_counts), (dtype, mask, off, axis)
             assert int(pc.counts[0].sum()) == npairs
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "float16", "int32", "uint8"])
+@pytest.mark.parametrize("pattern", ["none", "blocks", "alternating", "sparse", "ends", "all", "slabs"])
+def test_both_flavours_of_the_masked_kernels_agree_with_the_oracle(dtype, pattern):
+    """The masked fast kernels exist in a boundary-correction ("sparse") and a three-stream
+    ("dense") flavour, picked on the device from a sampled boundary density.  Forced either
+    way, and left to choose, each must give the oracle's counts on every mask pattern."""
+    import torch
+
+    from xbitinfo_b200.device import PairCounter
+
+    isfloat = np.dtype(dtype).kind == "f"
+    rng = np.random.default_rng(41)
+    for shape, axis in (((24, 8200), 1), ((900, 3, 64), 0)):
+        if isfloat:
+            x = smooth_field(rng, shape, dtype, axis=axis, scale=0.3, base=2.0)
+        else:
+            info = np.iinfo(dtype)
+            x = rng.integers(info.min, info.max, size=shape, dtype=dtype, endpoint=True)
+        mv = float("nan") if isfloat else 7
+        _mask_pattern(x, pattern, rng, mv)
+        ref_counts, npairs, _ = bo.bitinformation(x, axis, masked_value=mv)
+        t = torch.from_numpy(x).cuda()
+        for flavour in ("sparse", "dense", None):
+            pc = PairCounter(t.dtype, t.device)
+            before = nat.fast_path_launches()
+            pc.add(t, axis, masked_value=mv, flavour=flavour)
+            assert nat.fast_path_launches() > before
+            assert np.array_equal(pc.counts.cpu().numpy(), ref_counts), (dtype, pattern, shape, flavour)
+            assert int(pc.counts[0].sum()) == npairs

@@ -87,6 +87,15 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
     bool edges_done = false;
     if (!(flags & XBI_FORCE_GENERIC)) {
         const bool timed = g_prof.enabled && g_prof.used < Profile::kMax;
+        // masked modes: sample the density of validity boundaries; the sparse and the dense flavour of
+        // the fast kernels both read it and one of them returns at once
+        if (flags & XBI_FORCE_DENSE) {
+            static const unsigned long long kForceDense[2] = {1ull, 0ull};  // "every sampled pair is a boundary"
+            XBI_CUDA(cudaMemcpyAsync(ws->plus.pad, kForceDense, sizeof(kForceDense), cudaMemcpyHostToDevice, stream),
+                     "cudaMemcpyAsync(flavour)");
+        } else if (!(flags & XBI_FORCE_SPARSE)) {
+            XBI_CUDA(launch_mask_density(job, npairs_flat, ws, stream), "mask density sample");
+        }
         if (timed) XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used), stream), "cudaEventRecord");
         if (job.inner == 1)
             XBI_CUDA(launch_pairs_tma(job, npairs_flat, ws, stream, &dlo, &dhi, &edges_done), "pair counting (TMA rows)");

@@ -41,6 +41,13 @@ struct Workspace {
 
 enum Stream { S_A = 0, S_B = 1, S_AB = 2 };
 
+// plus.pad[0] / pad[1]: validity boundaries / pairs seen by the sampling kernel.  The masked
+// fast kernels take the dense flavour when more than one sampled pair in `one_in` is a boundary.
+__device__ __forceinline__ bool sampled_mask_is_dense(const RawSums* plus, unsigned long long one_in) {
+    const volatile unsigned long long* p = plus->pad;
+    return p[0] * one_in > p[1];
+}
+
 // ---------------------------------------------------------------------------------
 // carry-save adder on bit planes: (hi, lo) = a + b + c per bit position
 // ---------------------------------------------------------------------------------

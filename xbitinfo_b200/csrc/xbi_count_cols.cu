@@ -81,15 +81,18 @@ struct ColWalker {
     static constexpr int BYTES = Elem<KIND>::kBytes;
     static constexpr bool K64 = (BYTES == 8);
     static constexpr bool MASKED = (MASK != kMaskNone);
+    static constexpr bool DENSE = MaskMode<MASK>::kDense;  // three explicit streams under keep-masks (scattered masks)
+    static constexpr int MT = MaskMode<MASK>::kTest;       // kMaskNone / kMaskNaN / kMaskValue
     static constexpr int NL = K64 ? 2 : 1;    // ladders per stream (low / high words)
     static constexpr int LOGC = K64 ? 3 : 4;  // 4 rows give 8 low + 8 high words, or 16 words
     static constexpr bool WHOLE = (BYTES >= 4);  // an element is one or two whole words
     static constexpr int WPE = K64 ? 2 : 1;      // words per element (whole-word types)
     static constexpr int EPC = 16 / BYTES;       // elements per 16-byte chunk
-    using L = Ladder<3, (NL * 2 >= 4 ? 5 : 8), LOGC>;
+    static constexpr int kNumLadders = NL * (DENSE ? 3 : 2);
+    using L = Ladder<3, (kNumLadders >= 6 ? 4 : kNumLadders >= 4 ? 5 : 8), LOGC>;
 
-    L Bl[NL], ABl[NL];
-    unsigned long long accB[NL], accAB[NL];
+    L Bl[NL], ABl[NL], Al[DENSE ? NL : 1];
+    unsigned long long accB[NL], accAB[NL], accA[NL];
     uint32_t prev[4];
     uint32_t pm;            // masked modes, whole-word types: bit e = element e of prev is masked
     uint32_t prev_keep[4];  // masked modes, packed types: keep-mask of prev ...
@@ -98,9 +101,9 @@ struct ColWalker {
     uint32_t vrep;      // whole-word types: bit EPC*r + e set = element e of the chunk exists (last chunk
                         // of a row whose length is not a multiple of 16 bytes), replicated for 4 rows
     uint32_t it;
-    uint32_t ninvalid;  // pairs with a masked element since the last flush
+    uint32_t ninvalid;  // sparse flavour: pairs with a masked element, dense flavour: valid pairs (since the last flush)
     unsigned long long ninvalid_total;
-    static constexpr int kEvWords = MASKED ? Elem<KIND>::kWords : 1;
+    static constexpr int kEvWords = (MASKED && !DENSE) ? Elem<KIND>::kWords : 1;
     static constexpr int kEvPlanes = K64 ? 3 : 5;  // 64-bit types (two words per element): 3 planes, one row per reserve
     EventPlanes<kEvWords, kEvPlanes> er;            // boundary corrections of the masked modes
     unsigned long long (*s_minus)[64];              // the block's shared correction totals (flush target)
@@ -108,7 +111,11 @@ struct ColWalker {
     __device__ __forceinline__ void init(unsigned long long (*shared_minus)[64]) {
         s_minus = shared_minus;
 #pragma unroll
-        for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); accB[i] = 0; accAB[i] = 0; }
+        for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); accB[i] = 0; accAB[i] = 0; accA[i] = 0; }
+        if (DENSE) {
+#pragma unroll
+            for (int i = 0; i < NL; ++i) Al[i].clear();
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) { prev[i] = 0u; prev_keep[i] = 0u; }
         prev_clean = true;
@@ -118,13 +125,13 @@ struct ColWalker {
         it = 0;
         ninvalid = 0;
         ninvalid_total = 0;
-        if (MASKED) er.init();
+        if (MASKED && !DENSE) er.init();
     }
 
     __device__ __forceinline__ void flush(uint32_t lane) {
         if (!lane_live) {  // whatever an idle lane gathered since the last flush is discarded
 #pragma unroll
-            for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); }
+            for (int i = 0; i < NL; ++i) { Bl[i].clear(); ABl[i].clear(); if (DENSE) Al[i].clear(); }
             ninvalid = 0;
         }
 #pragma unroll
@@ -132,6 +139,7 @@ struct ColWalker {
             accB[i] += Bl[i].warp_totals(lane, it);
             accAB[i] += ABl[i].warp_totals(lane, it);
             Bl[i].clear(); ABl[i].clear();
+            if (DENSE) { accA[i] += Al[i].warp_totals(lane, it); Al[i].clear(); }
         }
         ninvalid_total += ninvalid;
         ninvalid = 0;
@@ -141,18 +149,27 @@ struct ColWalker {
     // first row of a work item (raw words; `live` = the chunk exists)
     __device__ __forceinline__ void start(const uint4& v, bool live, uint32_t mlo, uint32_t mhi) {
         prev[0] = v.x; prev[1] = v.y; prev[2] = v.z; prev[3] = v.w;
+        if constexpr (DENSE) {
+            keep_chunk<KIND, MT>(prev, mlo, mhi, prev_keep);
+            xform_chunk<KIND, XFORM>(prev);
+            if (!live) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { prev[i] = 0u; prev_keep[i] = 0u; }
+            }
+            return;
+        }
         if constexpr (MASKED && WHOLE) {
             pm = 0u;
 #pragma unroll
             for (int e = 0; e < EPC; ++e) {
-                if (masked_elem<KIND, MASK>(prev[WPE * e], prev[WPE * e + WPE - 1], mlo, mhi)) {
+                if (masked_elem<KIND, MT>(prev[WPE * e], prev[WPE * e + WPE - 1], mlo, mhi)) {
                     pm |= 1u << e;
 #pragma unroll
                     for (int k = 0; k < WPE; ++k) prev[WPE * e + k] = neutral_word<KIND, XFORM>(k);
                 }
             }
         } else if constexpr (MASKED) {
-            keep_chunk<KIND, MASK>(prev, mlo, mhi, prev_keep);
+            keep_chunk<KIND, MT>(prev, mlo, mhi, prev_keep);
         }
         xform_chunk<KIND, XFORM>(prev);
         if constexpr (MASKED && !WHOLE) {
@@ -170,6 +187,62 @@ struct ColWalker {
 
     // fold 4 rows; rows >= nrows are absent (tail group only)
     __device__ __forceinline__ void process(const uint4 (&buf)[4], int nrows, uint32_t mlo, uint32_t mhi, uint32_t lane) {
+        if constexpr (DENSE) {
+            // ---- dense flavour: a, b and a&b formed explicitly under the pair's keep-mask ----
+            uint32_t wa[4][4], wb[4][4], wab[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                uint32_t c[4] = {buf[r].x, buf[r].y, buf[r].z, buf[r].w};
+                uint32_t keep[4], v[4];
+                keep_chunk<KIND, MT>(c, mlo, mhi, keep);
+                xform_chunk<KIND, XFORM>(c);
+                const bool present = r < nrows;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    v[i] = present ? (keep[i] & prev_keep[i]) : 0u;
+                    wa[r][i] = prev[i] & v[i];
+                    wb[r][i] = c[i] & v[i];
+                    wab[r][i] = wa[r][i] & wb[r][i];
+                    if (present) { prev_keep[i] = keep[i]; prev[i] = c[i]; }
+                }
+                ninvalid += count_chunk<BYTES>(v);
+            }
+            if constexpr (!K64) {
+                uint32_t f[16];
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wa[r][i];
+                Al[0].add_chunk(f, it);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wb[r][i];
+                Bl[0].add_chunk(f, it);
+#pragma unroll
+                for (int r = 0; r < 4; ++r)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) f[4 * r + i] = wab[r][i];
+                ABl[0].add_chunk(f, it);
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t f[1 << LOGC];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { f[2 * r] = wa[r][h]; f[2 * r + 1] = wa[r][h + 2]; }
+                    Al[DENSE ? h % NL : 0].add_chunk(f, it);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { f[2 * r] = wb[r][h]; f[2 * r + 1] = wb[r][h + 2]; }
+                    Bl[h % NL].add_chunk(f, it);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) { f[2 * r] = wab[r][h]; f[2 * r + 1] = wab[r][h + 2]; }
+                    ABl[h % NL].add_chunk(f, it);
+                }
+            }
+            ++it;
+            if (it == L::kFlushChunks) flush(lane);
+            return;
+        }
         uint32_t cur[4][4];
         bool skip = false;  // warp-uniform: nothing in this group (nor the row above it) is valid
         if constexpr (MASKED && WHOLE) {
@@ -183,10 +256,10 @@ struct ColWalker {
                 uint32_t raw[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) raw[j] = cur[j >> 2][j & 3];
-                const bool tdirty = (pm != 0u) || may_contain_masked<KIND, MASK>(raw, mlo, mhi);
+                const bool tdirty = (pm != 0u) || may_contain_masked<KIND, MT>(raw, mlo, mhi);
                 if (__any_sync(0xFFFFFFFFu, tdirty)) {
                     warp_dirty = true;
-                    const bool allm = (pm == kRowMask) && all_masked_quick<KIND, MASK>(raw, mlo, mhi);
+                    const bool allm = (pm == kRowMask) && all_masked_quick<KIND, MT>(raw, mlo, mhi);
                     if (__all_sync(0xFFFFFFFFu, allm)) {
                         ninvalid += (uint32_t)nrows * (uint32_t)__popc(vrep & kRowMask);
                         return;  // nothing valid in the whole warp: prev stays zero, pm stays all-masked
@@ -194,7 +267,7 @@ struct ColWalker {
                     if (tdirty) {
 #pragma unroll
                         for (int j = 0; j < 4 * EPC; ++j) {
-                            if (masked_elem<KIND, MASK>(raw[WPE * j], raw[WPE * j + WPE - 1], mlo, mhi)) {
+                            if (masked_elem<KIND, MT>(raw[WPE * j], raw[WPE * j + WPE - 1], mlo, mhi)) {
                                 m |= 1u << j;
                                 // overwritten with the value whose transform is 0: drops out of every sum
 #pragma unroll
@@ -248,7 +321,7 @@ struct ColWalker {
             uint32_t raw[16];
 #pragma unroll
             for (int r = 0; r < 4; ++r) { raw[4 * r] = buf[r].x; raw[4 * r + 1] = buf[r].y; raw[4 * r + 2] = buf[r].z; raw[4 * r + 3] = buf[r].w; }
-            const bool dirty = __any_sync(0xFFFFFFFFu, !prev_clean || may_contain_masked<KIND, MASK>(raw, mlo, mhi));
+            const bool dirty = __any_sync(0xFFFFFFFFu, !prev_clean || may_contain_masked<KIND, MT>(raw, mlo, mhi));
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
 #pragma unroll
@@ -265,7 +338,7 @@ struct ColWalker {
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const uint32_t rw[4] = {raw[4 * r], raw[4 * r + 1], raw[4 * r + 2], raw[4 * r + 3]};
-                    keep_chunk<KIND, MASK>(rw, mlo, mhi, keep[r]);
+                    keep_chunk<KIND, MT>(rw, mlo, mhi, keep[r]);
                     if (r < nrows) anyk |= keep[r][0] | keep[r][1] | keep[r][2] | keep[r][3];
                 }
                 if (__all_sync(0xFFFFFFFFu, anyk == 0u)) {
@@ -381,29 +454,38 @@ struct ColWalker {
             const int j = K64 ? (i * 32 + (int)lane) : ((int)lane % (8 * BYTES));
             // the a-stream is the b-stream shifted up one row; the launcher adds the first row of
             // the matrix and subtracts the last one (row-plane passes)
-            if (accB[i]) atomicAdd(&s_sum[S_A][j], accB[i]);
+            const unsigned long long a = DENSE ? accA[i] : accB[i];
+            if (a) atomicAdd(&s_sum[S_A][j], a);
             if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
             if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
         }
         if (MASKED) {
             if (ninvalid_total) atomicAdd(s_n, ninvalid_total);
-            er.flush(lane, s_minus, 8 * BYTES);
+            if (!DENSE) er.flush(lane, s_minus, 8 * BYTES);
         }
         __syncthreads();
         for (int i = threadIdx.x; i < 3 * 64; i += nthreads) {
             const unsigned long long v = (&s_sum[0][0])[i];
             if (v) atomicAdd(&ws->plus.sums[0][0] + i, v);
         }
-        if (MASKED) {
+        if (MASKED && !DENSE) {
             for (int i = threadIdx.x; i < 2 * 64; i += nthreads) {
                 const unsigned long long v = (&s_minus[0][0])[i];
                 if (v) atomicAdd(&ws->minus.sums[0][0] + i, v);  // [S_A], [S_B] are the first two rows
             }
             if (threadIdx.x == 0 && *s_n) atomicAdd(&ws->minus.npairs, *s_n);
         }
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&ws->plus.npairs, flat_pairs);
+        if (DENSE) {
+            if (threadIdx.x == 0 && *s_n) atomicAdd(&ws->plus.npairs, *s_n);  // valid pairs, counted directly
+        } else if (blockIdx.x == 0 && threadIdx.x == 0) {
+            atomicAdd(&ws->plus.npairs, flat_pairs);
+        }
     }
 };
+
+// the column walkers take the dense flavour when more than one sampled pair in this many is a
+// validity boundary (measured break-even of the two flavours: about 1.4 % boundaries)
+constexpr unsigned long long kColsDenseOneIn = 96ull;
 
 constexpr int kStripBytes = 512;               // a warp's slice of a row: 32 lanes x 16 bytes
 constexpr int kTileBytes = 4 * kStripBytes;     // one 4-row group of a warp
@@ -466,6 +548,9 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
     using W = ColWalker<KIND, MASK, XFORM>;
     constexpr int BYTES = W::BYTES;
     static_assert(G == 16 || G == BYTES, "short copies are element sized");
+    // sparse and dense flavours are both launched; the sampled boundary density picks one
+    // (element-aligned rows exist in the sparse flavour only: it knows about the padded last chunk)
+    if (W::MASKED && G == 16 && sampled_mask_is_dense(&ws->plus, kColsDenseOneIn) != W::DENSE) return;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
@@ -804,6 +889,10 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
         cudaError_t e;
         if (aligned) {
             e = launch_cols_async<KIND, MASK, XFORM, 16>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
+            if constexpr (MASK != kMaskNone) {  // the other flavour; one of the two returns at once
+                if (e == cudaSuccess)
+                    e = launch_cols_async<KIND, MASK + 2, XFORM, 16>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
+            }
         } else {
             if constexpr (BYTES >= 4) e = launch_cols_async<KIND, MASK, XFORM, BYTES>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
             else e = cudaErrorInvalidValue;
@@ -812,10 +901,12 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
     }
     {
         // a-stream correction: + planes(first row) - planes(row after the last pair row)
-        // (masked elements contribute nothing, as in the walkers)
-        cudaError_t e = launch_elem_planes(job, 0, job.inner, &ws->plus, stream);
+        // (masked elements contribute nothing, as in the walkers; the dense flavour forms its
+        // a-stream explicitly, so these passes return at once when it is the one that ran)
+        const RawSums* flavour = (MASK != kMaskNone && aligned) ? &ws->plus : nullptr;
+        cudaError_t e = launch_elem_planes(job, 0, job.inner, &ws->plus, stream, flavour, kColsDenseOneIn);
         if (e != cudaSuccess) return e;
-        e = launch_elem_planes(job, pair_rows * job.inner, job.inner, &ws->minus, stream);
+        e = launch_elem_planes(job, pair_rows * job.inner, job.inner, &ws->minus, stream, flavour, kColsDenseOneIn);
         if (e != cudaSuccess) return e;
     }
     if (job.outer > 1 && aligned) {

@@ -22,8 +22,10 @@ constexpr int kPairsPerTile = 16 * kThreads;
 template <int KIND, int MASK, bool XFORM, int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long long n, long long inner,
-                uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst) {
+                uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst, const RawSums* dense_probe,
+                unsigned long long dense_one_in) {
     using E = Elem<KIND>;
+    if (MODE == 2 && dense_probe != nullptr && sampled_mask_is_dense(dense_probe, dense_one_in)) return;
     constexpr int NW = E::kWords;
     using L = Ladder<3, 6>;
     L A[NW], B[NW], AB[NW];
@@ -131,8 +133,52 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
     if (threadIdx.x == 0 && s_n) atomicAdd(&dst->npairs, s_n);
 }
 
+// validity boundaries among `nsamples` flat pairs (f, f + inner), f = i * stride
+template <int KIND, int MASK>
+__global__ void __launch_bounds__(kThreads)
+k_mask_density(const void* __restrict__ x, long long nsamples, long long stride, long long inner, uint32_t mask_lo,
+               uint32_t mask_hi, RawSums* __restrict__ plus) {
+    using E = Elem<KIND>;
+    unsigned bnd = 0, pairs = 0;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nsamples; i += (long long)gridDim.x * kThreads) {
+        const long long f = i * stride;
+        uint32_t a[E::kWords], b[E::kWords];
+        E::load(x, f, a);
+        E::load(x, f + inner, b);
+        const bool ma = (MASK == kMaskNaN) ? E::is_nan(a) : E::equals(a, mask_lo, mask_hi);
+        const bool mb = (MASK == kMaskNaN) ? E::is_nan(b) : E::equals(b, mask_lo, mask_hi);
+        bnd += (ma != mb) ? 1u : 0u;
+        pairs += 1u;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        bnd += __shfl_xor_sync(0xFFFFFFFFu, bnd, o);
+        pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
+    }
+    if ((threadIdx.x & 31u) == 0u) {
+        if (bnd) atomicAdd(&plus->pad[0], (unsigned long long)bnd);
+        if (pairs) atomicAdd(&plus->pad[1], (unsigned long long)pairs);
+    }
+}
+
+template <int KIND>
+cudaError_t launch_density_kind(const CountJob& job, long long nsamples, long long stride, Workspace* ws, cudaStream_t stream) {
+    constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
+    const unsigned grid = (unsigned)((nsamples + kThreads - 1) / kThreads < 592 ? (nsamples + kThreads - 1) / kThreads : 592);
+    const uint32_t mlo = (uint32_t)(job.mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(job.mask_bits >> 32);
+    if (job.mask_mode == kMaskNaN) {
+        if constexpr (isf) k_mask_density<KIND, kMaskNaN><<<grid, kThreads, 0, stream>>>(job.x, nsamples, stride, job.inner, mlo, mhi, &ws->plus);
+        else return cudaErrorInvalidValue;
+    } else {
+        k_mask_density<KIND, kMaskValue><<<grid, kThreads, 0, stream>>>(job.x, nsamples, stride, job.inner, mlo, mhi, &ws->plus);
+    }
+    note_launch();
+    return cudaGetLastError();
+}
+
 template <int KIND, int MASK, bool XFORM, int MODE>
-cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
+cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream,
+                       const RawSums* dense_probe, unsigned long long dense_one_in) {
     if (count <= 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -142,44 +188,46 @@ cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSu
     if (grid > tiles) grid = tiles;
     k_pairs_generic<KIND, MASK, XFORM, MODE><<<(unsigned)grid, kThreads, 0, stream>>>(
         job.x, lo, count, job.n, job.inner, (uint32_t)(job.mask_bits & 0xFFFFFFFFu),
-        (uint32_t)(job.mask_bits >> 32), dst);
+        (uint32_t)(job.mask_bits >> 32), dst, dense_probe, dense_one_in);
     note_launch();
     return cudaGetLastError();
 }
 
 template <int KIND, int MODE>
-cudaError_t dispatch_mask(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
+cudaError_t dispatch_mask(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream,
+                          const RawSums* dense_probe, unsigned long long dense_one_in) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (job.transform) {
         if constexpr (isf) {
             switch (job.mask_mode) {
-                case kMaskNone: return launch_one<KIND, kMaskNone, true, MODE>(job, lo, count, dst, stream);
-                case kMaskNaN: return launch_one<KIND, kMaskNaN, true, MODE>(job, lo, count, dst, stream);
-                default: return launch_one<KIND, kMaskValue, true, MODE>(job, lo, count, dst, stream);
+                case kMaskNone: return launch_one<KIND, kMaskNone, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+                case kMaskNaN: return launch_one<KIND, kMaskNaN, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+                default: return launch_one<KIND, kMaskValue, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
             }
         } else {
             return cudaErrorInvalidValue;
         }
     }
     switch (job.mask_mode) {
-        case kMaskNone: return launch_one<KIND, kMaskNone, false, MODE>(job, lo, count, dst, stream);
+        case kMaskNone: return launch_one<KIND, kMaskNone, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
         case kMaskNaN:
-            if constexpr (isf) return launch_one<KIND, kMaskNaN, false, MODE>(job, lo, count, dst, stream);
+            if constexpr (isf) return launch_one<KIND, kMaskNaN, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
             return cudaErrorInvalidValue;
-        default: return launch_one<KIND, kMaskValue, false, MODE>(job, lo, count, dst, stream);
+        default: return launch_one<KIND, kMaskValue, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
     }
 }
 
 template <int MODE>
-cudaError_t dispatch_kind(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream) {
+cudaError_t dispatch_kind(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream,
+                          const RawSums* dense_probe = nullptr, unsigned long long dense_one_in = 0) {
     switch (job.dtype) {
-        case XBI_U8: return dispatch_mask<kU8, MODE>(job, lo, count, dst, stream);
-        case XBI_U16: return dispatch_mask<kU16, MODE>(job, lo, count, dst, stream);
-        case XBI_U32: return dispatch_mask<kU32, MODE>(job, lo, count, dst, stream);
-        case XBI_U64: return dispatch_mask<kU64, MODE>(job, lo, count, dst, stream);
-        case XBI_F16: return dispatch_mask<kF16, MODE>(job, lo, count, dst, stream);
-        case XBI_F32: return dispatch_mask<kF32, MODE>(job, lo, count, dst, stream);
-        case XBI_F64: return dispatch_mask<kF64, MODE>(job, lo, count, dst, stream);
+        case XBI_U8: return dispatch_mask<kU8, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_U16: return dispatch_mask<kU16, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_U32: return dispatch_mask<kU32, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_U64: return dispatch_mask<kU64, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_F16: return dispatch_mask<kF16, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_F32: return dispatch_mask<kF32, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_F64: return dispatch_mask<kF64, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -200,8 +248,27 @@ cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int
     return dispatch_kind<1>(job, t_begin, t_end - t_begin, dst, stream);
 }
 
-cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream) {
-    return dispatch_kind<2>(job, lo, count, dst, stream);
+cudaError_t launch_mask_density(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream) {
+    if (job.mask_mode == kMaskNone || npairs_flat <= 0) return cudaSuccess;
+    long long nsamples = npairs_flat < (1ll << 18) ? npairs_flat : (1ll << 18);
+    long long stride = npairs_flat / nsamples;
+    if (stride > 1) stride |= 1;  // odd: does not lock onto even row lengths
+    while (stride > 1 && (nsamples - 1) * stride >= npairs_flat) --nsamples;
+    switch (job.dtype) {
+        case XBI_U8: return launch_density_kind<kU8>(job, nsamples, stride, ws, stream);
+        case XBI_U16: return launch_density_kind<kU16>(job, nsamples, stride, ws, stream);
+        case XBI_U32: return launch_density_kind<kU32>(job, nsamples, stride, ws, stream);
+        case XBI_U64: return launch_density_kind<kU64>(job, nsamples, stride, ws, stream);
+        case XBI_F16: return launch_density_kind<kF16>(job, nsamples, stride, ws, stream);
+        case XBI_F32: return launch_density_kind<kF32>(job, nsamples, stride, ws, stream);
+        case XBI_F64: return launch_density_kind<kF64>(job, nsamples, stride, ws, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream,
+                               const RawSums* dense_probe, unsigned long long dense_one_in) {
+    return dispatch_kind<2>(job, lo, count, dst, stream, dense_probe, dense_one_in);
 }
 
 }  // namespace xbi

@@ -97,8 +97,12 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     constexpr int BYTES = S::kBytes;
     constexpr int NL = S::kLaddersPerStream;
     constexpr bool MASKED = (MASK != kMaskNone);
-    constexpr int kNumLadders = NL * 2;
-    using L = Ladder<3, (kNumLadders >= 4 ? 5 : 8)>;
+    constexpr bool DENSE = MaskMode<MASK>::kDense;  // three explicit streams (scattered masks)
+    constexpr int MT = MaskMode<MASK>::kTest;       // kMaskNone / kMaskNaN / kMaskValue
+    constexpr int kNumLadders = NL * (DENSE ? 3 : 2);
+    using L = Ladder<3, (kNumLadders >= 6 ? 3 : kNumLadders >= 4 ? 5 : 8)>;
+    // sparse and dense flavours are both launched; the sampled boundary density picks one
+    if (MASKED && sampled_mask_is_dense(dst, 512ull) != DENSE) return;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
@@ -172,8 +176,8 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                     a[0] = v.x; b[0] = v.y;
                 }
                 bool ok = (okmask >> k) & 1u;
-                if (MASK == kMaskNaN) ok = ok && !(E::is_nan(a) || E::is_nan(b));
-                if (MASK == kMaskValue) ok = ok && !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
+                if (MT == kMaskNaN) ok = ok && !(E::is_nan(a) || E::is_nan(b));
+                if (MT == kMaskValue) ok = ok && !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
                 if (XFORM) { E::transform(a); E::transform(b); }
 #pragma unroll
                 for (int w = 0; w < NW; ++w) { wa[w][k] = ok ? a[w] : 0u; wb[w][k] = ok ? b[w] : 0u; }
@@ -279,15 +283,20 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     const uint32_t nb_off = nb_same_row ? (row * kRowBytes + (((cbase + S::kSegChunks) ^ swz) << 4))
                                         : ((row + 1) * kRowBytes + (((row + 1) & 7u) << 4));
 
-    L A[NL], AB[NL];
+    L A[NL], AB[NL], B[DENSE ? NL : 1];
 #pragma unroll
     for (int i = 0; i < NL; ++i) { A[i].clear(); AB[i].clear(); }
-    unsigned long long accA[NL], accAB[NL];
+    if (DENSE) {
 #pragma unroll
-    for (int i = 0; i < NL; ++i) { accA[i] = 0; accAB[i] = 0; }
-    uint32_t ninvalid = 0;  // pairs with a masked element (this thread, since the last flush)
+        for (int i = 0; i < NL; ++i) B[i].clear();
+    }
+    unsigned long long accA[NL], accAB[NL], accB[NL];
+#pragma unroll
+    for (int i = 0; i < NL; ++i) { accA[i] = 0; accAB[i] = 0; accB[i] = 0; }
+    // sparse flavour: pairs with a masked element; dense flavour: valid pairs (this thread, since the last flush)
+    uint32_t ninvalid = 0;
     unsigned long long ninvalid_total = 0;
-    BoundaryEvents<MASKED ? Elem<KIND>::kWords : 1> ev;
+    BoundaryEvents<(MASKED && !DENSE) ? Elem<KIND>::kWords : 1> ev;
     ev.init();
     uint32_t it = 0;
 
@@ -297,6 +306,7 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
             accA[i] += A[i].warp_totals(lane, it);
             accAB[i] += AB[i].warp_totals(lane, it);
             A[i].clear(); AB[i].clear();
+            if (DENSE) { accB[i] += B[i].warp_totals(lane, it); B[i].clear(); }
         }
         ninvalid_total += ninvalid;
         ninvalid = 0;
@@ -327,15 +337,51 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
         }
         bool skip = false;  // warp-uniform: every element this warp holds is masked
 
-        if constexpr (BYTES < 4) {
+        if constexpr (DENSE) {
+            // ---- dense flavour: a, b and a&b formed explicitly under the pair's keep-mask ----
+            if constexpr (!S::k64) {
+                uint32_t tw[17], keep[17];
+#pragma unroll
+                for (int i = 0; i < 17; ++i) { tw[i] = xform_word<KIND, XFORM>(w[i]); keep[i] = keep_word<KIND, MT>(w[i], mask_lo); }
+                uint32_t a[16], b[16], ab[16];
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const uint32_t v = keep[i] & successor_word<BYTES>(keep[i], keep[i + 1]);
+                    a[i] = tw[i] & v;
+                    b[i] = successor_word<BYTES>(tw[i], tw[i + 1]) & v;
+                    ab[i] = a[i] & b[i];
+                    ninvalid += count_fields<BYTES>(v);
+                }
+                A[0].add16(a, it);
+                B[0].add16(b, it);
+                AB[0].add16(ab, it);
+            } else {
+                uint32_t lo[17], hi[17], keep[17];
+#pragma unroll
+                for (int e = 0; e < 17; ++e) {
+                    lo[e] = w[2 * e];
+                    hi[e] = (XFORM && KIND == kF64) ? sexp_f64_hi(w[2 * e + 1]) : w[2 * e + 1];
+                    keep[e] = keep_elem64<KIND, MT>(w[2 * e], w[2 * e + 1], mask_lo, mask_hi);
+                }
+                uint32_t v[16], x0[16], x1[16], x2[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { v[e] = keep[e] & keep[e + 1]; ninvalid += v[e] & 1u; }
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { x0[e] = lo[e] & v[e]; x1[e] = lo[e + 1] & v[e]; x2[e] = x0[e] & x1[e]; }
+                A[0].add16(x0, it); B[0].add16(x1, it); AB[0].add16(x2, it);
+#pragma unroll
+                for (int e = 0; e < 16; ++e) { x0[e] = hi[e] & v[e]; x1[e] = hi[e + 1] & v[e]; x2[e] = x0[e] & x1[e]; }
+                A[NL - 1].add16(x0, it); B[DENSE ? NL - 1 : 0].add16(x1, it); AB[NL - 1].add16(x2, it);
+            }
+        } else if constexpr (BYTES < 4) {
             // ---- packed 8/16-bit elements (a NaN / value mask is decided on keep-masks) ----
             uint32_t tw[17];
 #pragma unroll
             for (int i = 0; i < 17; ++i) tw[i] = xform_word<KIND, XFORM>(w[i]);
-            if (MASKED && __any_sync(0xFFFFFFFFu, may_contain_masked<KIND, MASK>(w, mask_lo, mask_hi))) {
+            if (MASKED && __any_sync(0xFFFFFFFFu, may_contain_masked<KIND, MT>(w, mask_lo, mask_hi))) {
                 uint32_t keep[17], anyk = 0u;
 #pragma unroll
-                for (int i = 0; i < 17; ++i) { keep[i] = keep_word<KIND, MASK>(w[i], mask_lo); anyk |= keep[i]; }
+                for (int i = 0; i < 17; ++i) { keep[i] = keep_word<KIND, MT>(w[i], mask_lo); anyk |= keep[i]; }
                 if (__all_sync(0xFFFFFFFFu, anyk == 0u)) {
                     ninvalid += 16u * (4u / BYTES);
                     skip = true;
@@ -377,16 +423,16 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
             // hold one pay for the exact test, the zeroing and the corrections. ----
             constexpr int WPE = S::k64 ? 2 : 1;
             if (MASKED) {
-                const bool tdirty = may_contain_masked<KIND, MASK>(w, mask_lo, mask_hi);
+                const bool tdirty = may_contain_masked<KIND, MT>(w, mask_lo, mask_hi);
                 if (__any_sync(0xFFFFFFFFu, tdirty)) {
-                    if (__all_sync(0xFFFFFFFFu, all_masked_quick<KIND, MASK>(w, mask_lo, mask_hi))) {
+                    if (__all_sync(0xFFFFFFFFu, all_masked_quick<KIND, MT>(w, mask_lo, mask_hi))) {
                         ninvalid += 16u;
                         skip = true;
                     } else if (tdirty) {
                         uint32_t m = 0u;  // bit e: element e (0..16) is masked
 #pragma unroll
                         for (int e = 0; e < 17; ++e) {
-                            if (masked_elem<KIND, MASK>(w[WPE * e], w[WPE * e + WPE - 1], mask_lo, mask_hi)) {
+                            if (masked_elem<KIND, MT>(w[WPE * e], w[WPE * e + WPE - 1], mask_lo, mask_hi)) {
                                 m |= 1u << e;
                                 // overwritten with the value whose transform is 0: drops out of every sum
 #pragma unroll
@@ -475,26 +521,31 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
         const int j = S::k64 ? (i * 32 + (int)lane) : ((int)lane % S::kBits);
         if (accA[i]) atomicAdd(&s_sum[S_A][j], accA[i]);
         if (accAB[i]) atomicAdd(&s_sum[S_AB][j], accAB[i]);
-        if (accA[i]) atomicAdd(&s_sum[S_B][j], accA[i]);  // shifted by one element: corrected below (block 0)
+        if (DENSE) {
+            if (accB[i]) atomicAdd(&s_sum[S_B][j], accB[i]);
+        } else {
+            if (accA[i]) atomicAdd(&s_sum[S_B][j], accA[i]);  // shifted by one element: corrected below (block 0)
+        }
     }
     if (MASKED) {
         if (ninvalid_total) atomicAdd(&s_ninvalid, ninvalid_total);
-        ev.drain(s_minus, S::kBits, lane);
+        if (!DENSE) ev.drain(s_minus, S::kBits, lane);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
     for (int i = t; i < 3 * 64; i += kCountThreads) {
         const unsigned long long v = (&s_sum[0][0])[i];
         if (v) atomicAdd(&dst->sums[0][0] + i, v);
     }
-    if (MASKED) {
+    if (MASKED && !DENSE) {
         for (int i = t; i < 2 * 64; i += kCountThreads) {
             const unsigned long long v = (&s_minus[0][0])[i];
             if (v) atomicAdd(&dst_minus->sums[0][0] + i, v);  // [S_A], [S_B] are the first two rows
         }
         if (t == 0 && s_ninvalid) atomicAdd(&dst_minus->npairs, s_ninvalid);
     }
+    if (DENSE && t == 0 && s_ninvalid) atomicAdd(&dst->npairs, s_ninvalid);  // valid pairs, counted directly
 
-    if (blockIdx.x == 0 && t < 64) {
+    if (!DENSE && blockIdx.x == 0 && t < 64) {
         // b-stream = a-stream shifted by one element: + bits(element after the region) - bits(first element)
         using E = Elem<KIND>;
         const long long last = nstages * (long long)S::kElemsPerStage;
@@ -502,8 +553,8 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
         E::load(region, 0, first_w);
         E::load(region, last, last_w);
         bool first_ok = true, last_ok = true;
-        if (MASK == kMaskNaN) { first_ok = !E::is_nan(first_w); last_ok = !E::is_nan(last_w); }
-        if (MASK == kMaskValue) { first_ok = !E::equals(first_w, mask_lo, mask_hi); last_ok = !E::equals(last_w, mask_lo, mask_hi); }
+        if (MT == kMaskNaN) { first_ok = !E::is_nan(first_w); last_ok = !E::is_nan(last_w); }
+        if (MT == kMaskValue) { first_ok = !E::equals(first_w, mask_lo, mask_hi); last_ok = !E::equals(last_w, mask_lo, mask_hi); }
         if (XFORM) { E::transform(first_w); E::transform(last_w); }
         if ((int)t < S::kBits) {
             const uint32_t wsel = t >> 5, bsel = t & 31u;
@@ -580,8 +631,17 @@ cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, Workspace* d
         if constexpr (isf) {
             switch (job.mask_mode) {
                 case kMaskNone: return launch_rows<KIND, kMaskNone, true>(job, npairs_flat, dst, stream, lo, hi, ed);
-                case kMaskNaN: return launch_rows<KIND, kMaskNaN, true>(job, npairs_flat, dst, stream, lo, hi, ed);
-                default: return launch_rows<KIND, kMaskValue, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                // masked: both flavours are launched, one of them returns at once (see xbi_internal.h)
+                case kMaskNaN: {
+                    const cudaError_t e = launch_rows<KIND, kMaskNaN, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                    if (e != cudaSuccess || *hi <= *lo) return e;
+                    return launch_rows<KIND, kMaskNaNDense, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                }
+                default: {
+                    const cudaError_t e = launch_rows<KIND, kMaskValue, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                    if (e != cudaSuccess || *hi <= *lo) return e;
+                    return launch_rows<KIND, kMaskValueDense, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                }
             }
         }
         return cudaSuccess;
@@ -591,7 +651,9 @@ cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, Workspace* d
     if (job.mask_mode == kMaskNaN) return cudaSuccess;
     constexpr int UK = (KIND == kF16) ? kU16 : (KIND == kF32) ? kU32 : (KIND == kF64) ? kU64 : KIND;
     if (job.mask_mode == kMaskNone) return launch_rows<UK, kMaskNone, false>(job, npairs_flat, dst, stream, lo, hi, ed);
-    return launch_rows<UK, kMaskValue, false>(job, npairs_flat, dst, stream, lo, hi, ed);
+    const cudaError_t e = launch_rows<UK, kMaskValue, false>(job, npairs_flat, dst, stream, lo, hi, ed);
+    if (e != cudaSuccess || *hi <= *lo) return e;
+    return launch_rows<UK, kMaskValueDense, false>(job, npairs_flat, dst, stream, lo, hi, ed);
 }
 
 }  // namespace

@@ -17,6 +17,17 @@ constexpr int kF16 = XBI_F16, kF32 = XBI_F32, kF64 = XBI_F64;
 
 // how masked elements are recognised
 constexpr int kMaskNone = 0, kMaskNaN = 1, kMaskValue = 2;
+// The fast kernels exist in two masked flavours.  "Sparse" (kMaskNaN / kMaskValue): two streams
+// over zeroed elements + corrections at validity boundaries -- near the unmasked speed when
+// masked elements come in runs (land masks) or not at all.  "Dense" (the values below): three
+// explicit streams with keep-masks, flat 1.8x the unmasked cost whatever the data -- better when
+// masked elements are scattered.  Both are launched; each reads the sampled boundary density from
+// the workspace (k_mask_density) and returns at once unless it is the one for this data.
+constexpr int kMaskNaNDense = 3, kMaskValueDense = 4;
+template <int M> struct MaskMode {
+    static constexpr bool kDense = (M >= kMaskNaNDense);
+    static constexpr int kTest = kDense ? M - 2 : M;  // which test: kMaskNone / kMaskNaN / kMaskValue
+};
 
 inline int dtype_bytes(int dtype) {
     switch (dtype) {
@@ -53,7 +64,10 @@ cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int
 
 // Bit planes of the single elements f in [lo, lo+count) added to dst->sums[S_A] (transform
 // applied, masked elements skipped): the a-stream correction of the column walkers.
-cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream);
+// With `dense_probe` the pass returns at once when the sampled mask density (dense_probe->pad) says
+// the dense flavour of the column walkers ran (which needs no a-stream correction).
+cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream,
+                               const RawSums* dense_probe = nullptr, unsigned long long dense_one_in = 0);
 
 // TMA fast paths.  Each consumes as much of [0, numel-inner) as its alignment rules
 // allow, reports the flat range it covered in [*done_lo, *done_hi) (empty if none), and
@@ -66,6 +80,10 @@ cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, Workspace
 // *edges_done: the block-boundary pairs have been subtracted as well (all of them).
 cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
                               int64_t* done_hi, bool* edges_done);
+
+// Samples ~2^18 flat pairs and leaves (#pairs whose two elements differ in validity, #pairs sampled)
+// in ws->plus.pad[0], pad[1] for the masked fast kernels to choose their flavour.
+cudaError_t launch_mask_density(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream);
 
 cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* counts, cudaStream_t stream);
 cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, int set_zero,

@@ -77,7 +77,7 @@ class PairCounter:
         self.counts.zero_()
 
     def add(self, x: torch.Tensor, axis: int = -1, *, transform: bool = True, masked_value=None,
-            force_generic: bool = False, dims=None) -> None:
+            force_generic: bool = False, dims=None, flavour: str | None = None) -> None:
         """counts += pair histogram of ``x`` along ``axis`` (K1).  ``dims`` overrides the
         (outer, n, inner) split, e.g. to describe a slab with a halo row."""
         require_cuda_tensor(x)
@@ -90,6 +90,8 @@ class PairCounter:
             flags |= nat.SIGNED_EXPONENT
         if force_generic:
             flags |= nat.FORCE_GENERIC
+        if flavour is not None:  # testing: "sparse" / "dense" flavour of the masked fast kernels
+            flags |= {"sparse": nat.FORCE_SPARSE, "dense": nat.FORCE_DENSE}[flavour]
         with torch.cuda.device(x.device):
             rc = nat.lib().xbi_count_pairs(
                 x.data_ptr(), self.code, outer, n, inner, flags, bits, self.counts.data_ptr(),
