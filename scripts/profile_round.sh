@@ -1,3 +1,4 @@
+# the measurement + profiling pass behind profiles/ (run on a B200 box: gpurun -- bash scripts/profile_round.sh)
 set -x
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
