@@ -209,3 +209,77 @@ def test_sharded_counts_add_up_to_global_counts():
                 if slab.shape[axis] >= 2:
                     total += bo.bitinformation(slab, axis)[0]
             assert np.array_equal(total, ref), (axis, world)
+
+
+# ---------------------------------------------------------------------------------------
+# host logic of the "next" rows (streaming front end, per-chunk mode, multi-file flow): CPU only
+# ---------------------------------------------------------------------------------------
+def test_slab_plan_respects_the_sources_chunks():
+    from xbitinfo_b200.streaming import _chunk_edges_axis0, is_lazy_array, slab_plan
+
+    edges = [0, 6, 12, 18, 24, 30, 36, 42, 48, 50]
+    row = 24 * 36 * 4
+    # analysed axis is not the sliced one: slabs end on chunk boundaries, every row exactly once
+    plan = slab_plan((50, 24, 36), 2, 4, 13 * row, edges)
+    assert plan == [(0, 12, 0), (12, 24, 0), (24, 36, 0), (36, 48, 0), (48, 50, 0)]
+    # a chunk larger than a slab is cut
+    assert slab_plan((50, 24, 36), 1, 4, 4 * row, [0, 25, 50])[:3] == [(0, 4, 0), (4, 8, 0), (8, 12, 0)]
+    # the sliced axis is the analysed one: one halo row per slab, the pairs tile [0, n-1)
+    plan0 = slab_plan((50, 24, 36), 0, 4, 13 * row, edges)
+    assert all(h == 1 for _, _, h in plan0) and plan0[0][0] == 0 and plan0[-1][1] == 49
+    assert all(a[1] == b[0] for a, b in zip(plan0, plan0[1:]))
+
+    class Lazy:
+        shape, dtype = (50, 24, 36), np.dtype("float32")
+
+        def __init__(self, chunks):
+            self.chunks = chunks
+
+        def __getitem__(self, k):
+            raise AssertionError("not read")
+
+    assert is_lazy_array(Lazy(None)) and not is_lazy_array(np.zeros(3)) and not is_lazy_array(3.0)
+    assert _chunk_edges_axis0(Lazy(((6,) * 8 + (2,), (24,), (36,)))) == edges  # dask style
+    assert _chunk_edges_axis0(Lazy((6, 24, 36))) == edges                      # zarr / h5py style
+    assert _chunk_edges_axis0(Lazy(None)) is None
+
+
+def test_chunk_helpers_of_the_chunking_notebook():
+    from xbitinfo_b200.chunked import keepbits_of_information, normalize_chunks, slices_from_chunks
+
+    # the doctest of docs/chunking.ipynb cell 8
+    assert slices_from_chunks(((2, 2), (3, 3, 3))) == [
+        (slice(0, 2), slice(0, 3)), (slice(0, 2), slice(3, 6)), (slice(0, 2), slice(6, 9)),
+        (slice(2, 4), slice(0, 3)), (slice(2, 4), slice(3, 6)), (slice(2, 4), slice(6, 9))]
+    assert normalize_chunks((2920, 25, 53), {1: 5, 2: 10}) == ((2920,), (5,) * 5, (10,) * 5 + (3,))
+    assert normalize_chunks((4, 9), ((2, 2), 3)) == ((2, 2), (3, 3, 3))
+    with pytest.raises(ValueError):
+        normalize_chunks((4,), ((3, 2),))
+    rng = np.random.default_rng(0)
+    for dtype in ("float16", "float32", "float64"):
+        nbits = np.dtype(dtype).itemsize * 8
+        info = np.sort(rng.random(nbits))[::-1] * (rng.random(nbits) > 0.2)
+        for lvl in (0.9, 0.99, 1.0):
+            assert keepbits_of_information(info, dtype, lvl) == ko.keepbits_from_info(info, dtype, lvl)
+
+
+def test_flow_path_selection_and_container_round_trip(tmp_path):
+    from xbitinfo_b200 import flow
+
+    paths = [f"f{i}.npz" for i in range(7)]
+    assert flow.select_analysis_paths(paths, "first") == ["f0.npz"]
+    assert flow.select_analysis_paths(paths, "first_last") == ["f0.npz", "f6.npz"]
+    assert flow.select_analysis_paths(paths, "all") == paths
+    assert flow.select_analysis_paths(paths, 3) == ["f0.npz", "f3.npz", "f6.npz"]
+    for bad in ("last", "middle", 2.5, True):
+        with pytest.raises(ValueError):
+            flow.select_analysis_paths(paths, bad)
+    with pytest.raises(ValueError, match="Please provide paths"):
+        flow.xbitinfo_pipeline([])
+    ds = xb.Dataset({"a": xb.DataArray(np.arange(24, dtype="float32").reshape(2, 3, 4), dims=("t", "y", "x"), name="a"),
+                     "b": xb.DataArray(np.arange(6, dtype="int16").reshape(2, 3), dims=("t", "y"), name="b")})
+    p = str(tmp_path / "x.npz")
+    flow.save_npz(ds, p)
+    back = flow.open_npz(p)
+    assert list(back.data_vars) == ["a", "b"] and back["a"].dims == ("t", "y", "x") and back["b"].dims == ("t", "y")
+    assert np.array_equal(back["a"].values, ds["a"].values) and back["b"].dtype == np.dtype("int16")
