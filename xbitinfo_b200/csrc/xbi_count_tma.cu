@@ -102,7 +102,9 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     constexpr int kNumLadders = NL * (DENSE ? 3 : 2);
     using L = Ladder<3, (kNumLadders >= 6 ? 3 : kNumLadders >= 4 ? 5 : 8)>;
     // sparse and dense flavours are both launched; the sampled boundary density picks one
-    if (MASKED && sampled_mask_is_dense(dst, 512ull) != DENSE) return;
+    // (break-even of the two flavours: about one boundary in 512 pairs; the dense flavour of the
+    // 64-bit types is slower, so they stay sparse up to one in 256)
+    if (MASKED && sampled_mask_is_dense(dst, S::k64 ? 256ull : 512ull) != DENSE) return;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 1023u) & ~1023u;
