@@ -110,6 +110,32 @@ int xbi_mutual_information(const unsigned long long* counts_dev, int nbits,
                            int set_zero_insignificant, double confidence, double* mi_dev,
                            void* stream);
 
+/* K2 on `nbatch` consecutive (nbits,2,2) tables: mi_dev receives nbatch*nbits doubles. */
+int xbi_mutual_information_batched(const unsigned long long* counts_dev, int nbits, int64_t nbatch,
+                                   int set_zero_insignificant, double confidence, double* mi_dev, void* stream);
+
+/*
+ * K1 / K3 over a regular chunk grid, in a constant number of launches: the per-block workflow of
+ * the reference's docs/chunking.ipynb (cells 8-10: get_bitinformation -> get_keepbits ->
+ * xr_bitround on every dask block on its own; backend xbitinfo/xbitinfo.py:337-370 and
+ * xbitinfo/bitround.py:7-12 called once per block there).
+ *   The array is C-contiguous with `ndim` (<= XBI_MAX_DIMS) extents `shape`; chunk_shape[d] is the
+ *   chunk length along dimension d (the last chunk of a dimension may be shorter; values above
+ *   shape[d] mean "not chunked").  Chunks are numbered in C order of the chunk grid.
+ *   xbi_count_pairs_chunked: counts_dev[chunk][nbits][4] is OVERWRITTEN with the pair histogram of
+ *   every chunk taken on its own along `axis` (pairs never cross a chunk boundary); flags and
+ *   mask_bits as for xbi_count_pairs (the XBI_FORCE_* flags are ignored).
+ *   xbi_bitround_chunked: chunk c is rounded in place to keepbits_dev[c] mantissa bits (values are
+ *   clamped to 0..mantissa bits; mantissa bits = unchanged).
+ * XBI_ERR_UNSUPPORTED: more than 5 dimensions remain after merging unchunked neighbours, a chunk
+ * extent or the number of chunks reaches 2^31.
+ */
+#define XBI_MAX_DIMS 8
+int xbi_count_pairs_chunked(const void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                            int axis, unsigned flags, uint64_t mask_bits, unsigned long long* counts_dev, void* stream);
+int xbi_bitround_chunked(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                         const int32_t* keepbits_dev, void* stream);
+
 /*
  * K3: round to nearest (ties to even) keeping `keepbits` explicit mantissa bits, in
  * place.  Replaces the arithmetic of _np_bitround (xbitinfo/bitround.py:7-12).

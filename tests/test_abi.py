@@ -54,6 +54,28 @@ def test_argument_errors_do_not_need_a_gpu():
     assert rc == nat.ERR_ARG
 
 
+def test_chunk_grid_argument_errors_do_not_need_a_gpu():
+    lib = nat.lib()
+    i64 = nat.int64_array
+    rc = lib.xbi_count_pairs_chunked(None, nat.F32, 0, i64([]), i64([]), 0, 0, 0, None, None)
+    assert rc == nat.ERR_ARG and b"ndim" in lib.xbi_last_error()
+    rc = lib.xbi_count_pairs_chunked(None, nat.F32, 2, i64([4, 4]), i64([2, 2]), 2, 0, 0, None, None)
+    assert rc == nat.ERR_ARG and b"axis" in lib.xbi_last_error()
+    rc = lib.xbi_count_pairs_chunked(None, nat.F32, 2, i64([4, 4]), i64([2, 0]), 1, 0, 0, None, None)
+    assert rc == nat.ERR_ARG and b"chunk extents" in lib.xbi_last_error()
+    rc = lib.xbi_count_pairs_chunked(None, nat.F32, 6, i64([2] * 6), i64([1] * 6), 0, 0, 0, None, None)
+    assert rc == nat.ERR_UNSUPPORTED
+    with pytest.raises(NotImplementedError):
+        nat.check(rc)
+    rc = lib.xbi_bitround_chunked(None, nat.U32, 1, i64([4]), i64([2]), None, None)
+    assert rc == nat.ERR_ARG and b"float" in lib.xbi_last_error()
+    rc = lib.xbi_mutual_information_batched(None, 65, 1, 0, 0.99, None, None)
+    assert rc == nat.ERR_ARG
+    # nothing to do: no chunks, no pointers needed
+    assert lib.xbi_count_pairs_chunked(None, nat.F32, 2, i64([0, 4]), i64([2, 2]), 1, 0, 0, None, None) == 0
+    assert lib.xbi_mutual_information_batched(None, 32, 0, 0, 0.99, None, None) == 0
+
+
 @pytest.mark.skipif(_have_gpu(), reason="only meaningful on a box without a GPU")
 def test_product_path_fails_loudly_without_a_gpu():
     from xbitinfo_b200 import engine

@@ -78,6 +78,12 @@ def lib() -> C.CDLL:
     L.xbi_count_pairs.argtypes = [vp, i32, i64, i64, i64, u32, u64, vp, vp, C.c_size_t, vp]
     L.xbi_mutual_information.restype = i32
     L.xbi_mutual_information.argtypes = [vp, i32, i32, dbl, vp, vp]
+    L.xbi_mutual_information_batched.restype = i32
+    L.xbi_mutual_information_batched.argtypes = [vp, i32, i64, i32, dbl, vp, vp]
+    L.xbi_count_pairs_chunked.restype = i32
+    L.xbi_count_pairs_chunked.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64), i32, u32, u64, vp, vp]
+    L.xbi_bitround_chunked.restype = i32
+    L.xbi_bitround_chunked.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64), vp, vp]
     L.xbi_bitround_inplace.restype = i32
     L.xbi_bitround_inplace.argtypes = [vp, i32, i64, i32, vp]
     L.xbi_shuffle.restype = i32
@@ -101,6 +107,7 @@ EXPORTED_SYMBOLS = (
     "xbi_workspace_bytes", "xbi_profile_enable", "xbi_profile_collect",
     "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace", "xbi_shuffle", "xbi_bitround_shuffle",
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
+    "xbi_mutual_information_batched", "xbi_count_pairs_chunked", "xbi_bitround_chunked",
 )
 
 
@@ -114,6 +121,12 @@ def check(rc: int) -> None:
     if rc == ERR_UNSUPPORTED:
         raise NotImplementedError(msg)
     raise XbiError(f"[xbi rc={rc}] {msg}")
+
+
+def int64_array(values):
+    """ctypes int64[] of a sequence of ints (shape / chunk_shape arguments)."""
+    values = [int(v) for v in values]
+    return (C.c_int64 * len(values))(*values)
 
 
 def kernel_launches() -> int:

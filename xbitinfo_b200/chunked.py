@@ -4,7 +4,8 @@
 blocks cut and processed on the device.
 
 Every block is an independent K1 -> K2 -> (host: keepbits) -> K3 job; the array stays in HBM,
-only ``nbits`` doubles per block come back to the host for the keepbits decision.
+only ``nbits`` doubles per block come back to the host for the keepbits decision.  Regular chunk
+grids go through the batched kernels of ``csrc/xbi_chunked.cu`` (all blocks in one launch per stage).
 """
 from __future__ import annotations
 
@@ -61,8 +62,48 @@ def keepbits_of_information(info, np_dtype, inflevel=0.99) -> int:
         return int((cdf > inflevel).argmax() + 1 - (n_bits - n_mant))
 
 
+def _regular_chunk_shape(grid):
+    """Chunk extents of a regular grid (equal chunks, the last of a dimension possibly shorter), else None."""
+    out = []
+    for c in grid:
+        if len(c) == 0:
+            out.append(1)
+            continue
+        if any(v != c[0] for v in c[:-1]) or c[-1] > c[0] or min(c) < 1:
+            return None
+        out.append(int(c[0]))
+    return tuple(out)
+
+
+def keepbits_of_information_batched(info, np_dtype, inflevel=0.99) -> np.ndarray:
+    """``get_keepbits`` on a stack of information vectors ``(..., nbits)`` -> int64 ``(...)``."""
+    n_bits, _, _, n_mant = bit_partitioning(np_dtype)
+    info = np.asarray(info, dtype="float64")
+    if inflevel == 1.0:
+        return np.full(info.shape[:-1], n_mant, dtype="int64")
+    cdf = _cdf_from_info_per_bit(info)
+    with np.errstate(invalid="ignore"):
+        return ((cdf > inflevel).argmax(axis=-1) + 1 - (n_bits - n_mant)).astype("int64")
+
+
+def bitinformation_by_chunks(x, chunks, axis: int, masked_value=float("nan"), set_zero_insignificant: bool = True,
+                             confidence: float = 0.99):
+    """Information per bit of every chunk of a regular grid on its own: ``(info, counts)`` as CUDA tensors of
+    shape ``chunks-per-dimension + (nbits,)`` and ``+ (nbits, 2, 2)``.  One counting launch for all chunks
+    (``xbi_count_pairs_chunked``) and one for the mutual information."""
+    from .device import count_pairs_chunked, information_batched
+
+    t = torch.from_numpy(np.ascontiguousarray(x)).cuda() if isinstance(x, np.ndarray) else x.contiguous()
+    grid = normalize_chunks(tuple(t.shape), chunks)
+    chunk_shape = _regular_chunk_shape(grid)
+    if chunk_shape is None:
+        raise NotImplementedError("irregular chunk grids are processed chunk by chunk (bitround_by_chunks)")
+    counts = count_pairs_chunked(t, chunk_shape, axis, masked_value=masked_value)
+    return information_batched(counts, set_zero_insignificant, confidence), counts
+
+
 def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_value=float("nan"),
-                       set_zero_insignificant: bool = True, confidence: float = 0.99):
+                       set_zero_insignificant: bool = True, confidence: float = 0.99, batched: bool | None = None):
     """Round every chunk of ``x`` to its own keepbits.
 
     ``x``: numpy array or CUDA tensor (floats); ``chunks``: ``{axis: size}``, per-axis sizes or
@@ -71,6 +112,11 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
     and ``keepbits`` an int64 array with one entry per chunk (shape = chunks per axis).
     Negative keepbits (not even all exponent bits carry information) are clamped to 0, as the
     reference's multi-file flow does (``xbitinfo/xbitinfo.py:867-868``).
+
+    A regular grid (dask's usual case) runs in three launches whatever the number of chunks:
+    ``xbi_count_pairs_chunked`` -> ``xbi_mutual_information_batched`` -> (one D2H of the
+    information, keepbits on the host, one H2D of ``nchunks`` ints) -> ``xbi_bitround_chunked``.
+    An irregular grid (``batched=False`` forces this route) is walked chunk by chunk with K1/K2/K3.
     """
     is_np = isinstance(x, np.ndarray)
     t = torch.from_numpy(np.ascontiguousarray(x)).cuda() if is_np else x.contiguous().clone()
@@ -79,8 +125,22 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
     np_dtype = np.dtype(str(t.dtype).replace("torch.", ""))
     grid = normalize_chunks(tuple(t.shape), chunks)
     keep = np.zeros([len(c) for c in grid], dtype="int64")
-    pc = PairCounter(t.dtype, t.device)
     axis %= t.dim()
+    chunk_shape = _regular_chunk_shape(grid)
+    if batched is None:
+        batched = chunk_shape is not None
+    if batched:
+        if chunk_shape is None:
+            raise ValueError("batched=True needs a regular chunk grid")
+        from .device import bitround_chunked_, count_pairs_chunked, information_batched
+
+        counts = count_pairs_chunked(t, chunk_shape, axis, masked_value=masked_value)
+        info = information_batched(counts, set_zero_insignificant, confidence).cpu().numpy()
+        keep = np.clip(keepbits_of_information_batched(info, np_dtype, inflevel), 0, _MANT[t.dtype]).reshape(keep.shape)
+        if keep.size:
+            bitround_chunked_(t, chunk_shape, torch.from_numpy(keep.astype("int32").ravel()).to(t.device))
+        return (t.cpu().numpy() if is_np else t), keep
+    pc = PairCounter(t.dtype, t.device)
     for idx, sl in zip(np.ndindex(*keep.shape), slices_from_chunks(grid)):
         blk = t[sl].contiguous()
         pc.reset()

@@ -228,18 +228,149 @@ int xbi_count_pairs(const void* x_dev, int dtype, int64_t outer, int64_t n, int6
                             static_cast<cudaStream_t>(stream));
 }
 
-int xbi_mutual_information(const unsigned long long* counts_dev, int nbits, int set_zero_insignificant,
-                           double confidence, double* mi_dev, void* stream) {
-    if (!counts_dev || !mi_dev) return fail(XBI_ERR_ARG, "null pointer");
+int xbi_mutual_information_batched(const unsigned long long* counts_dev, int nbits, int64_t nbatch,
+                                   int set_zero_insignificant, double confidence, double* mi_dev, void* stream) {
+    if (nbatch < 0) return fail(XBI_ERR_ARG, "negative nbatch");
     if (nbits < 1 || nbits > 64) return fail(XBI_ERR_ARG, "nbits must be in 1..64");
+    if (nbatch == 0) return XBI_OK;
+    if (!counts_dev || !mi_dev) return fail(XBI_ERR_ARG, "null pointer");
     double z = 0.0;
     if (set_zero_insignificant) {
         if (!(confidence > 0.0 && confidence < 1.0)) return fail(XBI_ERR_ARG, "confidence must be in (0,1)");
         z = normal_quantile(1.0 - (1.0 - confidence) / 2.0);
     }
-    XBI_CUDA(launch_mutual_information(counts_dev, nbits, set_zero_insignificant ? 1 : 0, z, mi_dev,
+    XBI_CUDA(launch_mutual_information(counts_dev, nbits, nbatch, set_zero_insignificant ? 1 : 0, z, mi_dev,
                                        static_cast<cudaStream_t>(stream)),
              "mutual information");
+    return XBI_OK;
+}
+
+int xbi_mutual_information(const unsigned long long* counts_dev, int nbits, int set_zero_insignificant,
+                           double confidence, double* mi_dev, void* stream) {
+    if (!counts_dev || !mi_dev) return fail(XBI_ERR_ARG, "null pointer");
+    return xbi_mutual_information_batched(counts_dev, nbits, 1, set_zero_insignificant, confidence, mi_dev, stream);
+}
+
+// Regular chunk grid of an N-d C-contiguous array -> ChunkGrid of at most kMaxChunkDims dimensions.
+// Neighbouring dimensions are merged when the inner one is not chunked and neither is the analysed
+// one (the chunk order stays the C order of the chunk grid); dimensions of length 1 disappear.
+// *nchunks: chunks in the grid; *empty: nothing to do (no elements, or no pairs along the axis).
+static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_shape, int axis, ChunkGrid& g,
+                           int64_t* nchunks, bool* empty) {
+    if (ndim < 1 || ndim > XBI_MAX_DIMS) return fail(XBI_ERR_ARG, "ndim must be in 1..XBI_MAX_DIMS");
+    if (!shape || !chunk_shape) return fail(XBI_ERR_ARG, "null shape pointer");
+    if (axis < -1 || axis >= ndim) return fail(XBI_ERR_ARG, "axis out of range");
+    int64_t total_chunks = 1, numel = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] < 0) return fail(XBI_ERR_ARG, "negative extent");
+        if (chunk_shape[d] < 1) return fail(XBI_ERR_ARG, "chunk extents must be positive");
+        const int64_t c = chunk_shape[d] < shape[d] ? chunk_shape[d] : (shape[d] > 0 ? shape[d] : 1);
+        const int64_t nc = shape[d] > 0 ? (shape[d] + c - 1) / c : 0;
+        if (nc > 0 && total_chunks > (int64_t)0x7FFFFFFF / nc) return fail(XBI_ERR_UNSUPPORTED, "more than 2^31-1 chunks");
+        total_chunks *= nc;
+        numel *= shape[d];
+    }
+    *nchunks = total_chunks;
+    *empty = numel == 0 || (axis >= 0 && shape[axis] < 2);
+    if (numel == 0) return XBI_OK;
+
+    // innermost first: merge dimension d into the group built so far when that group is unchunked
+    int64_t mshape[XBI_MAX_DIMS], mchunk[XBI_MAX_DIMS], mstride[XBI_MAX_DIMS];
+    int maxis = -1, m = 0;  // groups are collected innermost first
+    int64_t stride = 1;
+    bool can_merge = false;  // the current (innermost so far) group may take another outer dimension
+    for (int d = ndim - 1; d >= 0; --d) {
+        const int64_t c = chunk_shape[d] < shape[d] ? chunk_shape[d] : shape[d];
+        const bool is_axis = d == axis;
+        if (shape[d] == 1 && !is_axis) { stride *= shape[d]; continue; }
+        if (m > 0 && can_merge && !is_axis && mchunk[m - 1] == mshape[m - 1] &&
+            c <= (int64_t)0x7FFFFFFF / mshape[m - 1]) {
+            mchunk[m - 1] = c * mshape[m - 1];
+            mshape[m - 1] *= shape[d];
+        } else {
+            mshape[m] = shape[d];
+            mchunk[m] = c;
+            mstride[m] = stride;
+            if (is_axis) maxis = m;
+            can_merge = !is_axis;
+            ++m;
+        }
+        stride *= shape[d];
+    }
+    if (m == 0) { mshape[0] = 1; mchunk[0] = 1; mstride[0] = 1; m = 1; }  // a single element
+    if (m > kMaxChunkDims)
+        return fail(XBI_ERR_UNSUPPORTED, "more than 5 chunked dimensions after merging; process the chunks one by one");
+    double full = 1.0;
+    for (int i = 0; i < kMaxChunkDims; ++i) { g.shape[i] = 1; g.stride[i] = 0; g.chunk[i] = 1; g.nchunk[i] = 1; }
+    g.axis = -1;
+    for (int i = 0; i < m; ++i) {  // group i (innermost first) -> slot kMaxChunkDims-1-i
+        const int slot = kMaxChunkDims - 1 - i;
+        if (mchunk[i] > (int64_t)0x7FFFFFFF)
+            return fail(XBI_ERR_UNSUPPORTED, "a chunk extent of 2^31 or more; use xbi_count_pairs on that chunk");
+        g.shape[slot] = mshape[i];
+        g.stride[slot] = mstride[i];
+        g.chunk[slot] = (unsigned)mchunk[i];
+        g.nchunk[slot] = (unsigned)((mshape[i] + mchunk[i] - 1) / mchunk[i]);
+        if (i == maxis) g.axis = slot;
+        full *= (double)mchunk[i];
+    }
+    if (full >= 9.0e18) return fail(XBI_ERR_UNSUPPORTED, "chunk too large");
+    unsigned long long full_numel = 1;
+    for (int i = 0; i < kMaxChunkDims; ++i) full_numel *= g.chunk[i];
+    const unsigned long long tile = 4096ull;
+    const unsigned long long tiles_per_chunk = (full_numel + tile - 1) / tile;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned long long target_items = (unsigned long long)sms * 16ull;
+    unsigned long long groups = (target_items + (unsigned long long)total_chunks - 1) / (unsigned long long)total_chunks;
+    if (groups < 1) groups = 1;
+    if (groups > tiles_per_chunk) groups = tiles_per_chunk;
+    unsigned long long tpg = (tiles_per_chunk + groups - 1) / groups;
+    groups = (tiles_per_chunk + tpg - 1) / tpg;
+    if (tpg > 0xFFFFFFFFull || groups * (unsigned long long)total_chunks > 0xFFFFFFFFull)
+        return fail(XBI_ERR_UNSUPPORTED, "chunk grid too large for one launch");
+    g.groups = (unsigned)groups;
+    g.tiles_per_group = (unsigned)tpg;
+    g.items = (unsigned)(groups * (unsigned long long)total_chunks);
+    return XBI_OK;
+}
+
+int xbi_count_pairs_chunked(const void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                            int axis, unsigned flags, uint64_t mask_bits, unsigned long long* counts_dev, void* stream) {
+    CountJob job;
+    if (int rc = make_job(job, x_dev, dtype, 0, 0, 0, flags, mask_bits)) return rc;
+    if (axis < 0) return fail(XBI_ERR_ARG, "axis out of range");
+    ChunkGrid g;
+    int64_t nchunks = 0;
+    bool empty = false;
+    if (int rc = plan_chunk_grid(ndim, shape, chunk_shape, axis, g, &nchunks, &empty)) return rc;
+    if (nchunks == 0) return XBI_OK;
+    if (!counts_dev) return fail(XBI_ERR_ARG, "null counts pointer");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t table = (size_t)8 * dtype_bytes(dtype) * 4 * sizeof(unsigned long long);
+    XBI_CUDA(cudaMemsetAsync(counts_dev, 0, (size_t)nchunks * table, st), "cudaMemsetAsync(counts)");
+    if (empty) return XBI_OK;
+    if (!x_dev) return fail(XBI_ERR_ARG, "null data pointer");
+    XBI_CUDA(launch_pairs_chunked(x_dev, dtype, g, (unsigned)nchunks, job.transform, job.mask_mode, job.mask_bits,
+                                  counts_dev, st),
+             "pair counting (chunk grid)");
+    return XBI_OK;
+}
+
+int xbi_bitround_chunked(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                         const int32_t* keepbits_dev, void* stream) {
+    if (!dtype_is_float(dtype)) return fail(XBI_ERR_ARG, "Only float arrays (16-64bit) can be bit-rounded");
+    ChunkGrid g;
+    int64_t nchunks = 0;
+    bool empty = false;
+    if (int rc = plan_chunk_grid(ndim, shape, chunk_shape, -1, g, &nchunks, &empty)) return rc;
+    if (nchunks == 0 || empty) return XBI_OK;
+    if (!x_dev || !keepbits_dev) return fail(XBI_ERR_ARG, "null pointer");
+    if (reinterpret_cast<uintptr_t>(x_dev) % dtype_bytes(dtype) != 0)
+        return fail(XBI_ERR_ARG, "data pointer is not element-aligned");
+    XBI_CUDA(launch_bitround_chunked(x_dev, dtype, g, keepbits_dev, static_cast<cudaStream_t>(stream)),
+             "bitround (chunk grid)");
     return XBI_OK;
 }
 

@@ -1,0 +1,366 @@
+// K1 and K3 batched over a regular chunk grid: the per-chunk workflow of the reference's
+// docs/chunking.ipynb (cells 8-10: get_bitinformation -> get_keepbits -> xr_bitround on every
+// dask block on its own) in a constant number of launches, whatever the number of chunks.
+//
+// The array stays as the caller has it (C-contiguous, N-d).  A work item is (chunk, group of
+// 4096-element tiles of that chunk); a CTA walks its tiles in the chunk's own row-major order,
+// 256 consecutive elements of that order per step, so a warp reads runs of the chunk's rows
+// (coalesced up to the chunk's width).  Every thread keeps its position as a mixed-radix
+// "odometer" over the chunk's extents and advances it by 256 elements per step with one
+// compare/subtract per dimension that moves -- no divisions after the per-item set-up.
+//
+// Counting: a pair (x[c], x[c + e_axis]) exists when the element is not the last of ITS CHUNK
+// along the analysed axis (xbitinfo/_py_bitinfo.py:155-160 applied to the block alone); the
+// three word streams a, b, a&b of the valid pairs go into vertical counters (xbi_common.cuh) as
+// in the generic kernel, and each item ends with one warp butterfly, a block reduction and one
+// atomic per counter into the chunk's table.
+#include <type_traits>
+
+#include "xbi_common.cuh"
+#include "xbi_elem.cuh"
+#include "xbi_internal.h"
+
+namespace xbi {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPerThread = 16;
+constexpr unsigned kTile = kThreads * kPerThread;
+constexpr int kD = kMaxChunkDims;
+
+// position of one thread inside one chunk
+struct Walker {
+    unsigned c[kD];     // local coordinates (c[0] is allowed to run past e[0]: past the end of the chunk)
+    unsigned e[kD];     // extents of this chunk (ragged at the upper array edges)
+    unsigned inc[kD];   // kThreads as a mixed-radix number over e
+    long long wrap[kD];  // offset correction when dimension d wraps and carries into d-1
+    long long off;       // element offset of the current element in the array
+    long long incoff;    // offset change of one step without wraps
+    long long left;      // elements from the current one to the end of the chunk (<= 0: past the end)
+    long long numel;
+
+    __device__ __forceinline__ void init(const ChunkGrid& g, unsigned cid, unsigned long long l0) {
+        long long base = 0;
+        numel = 1;
+        unsigned r = cid;
+#pragma unroll
+        for (int d = kD - 1; d >= 0; --d) {
+            unsigned q = r;
+            if (d > 0) { q = r % g.nchunk[d]; r /= g.nchunk[d]; }
+            const long long start = (long long)q * g.chunk[d];
+            const long long ext = g.shape[d] - start;
+            e[d] = ext < (long long)g.chunk[d] ? (unsigned)ext : g.chunk[d];
+            base += start * g.stride[d];
+            numel *= e[d];
+        }
+        if (numel < (1ll << 31)) {
+            unsigned l = (unsigned)l0;
+#pragma unroll
+            for (int d = kD - 1; d >= 1; --d) { c[d] = l % e[d]; l /= e[d]; }
+            c[0] = l;
+        } else {
+            unsigned long long l = l0;
+#pragma unroll
+            for (int d = kD - 1; d >= 1; --d) { c[d] = (unsigned)(l % e[d]); l /= e[d]; }
+            c[0] = (unsigned)l;
+        }
+        unsigned rem = kThreads;
+#pragma unroll
+        for (int d = kD - 1; d >= 1; --d) { inc[d] = rem % e[d]; rem /= e[d]; }
+        inc[0] = rem;
+        off = base;
+        incoff = 0;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) {
+            off += (long long)c[d] * g.stride[d];
+            incoff += (long long)inc[d] * g.stride[d];
+            wrap[d] = d > 0 ? g.stride[d - 1] - (long long)e[d] * g.stride[d] : 0;
+        }
+        left = numel - (long long)l0;
+    }
+
+    // advance by kThreads elements of the chunk's row-major order
+    __device__ __forceinline__ void step() {
+        off += incoff;
+        left -= kThreads;
+        unsigned carry = 0;
+#pragma unroll
+        for (int d = kD - 1; d >= 1; --d) {
+            if (inc[d] | carry) {
+                unsigned v = c[d] + inc[d] + carry;  // < 2 e[d]
+                carry = 0;
+                if (v >= e[d]) { v -= e[d]; carry = 1; off += wrap[d]; }
+                c[d] = v;
+            }
+        }
+        c[0] += inc[0] + carry;
+    }
+
+    // coordinate / extent along a dimension known only at run time (uniform), without indexing
+    // the register arrays dynamically
+    __device__ __forceinline__ unsigned coord(int axis) const {
+        unsigned v = 0;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) if (d == axis) v = c[d];
+        return v;
+    }
+    __device__ __forceinline__ unsigned extent(int axis) const {
+        unsigned v = 1;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) if (d == axis) v = e[d];
+        return v;
+    }
+};
+
+// counts: [nchunks][nbits][4] accumulated RAW here (slot 0 of bit 0: pairs; slots 1, 2, 3 of bit k:
+// B, A, AB plane sums), turned into the 2x2 tables by k_chunk_finalize.
+template <int KIND, int MASK, bool XFORM>
+__global__ void __launch_bounds__(kThreads)
+k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
+                unsigned long long* __restrict__ counts) {
+    using E = Elem<KIND>;
+    constexpr int NW = E::kWords;
+    constexpr int NBITS = E::kBits;
+    using L = Ladder<3, 6>;
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_n;
+    const uint32_t lane = threadIdx.x & 31u;
+    long long pstride = 0;
+#pragma unroll
+    for (int d = 0; d < kD; ++d) if (d == g.axis) pstride = g.stride[d];
+
+    for (unsigned item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const unsigned cid = item / g.groups, grp = item - cid * g.groups;
+        const unsigned long long group_base = (unsigned long long)grp * g.tiles_per_group * kTile;
+        Walker w;
+        w.init(g, cid, group_base + threadIdx.x);
+        long long tiles_left = (w.numel - (long long)group_base + (long long)kTile - 1) / (long long)kTile;  // uniform
+        if (tiles_left <= 0) continue;  // an edge chunk with fewer tiles than the full ones
+        if (tiles_left > (long long)g.tiles_per_group) tiles_left = g.tiles_per_group;
+        const unsigned ea = w.extent(g.axis);
+
+        L A[NW], B[NW], AB[NW];
+        unsigned long long accA[NW], accB[NW], accAB[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            A[k].clear(); B[k].clear(); AB[k].clear();
+            accA[k] = 0; accB[k] = 0; accAB[k] = 0;
+        }
+        uint32_t nvalid = 0, it = 0;
+        unsigned long long nvalid_total = 0;
+        auto flush = [&]() {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                accA[k] += A[k].warp_totals(lane, it);
+                accB[k] += B[k].warp_totals(lane, it);
+                accAB[k] += AB[k].warp_totals(lane, it);
+                A[k].clear(); B[k].clear(); AB[k].clear();
+            }
+            nvalid_total += nvalid;
+            nvalid = 0;
+            it = 0;
+        };
+
+        for (long long t = 0; t < tiles_left; ++t) {
+            uint32_t wa[NW][kPerThread], wb[NW][kPerThread];
+#pragma unroll
+            for (int u = 0; u < kPerThread; ++u) {
+                uint32_t a[NW], b[NW];
+#pragma unroll
+                for (int k = 0; k < NW; ++k) { a[k] = 0; b[k] = 0; }
+                if (w.left > 0 && w.coord(g.axis) + 1u < ea) {
+                    E::load(x, w.off, a);
+                    E::load(x, w.off + pstride, b);
+                    bool ok = true;
+                    if (MASK == kMaskNaN) ok = !(E::is_nan(a) || E::is_nan(b));
+                    if (MASK == kMaskValue) ok = !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
+                    if (XFORM) { E::transform(a); E::transform(b); }
+                    if (!ok) {
+#pragma unroll
+                        for (int k = 0; k < NW; ++k) { a[k] = 0; b[k] = 0; }
+                    }
+                    nvalid += ok ? 1u : 0u;
+                }
+#pragma unroll
+                for (int k = 0; k < NW; ++k) { wa[k][u] = a[k]; wb[k][u] = b[k]; }
+                w.step();
+            }
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                uint32_t wab[kPerThread];
+#pragma unroll
+                for (int u = 0; u < kPerThread; ++u) wab[u] = wa[k][u] & wb[k][u];
+                A[k].add16(wa[k], it);
+                B[k].add16(wb[k], it);
+                AB[k].add16(wab, it);
+            }
+            ++it;
+            if (it == L::kFlushChunks) flush();
+        }
+        flush();
+
+        // block reduction, then one atomic per non-zero counter into the chunk's table
+        for (int i = threadIdx.x; i < 3 * 64; i += kThreads) (&s_sum[0][0])[i] = 0;
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int j = k * 32 + lane;
+            if (accA[k]) atomicAdd(&s_sum[S_A][j], accA[k]);
+            if (accB[k]) atomicAdd(&s_sum[S_B][j], accB[k]);
+            if (accAB[k]) atomicAdd(&s_sum[S_AB][j], accAB[k]);
+        }
+        if (nvalid_total) atomicAdd(&s_n, nvalid_total);
+        __syncthreads();
+        unsigned long long* dst = counts + (size_t)cid * NBITS * 4;
+        for (int i = threadIdx.x; i < 3 * NBITS; i += kThreads) {
+            const int s = i / NBITS, j = i - s * NBITS;  // stream, bit from the least significant one
+            const unsigned long long v = s_sum[s][j];
+            const int slot = (s == S_A) ? 2 : (s == S_B) ? 1 : 3;
+            if (v) atomicAdd(dst + 4 * (NBITS - 1 - j) + slot, v);
+        }
+        if (threadIdx.x == 0 && s_n) atomicAdd(dst, s_n);
+        __syncthreads();  // s_sum is zeroed again by the next item
+    }
+}
+
+// raw sums -> [[N-A-B+AB, B-AB], [A-AB, AB]] in place (bitpaircount layout, _py_bitinfo.py:128-140)
+__global__ void __launch_bounds__(kThreads)
+k_chunk_finalize(unsigned long long* __restrict__ counts, int nbits, unsigned nchunks) {
+    const unsigned per = kThreads / nbits;
+    const unsigned ci = blockIdx.x * per + threadIdx.x / nbits;
+    const unsigned k = threadIdx.x % nbits;
+    const bool ok = ci < nchunks;
+    unsigned long long N = 0, A = 0, B = 0, AB = 0;
+    unsigned long long* c = counts + (size_t)ci * nbits * 4;
+    if (ok) {
+        N = c[0];
+        B = c[4 * k + 1];
+        A = c[4 * k + 2];
+        AB = c[4 * k + 3];
+    }
+    __syncthreads();  // every N of the block's chunks has been read before slot 0 of bit 0 is rewritten
+    if (ok) {
+        c[4 * k + 0] = N - A - B + AB;
+        c[4 * k + 1] = B - AB;
+        c[4 * k + 2] = A - AB;
+    }
+}
+
+// K3 per chunk: keepbits[chunk] mantissa bits kept (clamped to 0..mant; mant = identity)
+template <int BYTES>
+__global__ void __launch_bounds__(kThreads)
+k_bitround_chunked(void* __restrict__ x, const __grid_constant__ ChunkGrid g, const int* __restrict__ keepbits, int mant) {
+    using T = typename std::conditional<BYTES == 2, uint16_t, typename std::conditional<BYTES == 4, uint32_t, unsigned long long>::type>::type;
+    T* __restrict__ p = static_cast<T*>(x);
+    for (unsigned item = blockIdx.x; item < g.items; item += gridDim.x) {
+        const unsigned cid = item / g.groups, grp = item - cid * g.groups;
+        int kb = keepbits[cid];
+        kb = kb < 0 ? 0 : kb > mant ? mant : kb;
+        const uint32_t drop = (uint32_t)(mant - kb);
+        if (drop == 0) continue;
+        const unsigned long long full = BYTES == 8 ? ~0ull : ((1ull << (8 * BYTES)) - 1ull);
+        const unsigned long long keep = (full >> drop) << drop;
+        const unsigned long long half_m1 = (1ull << (drop - 1)) - 1ull;
+        const unsigned long long group_base = (unsigned long long)grp * g.tiles_per_group * kTile;
+        Walker w;
+        w.init(g, cid, group_base + threadIdx.x);
+        long long tiles_left = (w.numel - (long long)group_base + (long long)kTile - 1) / (long long)kTile;
+        if (tiles_left > (long long)g.tiles_per_group) tiles_left = g.tiles_per_group;
+        for (long long t = 0; t < tiles_left; ++t) {
+            long long offs[kPerThread];
+            T v[kPerThread];
+#pragma unroll
+            for (int u = 0; u < kPerThread; ++u) {
+                offs[u] = w.left > 0 ? w.off : -1;
+                w.step();
+            }
+#pragma unroll
+            for (int u = 0; u < kPerThread; ++u) if (offs[u] >= 0) v[u] = p[offs[u]];
+#pragma unroll
+            for (int u = 0; u < kPerThread; ++u) {
+                if (offs[u] >= 0) {
+                    const unsigned long long b = v[u];
+                    p[offs[u]] = (T)((b + ((b >> drop) & 1ull) + half_m1) & keep);
+                }
+            }
+        }
+    }
+}
+
+unsigned grid_for(const ChunkGrid& g, int per_sm) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const unsigned cap = (unsigned)(sms * per_sm);
+    return g.items < cap ? g.items : cap;
+}
+
+template <int KIND>
+cudaError_t launch_count_kind(const void* x, const ChunkGrid& g, bool transform, int mask_mode, uint64_t mask_bits,
+                              unsigned long long* counts, cudaStream_t stream) {
+    constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
+    const unsigned grid = grid_for(g, 4);
+    const uint32_t mlo = (uint32_t)(mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(mask_bits >> 32);
+#define XBI_LAUNCH_CHUNKED(MASK, XF) k_pairs_chunked<KIND, MASK, XF><<<grid, kThreads, 0, stream>>>(x, g, mlo, mhi, counts)
+    if (transform) {
+        if constexpr (isf) {
+            switch (mask_mode) {
+                case kMaskNone: XBI_LAUNCH_CHUNKED(kMaskNone, true); break;
+                case kMaskNaN: XBI_LAUNCH_CHUNKED(kMaskNaN, true); break;
+                default: XBI_LAUNCH_CHUNKED(kMaskValue, true); break;
+            }
+        } else {
+            return cudaErrorInvalidValue;
+        }
+    } else {
+        switch (mask_mode) {
+            case kMaskNone: XBI_LAUNCH_CHUNKED(kMaskNone, false); break;
+            case kMaskNaN:
+                if constexpr (isf) { XBI_LAUNCH_CHUNKED(kMaskNaN, false); break; }
+                return cudaErrorInvalidValue;
+            default: XBI_LAUNCH_CHUNKED(kMaskValue, false); break;
+        }
+    }
+#undef XBI_LAUNCH_CHUNKED
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
+                                 int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream) {
+    cudaError_t e;
+    switch (dtype) {
+        case XBI_U8: e = launch_count_kind<kU8>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
+        case XBI_U16: e = launch_count_kind<kU16>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
+        case XBI_U32: e = launch_count_kind<kU32>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
+        case XBI_U64: e = launch_count_kind<kU64>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
+        case XBI_F16: e = launch_count_kind<kF16>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
+        case XBI_F32: e = launch_count_kind<kF32>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
+        case XBI_F64: e = launch_count_kind<kF64>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
+        default: return cudaErrorInvalidValue;
+    }
+    if (e != cudaSuccess) return e;
+    const int nbits = 8 * dtype_bytes(dtype);
+    const unsigned per = kThreads / nbits;
+    k_chunk_finalize<<<(nchunks + per - 1) / per, kThreads, 0, stream>>>(counts, nbits, nchunks);
+    note_launch();
+    return cudaGetLastError();
+}
+
+cudaError_t launch_bitround_chunked(void* x, int dtype, const ChunkGrid& g, const int* keepbits, cudaStream_t stream) {
+    const unsigned grid = grid_for(g, 8);
+    switch (dtype) {
+        case XBI_F16: k_bitround_chunked<2><<<grid, kThreads, 0, stream>>>(x, g, keepbits, 10); break;
+        case XBI_F32: k_bitround_chunked<4><<<grid, kThreads, 0, stream>>>(x, g, keepbits, 23); break;
+        case XBI_F64: k_bitround_chunked<8><<<grid, kThreads, 0, stream>>>(x, g, keepbits, 52); break;
+        default: return cudaErrorInvalidValue;
+    }
+    note_launch();
+    return cudaGetLastError();
+}
+
+}  // namespace xbi

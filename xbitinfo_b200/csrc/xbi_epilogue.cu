@@ -33,10 +33,11 @@ __global__ void k_combine(const Workspace* __restrict__ ws, int nbits, unsigned 
 //   pr = row sums, ps = column sums        (lines 149-150)
 //   sum p * log(p / (pr * ps)) / log(2)    (line 151), summed in the order 00,01,10,11
 // Round-to-nearest intrinsics keep ptxas from contracting mul+add into FMA.
-__global__ void k_mutual_information(const unsigned long long* __restrict__ counts, int nbits, int set_zero,
+// One thread per (table, bit): `total` = number of tables x nbits.
+__global__ void k_mutual_information(const unsigned long long* __restrict__ counts, long long total, int set_zero,
                                      double z, double* __restrict__ mi) {
-    const int k = threadIdx.x;
-    if (k >= nbits) return;
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= total) return;
     const unsigned long long c00 = counts[4 * k + 0], c01 = counts[4 * k + 1];
     const unsigned long long c10 = counts[4 * k + 2], c11 = counts[4 * k + 3];
     const unsigned long long n = c00 + c01 + c10 + c11;
@@ -78,9 +79,13 @@ cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* c
     return cudaGetLastError();
 }
 
-cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, int set_zero, double z_quantile,
-                                      double* mi, cudaStream_t stream) {
-    k_mutual_information<<<1, 64, 0, stream>>>(counts, nbits, set_zero, z_quantile, mi);
+cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, long long nbatch, int set_zero,
+                                      double z_quantile, double* mi, cudaStream_t stream) {
+    const long long total = nbatch * nbits;
+    if (total <= 0) return cudaSuccess;
+    const int threads = total < 256 ? 64 : 256;
+    k_mutual_information<<<(unsigned)((total + threads - 1) / threads), threads, 0, stream>>>(counts, total, set_zero,
+                                                                                             z_quantile, mi);
     note_launch();
     return cudaGetLastError();
 }

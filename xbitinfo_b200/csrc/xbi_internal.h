@@ -86,7 +86,8 @@ cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t s
 cudaError_t launch_mask_density(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream);
 
 cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* counts, cudaStream_t stream);
-cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, int set_zero,
+// K2 on `nbatch` consecutive (nbits,2,2) tables -> mi[nbatch][nbits]
+cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, long long nbatch, int set_zero,
                                       double z_quantile, double* mi, cudaStream_t stream);
 cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cudaStream_t stream);
 // K4: byte (bits == false) or bit (bits == true) shuffle of numel elements of itemsize bytes,
@@ -94,6 +95,26 @@ cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cud
 // bitrounded (K3's arithmetic, that many trailing mantissa bits dropped) on their way through.
 cudaError_t launch_shuffle(const void* src, void* dst, int itemsize, int64_t numel, bool bits, bool forward,
                            int drop_bits, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------
+// batched per-chunk kernels (xbi_chunked.cu)
+// ---------------------------------------------------------------------------------
+constexpr int kMaxChunkDims = 5;  // after merging unchunked neighbours (xbi_api.cu: plan_chunk_grid)
+// A regular chunk grid over a C-contiguous array.  Unused LEADING dimensions hold extent 1.
+struct ChunkGrid {
+    long long shape[kMaxChunkDims];   // array extents
+    long long stride[kMaxChunkDims];  // element strides
+    unsigned chunk[kMaxChunkDims];    // chunk extents (< 2^31; the last chunk of a dimension may be shorter)
+    unsigned nchunk[kMaxChunkDims];   // chunks per dimension
+    int axis;                         // analysed dimension, -1: none (bitround)
+    unsigned groups;                  // work items per chunk
+    unsigned tiles_per_group;         // 4096-element tiles per work item
+    unsigned items;                   // nchunks * groups
+};
+// counts[nchunks][nbits][4] must be zero on entry and holds the 2x2 tables on completion
+cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
+                                 int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream);
+cudaError_t launch_bitround_chunked(void* x, int dtype, const ChunkGrid& g, const int* keepbits, cudaStream_t stream);
 
 double normal_quantile(double p);  // AS241, host
 

@@ -116,3 +116,78 @@ def bitround_(x: torch.Tensor, keepbits: int) -> torch.Tensor:
         rc = nat.lib().xbi_bitround_inplace(x.data_ptr(), code, x.numel(), int(keepbits), _stream_ptr(x.device))
     nat.check(rc)
     return x
+
+
+# --------------------------------------------------------------------------------------
+# batched over a regular chunk grid (docs/chunking.ipynb workflow, csrc/xbi_chunked.cu)
+# --------------------------------------------------------------------------------------
+def chunk_grid_shape(shape, chunk_shape):
+    """Chunks per dimension of a regular grid (the last chunk of a dimension may be shorter)."""
+    if len(shape) != len(chunk_shape):
+        raise ValueError("chunk_shape needs one entry per dimension")
+    out = []
+    for n, c in zip(shape, chunk_shape):
+        c = int(c)
+        if c < 1:
+            raise ValueError("chunk extents must be positive")
+        out.append(-(-int(n) // min(c, max(int(n), 1))) if n else 0)
+    return tuple(out)
+
+
+def count_pairs_chunked(x: torch.Tensor, chunk_shape, axis: int, *, transform: bool = True,
+                        masked_value=None) -> torch.Tensor:
+    """K1 on every chunk of a regular grid on its own, one launch: int64 tensor of shape
+    ``chunks-per-dimension + (nbits, 2, 2)`` (chunks in C order of the grid)."""
+    require_cuda_tensor(x)
+    code = torch_dtype_code(x.dtype)
+    nd = x.dim()
+    if not -nd <= axis < nd:
+        raise ValueError(f"axis {axis} out of range for {nd}-d array")
+    axis %= nd
+    grid = chunk_grid_shape(tuple(x.shape), chunk_shape)
+    nbits = 8 * x.element_size()
+    counts = torch.empty(grid + (nbits, 2, 2), dtype=torch.int64, device=x.device)
+    np_dtype = numpy_dtype_of(x)
+    flags, bits = nat.mask_spec(np_dtype, masked_value)
+    if np_dtype.kind == "f" and transform:
+        flags |= nat.SIGNED_EXPONENT
+    with torch.cuda.device(x.device):
+        rc = nat.lib().xbi_count_pairs_chunked(
+            x.data_ptr(), code, nd, nat.int64_array(x.shape), nat.int64_array(chunk_shape), axis, flags, bits,
+            counts.data_ptr(), _stream_ptr(x.device))
+    nat.check(rc)
+    return counts
+
+
+def information_batched(counts: torch.Tensor, set_zero_insignificant: bool = False,
+                        confidence: float = 0.99) -> torch.Tensor:
+    """K2 on a stack of (nbits, 2, 2) tables -> float64 tensor ``counts.shape[:-3] + (nbits,)``."""
+    require_cuda_tensor(counts)
+    if counts.dtype != torch.int64 or counts.dim() < 3 or tuple(counts.shape[-2:]) != (2, 2):
+        raise ValueError("counts must be an int64 tensor of shape (..., nbits, 2, 2)")
+    nbits = int(counts.shape[-3])
+    nbatch = counts.numel() // (nbits * 4) if nbits else 0
+    mi = torch.empty(tuple(counts.shape[:-2]), dtype=torch.float64, device=counts.device)
+    with torch.cuda.device(counts.device):
+        rc = nat.lib().xbi_mutual_information_batched(
+            counts.data_ptr(), nbits, nbatch, int(bool(set_zero_insignificant)), float(confidence),
+            mi.data_ptr(), _stream_ptr(counts.device))
+    nat.check(rc)
+    return mi
+
+
+def bitround_chunked_(x: torch.Tensor, chunk_shape, keepbits: torch.Tensor) -> torch.Tensor:
+    """K3 in place, chunk c of the regular grid rounded to ``keepbits[c]`` mantissa bits
+    (int32 CUDA tensor with one entry per chunk, C order of the grid)."""
+    require_cuda_tensor(x)
+    require_cuda_tensor(keepbits)
+    code = torch_dtype_code(x.dtype)
+    grid = chunk_grid_shape(tuple(x.shape), chunk_shape)
+    if keepbits.dtype != torch.int32 or keepbits.numel() != math.prod(grid):
+        raise ValueError("keepbits must be an int32 tensor with one entry per chunk")
+    with torch.cuda.device(x.device):
+        rc = nat.lib().xbi_bitround_chunked(
+            x.data_ptr(), code, x.dim(), nat.int64_array(x.shape), nat.int64_array(chunk_shape),
+            keepbits.data_ptr(), _stream_ptr(x.device))
+    nat.check(rc)
+    return x
