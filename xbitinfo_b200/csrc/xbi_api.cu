@@ -303,6 +303,7 @@ static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_
     double full = 1.0;
     for (int i = 0; i < kMaxChunkDims; ++i) { g.shape[i] = 1; g.stride[i] = 0; g.chunk[i] = 1; g.nchunk[i] = 1; }
     g.axis = -1;
+    g.lo = kMaxChunkDims - m;
     for (int i = 0; i < m; ++i) {  // group i (innermost first) -> slot kMaxChunkDims-1-i
         const int slot = kMaxChunkDims - 1 - i;
         if (mchunk[i] > (int64_t)0x7FFFFFFF)

@@ -80,21 +80,23 @@ struct Walker {
         left = numel - (long long)l0;
     }
 
-    // advance by kThreads elements of the chunk's row-major order
-    __device__ __forceinline__ void step() {
+    // advance by kThreads elements of the chunk's row-major order.  Branch-free per dimension (selects);
+    // `lo` = first dimension in use (uniform): the padded leading ones are skipped.
+    __device__ __forceinline__ void step(int lo) {
         off += incoff;
         left -= kThreads;
         unsigned carry = 0;
 #pragma unroll
         for (int d = kD - 1; d >= 1; --d) {
-            if (inc[d] | carry) {
-                unsigned v = c[d] + inc[d] + carry;  // < 2 e[d]
-                carry = 0;
-                if (v >= e[d]) { v -= e[d]; carry = 1; off += wrap[d]; }
-                c[d] = v;
+            if (d >= lo) {
+                const unsigned v = c[d] + inc[d] + carry;  // < 2 e[d]
+                const bool wr = v >= e[d];
+                c[d] = wr ? v - e[d] : v;
+                off += wr ? wrap[d] : 0ll;
+                carry = wr ? 1u : 0u;
             }
         }
-        c[0] += inc[0] + carry;
+        c[0] += inc[0] + carry;  // (a carry out of dimension `lo` only happens past the end of the chunk)
     }
 
     // coordinate / extent along a dimension known only at run time (uniform), without indexing
@@ -116,7 +118,7 @@ struct Walker {
 // counts: [nchunks][nbits][4] accumulated RAW here (slot 0 of bit 0: pairs; slots 1, 2, 3 of bit k:
 // B, A, AB plane sums), turned into the 2x2 tables by k_chunk_finalize.
 template <int KIND, int MASK, bool XFORM>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, Elem<KIND>::kWords == 1 ? 2 : 1)
 k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
                 unsigned long long* __restrict__ counts) {
     using E = Elem<KIND>;
@@ -164,27 +166,39 @@ k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g,
 
         for (long long t = 0; t < tiles_left; ++t) {
             uint32_t wa[NW][kPerThread], wb[NW][kPerThread];
+            // phase 1: where this thread's 16 pairs are (pure index arithmetic); pairs that do not exist
+            // (past the end of the chunk, last element along the axis) read element 0 and its partner instead
+            long long offs[kPerThread];
+            uint32_t live = 0;
+#pragma unroll
+            for (int u = 0; u < kPerThread; ++u) {
+                const bool pair = w.left > 0 && w.coord(g.axis) + 1u < ea;
+                offs[u] = pair ? w.off : 0ll;
+                live |= (pair ? 1u : 0u) << u;
+                w.step(g.lo);
+            }
+            // phase 2: all 32 loads in flight
+#pragma unroll
+            for (int u = 0; u < kPerThread; ++u) {
+                uint32_t a[NW], b[NW];
+                E::load(x, offs[u], a);
+                E::load(x, offs[u] + pstride, b);
+#pragma unroll
+                for (int k = 0; k < NW; ++k) { wa[k][u] = a[k]; wb[k][u] = b[k]; }
+            }
+            // phase 3: mask test, transform, dead pairs zeroed
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) {
                 uint32_t a[NW], b[NW];
 #pragma unroll
-                for (int k = 0; k < NW; ++k) { a[k] = 0; b[k] = 0; }
-                if (w.left > 0 && w.coord(g.axis) + 1u < ea) {
-                    E::load(x, w.off, a);
-                    E::load(x, w.off + pstride, b);
-                    bool ok = true;
-                    if (MASK == kMaskNaN) ok = !(E::is_nan(a) || E::is_nan(b));
-                    if (MASK == kMaskValue) ok = !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
-                    if (XFORM) { E::transform(a); E::transform(b); }
-                    if (!ok) {
+                for (int k = 0; k < NW; ++k) { a[k] = wa[k][u]; b[k] = wb[k][u]; }
+                bool ok = (live >> u) & 1u;
+                if (MASK == kMaskNaN) ok = ok && !(E::is_nan(a) || E::is_nan(b));
+                if (MASK == kMaskValue) ok = ok && !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
+                if (XFORM) { E::transform(a); E::transform(b); }
 #pragma unroll
-                        for (int k = 0; k < NW; ++k) { a[k] = 0; b[k] = 0; }
-                    }
-                    nvalid += ok ? 1u : 0u;
-                }
-#pragma unroll
-                for (int k = 0; k < NW; ++k) { wa[k][u] = a[k]; wb[k][u] = b[k]; }
-                w.step();
+                for (int k = 0; k < NW; ++k) { wa[k][u] = ok ? a[k] : 0u; wb[k][u] = ok ? b[k] : 0u; }
+                nvalid += ok ? 1u : 0u;
             }
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
@@ -274,7 +288,7 @@ k_bitround_chunked(void* __restrict__ x, const __grid_constant__ ChunkGrid g, co
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) {
                 offs[u] = w.left > 0 ? w.off : -1;
-                w.step();
+                w.step(g.lo);
             }
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) if (offs[u] >= 0) v[u] = p[offs[u]];

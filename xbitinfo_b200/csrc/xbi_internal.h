@@ -107,6 +107,7 @@ struct ChunkGrid {
     unsigned chunk[kMaxChunkDims];    // chunk extents (< 2^31; the last chunk of a dimension may be shorter)
     unsigned nchunk[kMaxChunkDims];   // chunks per dimension
     int axis;                         // analysed dimension, -1: none (bitround)
+    int lo;                           // first dimension in use (the ones before it are padding)
     unsigned groups;                  // work items per chunk
     unsigned tiles_per_group;         // 4096-element tiles per work item
     unsigned items;                   // nchunks * groups
