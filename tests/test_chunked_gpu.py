@@ -176,3 +176,45 @@ def test_unsupported_and_bad_arguments():
         bitround_chunked_(x, (2, 2, 2, 2, 2, 1), torch.zeros(3, dtype=torch.int32, device="cuda"))
     empty = torch.zeros((0, 4), dtype=torch.float32, device="cuda")
     assert count_pairs_chunked(empty, (2, 2), 1).shape == (0, 2, 32, 2, 2)
+
+
+def test_arrays_of_more_than_2_to_32_elements_use_64_bit_offsets():
+    """The kernels switch to 64-bit element offsets at 2^32 elements.  Checked against the single-array
+    kernels (K1 / K3, themselves pinned to the oracle) applied to every chunk's contiguous copy."""
+    from xbitinfo_b200.device import PairCounter, bitround_
+
+    if torch.cuda.mem_get_info()[0] < 30 << 30:
+        pytest.skip("needs 30 GB of free device memory")
+    g = torch.Generator(device="cuda").manual_seed(3)
+    shape, chunk = (66000, 256, 256), (66000, 64, 128)  # 4.33e9 elements, 8 chunks
+    x = torch.empty(shape, dtype=torch.float16, device="cuda")
+    for lo in range(0, shape[0], 6000):
+        blk = torch.empty((min(6000, shape[0] - lo),) + shape[1:], dtype=torch.float32, device="cuda")
+        blk.normal_(0.0, 0.05, generator=g)
+        torch.cumsum(blk, dim=1, out=blk)
+        x[lo:lo + blk.shape[0]] = (blk + 3.0).to(torch.float16)
+        del blk
+    assert x.numel() >= 1 << 32
+    for axis in (0, 2):
+        got = count_pairs_chunked(x, chunk, axis, masked_value=None)
+        pc = PairCounter(x.dtype, x.device)
+        for i in range(4):
+            for j in range(2):
+                blk = x[:, 64 * i:64 * (i + 1), 128 * j:128 * (j + 1)].contiguous()
+                pc.reset()
+                pc.add(blk, axis, masked_value=None)
+                assert torch.equal(got[0, i, j], pc.counts), (axis, i, j)
+                del blk
+    keep = torch.tensor([0, 1, 2, 3, 4, 5, 7, 10], dtype=torch.int32, device="cuda")
+    ref_blocks = []
+    for i in range(4):
+        for j in range(2):
+            blk = x[:, 64 * i:64 * (i + 1), 128 * j:128 * (j + 1)].contiguous()
+            bitround_(blk, int(keep[2 * i + j]))
+            ref_blocks.append(blk[::977].clone())  # a sample of rows of the reference result
+            del blk
+    bitround_chunked_(x, chunk, keep)
+    for i in range(4):
+        for j in range(2):
+            got_rows = x[::977, 64 * i:64 * (i + 1), 128 * j:128 * (j + 1)]
+            assert torch.equal(got_rows.view(torch.int16), ref_blocks[2 * i + j].view(torch.int16)), (i, j)

@@ -29,16 +29,45 @@ constexpr int kPerThread = 16;
 constexpr unsigned kTile = kThreads * kPerThread;
 constexpr int kD = kMaxChunkDims;
 
-// position of one thread inside one chunk
+// Position of one thread inside one chunk.  A thread's 16 elements of a tile are 4 "chains" x 4
+// rounds: chain j sits at local index l0 + 256 j and every chain advances by 1024 per round, so the
+// four odometers are independent instruction streams (one chain stepped 16 times in a row was a
+// 16-deep dependent sequence per tile).  WIDE: 64-bit element offsets (arrays of 2^32 elements or
+// more); otherwise offsets are 32-bit and wrap-around arithmetic is exact.
+constexpr int kChains = 4;
+template <bool WIDE>
 struct Walker {
-    unsigned c[kD];     // local coordinates (c[0] is allowed to run past e[0]: past the end of the chunk)
-    unsigned e[kD];     // extents of this chunk (ragged at the upper array edges)
-    unsigned inc[kD];   // kThreads as a mixed-radix number over e
-    long long wrap[kD];  // offset correction when dimension d wraps and carries into d-1
-    long long off;       // element offset of the current element in the array
-    long long incoff;    // offset change of one step without wraps
-    long long left;      // elements from the current one to the end of the chunk (<= 0: past the end)
+    using Off = typename std::conditional<WIDE, long long, unsigned>::type;
+    unsigned c[kChains][kD];  // local coordinates (the outermost one may run past its extent: past the end)
+    Off off[kChains];         // element offset of the chain's current element in the array
+    unsigned e[kD];           // extents of this chunk (ragged at the upper array edges)
+    unsigned inc[kD];         // kChains * kThreads as a mixed-radix number over e
+    Off wrap[kD];             // offset correction when dimension d wraps and carries into d-1
+    Off incoff;               // offset change of one step without wraps
+    long long left;           // elements from chain 0's current one to the end of the chunk
     long long numel;
+
+    static __device__ __forceinline__ void decompose(unsigned v, const unsigned (&e)[kD], unsigned (&out)[kD]) {
+#pragma unroll
+        for (int d = kD - 1; d >= 1; --d) { out[d] = v % e[d]; v /= e[d]; }
+        out[0] = v;
+    }
+    // (c, off) += step, branch-free per dimension; `lo` = first dimension in use (uniform)
+    __device__ __forceinline__ void advance(unsigned (&cc)[kD], Off& o, const unsigned (&step)[kD], Off stepoff, int lo) const {
+        o += stepoff;
+        unsigned carry = 0;
+#pragma unroll
+        for (int d = kD - 1; d >= 1; --d) {
+            if (d >= lo) {
+                const unsigned v = cc[d] + step[d] + carry;  // < 2 e[d]
+                const bool wr = v >= e[d];
+                cc[d] = wr ? v - e[d] : v;
+                o += wr ? wrap[d] : (Off)0;
+                carry = wr ? 1u : 0u;
+            }
+        }
+        cc[0] += step[0] + carry;  // (a carry out of dimension `lo` only happens past the end of the chunk)
+    }
 
     __device__ __forceinline__ void init(const ChunkGrid& g, unsigned cid, unsigned long long l0) {
         long long base = 0;
@@ -55,56 +84,52 @@ struct Walker {
             numel *= e[d];
         }
         if (numel < (1ll << 31)) {
-            unsigned l = (unsigned)l0;
-#pragma unroll
-            for (int d = kD - 1; d >= 1; --d) { c[d] = l % e[d]; l /= e[d]; }
-            c[0] = l;
+            decompose((unsigned)l0, e, c[0]);
         } else {
             unsigned long long l = l0;
 #pragma unroll
-            for (int d = kD - 1; d >= 1; --d) { c[d] = (unsigned)(l % e[d]); l /= e[d]; }
-            c[0] = (unsigned)l;
+            for (int d = kD - 1; d >= 1; --d) { c[0][d] = (unsigned)(l % e[d]); l /= e[d]; }
+            c[0][0] = (unsigned)l;
         }
-        unsigned rem = kThreads;
-#pragma unroll
-        for (int d = kD - 1; d >= 1; --d) { inc[d] = rem % e[d]; rem /= e[d]; }
-        inc[0] = rem;
-        off = base;
-        incoff = 0;
+        long long o0 = base;
 #pragma unroll
         for (int d = 0; d < kD; ++d) {
-            off += (long long)c[d] * g.stride[d];
-            incoff += (long long)inc[d] * g.stride[d];
-            wrap[d] = d > 0 ? g.stride[d - 1] - (long long)e[d] * g.stride[d] : 0;
+            o0 += (long long)c[0][d] * g.stride[d];
+            wrap[d] = d > 0 ? (Off)(g.stride[d - 1] - (long long)e[d] * g.stride[d]) : (Off)0;
         }
+        off[0] = (Off)o0;
+        // chains 1.. : one step of kThreads each
+        unsigned s1[kD];
+        decompose(kThreads, e, s1);
+        long long s1off = 0;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) s1off += (long long)s1[d] * g.stride[d];
+#pragma unroll
+        for (int j = 1; j < kChains; ++j) {
+#pragma unroll
+            for (int d = 0; d < kD; ++d) c[j][d] = c[j - 1][d];
+            off[j] = off[j - 1];
+            advance(c[j], off[j], s1, (Off)s1off, g.lo);
+        }
+        decompose(kChains * kThreads, e, inc);
+        long long io = 0;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) io += (long long)inc[d] * g.stride[d];
+        incoff = (Off)io;
         left = numel - (long long)l0;
     }
 
-    // advance by kThreads elements of the chunk's row-major order.  Branch-free per dimension (selects);
-    // `lo` = first dimension in use (uniform): the padded leading ones are skipped.
-    __device__ __forceinline__ void step(int lo) {
-        off += incoff;
-        left -= kThreads;
-        unsigned carry = 0;
-#pragma unroll
-        for (int d = kD - 1; d >= 1; --d) {
-            if (d >= lo) {
-                const unsigned v = c[d] + inc[d] + carry;  // < 2 e[d]
-                const bool wr = v >= e[d];
-                c[d] = wr ? v - e[d] : v;
-                off += wr ? wrap[d] : 0ll;
-                carry = wr ? 1u : 0u;
-            }
-        }
-        c[0] += inc[0] + carry;  // (a carry out of dimension `lo` only happens past the end of the chunk)
-    }
+    // chain j to its next round
+    __device__ __forceinline__ void step(int j, int lo) { advance(c[j], off[j], inc, incoff, lo); }
+    __device__ __forceinline__ bool inside(int j) const { return left > (long long)j * kThreads; }
+    __device__ __forceinline__ void next_round() { left -= kChains * kThreads; }
 
     // coordinate / extent along a dimension known only at run time (uniform), without indexing
     // the register arrays dynamically
-    __device__ __forceinline__ unsigned coord(int axis) const {
+    __device__ __forceinline__ unsigned coord(int j, int axis) const {
         unsigned v = 0;
 #pragma unroll
-        for (int d = 0; d < kD; ++d) if (d == axis) v = c[d];
+        for (int d = 0; d < kD; ++d) if (d == axis) v = c[j][d];
         return v;
     }
     __device__ __forceinline__ unsigned extent(int axis) const {
@@ -117,7 +142,7 @@ struct Walker {
 
 // counts: [nchunks][nbits][4] accumulated RAW here (slot 0 of bit 0: pairs; slots 1, 2, 3 of bit k:
 // B, A, AB plane sums), turned into the 2x2 tables by k_chunk_finalize.
-template <int KIND, int MASK, bool XFORM>
+template <int KIND, int MASK, bool XFORM, bool WIDE>
 __global__ void __launch_bounds__(kThreads, Elem<KIND>::kWords == 1 ? 2 : 1)
 k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
                 unsigned long long* __restrict__ counts) {
@@ -128,14 +153,15 @@ k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g,
     __shared__ unsigned long long s_sum[3][64];
     __shared__ unsigned long long s_n;
     const uint32_t lane = threadIdx.x & 31u;
-    long long pstride = 0;
+    using Off = typename Walker<WIDE>::Off;
+    Off pstride = 0;
 #pragma unroll
-    for (int d = 0; d < kD; ++d) if (d == g.axis) pstride = g.stride[d];
+    for (int d = 0; d < kD; ++d) if (d == g.axis) pstride = (Off)g.stride[d];
 
     for (unsigned item = blockIdx.x; item < g.items; item += gridDim.x) {
         const unsigned cid = item / g.groups, grp = item - cid * g.groups;
         const unsigned long long group_base = (unsigned long long)grp * g.tiles_per_group * kTile;
-        Walker w;
+        Walker<WIDE> w;
         w.init(g, cid, group_base + threadIdx.x);
         long long tiles_left = (w.numel - (long long)group_base + (long long)kTile - 1) / (long long)kTile;  // uniform
         if (tiles_left <= 0) continue;  // an edge chunk with fewer tiles than the full ones
@@ -168,21 +194,23 @@ k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g,
             uint32_t wa[NW][kPerThread], wb[NW][kPerThread];
             // phase 1: where this thread's 16 pairs are (pure index arithmetic); pairs that do not exist
             // (past the end of the chunk, last element along the axis) read element 0 and its partner instead
-            long long offs[kPerThread];
+            Off offs[kPerThread];
             uint32_t live = 0;
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) {
-                const bool pair = w.left > 0 && w.coord(g.axis) + 1u < ea;
-                offs[u] = pair ? w.off : 0ll;
+                const int j = u % kChains;  // element u = chain j in round u / kChains
+                const bool pair = w.inside(j) && w.coord(j, g.axis) + 1u < ea;
+                offs[u] = pair ? w.off[j] : (Off)0;
                 live |= (pair ? 1u : 0u) << u;
-                w.step(g.lo);
+                w.step(j, g.lo);
+                if (j == kChains - 1) w.next_round();
             }
             // phase 2: all 32 loads in flight
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) {
                 uint32_t a[NW], b[NW];
-                E::load(x, offs[u], a);
-                E::load(x, offs[u] + pstride, b);
+                E::load(x, (long long)offs[u], a);
+                E::load(x, (long long)(Off)(offs[u] + pstride), b);
 #pragma unroll
                 for (int k = 0; k < NW; ++k) { wa[k][u] = a[k]; wb[k][u] = b[k]; }
             }
@@ -263,7 +291,7 @@ k_chunk_finalize(unsigned long long* __restrict__ counts, int nbits, unsigned nc
 }
 
 // K3 per chunk: keepbits[chunk] mantissa bits kept (clamped to 0..mant; mant = identity)
-template <int BYTES>
+template <int BYTES, bool WIDE>
 __global__ void __launch_bounds__(kThreads)
 k_bitround_chunked(void* __restrict__ x, const __grid_constant__ ChunkGrid g, const int* __restrict__ keepbits, int mant) {
     using T = typename std::conditional<BYTES == 2, uint16_t, typename std::conditional<BYTES == 4, uint32_t, unsigned long long>::type>::type;
@@ -278,29 +306,40 @@ k_bitround_chunked(void* __restrict__ x, const __grid_constant__ ChunkGrid g, co
         const unsigned long long keep = (full >> drop) << drop;
         const unsigned long long half_m1 = (1ull << (drop - 1)) - 1ull;
         const unsigned long long group_base = (unsigned long long)grp * g.tiles_per_group * kTile;
-        Walker w;
+        Walker<WIDE> w;
         w.init(g, cid, group_base + threadIdx.x);
         long long tiles_left = (w.numel - (long long)group_base + (long long)kTile - 1) / (long long)kTile;
         if (tiles_left > (long long)g.tiles_per_group) tiles_left = g.tiles_per_group;
         for (long long t = 0; t < tiles_left; ++t) {
-            long long offs[kPerThread];
+            typename Walker<WIDE>::Off offs[kPerThread];
+            uint32_t live = 0;
             T v[kPerThread];
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) {
-                offs[u] = w.left > 0 ? w.off : -1;
-                w.step(g.lo);
+                const int j = u % kChains;
+                offs[u] = w.off[j];
+                live |= (w.inside(j) ? 1u : 0u) << u;
+                w.step(j, g.lo);
+                if (j == kChains - 1) w.next_round();
             }
 #pragma unroll
-            for (int u = 0; u < kPerThread; ++u) if (offs[u] >= 0) v[u] = p[offs[u]];
+            for (int u = 0; u < kPerThread; ++u) if ((live >> u) & 1u) v[u] = p[offs[u]];
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) {
-                if (offs[u] >= 0) {
+                if ((live >> u) & 1u) {
                     const unsigned long long b = v[u];
                     p[offs[u]] = (T)((b + ((b >> drop) & 1ull) + half_m1) & keep);
                 }
             }
         }
     }
+}
+
+// 32-bit element offsets are exact when the whole array has fewer than 2^32 elements
+bool needs_wide_offsets(const ChunkGrid& g) {
+    double numel = 1.0;
+    for (int d = 0; d < kD; ++d) numel *= (double)g.shape[d];
+    return numel >= 4294967296.0;
 }
 
 unsigned grid_for(const ChunkGrid& g, int per_sm) {
@@ -317,7 +356,12 @@ cudaError_t launch_count_kind(const void* x, const ChunkGrid& g, bool transform,
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     const unsigned grid = grid_for(g, 4);
     const uint32_t mlo = (uint32_t)(mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(mask_bits >> 32);
-#define XBI_LAUNCH_CHUNKED(MASK, XF) k_pairs_chunked<KIND, MASK, XF><<<grid, kThreads, 0, stream>>>(x, g, mlo, mhi, counts)
+    const bool wide = needs_wide_offsets(g);
+#define XBI_LAUNCH_CHUNKED(MASK, XF)                                                                   \
+    do {                                                                                               \
+        if (wide) k_pairs_chunked<KIND, MASK, XF, true><<<grid, kThreads, 0, stream>>>(x, g, mlo, mhi, counts);  \
+        else k_pairs_chunked<KIND, MASK, XF, false><<<grid, kThreads, 0, stream>>>(x, g, mlo, mhi, counts);      \
+    } while (0)
     if (transform) {
         if constexpr (isf) {
             switch (mask_mode) {
@@ -367,10 +411,17 @@ cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, u
 
 cudaError_t launch_bitround_chunked(void* x, int dtype, const ChunkGrid& g, const int* keepbits, cudaStream_t stream) {
     const unsigned grid = grid_for(g, 8);
+    const bool wide = needs_wide_offsets(g);
     switch (dtype) {
-        case XBI_F16: k_bitround_chunked<2><<<grid, kThreads, 0, stream>>>(x, g, keepbits, 10); break;
-        case XBI_F32: k_bitround_chunked<4><<<grid, kThreads, 0, stream>>>(x, g, keepbits, 23); break;
-        case XBI_F64: k_bitround_chunked<8><<<grid, kThreads, 0, stream>>>(x, g, keepbits, 52); break;
+#define XBI_LAUNCH_ROUND(B, M)                                                                        \
+    do {                                                                                              \
+        if (wide) k_bitround_chunked<B, true><<<grid, kThreads, 0, stream>>>(x, g, keepbits, M);      \
+        else k_bitround_chunked<B, false><<<grid, kThreads, 0, stream>>>(x, g, keepbits, M);          \
+    } while (0)
+        case XBI_F16: XBI_LAUNCH_ROUND(2, 10); break;
+        case XBI_F32: XBI_LAUNCH_ROUND(4, 23); break;
+        case XBI_F64: XBI_LAUNCH_ROUND(8, 52); break;
+#undef XBI_LAUNCH_ROUND
         default: return cudaErrorInvalidValue;
     }
     note_launch();

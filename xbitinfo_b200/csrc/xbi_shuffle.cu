@@ -158,8 +158,8 @@ template <int S, bool FORWARD>
 __global__ void __launch_bounds__(kThreads)
 k_byte_shuffle(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long long n, long long ngroups, RoundSpec rs) {
     const long long stride = (long long)gridDim.x * kThreads;
-    for (long long g = (long long)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
-        if (FORWARD) {
+    if (FORWARD) {
+        for (long long g = (long long)blockIdx.x * kThreads + threadIdx.x; g < ngroups; g += stride) {
             uint32_t in[4 * S], out[S][4];
             const uint4* p = reinterpret_cast<const uint4*>(src) + g * S;
 #pragma unroll
@@ -175,17 +175,38 @@ k_byte_shuffle(const uint8_t* __restrict__ src, uint8_t* __restrict__ dst, long 
 #pragma unroll
             for (int j = 0; j < S; ++j)
                 *reinterpret_cast<uint4*>(dst + j * n + 16 * g) = make_uint4(out[j][0], out[j][1], out[j][2], out[j][3]);
-        } else {
-            uint32_t in[S][4], out[4 * S];
+        }
+    } else {
+        // A lane rebuilds 16 elements = S consecutive 16-byte vectors; written directly, a warp's store
+        // instruction would scatter 32 vectors 16*S bytes apart (half-filled sectors for S >= 4).  The
+        // vectors are turned through shared memory (rows of S vectors, pitch S+1: conflict free both ways)
+        // so that every store instruction of the warp covers 512 contiguous bytes.
+        __shared__ uint4 turn[kThreads / 32][32 * (S + 1)];
+        const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+        uint4* tw = turn[warp];
+        for (long long g0 = ((long long)blockIdx.x * kThreads + threadIdx.x) & ~31ll; g0 < ngroups; g0 += stride) {
+            const long long g = g0 + lane;
+            if (g < ngroups) {
+                uint32_t in[S][4], out[4 * S];
 #pragma unroll
-            for (int j = 0; j < S; ++j) {
-                const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + j * n + 16 * g));
-                in[j][0] = v.x; in[j][1] = v.y; in[j][2] = v.z; in[j][3] = v.w;
+                for (int j = 0; j < S; ++j) {
+                    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + j * n + 16 * g));
+                    in[j][0] = v.x; in[j][1] = v.y; in[j][2] = v.z; in[j][3] = v.w;
+                }
+                planes_to_bytes<S>(in, out);
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    tw[lane * (S + 1) + k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
             }
-            planes_to_bytes<S>(in, out);
-            uint4* p = reinterpret_cast<uint4*>(dst) + g * S;
+            __syncwarp();
+            const long long nvec = (ngroups - g0 < 32 ? ngroups - g0 : 32) * S;  // vectors this warp holds
+            uint4* p = reinterpret_cast<uint4*>(dst) + g0 * S;
 #pragma unroll
-            for (int k = 0; k < S; ++k) p[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+            for (int k = 0; k < S; ++k) {
+                const uint32_t f = k * 32 + lane;  // vector index in the warp's output
+                if (f < nvec) p[f] = tw[(f / S) * (S + 1) + (f % S)];
+            }
+            __syncwarp();
         }
     }
     // elements outside the 16-element groups (unaligned buffers take this path entirely)
@@ -302,6 +323,8 @@ k_bit_shuffle(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long
                 }
             }
         } else {
+            uint32_t lo64[S == 8 ? 32 : 1];  // S == 8: low words of this lane's 16 output vectors
+            (void)lo64;
 #pragma unroll
             for (int sub = 0; sub < NSUB; ++sub) {
                 uint32_t a[32];
@@ -333,12 +356,16 @@ k_bit_shuffle(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, long
                     *reinterpret_cast<uint4*>(&st[lane * kPitch + 4 * k]) = make_uint4(a[4 * k], a[4 * k + 1], a[4 * k + 2], a[4 * k + 3]);
                 __syncwarp();
                 if constexpr (S == 8) {
-                    // interleave with the other half: write this half's words with stride 2
-                    uint32_t* q = dst + tile * WPT + sub;
+                    // the low words of the tile's elements wait in registers for the high words; then
+                    // 16-byte vectors (lo hi lo hi) of elements 2m, 2m+1 go out, 512 contiguous bytes per
+                    // store instruction of the warp
+                    uint4* q = reinterpret_cast<uint4*>(dst + tile * WPT);
 #pragma unroll
-                    for (int k = 0; k < 32; ++k) {
-                        const uint32_t e = lane + 32 * k;  // element index in the tile
-                        q[2 * e] = st[(e >> 5) * kPitch + (e & 31u)];
+                    for (int k = 0; k < 16; ++k) {
+                        const uint32_t m = lane + 32 * k, e = 2 * m;  // vector / first element in the tile
+                        const uint2 v = *reinterpret_cast<const uint2*>(&st[(e >> 5) * kPitch + (e & 31u)]);
+                        if (sub == 0) { lo64[2 * k] = v.x; lo64[2 * k + 1] = v.y; }
+                        else q[m] = make_uint4(lo64[2 * k], v.x, lo64[2 * k + 1], v.y);
                     }
                 } else {
                     uint4* p = reinterpret_cast<uint4*>(dst + tile * WPT + sub * 1024);
