@@ -183,6 +183,19 @@ int xbi_bitinformation_host(const void* x_host, int dtype, int64_t outer, int64_
                             unsigned long long* counts_host, int device);
 int xbi_bitround_host(const void* src_host, void* dst_host, int dtype, int64_t numel,
                       int keepbits, int device);
+/*
+ * Several analysed dimensions of ONE host array in a single pass over PCIe: what
+ * get_bitinformation(ds, dim=None) asks for (xbitinfo/xbitinfo.py:373-406 loops the dimensions and
+ * runs the backend once per dimension).  The C-contiguous array (`ndim` extents `shape`) is staged
+ * in slabs of whole rows of its first dimension; every slab is counted along each of the `naxes`
+ * axes in `axes` while it is on the device (the first dimension with a one-row halo).  mi_host
+ * receives naxes*nbits doubles, counts_host (may be NULL) naxes*nbits*4 counters, in the order of
+ * `axes`.  Results are identical to naxes calls of xbi_bitinformation_host.
+ */
+int xbi_bitinformation_host_multi(const void* x_host, int dtype, int ndim, const int64_t* shape, int naxes,
+                                  const int* axes, unsigned flags, uint64_t mask_bits,
+                                  int set_zero_insignificant, double confidence, double* mi_host,
+                                  unsigned long long* counts_host, int device);
 void xbi_host_release(void);
 
 #ifdef __cplusplus

@@ -1,6 +1,10 @@
 """The public API with implementation="cuda" against the CPU oracle -- written after the
 reference's own tests (tests/test_get_bitinformation.py, test_get_keepbits.py,
 test_bitround.py), on synthetic stand-ins for the tutorial datasets (no network here)."""
+import os
+import subprocess
+import sys
+
 import numpy as np
 import pytest
 import torch
@@ -223,6 +227,99 @@ print("ok")
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
                        cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("env_extra", [{}, {"XBI_HOST_STAGING": "0"}, {"XBI_HOST_THREADS": "3"}])
+def test_pageable_and_pinned_host_buffers_give_identical_results(env_extra):
+    """Pageable numpy memory goes through the pinned ring and the copy threads (csrc/xbi_hostpool.cu),
+    page-locked memory straight to the DMA engine; contiguous slabs, pitched column strips (4 MB staging
+    buffer) and bitround into a fresh / the same / a pinned array must all agree with the oracle."""
+    code = r'''
+import sys
+import numpy as np, torch
+sys.path.insert(0, "tests")
+from conftest import smooth_field
+from oracle import bitinfo_oracle as bo
+from oracle import bitround_oracle as bro
+from xbitinfo_b200 import engine
+rng = np.random.default_rng(21)
+x = smooth_field(rng, (3, 2000, 1024), "float32", axis=1, scale=0.3)     # 24.6 MB, staging is 4 MB
+pinned = torch.empty(x.shape, dtype=torch.float32, pin_memory=True).numpy()
+pinned[...] = x
+for ax in range(3):
+    want = bo.bitinformation(x, ax)[0]
+    for arr in (x, pinned):
+        mi, c = engine.bitinformation(arr, ax, return_counts=True)
+        assert np.array_equal(c, want), ax
+y = smooth_field(rng, (11_000_003,), "float32", axis=0, scale=0.3)       # 44 MB: several pinned slots, ragged end
+want = bro.bitround(y, 6).view("u4")
+assert np.array_equal(engine.bitround(y, 6).view("u4"), want)
+yp = torch.empty(y.shape, dtype=torch.float32, pin_memory=True).numpy()
+yp[...] = y
+assert np.array_equal(engine.bitround(yp, 6).view("u4"), want)
+# the C entry point allows src == dst
+import ctypes as C
+from xbitinfo_b200 import _native as nat
+z = y.copy()
+nat.check(nat.lib().xbi_bitround_host(z.ctypes.data_as(C.c_void_p), z.ctypes.data_as(C.c_void_p), nat.F32, z.size, 6, 0))
+assert np.array_equal(z.view("u4"), want)
+out_pinned = torch.empty(y.shape, dtype=torch.float32, pin_memory=True).numpy()
+nat.check(nat.lib().xbi_bitround_host(y.ctypes.data_as(C.c_void_p), out_pinned.ctypes.data_as(C.c_void_p), nat.F32, y.size, 6, 0))
+assert np.array_equal(out_pinned.view("u4"), want)
+d = smooth_field(rng, (5_000_001,), "float64", axis=0, scale=0.3)
+assert np.array_equal(engine.bitround(d, 20).view("u8"), bro.bitround(d, 20).view("u8"))
+print("ok")
+'''
+    env = dict(os.environ, XBI_STAGING_MB="4", **env_extra)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+@pytest.mark.parametrize("staging_mb", ["1", "256"])
+def test_all_axes_in_one_pass_over_the_host_array(staging_mb):
+    """xbi_bitinformation_host_multi (every slab on the device once for all the analysed axes; one halo row
+    for the first dimension) gives exactly the per-axis results and the oracle's; 1 MB staging = many slabs."""
+    code = r'''
+import sys
+import numpy as np
+sys.path.insert(0, "tests")
+from conftest import smooth_field
+from oracle import bitinfo_oracle as bo
+from xbitinfo_b200 import engine
+rng = np.random.default_rng(31)
+cases = [
+    (smooth_field(rng, (41, 30, 50, 24), "float32", axis=1, scale=0.3), None),
+    (smooth_field(rng, (300, 65, 33), "float64", axis=0, scale=0.3), float("nan")),
+    (smooth_field(rng, (2, 700, 512), "float16", axis=1, scale=0.05, base=3.0), None),   # one row > half the 1 MB buffer
+    (rng.integers(-900, 900, size=(57, 120, 40), dtype="int16"), 7),
+    (smooth_field(rng, (100000,), "float32", axis=0, scale=0.3), None),
+]
+cases[1][0][rng.random(cases[1][0].shape) < 0.1] = np.nan
+for x, mv in cases:
+    axes = list(range(x.ndim))[::-1]
+    got = engine.bitinformation_multi(x, axes + axes[:1], masked_value=mv, set_zero_insignificant=True, return_counts=True)
+    assert len(got) == x.ndim + 1
+    for a, (mi, c) in zip(axes + axes[:1], got):
+        want_c, _, want_mi = bo.bitinformation(x, a, masked_value=mv, set_zero_insignificant_flag=True)
+        assert np.array_equal(c, want_c), (x.shape, a)
+        mi1, c1 = engine.bitinformation(x, a, masked_value=mv, set_zero_insignificant=True, return_counts=True)
+        assert np.array_equal(c, c1) and np.array_equal(mi, mi1, equal_nan=True), (x.shape, a)
+print("ok")
+'''
+    env = dict(os.environ, XBI_STAGING_MB=staging_mb)
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True,
+                       cwd=os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    assert r.returncode == 0 and "ok" in r.stdout, r.stdout + r.stderr
+
+
+def test_get_bitinformation_all_dims_equals_dim_by_dim():
+    ds = eraint_like()
+    every = xb.get_bitinformation(ds)
+    for d in every.coords["dim"].values:
+        one = xb.get_bitinformation(ds, dim=str(d))
+        for v in ds.data_vars:
+            assert np.array_equal(every[v].sel(dim=d).values, one[v].values, equal_nan=True), (v, d)
 
 
 def test_launch_counters_move():

@@ -26,6 +26,7 @@ def fake_engine(data, axis, masked_value=None, set_zero_insignificant=False, con
 @pytest.fixture
 def oracle_backend(monkeypatch):
     monkeypatch.setattr(engine, "bitinformation", fake_engine)
+    monkeypatch.setattr(engine, "bitinformation_multi", lambda data, axes, **kw: [fake_engine(data, a, **kw) for a in axes])
 
 
 def rasm_like(seed=0):

@@ -92,6 +92,9 @@ def lib() -> C.CDLL:
     L.xbi_bitround_shuffle.argtypes = [vp, vp, i32, i64, i32, i32, vp]
     L.xbi_bitinformation_host.restype = i32
     L.xbi_bitinformation_host.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, i32]
+    L.xbi_bitinformation_host_multi.restype = i32
+    L.xbi_bitinformation_host_multi.argtypes = [vp, i32, i32, C.POINTER(i64), i32, C.POINTER(i32), u32, u64, i32, dbl,
+                                                vp, vp, i32]
     L.xbi_bitround_host.restype = i32
     L.xbi_bitround_host.argtypes = [vp, vp, i32, i64, i32, i32]
     L.xbi_host_release.restype = None
@@ -108,6 +111,7 @@ EXPORTED_SYMBOLS = (
     "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace", "xbi_shuffle", "xbi_bitround_shuffle",
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
     "xbi_mutual_information_batched", "xbi_count_pairs_chunked", "xbi_bitround_chunked",
+    "xbi_bitinformation_host_multi",
 )
 
 

@@ -198,10 +198,11 @@ def _resolve_kwargs(da_dtype, kwargs):
     return masked_value, set_zero, confidence
 
 
-def _cuda_get_bitinformation(ds, var, axis, dim, kwargs={}):
+def _cuda_get_bitinformation(ds, var, axis, dim, kwargs={}, precomputed=None):
     """The backend function of the drop-in boundary: same signature and result dictionary
     as ``_py_get_bitinformation`` / ``_jl_get_bitinformation`` [309-370]; ``None`` when the
-    variable does not have the dimension."""
+    variable does not have the dimension.  ``precomputed``: ``{(var, dim): bitinfo}`` from
+    :func:`_cuda_precompute_dims` (the all-dimensions call analyses a variable once for all of them)."""
     da = ds[var]
     masked_value, set_zero, confidence = _resolve_kwargs(da.dtype, kwargs)
     if axis is not None:
@@ -212,13 +213,35 @@ def _cuda_get_bitinformation(ds, var, axis, dim, kwargs={}):
         except ValueError:
             logging.info(f"Variable {var} does not have dimension {dim}. Skipping.")
             return None
-    logging.info("Calling cuda implementation now")
-    bitinfo = engine.bitinformation(_xr.raw_data(da), axis, masked_value=masked_value,
-                                    set_zero_insignificant=set_zero, confidence=confidence)
+    if precomputed is not None and (var, dim) in precomputed:
+        bitinfo = precomputed[(var, dim)]
+    else:
+        logging.info("Calling cuda implementation now")
+        bitinfo = engine.bitinformation(_xr.raw_data(da), axis, masked_value=masked_value,
+                                        set_zero_insignificant=set_zero, confidence=confidence)
     return {"bitinfo": bitinfo, "dim": dim, "axis": int(axis), "dtype": str(np.dtype(da.dtype))}
 
 
-def _get_bitinformation_along_axis(ds, implementation, axis, dim, **kwargs):
+def _cuda_precompute_dims(ds, dims, kwargs):
+    """``{(var, dim): bitinfo}`` for every variable and every one of ``dims`` it has, each variable
+    crossing PCIe once for all its dimensions (``engine.bitinformation_multi``) instead of once per
+    dimension as the reference's loop over dimensions would [387-399]."""
+    out = {}
+    for var in ds.data_vars:
+        da = ds[var]
+        mine = [d for d in dims if d in da.dims]
+        if len(mine) < 2:
+            continue
+        masked_value, set_zero, confidence = _resolve_kwargs(da.dtype, kwargs)
+        axes = [da.get_axis_num(d) for d in mine]
+        infos = engine.bitinformation_multi(_xr.raw_data(da), axes, masked_value=masked_value,
+                                            set_zero_insignificant=set_zero, confidence=confidence)
+        for d, info in zip(mine, infos):
+            out[(var, d)] = info
+    return out
+
+
+def _get_bitinformation_along_axis(ds, implementation, axis, dim, precomputed=None, **kwargs):
     """Per-variable loop and implementation dispatch  [409-441]."""
     info_per_bit = {}
     for var in ds.data_vars:
@@ -230,7 +253,7 @@ def _get_bitinformation_along_axis(ds, implementation, axis, dim, **kwargs):
                 category=UserWarning,
             )
         if implementation == "cuda":
-            info_per_bit_var = _cuda_get_bitinformation(ds, var, axis, dim, kwargs)
+            info_per_bit_var = _cuda_get_bitinformation(ds, var, axis, dim, kwargs, precomputed)
             if info_per_bit_var is None:
                 continue
             info_per_bit[var] = info_per_bit_var
@@ -252,12 +275,21 @@ def _get_bitinformation_along_dims(ds, dim=None, label=None, overwrite=False, im
     coordinate alphabetically and fills variables that lack a dimension with NaN."""
     if dim is None:
         dim = list(ds.dims)
+    precomputed = None
+    if implementation == "cuda" and len(dim) > 1:
+        # silence the per-call default-mask warning here; the per-dimension loop below issues it as before
+        level = logging.getLogger().level
+        logging.getLogger().setLevel(max(level, logging.ERROR))
+        try:
+            precomputed = _cuda_precompute_dims(ds, dim, kwargs)
+        finally:
+            logging.getLogger().setLevel(level)
     per_dim = {}
     for d in dim:
         logging.info(f"Get bitinformation along dimension {d}")
         if label is not None:
             label = "_".join([label, d])  # (sic) the suffix accumulates, as in the reference [392-393]
-        info = _get_bitinformation_along_axis(ds, implementation, None, d, **kwargs)
+        info = _get_bitinformation_along_axis(ds, implementation, None, d, precomputed=precomputed, **kwargs)
         if label is not None:
             out_fn = label + ".json"
             if not os.path.exists(out_fn) or overwrite:

@@ -13,12 +13,12 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libxbitinfo_b200.so")
-SOURCES = ["xbi_api.cu", "xbi_count_generic.cu", "xbi_count_tma.cu", "xbi_count_cols.cu", "xbi_epilogue.cu", "xbi_bitround.cu", "xbi_shuffle.cu", "xbi_chunked.cu"]
+SOURCES = ["xbi_api.cu", "xbi_count_generic.cu", "xbi_count_tma.cu", "xbi_count_cols.cu", "xbi_epilogue.cu", "xbi_bitround.cu", "xbi_shuffle.cu", "xbi_chunked.cu", "xbi_hostpool.cu"]
 HEADERS = ["xbi_common.cuh", "xbi_elem.cuh", "xbi_mask.cuh", "xbi_tma.cuh", "xbi_tmap.h", "xbi_internal.h", "../../include/xbitinfo_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-std=c++17", "-lineinfo",
-    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas",
+    "-Xcompiler", "-fPIC,-O2,-Wall,-Wno-unknown-pragmas,-pthread",
     "-Xptxas", "-v",
 ]
 
@@ -66,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 sys.stderr.write(r.stderr)
     if jobs or force or _stale(LIB, objs):
-        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static", "-Xlinker", "--no-undefined"]
+        cmd = [nvcc, "-shared", "-o", LIB, *objs, "-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

@@ -137,6 +137,15 @@ struct HostCtx {
     Workspace* ws[2] = {nullptr, nullptr};
     unsigned long long* counts = nullptr;  // 64*4
     double* mi = nullptr;                  // 64
+    unsigned long long* counts_multi = nullptr;  // XBI_MAX_DIMS tables (xbi_bitinformation_host_multi)
+    double* mi_multi = nullptr;
+    // pinned staging for pageable caller memory (allocated on first need): two slots per direction
+    static constexpr size_t kPinBytes = (size_t)32 << 20;
+    void* pin_in[2] = {nullptr, nullptr};
+    void* pin_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    bool in_busy[2] = {false, false};
+    int in_next = 0;
     void release() {
         if (device < 0) return;
         cudaSetDevice(device);
@@ -145,10 +154,17 @@ struct HostCtx {
             if (buf[i]) cudaFree(buf[i]);
             if (ws[i]) cudaFree(ws[i]);
             stream[i] = nullptr; buf[i] = nullptr; ws[i] = nullptr;
+            if (pin_in[i]) cudaFreeHost(pin_in[i]);
+            if (pin_out[i]) cudaFreeHost(pin_out[i]);
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+            pin_in[i] = nullptr; pin_out[i] = nullptr; ev_in[i] = nullptr; ev_out[i] = nullptr; in_busy[i] = false;
         }
         if (counts) cudaFree(counts);
         if (mi) cudaFree(mi);
-        counts = nullptr; mi = nullptr;
+        if (counts_multi) cudaFree(counts_multi);
+        if (mi_multi) cudaFree(mi_multi);
+        counts = nullptr; mi = nullptr; counts_multi = nullptr; mi_multi = nullptr;
         device = -1;
         buf_bytes = 0;
     }
@@ -180,6 +196,76 @@ static int ensure_ctx(int device) {
     }
     XBI_CUDA(cudaMalloc(&g_ctx.counts, 64 * 4 * sizeof(unsigned long long)), "cudaMalloc(counts)");
     XBI_CUDA(cudaMalloc(&g_ctx.mi, 64 * sizeof(double)), "cudaMalloc(mi)");
+    return XBI_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// pageable caller memory: threaded copies through the pinned ring (xbi_hostpool.cu)
+// ---------------------------------------------------------------------------------
+static bool staging_enabled() {
+    static const bool on = [] {
+        const char* env = std::getenv("XBI_HOST_STAGING");
+        return !(env && env[0] == '0');
+    }();
+    return on;
+}
+// true when `p` is ordinary (not page-locked, not CUDA-managed) host memory
+static bool is_pageable(const void* p) {
+    if (!p) return false;
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+static int ensure_pinned(HostCtx& c, bool in, bool out) {
+    for (int i = 0; i < 2; ++i) {
+        if (in && !c.pin_in[i]) {
+            XBI_CUDA(cudaHostAlloc(&c.pin_in[i], HostCtx::kPinBytes, cudaHostAllocDefault), "cudaHostAlloc(staging in)");
+            XBI_CUDA(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+        if (out && !c.pin_out[i]) {
+            XBI_CUDA(cudaHostAlloc(&c.pin_out[i], HostCtx::kPinBytes, cudaHostAllocDefault), "cudaHostAlloc(staging out)");
+            XBI_CUDA(cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming), "cudaEventCreate");
+        }
+    }
+    return XBI_OK;
+}
+// rows x row_bytes from pageable `from` (pitch src_pitch) -> contiguous device memory, in pieces of one
+// pinned slot: the pool fills slot k+1 while the DMA engine drains slot k.  *handled = false when a single
+// row does not fit a slot (the caller then copies directly).
+static int staged_h2d(HostCtx& c, void* dst_dev, const char* from, size_t src_pitch, size_t rows, size_t row_bytes,
+                      cudaStream_t st, bool* handled) {
+    *handled = false;
+    const bool contiguous = rows == 1 || src_pitch == row_bytes;
+    if (!contiguous && row_bytes > HostCtx::kPinBytes) return XBI_OK;
+    if (int rc = ensure_pinned(c, true, false)) return rc;
+    auto piece = [&](char* to_dev, const char* src, size_t pitch, size_t nrows, size_t rbytes) -> int {
+        const int slot = c.in_next;
+        c.in_next ^= 1;
+        if (c.in_busy[slot]) XBI_CUDA(cudaEventSynchronize(c.ev_in[slot]), "cudaEventSynchronize(staging)");
+        host_copy_parallel(c.pin_in[slot], rbytes, src, pitch, rbytes, nrows);
+        XBI_CUDA(cudaMemcpyAsync(to_dev, c.pin_in[slot], nrows * rbytes, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(H2D, staged)");
+        XBI_CUDA(cudaEventRecord(c.ev_in[slot], st), "cudaEventRecord(staging)");
+        c.in_busy[slot] = true;
+        return XBI_OK;
+    };
+    char* to = static_cast<char*>(dst_dev);
+    if (contiguous) {
+        const size_t total = rows * row_bytes;
+        for (size_t off = 0; off < total; off += HostCtx::kPinBytes) {
+            const size_t len = total - off < HostCtx::kPinBytes ? total - off : HostCtx::kPinBytes;
+            if (int rc = piece(to + off, from + off, len, 1, len)) return rc;
+        }
+    } else {
+        const size_t rows_per = HostCtx::kPinBytes / row_bytes;
+        for (size_t r0 = 0; r0 < rows; r0 += rows_per) {
+            const size_t k = rows - r0 < rows_per ? rows - r0 : rows_per;
+            if (int rc = piece(to + r0 * row_bytes, from + r0 * src_pitch, src_pitch, k, row_bytes)) return rc;
+        }
+    }
+    *handled = true;
     return XBI_OK;
 }
 
@@ -451,13 +537,20 @@ int xbi_bitinformation_host(const void* x_host, int dtype, int64_t outer, int64_
 
     const char* src = static_cast<const char*>(x_host);
     const int64_t cap = (int64_t)(c.buf_bytes / bytes);  // elements per staging buffer
+    const bool stage = numel > 0 && staging_enabled() && is_pageable(x_host);
     int which = 0;
     auto submit = [&](const void* from, size_t src_pitch, int64_t rows, int64_t cols, int64_t so, int64_t sn,
                       int64_t si) -> int {
         cudaStream_t st = c.stream[which];
         // the stream's previous slab (copy + kernels) must be finished before its buffer is reused:
         // same-stream ordering guarantees that.
-        if (src_pitch == (size_t)cols * bytes || rows == 1) {
+        bool staged = false;
+        if (stage)
+            if (int rc = staged_h2d(c, c.buf[which], static_cast<const char*>(from), src_pitch, (size_t)rows,
+                                    (size_t)cols * bytes, st, &staged))
+                return rc;
+        if (staged) {
+        } else if (src_pitch == (size_t)cols * bytes || rows == 1) {
             XBI_CUDA(cudaMemcpyAsync(c.buf[which], from, (size_t)rows * cols * bytes, cudaMemcpyHostToDevice, st),
                      "cudaMemcpyAsync(H2D)");
         } else {
@@ -529,6 +622,95 @@ int xbi_bitinformation_host(const void* x_host, int dtype, int64_t outer, int64_
     return XBI_OK;
 }
 
+int xbi_bitinformation_host_multi(const void* x_host, int dtype, int ndim, const int64_t* shape, int naxes,
+                                  const int* axes, unsigned flags, uint64_t mask_bits, int set_zero_insignificant,
+                                  double confidence, double* mi_host, unsigned long long* counts_host, int device) {
+    if (!mi_host) return fail(XBI_ERR_ARG, "null mi_host");
+    if (ndim < 1 || ndim > XBI_MAX_DIMS) return fail(XBI_ERR_ARG, "ndim must be in 1..XBI_MAX_DIMS");
+    if (naxes < 1 || naxes > XBI_MAX_DIMS) return fail(XBI_ERR_ARG, "naxes must be in 1..XBI_MAX_DIMS");
+    if (!shape || !axes) return fail(XBI_ERR_ARG, "null shape / axes pointer");
+    int64_t numel = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] < 0) return fail(XBI_ERR_ARG, "negative extent");
+        numel *= shape[d];
+    }
+    for (int a = 0; a < naxes; ++a)
+        if (axes[a] < 0 || axes[a] >= ndim) return fail(XBI_ERR_ARG, "axis out of range");
+    CountJob probe;
+    if (int rc = make_job(probe, x_host, dtype, 0, 0, 0, flags, mask_bits)) return rc;
+    const int bytes = dtype_bytes(dtype);
+    const int nbits = 8 * bytes;
+    auto dims_of = [&](int axis, int64_t rows0, int64_t* outer, int64_t* n, int64_t* inner) {
+        // (outer, n, inner) of an array whose first extent is rows0 instead of shape[0]
+        *outer = 1; *inner = 1;
+        for (int d = 0; d < axis; ++d) *outer *= (d == 0 ? rows0 : shape[d]);
+        *n = axis == 0 ? rows0 : shape[axis];
+        for (int d = axis + 1; d < ndim; ++d) *inner *= shape[d];
+    };
+    if (int rc = ensure_ctx(device)) return rc;
+    HostCtx& c = g_ctx;
+    const int64_t row = shape[0] > 0 ? numel / shape[0] : 0;  // elements of one index of the first dimension
+    const int64_t cap = (int64_t)(c.buf_bytes / bytes);
+    if (naxes == 1 || numel == 0 || row == 0 || 2 * row > cap) {
+        // nothing to share between the axes (or one row of the first dimension does not fit the staging
+        // buffer next to its halo): one pass over the host array per axis
+        for (int a = 0; a < naxes; ++a) {
+            int64_t outer, n, inner;
+            dims_of(axes[a], shape[0], &outer, &n, &inner);
+            if (int rc = xbi_bitinformation_host(x_host, dtype, outer, n, inner, flags, mask_bits, set_zero_insignificant,
+                                                 confidence, mi_host + (size_t)a * nbits,
+                                                 counts_host ? counts_host + (size_t)a * nbits * 4 : nullptr, device))
+                return rc;
+        }
+        return XBI_OK;
+    }
+    if (!x_host) return fail(XBI_ERR_ARG, "null data pointer");
+    const size_t table = (size_t)nbits * 4;
+    if (!c.counts_multi) {
+        XBI_CUDA(cudaMalloc(&c.counts_multi, XBI_MAX_DIMS * 64 * 4 * sizeof(unsigned long long)), "cudaMalloc(counts)");
+        XBI_CUDA(cudaMalloc(&c.mi_multi, XBI_MAX_DIMS * 64 * sizeof(double)), "cudaMalloc(mi)");
+    }
+    XBI_CUDA(cudaMemsetAsync(c.counts_multi, 0, naxes * table * sizeof(unsigned long long), c.stream[0]), "memset(counts)");
+    XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+    // Slabs of whole rows of the first dimension, each slab on the device ONCE for all the axes.  Along the
+    // first dimension a slab carries the first row of the next slab as halo (the pair across the cut belongs
+    // to it); the other axes count the slab's own rows only.
+    const bool stage = staging_enabled() && is_pageable(x_host);
+    const int64_t per = cap / row - 1;  // own rows per slab (>= 1)
+    const char* src = static_cast<const char*>(x_host);
+    int which = 0;
+    for (int64_t r0 = 0; r0 < shape[0]; r0 += per, which ^= 1) {
+        const int64_t own = shape[0] - r0 < per ? shape[0] - r0 : per;
+        const int64_t halo = r0 + own < shape[0] ? 1 : 0;
+        cudaStream_t st = c.stream[which];
+        const char* from = src + (size_t)r0 * row * bytes;
+        const size_t nb = (size_t)(own + halo) * row * bytes;
+        bool staged = false;
+        if (stage)
+            if (int rc = staged_h2d(c, c.buf[which], from, nb, 1, nb, st, &staged)) return rc;
+        if (!staged) XBI_CUDA(cudaMemcpyAsync(c.buf[which], from, nb, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(H2D)");
+        for (int a = 0; a < naxes; ++a) {
+            CountJob job = probe;
+            job.x = c.buf[which];
+            dims_of(axes[a], axes[a] == 0 ? own + halo : own, &job.outer, &job.n, &job.inner);
+            if (int rc = count_pairs_impl(job, flags, c.counts_multi + (size_t)a * table, c.ws[which], st)) return rc;
+        }
+    }
+    XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+    XBI_CUDA(cudaStreamSynchronize(c.stream[1]), "sync");
+    if (int rc = xbi_mutual_information_batched(c.counts_multi, nbits, naxes, set_zero_insignificant, confidence,
+                                                c.mi_multi, c.stream[0]))
+        return rc;
+    XBI_CUDA(cudaMemcpyAsync(mi_host, c.mi_multi, (size_t)naxes * nbits * sizeof(double), cudaMemcpyDeviceToHost, c.stream[0]),
+             "D2H(mi)");
+    if (counts_host)
+        XBI_CUDA(cudaMemcpyAsync(counts_host, c.counts_multi, (size_t)naxes * table * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, c.stream[0]),
+                 "D2H(counts)");
+    XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+    return XBI_OK;
+}
+
 int xbi_bitround_host(const void* src_host, void* dst_host, int dtype, int64_t numel, int keepbits, int device) {
     if (int rc = check_bitround_args(dtype, numel, keepbits)) return rc;
     if (numel == 0) return XBI_OK;
@@ -536,6 +718,56 @@ int xbi_bitround_host(const void* src_host, void* dst_host, int dtype, int64_t n
     if (int rc = ensure_ctx(device)) return rc;
     HostCtx& c = g_ctx;
     const int bytes = dtype_bytes(dtype);
+    const bool stage_in = staging_enabled() && is_pageable(src_host);
+    const bool stage_out = staging_enabled() && is_pageable(dst_host);
+    if (stage_in || stage_out) {
+        // slabs of one pinned slot; slot k of each direction belongs to stream k.  While the GPU works on
+        // slab i the pool copies slab i-1's result out and slab i+1 in.
+        if (int rc = ensure_pinned(c, stage_in, stage_out)) return rc;
+        const size_t slot = HostCtx::kPinBytes < c.buf_bytes ? HostCtx::kPinBytes : c.buf_bytes;
+        const int64_t per = (int64_t)(slot / bytes);
+        struct Pending { bool active; char* dst; size_t nbytes; } pend[2] = {{false, nullptr, 0}, {false, nullptr, 0}};
+        auto drain = [&](int k) -> int {
+            if (!pend[k].active) return XBI_OK;
+            XBI_CUDA(cudaEventSynchronize(c.ev_out[k]), "cudaEventSynchronize(staging out)");
+            host_copy_parallel(pend[k].dst, pend[k].nbytes, c.pin_out[k], pend[k].nbytes, pend[k].nbytes, 1);
+            pend[k].active = false;
+            return XBI_OK;
+        };
+        int k = 0;
+        for (int64_t off = 0; off < numel; off += per, k ^= 1) {
+            const int64_t cnt = (numel - off < per) ? (numel - off) : per;
+            const size_t nb = (size_t)cnt * bytes;
+            cudaStream_t st = c.stream[k];
+            if (int rc = drain(k)) return rc;
+            const char* from = static_cast<const char*>(src_host) + (size_t)off * bytes;
+            const void* h2d_src = from;
+            if (stage_in) {
+                if (c.in_busy[k]) XBI_CUDA(cudaEventSynchronize(c.ev_in[k]), "cudaEventSynchronize(staging in)");
+                host_copy_parallel(c.pin_in[k], nb, from, nb, nb, 1);
+                h2d_src = c.pin_in[k];
+            }
+            XBI_CUDA(cudaMemcpyAsync(c.buf[k], h2d_src, nb, cudaMemcpyHostToDevice, st), "cudaMemcpyAsync(H2D)");
+            if (stage_in) {
+                XBI_CUDA(cudaEventRecord(c.ev_in[k], st), "cudaEventRecord(staging in)");
+                c.in_busy[k] = true;
+            }
+            XBI_CUDA(launch_bitround(c.buf[k], dtype, cnt, keepbits, st), "bitround");
+            char* to = static_cast<char*>(dst_host) + (size_t)off * bytes;
+            if (stage_out) {
+                XBI_CUDA(cudaMemcpyAsync(c.pin_out[k], c.buf[k], nb, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(D2H, staged)");
+                XBI_CUDA(cudaEventRecord(c.ev_out[k], st), "cudaEventRecord(staging out)");
+                pend[k] = {true, to, nb};
+            } else {
+                XBI_CUDA(cudaMemcpyAsync(to, c.buf[k], nb, cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(D2H)");
+            }
+        }
+        if (int rc = drain(0)) return rc;
+        if (int rc = drain(1)) return rc;
+        XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
+        XBI_CUDA(cudaStreamSynchronize(c.stream[1]), "sync");
+        return XBI_OK;
+    }
     const int64_t cap = (int64_t)(c.buf_bytes / bytes);
     int which = 0;
     for (int64_t off = 0; off < numel; off += cap) {

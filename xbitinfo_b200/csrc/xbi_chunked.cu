@@ -52,10 +52,12 @@ struct Walker {
         for (int d = kD - 1; d >= 1; --d) { out[d] = v % e[d]; v /= e[d]; }
         out[0] = v;
     }
-    // (c, off) += step, branch-free per dimension; `lo` = first dimension in use (uniform)
-    __device__ __forceinline__ void advance(unsigned (&cc)[kD], Off& o, const unsigned (&step)[kD], Off stepoff, int lo) const {
+    // (c, off) += step, branch-free per dimension; `lo` = first dimension in use (uniform).  Returns the
+    // new coordinate along `axis` (uniform; -1: nobody asks), picked up where that dimension is stepped.
+    __device__ __forceinline__ unsigned advance(unsigned (&cc)[kD], Off& o, const unsigned (&step)[kD], Off stepoff, int lo,
+                                                int axis) const {
         o += stepoff;
-        unsigned carry = 0;
+        unsigned carry = 0, ca = 0;
 #pragma unroll
         for (int d = kD - 1; d >= 1; --d) {
             if (d >= lo) {
@@ -64,9 +66,12 @@ struct Walker {
                 cc[d] = wr ? v - e[d] : v;
                 o += wr ? wrap[d] : (Off)0;
                 carry = wr ? 1u : 0u;
+                if (d == axis) ca = cc[d];
             }
         }
         cc[0] += step[0] + carry;  // (a carry out of dimension `lo` only happens past the end of the chunk)
+        if (axis == 0) ca = cc[0];
+        return ca;
     }
 
     __device__ __forceinline__ void init(const ChunkGrid& g, unsigned cid, unsigned long long l0) {
@@ -109,7 +114,7 @@ struct Walker {
 #pragma unroll
             for (int d = 0; d < kD; ++d) c[j][d] = c[j - 1][d];
             off[j] = off[j - 1];
-            advance(c[j], off[j], s1, (Off)s1off, g.lo);
+            advance(c[j], off[j], s1, (Off)s1off, g.lo, -1);
         }
         decompose(kChains * kThreads, e, inc);
         long long io = 0;
@@ -117,21 +122,32 @@ struct Walker {
         for (int d = 0; d < kD; ++d) io += (long long)inc[d] * g.stride[d];
         incoff = (Off)io;
         left = numel - (long long)l0;
+        // The per-chunk constants are uniform, and left alone ptxas re-derives them from the kernel
+        // parameters in every step (7 uniform-pipe instructions per dimension and step); make them opaque
+        // so that they are computed once per item and stay in registers.
+#pragma unroll
+        for (int d = 0; d < kD; ++d) {
+            asm volatile("" : "+r"(e[d]), "+r"(inc[d]));
+            pin(wrap[d]);
+        }
+        pin(incoff);
     }
+    static __device__ __forceinline__ void pin(unsigned& v) { asm volatile("" : "+r"(v)); }
+    static __device__ __forceinline__ void pin(long long& v) { asm volatile("" : "+l"(v)); }
 
     // chain j to its next round
-    __device__ __forceinline__ void step(int j, int lo) { advance(c[j], off[j], inc, incoff, lo); }
-    __device__ __forceinline__ bool inside(int j) const { return left > (long long)j * kThreads; }
-    __device__ __forceinline__ void next_round() { left -= kChains * kThreads; }
-
-    // coordinate / extent along a dimension known only at run time (uniform), without indexing
-    // the register arrays dynamically
+    __device__ __forceinline__ unsigned step(int j, int lo, int axis) { return advance(c[j], off[j], inc, incoff, lo, axis); }
+    // coordinate along a dimension known only at run time (uniform), without indexing the register arrays dynamically
     __device__ __forceinline__ unsigned coord(int j, int axis) const {
         unsigned v = 0;
 #pragma unroll
         for (int d = 0; d < kD; ++d) if (d == axis) v = c[j][d];
         return v;
     }
+    __device__ __forceinline__ bool inside(int j) const { return left > (long long)j * kThreads; }
+    __device__ __forceinline__ void next_round() { left -= kChains * kThreads; }
+
+    // extent along a dimension known only at run time (uniform), without indexing the register array dynamically
     __device__ __forceinline__ unsigned extent(int axis) const {
         unsigned v = 1;
 #pragma unroll
@@ -167,6 +183,9 @@ k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g,
         if (tiles_left <= 0) continue;  // an edge chunk with fewer tiles than the full ones
         if (tiles_left > (long long)g.tiles_per_group) tiles_left = g.tiles_per_group;
         const unsigned ea = w.extent(g.axis);
+        unsigned ca[kChains];  // coordinate of every chain along the analysed axis
+#pragma unroll
+        for (int j = 0; j < kChains; ++j) ca[j] = w.coord(j, g.axis);
 
         L A[NW], B[NW], AB[NW];
         unsigned long long accA[NW], accB[NW], accAB[NW];
@@ -199,10 +218,10 @@ k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g,
 #pragma unroll
             for (int u = 0; u < kPerThread; ++u) {
                 const int j = u % kChains;  // element u = chain j in round u / kChains
-                const bool pair = w.inside(j) && w.coord(j, g.axis) + 1u < ea;
+                const bool pair = w.inside(j) && ca[j] + 1u < ea;
                 offs[u] = pair ? w.off[j] : (Off)0;
                 live |= (pair ? 1u : 0u) << u;
-                w.step(j, g.lo);
+                ca[j] = w.step(j, g.lo, g.axis);
                 if (j == kChains - 1) w.next_round();
             }
             // phase 2: all 32 loads in flight
@@ -292,7 +311,7 @@ k_chunk_finalize(unsigned long long* __restrict__ counts, int nbits, unsigned nc
 
 // K3 per chunk: keepbits[chunk] mantissa bits kept (clamped to 0..mant; mant = identity)
 template <int BYTES, bool WIDE>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 k_bitround_chunked(void* __restrict__ x, const __grid_constant__ ChunkGrid g, const int* __restrict__ keepbits, int mant) {
     using T = typename std::conditional<BYTES == 2, uint16_t, typename std::conditional<BYTES == 4, uint32_t, unsigned long long>::type>::type;
     T* __restrict__ p = static_cast<T*>(x);
@@ -319,7 +338,7 @@ k_bitround_chunked(void* __restrict__ x, const __grid_constant__ ChunkGrid g, co
                 const int j = u % kChains;
                 offs[u] = w.off[j];
                 live |= (w.inside(j) ? 1u : 0u) << u;
-                w.step(j, g.lo);
+                w.step(j, g.lo, -1);
                 if (j == kChains - 1) w.next_round();
             }
 #pragma unroll

@@ -117,6 +117,11 @@ cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, u
                                  int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream);
 cudaError_t launch_bitround_chunked(void* x, int dtype, const ChunkGrid& g, const int* keepbits, cudaStream_t stream);
 
+// xbi_hostpool.cu: rows of row_bytes bytes copied host -> host by a small pool of threads
+// (XBI_HOST_THREADS, default min(8, cores)); blocks until done
+void host_copy_parallel(void* dst, size_t dst_pitch, const void* src, size_t src_pitch, size_t row_bytes, size_t rows);
+int host_copy_threads();
+
 double normal_quantile(double p);  // AS241, host
 
 }  // namespace xbi

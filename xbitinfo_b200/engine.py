@@ -73,6 +73,45 @@ def bitinformation(data, axis: int, masked_value=None, set_zero_insignificant: b
     return mi
 
 
+def bitinformation_multi(data, axes, masked_value=None, set_zero_insignificant: bool = False,
+                         confidence: float = 0.99, device: int | None = None, return_counts: bool = False):
+    """Information per bit along several axes of one array: list of float64[nbits] in the order of
+    ``axes`` (with ``return_counts`` a list of ``(mi, counts)``).  A host numpy array crosses PCIe once for
+    all the axes (``xbi_bitinformation_host_multi``); device tensors and lazy arrays are analysed axis by
+    axis (nothing to share: the data is resident / streamed on demand)."""
+    from .streaming import is_lazy_array
+
+    axes = [int(a) for a in axes]
+    if _is_torch_tensor(data) or is_lazy_array(data) or len(axes) < 2:
+        return [bitinformation(data, a, masked_value=masked_value, set_zero_insignificant=set_zero_insignificant,
+                               confidence=confidence, device=device, return_counts=return_counts) for a in axes]
+    x = np.asarray(data)
+    code = nat.dtype_code(x.dtype)
+    x = _native_contiguous(x)
+    if x.ndim == 0:
+        raise ValueError("cannot analyse a 0-d array")
+    if x.ndim > 8:
+        return [bitinformation(x, a, masked_value=masked_value, set_zero_insignificant=set_zero_insignificant,
+                               confidence=confidence, device=device, return_counts=return_counts) for a in axes]
+    axes = [a % x.ndim for a in axes]
+    nbits = 8 * x.dtype.itemsize
+    flags, bits = nat.mask_spec(x.dtype, masked_value)
+    if x.dtype.kind == "f":
+        flags |= nat.SIGNED_EXPONENT
+    mi = np.empty((len(axes), nbits), dtype=np.float64)
+    counts = np.empty((len(axes), nbits * 4), dtype=np.uint64)
+    if device is None:
+        device = _current_device()
+    rc = nat.lib().xbi_bitinformation_host_multi(
+        x.ctypes.data_as(C.c_void_p), code, x.ndim, nat.int64_array(x.shape), len(axes), (C.c_int * len(axes))(*axes),
+        flags, bits, int(bool(set_zero_insignificant)), float(confidence), mi.ctypes.data_as(C.c_void_p),
+        counts.ctypes.data_as(C.c_void_p), int(device))
+    nat.check(rc)
+    if return_counts:
+        return [(mi[i], counts[i].reshape(nbits, 2, 2).astype(np.int64)) for i in range(len(axes))]
+    return [mi[i] for i in range(len(axes))]
+
+
 def _current_device() -> int:
     try:
         import torch
