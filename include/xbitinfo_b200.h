@@ -135,6 +135,18 @@ int xbi_count_pairs_chunked(const void* x_dev, int dtype, int ndim, const int64_
                             int axis, unsigned flags, uint64_t mask_bits, unsigned long long* counts_dev, void* stream);
 int xbi_bitround_chunked(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
                          const int32_t* keepbits_dev, void* stream);
+/*
+ * The same over an IRREGULAR grid (dask's `.chunks` after a concatenation or an uneven rechunk):
+ * nchunks_dim[d] chunks along dimension d, whose offsets -- nchunks_dim[d]+1 ascending values from 0 to
+ * shape[d], dimension after dimension in one table -- are passed twice: bounds_host for planning,
+ * bounds_dev (the same values in device memory, alive until the kernels have run) for the kernels.
+ */
+int xbi_count_pairs_chunked_v(const void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* nchunks_dim,
+                              const int64_t* bounds_host, const int64_t* bounds_dev, int axis, unsigned flags,
+                              uint64_t mask_bits, unsigned long long* counts_dev, void* stream);
+int xbi_bitround_chunked_v(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* nchunks_dim,
+                           const int64_t* bounds_host, const int64_t* bounds_dev, const int32_t* keepbits_dev,
+                           void* stream);
 
 /*
  * K3: round to nearest (ties to even) keeping `keepbits` explicit mantissa bits, in

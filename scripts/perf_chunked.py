@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="744,721,1440")
 ap.add_argument("--dtype", default="float32")
 ap.add_argument("--loop", action="store_true", help="also time the chunk-by-chunk route (slow for many chunks)")
+ap.add_argument("--chunk", default=None, help="only this chunk shape (comma separated), e.g. for an ncu capture")
 args = ap.parse_args()
 shape = tuple(int(v) for v in args.shape.split(","))
 dt = getattr(torch, args.dtype)
@@ -48,6 +49,8 @@ grids = [
     (shape[0], 4, 4),
     (max(1, shape[0] // 12), 64, 64),
 ]
+if args.chunk:
+    grids = [tuple(int(v) for v in args.chunk.split(","))]
 print(f"{args.dtype} {shape}: {nbytes/1e9:.2f} GB")
 for chunk in grids:
     for axis in (0, len(shape) - 1):

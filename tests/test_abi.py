@@ -71,6 +71,13 @@ def test_chunk_grid_argument_errors_do_not_need_a_gpu():
     assert rc == nat.ERR_ARG and b"float" in lib.xbi_last_error()
     rc = lib.xbi_mutual_information_batched(None, 65, 1, 0, 0.99, None, None)
     assert rc == nat.ERR_ARG
+    dummy = C.c_void_p(8)  # never dereferenced: planning fails first
+    rc = lib.xbi_count_pairs_chunked_v(None, nat.F32, 1, i64([6]), i64([2]), i64([0, 4, 5]), dummy, 0, 0, 0, None, None)
+    assert rc == nat.ERR_ARG and b"from 0 to the extent" in lib.xbi_last_error()
+    rc = lib.xbi_count_pairs_chunked_v(None, nat.F32, 1, i64([6]), i64([2]), i64([0, 6, 6]), dummy, 0, 0, 0, None, None)
+    assert rc == nat.ERR_ARG and b"ascending" in lib.xbi_last_error()
+    rc = lib.xbi_bitround_chunked_v(None, nat.F32, 1, i64([6]), None, None, None, None, None)
+    assert rc == nat.ERR_ARG
     # nothing to do: no chunks, no pointers needed
     assert lib.xbi_count_pairs_chunked(None, nat.F32, 2, i64([0, 4]), i64([2, 2]), 1, 0, 0, None, None) == 0
     assert lib.xbi_mutual_information_batched(None, 32, 0, 0, 0.99, None, None) == 0

@@ -322,6 +322,29 @@ def test_get_bitinformation_all_dims_equals_dim_by_dim():
             assert np.array_equal(every[v].sel(dim=d).values, one[v].values, equal_nan=True), (v, d)
 
 
+def test_host_entry_points_from_several_threads():
+    """``xr.apply_ufunc(..., dask="parallelized")`` calls the bitround boundary from several worker threads
+    (xbitinfo/bitround.py:99): the host entry points keep their staging state per thread and share the copy
+    pool; concurrent calls must give the single-threaded results."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = np.random.default_rng(41)
+    blocks = [smooth_field(rng, (700_001 + 50_000 * i,), "float32", axis=0, scale=0.3) for i in range(8)]
+    fields = [smooth_field(rng, (9 + i, 300, 200), "float32", axis=1, scale=0.3) for i in range(8)]
+    want_round = [bro.bitround(b, 3 + i).view("u4") for i, b in enumerate(blocks)]
+    want_counts = [bo.bitinformation(f, 1)[0] for f in fields]
+
+    def work(i):
+        r = engine.bitround(blocks[i], 3 + i).view("u4")
+        _, c = engine.bitinformation(fields[i], 1, return_counts=True)
+        multi = engine.bitinformation_multi(fields[i], [1, 2], return_counts=True)
+        return np.array_equal(r, want_round[i]) and np.array_equal(c, want_counts[i]) and np.array_equal(multi[0][1], want_counts[i])
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        for _ in range(3):
+            assert all(ex.map(work, range(8)))
+
+
 def test_launch_counters_move():
     before = nat.kernel_launches()
     engine.bitinformation(np.zeros((8, 64), dtype="float32"), 1)

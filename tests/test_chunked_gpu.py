@@ -58,6 +58,13 @@ CASES = [
     ((3, 4, 5, 6, 7), (2, 3, 2, 4, 3), 2),    # five chunked dimensions
     ((2, 3, 4, 5, 6, 7), (1, 3, 4, 2, 6, 7), 3),  # six dimensions, three groups after merging
     ((9, 2), (4, 2), 1),                      # two elements along the axis: one pair per row
+    # irregular grids (dask-style tuples of chunk lengths), alone and mixed with regular dimensions
+    ((120, 25, 53), (120, (5, 7, 13), (53,)), 1),
+    ((120, 25, 53), ((100, 20), (5, 7, 13), (1, 30, 2, 20)), 2),
+    ((120, 25, 53), ((1, 119), 25, (50, 3)), 0),
+    ((6, 4, 5, 8), ((1, 2, 3), 4, 5, 8), 3),   # an irregular dimension takes the unchunked ones inside it
+    ((6, 4, 5, 8), (6, (3, 1), 5, (2, 6)), 2),
+    ((1000,), ((1, 2, 3, 994),), 0),
     ((9, 1), (4, 1), 1),                      # no pair at all
 ]
 
@@ -146,9 +153,12 @@ def test_batched_route_equals_chunk_by_chunk_route_and_the_oracle():
     assert len(np.unique(k1)) > 1
     info, counts = bitinformation_by_chunks(x, chunks, axis=1)
     assert tuple(info.shape) == k1.shape + (32,) and tuple(counts.shape) == k1.shape + (32, 2, 2)
-    # an irregular grid takes the chunk-by-chunk route
-    r3, k3 = bitround_by_chunks(x, ((120,), (5, 7, 13), (53,)), axis=1)
-    assert k3.shape == (1, 3, 1)
+    # irregular grids go through the same kernels (offset tables instead of a chunk length)
+    for irregular in (((120,), (5, 7, 13), (53,)), ((7, 100, 13), (25,), (20, 33))):
+        r3, k3 = bitround_by_chunks(x, irregular, axis=1)
+        r4, k4 = bitround_by_chunks(x, irregular, axis=1, batched=False)
+        assert k3.shape == tuple(len(c) for c in irregular)
+        assert np.array_equal(k3, k4) and np.array_equal(r3.view("u4"), r4.view("u4"))
 
 
 def test_launch_count_does_not_grow_with_the_number_of_chunks():
@@ -164,6 +174,21 @@ def test_launch_count_does_not_grow_with_the_number_of_chunks():
     assert nat.kernel_launches() - n0 == few <= 4
 
 
+def test_bitround_chunked_irregular_grid():
+    rng = np.random.default_rng(12)
+    x = smooth_field(rng, (40, 25, 53), "float64", axis=1, scale=0.3, base=3.0)
+    spec = ((13, 27), 5, (3, 30, 20))
+    grid = normalize_chunks(x.shape, spec)
+    shape = tuple(len(c) for c in grid)
+    keep = rng.integers(0, 52, size=shape, endpoint=True).astype("int32")
+    t = torch.from_numpy(x).cuda()
+    bitround_chunked_(t, spec, torch.from_numpy(keep.ravel()).cuda())
+    want = np.empty_like(x)
+    for idx, sl in zip(np.ndindex(*shape), slices_from_chunks(grid)):
+        want[sl] = bro.bitround(np.ascontiguousarray(x[sl]), int(keep[idx]))
+    assert np.array_equal(t.cpu().numpy().view("u8"), want.view("u8"))
+
+
 def test_unsupported_and_bad_arguments():
     x = torch.zeros((2, 2, 2, 2, 2, 2), dtype=torch.float32, device="cuda")
     with pytest.raises(NotImplementedError):
@@ -174,6 +199,8 @@ def test_unsupported_and_bad_arguments():
         count_pairs_chunked(x, (1, 1, 1, 1, 1, 0), 0)
     with pytest.raises(ValueError):
         bitround_chunked_(x, (2, 2, 2, 2, 2, 1), torch.zeros(3, dtype=torch.int32, device="cuda"))
+    with pytest.raises(ValueError):
+        count_pairs_chunked(x[0, 0, 0, 0], ((1, 2), 2), 0)   # lengths do not add up
     empty = torch.zeros((0, 4), dtype=torch.float32, device="cuda")
     assert count_pairs_chunked(empty, (2, 2), 1).shape == (0, 2, 32, 2, 2)
 

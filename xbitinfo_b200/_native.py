@@ -84,6 +84,11 @@ def lib() -> C.CDLL:
     L.xbi_count_pairs_chunked.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64), i32, u32, u64, vp, vp]
     L.xbi_bitround_chunked.restype = i32
     L.xbi_bitround_chunked.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64), vp, vp]
+    L.xbi_count_pairs_chunked_v.restype = i32
+    L.xbi_count_pairs_chunked_v.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, i32, u32, u64,
+                                            vp, vp]
+    L.xbi_bitround_chunked_v.restype = i32
+    L.xbi_bitround_chunked_v.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp]
     L.xbi_bitround_inplace.restype = i32
     L.xbi_bitround_inplace.argtypes = [vp, i32, i64, i32, vp]
     L.xbi_shuffle.restype = i32
@@ -111,7 +116,7 @@ EXPORTED_SYMBOLS = (
     "xbi_count_pairs", "xbi_mutual_information", "xbi_bitround_inplace", "xbi_shuffle", "xbi_bitround_shuffle",
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
     "xbi_mutual_information_batched", "xbi_count_pairs_chunked", "xbi_bitround_chunked",
-    "xbi_bitinformation_host_multi",
+    "xbi_bitinformation_host_multi", "xbi_count_pairs_chunked_v", "xbi_bitround_chunked_v",
 )
 
 

@@ -62,16 +62,17 @@ def keepbits_of_information(info, np_dtype, inflevel=0.99) -> int:
         return int((cdf > inflevel).argmax() + 1 - (n_bits - n_mant))
 
 
-def _regular_chunk_shape(grid):
-    """Chunk extents of a regular grid (equal chunks, the last of a dimension possibly shorter), else None."""
+def _chunk_spec(grid):
+    """Per-dimension chunk description for the batched kernels: an int where the dimension is cut regularly
+    (equal chunks, the last possibly shorter), else the tuple of chunk lengths."""
     out = []
     for c in grid:
         if len(c) == 0:
             out.append(1)
-            continue
-        if any(v != c[0] for v in c[:-1]) or c[-1] > c[0] or min(c) < 1:
-            return None
-        out.append(int(c[0]))
+        elif all(v == c[0] for v in c[:-1]) and c[-1] <= c[0]:
+            out.append(int(c[0]))
+        else:
+            out.append(tuple(int(v) for v in c))
     return tuple(out)
 
 
@@ -88,17 +89,14 @@ def keepbits_of_information_batched(info, np_dtype, inflevel=0.99) -> np.ndarray
 
 def bitinformation_by_chunks(x, chunks, axis: int, masked_value=float("nan"), set_zero_insignificant: bool = True,
                              confidence: float = 0.99):
-    """Information per bit of every chunk of a regular grid on its own: ``(info, counts)`` as CUDA tensors of
+    """Information per bit of every chunk of the grid on its own: ``(info, counts)`` as CUDA tensors of
     shape ``chunks-per-dimension + (nbits,)`` and ``+ (nbits, 2, 2)``.  One counting launch for all chunks
     (``xbi_count_pairs_chunked``) and one for the mutual information."""
     from .device import count_pairs_chunked, information_batched
 
     t = torch.from_numpy(np.ascontiguousarray(x)).cuda() if isinstance(x, np.ndarray) else x.contiguous()
     grid = normalize_chunks(tuple(t.shape), chunks)
-    chunk_shape = _regular_chunk_shape(grid)
-    if chunk_shape is None:
-        raise NotImplementedError("irregular chunk grids are processed chunk by chunk (bitround_by_chunks)")
-    counts = count_pairs_chunked(t, chunk_shape, axis, masked_value=masked_value)
+    counts = count_pairs_chunked(t, _chunk_spec(grid), axis, masked_value=masked_value)
     return information_batched(counts, set_zero_insignificant, confidence), counts
 
 
@@ -113,10 +111,11 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
     Negative keepbits (not even all exponent bits carry information) are clamped to 0, as the
     reference's multi-file flow does (``xbitinfo/xbitinfo.py:867-868``).
 
-    A regular grid (dask's usual case) runs in three launches whatever the number of chunks:
-    ``xbi_count_pairs_chunked`` -> ``xbi_mutual_information_batched`` -> (one D2H of the
-    information, keepbits on the host, one H2D of ``nchunks`` ints) -> ``xbi_bitround_chunked``.
-    An irregular grid (``batched=False`` forces this route) is walked chunk by chunk with K1/K2/K3.
+    The grid (regular, or dask-style tuples of uneven chunk lengths) is processed in a constant number
+    of launches whatever the number of chunks: ``xbi_count_pairs_chunked[_v]`` ->
+    ``xbi_mutual_information_batched`` -> (one D2H of the information, keepbits on the host, one H2D of
+    ``nchunks`` ints) -> ``xbi_bitround_chunked[_v]``.  ``batched=False`` walks the grid chunk by chunk with
+    K1/K2/K3 instead (the reference notebook's loop; kept for comparison).
     """
     is_np = isinstance(x, np.ndarray)
     t = torch.from_numpy(np.ascontiguousarray(x)).cuda() if is_np else x.contiguous().clone()
@@ -126,12 +125,10 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
     grid = normalize_chunks(tuple(t.shape), chunks)
     keep = np.zeros([len(c) for c in grid], dtype="int64")
     axis %= t.dim()
-    chunk_shape = _regular_chunk_shape(grid)
+    chunk_shape = _chunk_spec(grid)
     if batched is None:
-        batched = chunk_shape is not None
+        batched = True
     if batched:
-        if chunk_shape is None:
-            raise ValueError("batched=True needs a regular chunk grid")
         from .device import bitround_chunked_, count_pairs_chunked, information_batched
 
         counts = count_pairs_chunked(t, chunk_shape, axis, masked_value=masked_value)

@@ -5,6 +5,8 @@
 #include <cstring>
 #include <string>
 
+#include <sys/mman.h>
+
 #include "xbi_common.cuh"
 #include "xbi_internal.h"
 
@@ -337,22 +339,51 @@ int xbi_mutual_information(const unsigned long long* counts_dev, int nbits, int 
     return xbi_mutual_information_batched(counts_dev, nbits, 1, set_zero_insignificant, confidence, mi_dev, stream);
 }
 
-// Regular chunk grid of an N-d C-contiguous array -> ChunkGrid of at most kMaxChunkDims dimensions.
+// Chunk grid of an N-d C-contiguous array -> ChunkGrid of at most kMaxChunkDims dimensions.
+// The grid is regular (chunk_shape) or given by per-dimension offset tables (nchunks_dim + bounds: for every
+// dimension in turn nchunks_dim[d]+1 ascending offsets from 0 to shape[d]; the same table on the host for
+// planning and on the device for the kernels; a dimension whose table is regular is treated as such).
 // Neighbouring dimensions are merged when the inner one is not chunked and neither is the analysed
 // one (the chunk order stays the C order of the chunk grid); dimensions of length 1 disappear.
 // *nchunks: chunks in the grid; *empty: nothing to do (no elements, or no pairs along the axis).
-static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_shape, int axis, ChunkGrid& g,
+static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_shape, const int64_t* nchunks_dim,
+                           const int64_t* bounds_host, const int64_t* bounds_dev, int axis, ChunkGrid& g,
                            int64_t* nchunks, bool* empty) {
     if (ndim < 1 || ndim > XBI_MAX_DIMS) return fail(XBI_ERR_ARG, "ndim must be in 1..XBI_MAX_DIMS");
-    if (!shape || !chunk_shape) return fail(XBI_ERR_ARG, "null shape pointer");
+    if (!shape || (!chunk_shape && !(nchunks_dim && bounds_host && bounds_dev)))
+        return fail(XBI_ERR_ARG, "null shape / chunk description pointer");
     if (axis < -1 || axis >= ndim) return fail(XBI_ERR_ARG, "axis out of range");
     int64_t total_chunks = 1, numel = 1;
+    int64_t cmax[XBI_MAX_DIMS];                 // (largest) chunk extent per dimension
+    int64_t ncd[XBI_MAX_DIMS];                  // chunks per dimension
+    const int64_t* table[XBI_MAX_DIMS];         // device offsets of the irregular dimensions, else nullptr
+    size_t toff = 0;
     for (int d = 0; d < ndim; ++d) {
         if (shape[d] < 0) return fail(XBI_ERR_ARG, "negative extent");
-        if (chunk_shape[d] < 1) return fail(XBI_ERR_ARG, "chunk extents must be positive");
-        const int64_t c = chunk_shape[d] < shape[d] ? chunk_shape[d] : (shape[d] > 0 ? shape[d] : 1);
-        const int64_t nc = shape[d] > 0 ? (shape[d] + c - 1) / c : 0;
+        int64_t nc;
+        table[d] = nullptr;
+        if (chunk_shape) {
+            if (chunk_shape[d] < 1) return fail(XBI_ERR_ARG, "chunk extents must be positive");
+            cmax[d] = chunk_shape[d] < shape[d] ? chunk_shape[d] : (shape[d] > 0 ? shape[d] : 1);
+            nc = shape[d] > 0 ? (shape[d] + cmax[d] - 1) / cmax[d] : 0;
+        } else {
+            nc = nchunks_dim[d];
+            if (nc < 0 || (nc == 0) != (shape[d] == 0)) return fail(XBI_ERR_ARG, "chunk count does not fit the extent");
+            const int64_t* b = bounds_host + toff;
+            if (b[0] != 0 || b[nc] != shape[d]) return fail(XBI_ERR_ARG, "chunk offsets must run from 0 to the extent");
+            bool regular = true;
+            cmax[d] = nc > 0 ? b[1] - b[0] : 1;
+            for (int64_t q = 0; q < nc; ++q) {
+                const int64_t ext = b[q + 1] - b[q];
+                if (ext < 1) return fail(XBI_ERR_ARG, "chunk offsets must be strictly ascending");
+                if (q + 1 < nc ? ext != b[1] - b[0] : ext > b[1] - b[0]) regular = false;
+                if (ext > cmax[d]) cmax[d] = ext;
+            }
+            if (!regular) table[d] = bounds_dev + toff;
+            toff += (size_t)nc + 1;
+        }
         if (nc > 0 && total_chunks > (int64_t)0x7FFFFFFF / nc) return fail(XBI_ERR_UNSUPPORTED, "more than 2^31-1 chunks");
+        ncd[d] = nc;
         total_chunks *= nc;
         numel *= shape[d];
     }
@@ -361,22 +392,29 @@ static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_
     if (numel == 0) return XBI_OK;
 
     // innermost first: merge dimension d into the group built so far when that group is unchunked
-    int64_t mshape[XBI_MAX_DIMS], mchunk[XBI_MAX_DIMS], mstride[XBI_MAX_DIMS];
+    int64_t mshape[XBI_MAX_DIMS], mchunk[XBI_MAX_DIMS], mstride[XBI_MAX_DIMS], mscale[XBI_MAX_DIMS], mnchunk[XBI_MAX_DIMS];
+    const int64_t* mtable[XBI_MAX_DIMS];
     int maxis = -1, m = 0;  // groups are collected innermost first
     int64_t stride = 1;
     bool can_merge = false;  // the current (innermost so far) group may take another outer dimension
     for (int d = ndim - 1; d >= 0; --d) {
-        const int64_t c = chunk_shape[d] < shape[d] ? chunk_shape[d] : shape[d];
+        const int64_t c = cmax[d];
         const bool is_axis = d == axis;
         if (shape[d] == 1 && !is_axis) { stride *= shape[d]; continue; }
-        if (m > 0 && can_merge && !is_axis && mchunk[m - 1] == mshape[m - 1] &&
+        if (m > 0 && can_merge && !is_axis && mchunk[m - 1] == mshape[m - 1] && mtable[m - 1] == nullptr &&
             c <= (int64_t)0x7FFFFFFF / mshape[m - 1]) {
             mchunk[m - 1] = c * mshape[m - 1];
+            mscale[m - 1] = mshape[m - 1];  // offsets of dimension d count whole inner groups
+            mtable[m - 1] = table[d];
+            mnchunk[m - 1] = ncd[d];
             mshape[m - 1] *= shape[d];
         } else {
             mshape[m] = shape[d];
             mchunk[m] = c;
             mstride[m] = stride;
+            mscale[m] = 1;
+            mtable[m] = table[d];
+            mnchunk[m] = ncd[d];
             if (is_axis) maxis = m;
             can_merge = !is_axis;
             ++m;
@@ -387,7 +425,10 @@ static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_
     if (m > kMaxChunkDims)
         return fail(XBI_ERR_UNSUPPORTED, "more than 5 chunked dimensions after merging; process the chunks one by one");
     double full = 1.0;
-    for (int i = 0; i < kMaxChunkDims; ++i) { g.shape[i] = 1; g.stride[i] = 0; g.chunk[i] = 1; g.nchunk[i] = 1; }
+    for (int i = 0; i < kMaxChunkDims; ++i) {
+        g.shape[i] = 1; g.stride[i] = 0; g.chunk[i] = 1; g.nchunk[i] = 1; g.bounds[i] = nullptr; g.scale[i] = 1;
+    }
+    if (m == 0) { mscale[0] = 1; mtable[0] = nullptr; mnchunk[0] = 1; }
     g.axis = -1;
     g.lo = kMaxChunkDims - m;
     for (int i = 0; i < m; ++i) {  // group i (innermost first) -> slot kMaxChunkDims-1-i
@@ -397,7 +438,9 @@ static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_
         g.shape[slot] = mshape[i];
         g.stride[slot] = mstride[i];
         g.chunk[slot] = (unsigned)mchunk[i];
-        g.nchunk[slot] = (unsigned)((mshape[i] + mchunk[i] - 1) / mchunk[i]);
+        g.nchunk[slot] = (unsigned)mnchunk[i];
+        g.bounds[slot] = reinterpret_cast<const long long*>(mtable[i]);
+        g.scale[slot] = mscale[i];
         if (i == maxis) g.axis = slot;
         full *= (double)mchunk[i];
     }
@@ -423,15 +466,17 @@ static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_
     return XBI_OK;
 }
 
-int xbi_count_pairs_chunked(const void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
-                            int axis, unsigned flags, uint64_t mask_bits, unsigned long long* counts_dev, void* stream) {
+static int count_pairs_grid(const void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                            const int64_t* nchunks_dim, const int64_t* bounds_host, const int64_t* bounds_dev, int axis,
+                            unsigned flags, uint64_t mask_bits, unsigned long long* counts_dev, void* stream) {
     CountJob job;
     if (int rc = make_job(job, x_dev, dtype, 0, 0, 0, flags, mask_bits)) return rc;
     if (axis < 0) return fail(XBI_ERR_ARG, "axis out of range");
     ChunkGrid g;
     int64_t nchunks = 0;
     bool empty = false;
-    if (int rc = plan_chunk_grid(ndim, shape, chunk_shape, axis, g, &nchunks, &empty)) return rc;
+    if (int rc = plan_chunk_grid(ndim, shape, chunk_shape, nchunks_dim, bounds_host, bounds_dev, axis, g, &nchunks, &empty))
+        return rc;
     if (nchunks == 0) return XBI_OK;
     if (!counts_dev) return fail(XBI_ERR_ARG, "null counts pointer");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -445,13 +490,30 @@ int xbi_count_pairs_chunked(const void* x_dev, int dtype, int ndim, const int64_
     return XBI_OK;
 }
 
-int xbi_bitround_chunked(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+int xbi_count_pairs_chunked(const void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                            int axis, unsigned flags, uint64_t mask_bits, unsigned long long* counts_dev, void* stream) {
+    if (!chunk_shape) return fail(XBI_ERR_ARG, "null chunk_shape pointer");
+    return count_pairs_grid(x_dev, dtype, ndim, shape, chunk_shape, nullptr, nullptr, nullptr, axis, flags, mask_bits,
+                            counts_dev, stream);
+}
+
+int xbi_count_pairs_chunked_v(const void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* nchunks_dim,
+                              const int64_t* bounds_host, const int64_t* bounds_dev, int axis, unsigned flags,
+                              uint64_t mask_bits, unsigned long long* counts_dev, void* stream) {
+    if (!nchunks_dim || !bounds_host || !bounds_dev) return fail(XBI_ERR_ARG, "null chunk table pointer");
+    return count_pairs_grid(x_dev, dtype, ndim, shape, nullptr, nchunks_dim, bounds_host, bounds_dev, axis, flags,
+                            mask_bits, counts_dev, stream);
+}
+
+static int bitround_grid(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                         const int64_t* nchunks_dim, const int64_t* bounds_host, const int64_t* bounds_dev,
                          const int32_t* keepbits_dev, void* stream) {
     if (!dtype_is_float(dtype)) return fail(XBI_ERR_ARG, "Only float arrays (16-64bit) can be bit-rounded");
     ChunkGrid g;
     int64_t nchunks = 0;
     bool empty = false;
-    if (int rc = plan_chunk_grid(ndim, shape, chunk_shape, -1, g, &nchunks, &empty)) return rc;
+    if (int rc = plan_chunk_grid(ndim, shape, chunk_shape, nchunks_dim, bounds_host, bounds_dev, -1, g, &nchunks, &empty))
+        return rc;
     if (nchunks == 0 || empty) return XBI_OK;
     if (!x_dev || !keepbits_dev) return fail(XBI_ERR_ARG, "null pointer");
     if (reinterpret_cast<uintptr_t>(x_dev) % dtype_bytes(dtype) != 0)
@@ -459,6 +521,19 @@ int xbi_bitround_chunked(void* x_dev, int dtype, int ndim, const int64_t* shape,
     XBI_CUDA(launch_bitround_chunked(x_dev, dtype, g, keepbits_dev, static_cast<cudaStream_t>(stream)),
              "bitround (chunk grid)");
     return XBI_OK;
+}
+
+int xbi_bitround_chunked(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* chunk_shape,
+                         const int32_t* keepbits_dev, void* stream) {
+    if (!chunk_shape) return fail(XBI_ERR_ARG, "null chunk_shape pointer");
+    return bitround_grid(x_dev, dtype, ndim, shape, chunk_shape, nullptr, nullptr, nullptr, keepbits_dev, stream);
+}
+
+int xbi_bitround_chunked_v(void* x_dev, int dtype, int ndim, const int64_t* shape, const int64_t* nchunks_dim,
+                           const int64_t* bounds_host, const int64_t* bounds_dev, const int32_t* keepbits_dev,
+                           void* stream) {
+    if (!nchunks_dim || !bounds_host || !bounds_dev) return fail(XBI_ERR_ARG, "null chunk table pointer");
+    return bitround_grid(x_dev, dtype, ndim, shape, nullptr, nchunks_dim, bounds_host, bounds_dev, keepbits_dev, stream);
 }
 
 static int check_bitround_args(int dtype, int64_t numel, int keepbits) {
@@ -724,6 +799,13 @@ int xbi_bitround_host(const void* src_host, void* dst_host, int dtype, int64_t n
         // slabs of one pinned slot; slot k of each direction belongs to stream k.  While the GPU works on
         // slab i the pool copies slab i-1's result out and slab i+1 in.
         if (int rc = ensure_pinned(c, stage_in, stage_out)) return rc;
+        if (stage_out && src_host != dst_host) {
+            // a fresh output array is first touched here: with 2 MB pages the copy-out threads take 512x fewer
+            // page faults (numpy gives the same advice for its own large allocations; malloc'ed buffers do not)
+            const uintptr_t lo = (reinterpret_cast<uintptr_t>(dst_host) + ((uintptr_t)2 << 20) - 1) & ~(((uintptr_t)2 << 20) - 1);
+            const uintptr_t hi = (reinterpret_cast<uintptr_t>(dst_host) + (size_t)numel * bytes) & ~(((uintptr_t)2 << 20) - 1);
+            if (hi > lo) madvise(reinterpret_cast<void*>(lo), hi - lo, MADV_HUGEPAGE);
+        }
         const size_t slot = HostCtx::kPinBytes < c.buf_bytes ? HostCtx::kPinBytes : c.buf_bytes;
         const int64_t per = (int64_t)(slot / bytes);
         struct Pending { bool active; char* dst; size_t nbytes; } pend[2] = {{false, nullptr, 0}, {false, nullptr, 0}};

@@ -82,9 +82,16 @@ struct Walker {
         for (int d = kD - 1; d >= 0; --d) {
             unsigned q = r;
             if (d > 0) { q = r % g.nchunk[d]; r /= g.nchunk[d]; }
-            const long long start = (long long)q * g.chunk[d];
-            const long long ext = g.shape[d] - start;
-            e[d] = ext < (long long)g.chunk[d] ? (unsigned)ext : g.chunk[d];
+            long long start;
+            if (g.bounds[d] != nullptr) {  // irregular dimension (uniform branch)
+                const long long b0 = g.bounds[d][q], b1 = g.bounds[d][q + 1];
+                start = b0 * g.scale[d];
+                e[d] = (unsigned)((b1 - b0) * g.scale[d]);
+            } else {
+                start = (long long)q * g.chunk[d];
+                const long long ext = g.shape[d] - start;
+                e[d] = ext < (long long)g.chunk[d] ? (unsigned)ext : g.chunk[d];
+            }
             base += start * g.stride[d];
             numel *= e[d];
         }

@@ -106,6 +106,11 @@ struct ChunkGrid {
     long long stride[kMaxChunkDims];  // element strides
     unsigned chunk[kMaxChunkDims];    // chunk extents (< 2^31; the last chunk of a dimension may be shorter)
     unsigned nchunk[kMaxChunkDims];   // chunks per dimension
+    // irregular dimensions: device table of nchunk+1 ascending offsets (nullptr: regular, `chunk` applies);
+    // chunk q covers [bounds[q], bounds[q+1]) * scale (scale: the unchunked inner dimensions merged into it);
+    // `chunk` then holds the largest extent
+    const long long* bounds[kMaxChunkDims];
+    long long scale[kMaxChunkDims];
     int axis;                         // analysed dimension, -1: none (bitround)
     int lo;                           // first dimension in use (the ones before it are padding)
     unsigned groups;                  // work items per chunk

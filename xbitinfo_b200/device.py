@@ -121,12 +121,42 @@ def bitround_(x: torch.Tensor, keepbits: int) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # batched over a regular chunk grid (docs/chunking.ipynb workflow, csrc/xbi_chunked.cu)
 # --------------------------------------------------------------------------------------
+def _grid_tables(shape, chunk_shape, device):
+    """None for a regular grid (every entry of ``chunk_shape`` an int), else ``(nchunks per dimension,
+    offsets on the host, the same offsets as an int64 CUDA tensor)`` for per-dimension tuples of chunk
+    lengths (dask's ``.chunks``); ints and tuples may be mixed."""
+    if len(shape) != len(chunk_shape):
+        raise ValueError("chunk_shape needs one entry per dimension")
+    if not any(isinstance(c, (tuple, list)) for c in chunk_shape):
+        return None
+    nchunks, offsets = [], []
+    for n, c in zip(shape, chunk_shape):
+        n = int(n)
+        if isinstance(c, (tuple, list)):
+            lens = [int(v) for v in c]
+        else:
+            c = min(int(c), max(n, 1))
+            if c < 1:
+                raise ValueError("chunk extents must be positive")
+            lens = [c] * (n // c) + ([n % c] if n % c else [])
+        if sum(lens) != n or any(v < 1 for v in lens):
+            raise ValueError(f"chunk lengths {tuple(lens)} do not tile an extent of {n}")
+        nchunks.append(len(lens))
+        offsets.extend(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64).tolist())
+    host = np.asarray(offsets, dtype=np.int64)
+    return nchunks, host, torch.from_numpy(host).to(device)
+
+
 def chunk_grid_shape(shape, chunk_shape):
-    """Chunks per dimension of a regular grid (the last chunk of a dimension may be shorter)."""
+    """Chunks per dimension of a grid given by chunk lengths (ints: regular, the last chunk of a dimension
+    may be shorter; tuples: explicit lengths)."""
     if len(shape) != len(chunk_shape):
         raise ValueError("chunk_shape needs one entry per dimension")
     out = []
     for n, c in zip(shape, chunk_shape):
+        if isinstance(c, (tuple, list)):
+            out.append(len(c))
+            continue
         c = int(c)
         if c < 1:
             raise ValueError("chunk extents must be positive")
@@ -136,8 +166,9 @@ def chunk_grid_shape(shape, chunk_shape):
 
 def count_pairs_chunked(x: torch.Tensor, chunk_shape, axis: int, *, transform: bool = True,
                         masked_value=None) -> torch.Tensor:
-    """K1 on every chunk of a regular grid on its own, one launch: int64 tensor of shape
-    ``chunks-per-dimension + (nbits, 2, 2)`` (chunks in C order of the grid)."""
+    """K1 on every chunk of a grid on its own, one launch: int64 tensor of shape
+    ``chunks-per-dimension + (nbits, 2, 2)`` (chunks in C order of the grid).  ``chunk_shape``: one int
+    (regular) or one tuple of chunk lengths (dask's ``.chunks``) per dimension."""
     require_cuda_tensor(x)
     code = torch_dtype_code(x.dtype)
     nd = x.dim()
@@ -145,6 +176,7 @@ def count_pairs_chunked(x: torch.Tensor, chunk_shape, axis: int, *, transform: b
         raise ValueError(f"axis {axis} out of range for {nd}-d array")
     axis %= nd
     grid = chunk_grid_shape(tuple(x.shape), chunk_shape)
+    tables = _grid_tables(tuple(x.shape), chunk_shape, x.device)
     nbits = 8 * x.element_size()
     counts = torch.empty(grid + (nbits, 2, 2), dtype=torch.int64, device=x.device)
     np_dtype = numpy_dtype_of(x)
@@ -152,9 +184,17 @@ def count_pairs_chunked(x: torch.Tensor, chunk_shape, axis: int, *, transform: b
     if np_dtype.kind == "f" and transform:
         flags |= nat.SIGNED_EXPONENT
     with torch.cuda.device(x.device):
-        rc = nat.lib().xbi_count_pairs_chunked(
-            x.data_ptr(), code, nd, nat.int64_array(x.shape), nat.int64_array(chunk_shape), axis, flags, bits,
-            counts.data_ptr(), _stream_ptr(x.device))
+        if tables is None:
+            rc = nat.lib().xbi_count_pairs_chunked(
+                x.data_ptr(), code, nd, nat.int64_array(x.shape), nat.int64_array(chunk_shape), axis, flags, bits,
+                counts.data_ptr(), _stream_ptr(x.device))
+        else:
+            nchunks, host, dev = tables
+            rc = nat.lib().xbi_count_pairs_chunked_v(
+                x.data_ptr(), code, nd, nat.int64_array(x.shape), nat.int64_array(nchunks),
+                host.ctypes.data_as(nat.C.POINTER(nat.C.c_int64)), dev.data_ptr(), axis, flags, bits,
+                counts.data_ptr(), _stream_ptr(x.device))
+            dev.record_stream(torch.cuda.current_stream(x.device))
     nat.check(rc)
     return counts
 
@@ -177,17 +217,26 @@ def information_batched(counts: torch.Tensor, set_zero_insignificant: bool = Fal
 
 
 def bitround_chunked_(x: torch.Tensor, chunk_shape, keepbits: torch.Tensor) -> torch.Tensor:
-    """K3 in place, chunk c of the regular grid rounded to ``keepbits[c]`` mantissa bits
-    (int32 CUDA tensor with one entry per chunk, C order of the grid)."""
+    """K3 in place, chunk c of the grid rounded to ``keepbits[c]`` mantissa bits (int32 CUDA tensor
+    with one entry per chunk, C order of the grid; ``chunk_shape`` as for :func:`count_pairs_chunked`)."""
     require_cuda_tensor(x)
     require_cuda_tensor(keepbits)
     code = torch_dtype_code(x.dtype)
     grid = chunk_grid_shape(tuple(x.shape), chunk_shape)
     if keepbits.dtype != torch.int32 or keepbits.numel() != math.prod(grid):
         raise ValueError("keepbits must be an int32 tensor with one entry per chunk")
+    tables = _grid_tables(tuple(x.shape), chunk_shape, x.device)
     with torch.cuda.device(x.device):
-        rc = nat.lib().xbi_bitround_chunked(
-            x.data_ptr(), code, x.dim(), nat.int64_array(x.shape), nat.int64_array(chunk_shape),
-            keepbits.data_ptr(), _stream_ptr(x.device))
+        if tables is None:
+            rc = nat.lib().xbi_bitround_chunked(
+                x.data_ptr(), code, x.dim(), nat.int64_array(x.shape), nat.int64_array(chunk_shape),
+                keepbits.data_ptr(), _stream_ptr(x.device))
+        else:
+            nchunks, host, dev = tables
+            rc = nat.lib().xbi_bitround_chunked_v(
+                x.data_ptr(), code, x.dim(), nat.int64_array(x.shape), nat.int64_array(nchunks),
+                host.ctypes.data_as(nat.C.POINTER(nat.C.c_int64)), dev.data_ptr(), keepbits.data_ptr(),
+                _stream_ptr(x.device))
+            dev.record_stream(torch.cuda.current_stream(x.device))
     nat.check(rc)
     return x
