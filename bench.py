@@ -14,7 +14,7 @@ of a global (N*8760, 721, 1440) array ("weak"; ``--scaling strong`` splits the o
 ``--impl reference`` times the reference's CPU algorithm (the numpy restatement in
 oracle/, the reference package itself cannot be imported in this image) on a bounded
 sample of the same workload with the thread-level parallelism its dask graph has (one
-task per byte plane).
+task per byte plane and dask block), on every host core.
 """
 from __future__ import annotations
 
@@ -133,8 +133,10 @@ class ClockSampler:
 # the reference's CPU algorithm (oracle port) -- only the checker/baseline legs use it
 # --------------------------------------------------------------------------------------
 def reference_step(x, threads):
-    """One pass of the reference python path over ``x`` along the last axis with the
-    parallelism of its dask graph: one task per byte plane (xbitinfo/_py_bitinfo.py:128-140)."""
+    """One pass of the reference python path over ``x`` along the last axis with the parallelism its
+    dask graph has: one task per byte plane (xbitinfo/_py_bitinfo.py:128-140) and per dask block of the
+    array (``da.array`` cuts a large variable into ~128 MiB blocks, xbitinfo/xbitinfo.py:349; blocks along
+    the first axis never split a pair along the last one, and the per-block tables add up)."""
     from concurrent.futures import ThreadPoolExecutor
 
     import numpy as np
@@ -142,21 +144,30 @@ def reference_step(x, threads):
     from oracle import bitinfo_oracle as bo
 
     X = bo.to_analysis_words(x)
-    a, b = bo.adjacent_views(X, x.ndim - 1)
     nbytes = X.dtype.itemsize
-    a, b = np.broadcast_arrays(a, b)
+    nblocks = max(1, min(X.shape[0], -(-threads // nbytes))) if threads > 1 else 1
+    edges = np.linspace(0, X.shape[0], nblocks + 1).astype(int)
+    views = []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        a, b = bo.adjacent_views(X[lo:hi], x.ndim - 1)
+        views.append(np.broadcast_arrays(a, b))
 
-    def plane(i):
+    def task(t):
+        blk, i = divmod(t, nbytes)
+        a, b = views[blk]
         s = (nbytes - 1 - i) * 8
         return bo._paircount_byteplane((a >> s).astype("u1"), (b >> s).astype("u1"))
 
+    ntasks = nblocks * nbytes
     if threads > 1:
         with ThreadPoolExecutor(max_workers=threads) as ex:
-            planes = list(ex.map(plane, range(nbytes)))
+            parts = list(ex.map(task, range(ntasks)))
     else:
-        planes = [plane(i) for i in range(nbytes)]
+        parts = [task(t) for t in range(ntasks)]
+    planes = [sum(parts[blk * nbytes + i].astype(np.int64) for blk in range(nblocks)) for i in range(nbytes)]
     counts = np.concatenate(planes, axis=0).astype(np.int64)
-    return bo.mutual_information_from_counts(counts, a.size)
+    npairs = sum(a.size for a, _ in views)
+    return bo.mutual_information_from_counts(counts, npairs)
 
 
 def cpu_sample_rows(budget_s, per_step_steps, threads):
@@ -167,7 +178,9 @@ def cpu_sample_rows(budget_s, per_step_steps, threads):
     reference_step(x, threads)
     t1 = time.perf_counter() - t0
     rows = int(budget_s / max(per_step_steps, 1) / max(t1, 1e-3))
-    return max(1, min(rows, 16))
+    if threads > 1:
+        rows *= max(1, threads // 2)  # the one-row calibration ran four tasks; a real step feeds every core
+    return max(1, min(rows, 16 * max(1, threads // 4)))
 
 
 def run_reference(args):
@@ -175,7 +188,7 @@ def run_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    threads = min(4, cores)  # float32: four byte planes = four independent dask task chains
+    threads = cores  # byte planes x dask blocks: every host core gets a task
     steps, warm = args.steps, args.warmup
     rows = cpu_sample_rows(150.0, steps + warm, threads)
     x = synth_host((rows,) + FULL_SHAPE[1:], 1234)
