@@ -107,3 +107,23 @@ def test_product_package_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/xbitinfo_b200.h compiles as C99 with warnings as errors and a C program links against the
+    shared library: the boundary a cgo / JNI / C binding would use."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    exe = tmp_path / "abi_consumer"
+    libdir = os.path.dirname(nat.LIB_PATH)
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "c", "abi_consumer.c"), "-o", str(exe), "-L", libdir, "-lxbitinfo_b200",
+           f"-Wl,-rpath,{libdir}"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0 and "abi consumer ok" in r.stdout, (r.returncode, r.stdout, r.stderr)

@@ -189,6 +189,18 @@ def test_bitround_chunked_irregular_grid():
     assert np.array_equal(t.cpu().numpy().view("u8"), want.view("u8"))
 
 
+def test_single_element_and_all_ones_shapes():
+    """Found by scripts/fuzz_gpu.py: an array whose every dimension has length 1 leaves no group after the
+    planner drops them; the stand-in group must be fully initialised."""
+    for shape in ((1,), (1, 1), (1, 1, 1, 1)):
+        x = np.full(shape, 3.14159, dtype="float64")
+        t = torch.from_numpy(x).cuda()
+        bitround_chunked_(t, shape, torch.tensor([5], dtype=torch.int32, device="cuda"))
+        assert np.array_equal(t.cpu().numpy().view("u8"), bro.bitround(x, 5).view("u8"))
+        c = count_pairs_chunked(torch.from_numpy(x).cuda(), shape, 0)
+        assert int(c.abs().sum()) == 0 and tuple(c.shape) == shape + (64, 2, 2)
+
+
 def test_unsupported_and_bad_arguments():
     x = torch.zeros((2, 2, 2, 2, 2, 2), dtype=torch.float32, device="cuda")
     with pytest.raises(NotImplementedError):

@@ -421,14 +421,16 @@ static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_
         }
         stride *= shape[d];
     }
-    if (m == 0) { mshape[0] = 1; mchunk[0] = 1; mstride[0] = 1; m = 1; }  // a single element
+    if (m == 0) {  // a single element
+        mshape[0] = 1; mchunk[0] = 1; mstride[0] = 1; mscale[0] = 1; mtable[0] = nullptr; mnchunk[0] = 1;
+        m = 1;
+    }
     if (m > kMaxChunkDims)
         return fail(XBI_ERR_UNSUPPORTED, "more than 5 chunked dimensions after merging; process the chunks one by one");
     double full = 1.0;
     for (int i = 0; i < kMaxChunkDims; ++i) {
         g.shape[i] = 1; g.stride[i] = 0; g.chunk[i] = 1; g.nchunk[i] = 1; g.bounds[i] = nullptr; g.scale[i] = 1;
     }
-    if (m == 0) { mscale[0] = 1; mtable[0] = nullptr; mnchunk[0] = 1; }
     g.axis = -1;
     g.lo = kMaxChunkDims - m;
     for (int i = 0; i < m; ++i) {  // group i (innermost first) -> slot kMaxChunkDims-1-i
