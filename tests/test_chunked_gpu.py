@@ -161,6 +161,31 @@ def test_batched_route_equals_chunk_by_chunk_route_and_the_oracle():
         assert np.array_equal(k3, k4) and np.array_equal(r3.view("u4"), r4.view("u4"))
 
 
+def test_labelled_front_end_of_the_chunking_notebook():
+    import xbitinfo_b200 as xb
+    from xbitinfo_b200.chunked import xr_bitround_by_chunks
+
+    rng = np.random.default_rng(13)
+    air = smooth_field(rng, (60, 25, 53), "float32", axis=1, scale=0.3, base=280.0)
+    air[:, :10] *= 1e-3
+    ds = xb.Dataset({
+        "air": xb.DataArray(air, dims=("time", "lat", "lon"), name="air", attrs={"units": "K"}),
+        "orog": xb.DataArray(smooth_field(rng, (25, 53), "float32", axis=0), dims=("lat", "lon"), name="orog"),
+        "time_bnds": xb.DataArray(np.arange(60, dtype="float64"), dims=("time",), name="time_bnds"),
+    })
+    rounded, keep = xr_bitround_by_chunks(ds, {"lat": 5, "lon": (10, 10, 33)}, "lat", masked_value=None,
+                                          set_zero_insignificant=False)
+    assert keep["air"].dims == ("time", "lat", "lon") and keep["air"].shape == (1, 5, 3)
+    assert keep["orog"].shape == (5, 3) and "time_bnds" not in keep.data_vars
+    assert rounded["air"].attrs["units"] == "K"
+    assert np.array_equal(rounded["time_bnds"].values, ds["time_bnds"].values)
+    want, kwant = bitround_by_chunks(air, {1: 5, 2: (10, 10, 33)}, 1, masked_value=None, set_zero_insignificant=False)
+    assert np.array_equal(rounded["air"].values.view("u4"), want.view("u4")) and np.array_equal(keep["air"].values, kwant)
+    assert len(np.unique(keep["air"].values)) > 1
+    # the input is untouched
+    assert np.array_equal(ds["air"].values, air)
+
+
 def test_launch_count_does_not_grow_with_the_number_of_chunks():
     from xbitinfo_b200 import _native as nat
 

@@ -148,3 +148,41 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
         bitround_(blk, k)
         t[sl] = blk
     return (t.cpu().numpy() if is_np else t), keep
+
+
+def xr_bitround_by_chunks(obj, chunks, dim, inflevel: float = 0.99, **kwargs):
+    """The chunking notebook on a labelled object: every block of the grid ``chunks`` (``{dim name: chunk
+    length or tuple of lengths}``, dimensions left out are not cut -- what ``ds.chunk(chunks)`` would give)
+    is analysed along ``dim`` and rounded to its own keepbits at ``inflevel``.
+
+    Returns ``(rounded, keepbits)``: ``rounded`` like ``obj`` (Dataset or DataArray, attrs kept), ``keepbits``
+    an int64 DataArray per variable with the dimensions of the variable and one entry per block.  Variables
+    without ``dim`` are returned unchanged (as ``get_bitinformation`` skips them, ``xbitinfo.py:358-363``).
+    ``kwargs``: ``masked_value``, ``set_zero_insignificant``, ``confidence`` as for ``get_bitinformation``.
+    """
+    from . import _xr
+    from .bitinfo import _resolve_kwargs
+
+    ns = _xr.namespace_for(obj)
+    if _xr.is_dataset(obj):
+        rounded, keep = obj.copy(), ns.Dataset()
+        for v in obj.data_vars:
+            if dim not in obj[v].dims:
+                continue
+            rounded[v], keep[v] = xr_bitround_by_chunks(obj[v], chunks, dim, inflevel, **kwargs)
+        return rounded, keep
+    da = obj
+    if dim not in da.dims:
+        raise ValueError(f"{dim} is not a dimension of {da.name}")
+    chunks = {d: c for d, c in chunks.items() if d in da.dims}  # a Dataset-wide grid may name other dimensions
+    masked_value, set_zero, confidence = _resolve_kwargs(da.dtype, kwargs)
+    axis = list(da.dims).index(dim)
+    by_axis = {list(da.dims).index(d): c for d, c in chunks.items()}
+    data = _xr.raw_data(da)
+    new, keep = bitround_by_chunks(data, by_axis, axis, inflevel=inflevel, masked_value=masked_value,
+                                   set_zero_insignificant=set_zero, confidence=confidence)
+    if _xr.is_xarray(da):  # pragma: no cover - xarray is absent from the build image
+        out = da.copy(data=new)
+    else:
+        out = da._replace(new)
+    return out, ns.DataArray(keep, dims=list(da.dims), name=da.name)
