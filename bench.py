@@ -246,7 +246,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = None
     if world > 1:
+        # one process per GPU: keep each rank's host staging memory on its GPU's NUMA node
+        numa_node = xdist.bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
     shape = (args.time_steps,) + FULL_SHAPE[1:]
@@ -361,6 +364,7 @@ def run_ours(args):
     e2e = None
     if not args.no_e2e:
         e2e = run_e2e(args, x, rank, world, dev, sync_all)
+        e2e["numa_node_of_rank0"] = numa_node
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

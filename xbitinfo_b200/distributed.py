@@ -73,6 +73,37 @@ def world():
     return dist.get_rank(), dist.get_world_size()
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Restrict this process to the CPUs of the NUMA node its GPU hangs off, so that host staging memory
+    allocated afterwards (pinned buffers are placed by first touch) and the copy threads are local to the
+    GPU's PCIe root.  With one process per GPU on a two-socket box, unbound ranks end up reading half of
+    their host buffers across the socket interconnect.  Returns the node, or None when the topology is not
+    exposed (containers often hide it) or the CPUs are not available to this process; never raises."""
+    import os
+
+    try:
+        import torch
+
+        p = torch.cuda.get_device_properties(device_index)
+        sys_id = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{sys_id}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def allreduce_counts(counts, group=None):
     """In-place SUM all-reduce of a counts tensor (int64).  NCCL for CUDA tensors, gloo for
     CPU tensors (tests).  A no-op without an initialised process group."""
