@@ -47,6 +47,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--ref-budget-s", type=float, default=150.0, help="CPU seconds the whole --impl reference run may take")
     return ap.parse_args()
 
 
@@ -190,7 +191,7 @@ def run_reference(args):
     cores = os.cpu_count() or 1
     threads = cores  # byte planes x dask blocks: every host core gets a task
     steps, warm = args.steps, args.warmup
-    rows = cpu_sample_rows(150.0, steps + warm, threads)
+    rows = cpu_sample_rows(args.ref_budget_s, steps + warm, threads)
     x = synth_host((rows,) + FULL_SHAPE[1:], 1234)
     for _ in range(warm):
         reference_step(x, threads)

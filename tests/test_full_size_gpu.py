@@ -244,3 +244,29 @@ def test_config4_pipeline_share_of_one_gpu(dtype):
     y = x[: max(1, rows // 8)].clone()
     bitround_(y, keep)
     assert torch.equal(y, x[: max(1, rows // 8)])  # idempotent
+
+
+def test_bench_line_carries_every_key_of_the_contract():
+    """A short ``bench.py`` run (64 time steps of the workload's grid) prints one JSON line with the keys the
+    driver and the judge read."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--time-steps", "64", "--steps", "3", "--warmup", "3",
+                        "--e2e-steps", "1", "--no-cpu-baseline"], capture_output=True, text=True, cwd=root, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert key in line, key
+    assert line["n_gpus"] == 1 and line["steps"] == 3 and line["value"] > 0 and line["gpu_launches"] > 0
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in line["roofline"], key
+    assert line["roofline"]["bound"] == "hbm" and 0 < line["roofline"]["frac"] < 1.5
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in line["e2e"], key
+    assert line["e2e"]["h2d_bytes_per_step"] >= 64 * 721 * 1440 * 4 and line["e2e"]["value"] > 0
+    assert "workload" in line["config"] and "sm_mhz" in line["clocks"]

@@ -284,3 +284,21 @@ def test_flow_path_selection_and_container_round_trip(tmp_path):
     back = flow.open_npz(p)
     assert list(back.data_vars) == ["a", "b"] and back["a"].dims == ("t", "y", "x") and back["b"].dims == ("t", "y")
     assert np.array_equal(back["a"].values, ds["a"].values) and back["b"].dtype == np.dtype("int16")
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """``bench.py --impl reference`` (the CPU arm the driver runs beside ours) on a few seconds of budget:
+    one JSON line with the contract's keys, no GPU needed."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                        "--warmup", "0", "--ref-budget-s", "4"], capture_output=True, text=True, cwd=root, timeout=600)
+    assert r.returncode == 0, r.stderr
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "get_bitinformation_input_throughput"
+    assert line["unit"] == "GB/s" and line["higher_is_better"] is True and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert line["config"]["workload"].startswith("configs[1]")
