@@ -435,6 +435,44 @@ def test_lazy_arrays_are_streamed_on_chunk_boundaries(monkeypatch):
             assert lazy.rows_read == 50 + len(lazy.reads) - 1  # one halo row per slab but the last
 
 
+def test_lazy_arrays_are_read_once_for_all_dimensions():
+    """``get_bitinformation(ds)`` over every dimension of a lazy variable reads (decodes) the source once:
+    slabs on its chunk boundaries, one halo row per slab because the first dimension is analysed too."""
+    from xbitinfo_b200.streaming import bitinformation_streamed_multi
+
+    rng = np.random.default_rng(18)
+    x = smooth_field(rng, (50, 24, 36), "float32", axis=2, scale=0.4, base=280.0)
+    x[:, rng.random((24, 36)) < 0.2] = np.nan
+    lazy = _LazyChunked(x, chunk_rows=6)
+    got = bitinformation_streamed_multi(lazy, [0, 1, 2], slab_bytes=13 * 24 * 36 * 4, masked_value=float("nan"),
+                                        return_counts=True)
+    assert lazy.rows_read == 50 + len(lazy.reads) - 1 and len(lazy.reads) >= 4
+    assert all(lo % 6 == 0 for lo, _ in lazy.reads)
+    for a, (mi, c) in enumerate(got):
+        want_c, _, want_mi = bo.bitinformation(x, a, masked_value=float("nan"))
+        assert np.array_equal(c, want_c), a
+        assert_mi_close(mi, want_mi)
+    # without the first axis no halo is read; a subset in any order
+    lazy = _LazyChunked(x, chunk_rows=7)
+    got = bitinformation_streamed_multi(lazy, [2, 1], slab_bytes=10 * 24 * 36 * 4, return_counts=True)
+    assert lazy.rows_read == 50
+    assert np.array_equal(got[0][1], bo.bitinformation(x, 2)[0]) and np.array_equal(got[1][1], bo.bitinformation(x, 1)[0])
+    # one-row slabs, 2-d, first axis of length 1 (no pairs along it)
+    y = smooth_field(rng, (9, 40), "float64", axis=1, scale=0.3)
+    got = bitinformation_streamed_multi(_LazyChunked(y, chunk_rows=4), [0, 1], slab_bytes=1, return_counts=True)
+    assert np.array_equal(got[0][1], bo.bitinformation(y, 0)[0]) and np.array_equal(got[1][1], bo.bitinformation(y, 1)[0])
+    z = y[:1]
+    got = bitinformation_streamed_multi(_LazyChunked(z, chunk_rows=1), [0, 1], return_counts=True)
+    assert int(np.abs(got[0][1]).sum()) == 0 and np.array_equal(got[1][1], bo.bitinformation(z, 1)[0])
+    # the public API takes this route for dim=None
+    lazy = _LazyChunked(x, chunk_rows=6)
+    ds = xb.Dataset({"T": xb.DataArray(lazy, dims=("time", "y", "x"), name="T")})
+    every = xb.get_bitinformation(ds, implementation="cuda")
+    ref = xb.get_bitinformation(xb.Dataset({"T": xb.DataArray(x, dims=("time", "y", "x"), name="T")}))
+    assert np.array_equal(every["T"].values, ref["T"].values, equal_nan=True)
+    assert lazy.rows_read <= 50 + len(lazy.reads)
+
+
 def test_bitround_by_chunks_equals_the_per_block_loop_of_the_chunking_notebook():
     from xbitinfo_b200.chunked import bitround_by_chunks, slices_from_chunks, normalize_chunks
 

@@ -77,11 +77,18 @@ def bitinformation_multi(data, axes, masked_value=None, set_zero_insignificant: 
                          confidence: float = 0.99, device: int | None = None, return_counts: bool = False):
     """Information per bit along several axes of one array: list of float64[nbits] in the order of
     ``axes`` (with ``return_counts`` a list of ``(mi, counts)``).  A host numpy array crosses PCIe once for
-    all the axes (``xbi_bitinformation_host_multi``); device tensors and lazy arrays are analysed axis by
-    axis (nothing to share: the data is resident / streamed on demand)."""
+    all the axes (``xbi_bitinformation_host_multi``), a lazy array (dask / zarr / h5py) is read slab by slab
+    from its source once for all the axes; device tensors are analysed axis by axis (the data is resident)."""
     from .streaming import is_lazy_array
 
     axes = [int(a) for a in axes]
+    if is_lazy_array(data) and len(axes) >= 2:
+        # dask / zarr / h5py ...: every slab is read from the source once for all the axes
+        from .streaming import bitinformation_streamed_multi
+
+        return bitinformation_streamed_multi(data, axes, masked_value=masked_value,
+                                             set_zero_insignificant=set_zero_insignificant, confidence=confidence,
+                                             device=device, return_counts=return_counts)
     if _is_torch_tensor(data) or is_lazy_array(data) or len(axes) < 2:
         return [bitinformation(data, a, masked_value=masked_value, set_zero_insignificant=set_zero_insignificant,
                                confidence=confidence, device=device, return_counts=return_counts) for a in axes]

@@ -88,21 +88,68 @@ def bitinformation_streamed(source, axis: int, slab_bytes: int = 1 << 30, masked
                             return_counts: bool = False):
     """float64[nbits] information per bit of ``source`` along ``axis``, reading it slab by slab."""
     shape = tuple(int(s) for s in source.shape)
-    ndim = len(shape)
-    if ndim == 0:
+    if len(shape) == 0:
         raise ValueError("cannot analyse a 0-d array")
-    axis %= ndim
+    axis %= len(shape)
+    plan = slab_plan(shape, axis, np.dtype(source.dtype).itemsize, slab_bytes, _chunk_edges_axis0(source))
+    if shape[axis] < 2:
+        plan = []  # no pairs along the axis: nothing to read
+    return _stream(source, [axis], plan, masked_value, set_zero_insignificant, confidence, device, return_counts)[0]
+
+
+def bitinformation_streamed_multi(source, axes, slab_bytes: int = 1 << 30, masked_value=None,
+                                  set_zero_insignificant: bool = False, confidence: float = 0.99, device=None,
+                                  return_counts: bool = False):
+    """Information per bit along every axis in ``axes`` from ONE pass over ``source``: every slab is read
+    (decoded, for a compressed store) once and counted along each axis while it is on the device.  When the
+    sliced first axis is among them, every slab but the last carries the first row of the next one as halo;
+    the other axes count the slab's own rows only.  Returns a list in the order of ``axes``."""
+    shape = tuple(int(s) for s in source.shape)
+    if len(shape) == 0:
+        raise ValueError("cannot analyse a 0-d array")
+    axes = [int(a) % len(shape) for a in axes]
+    if len(axes) == 1:
+        return [bitinformation_streamed(source, axes[0], slab_bytes, masked_value, set_zero_insignificant,
+                                        confidence, device, return_counts)]
+    n0 = shape[0]
+    itemsize = np.dtype(source.dtype).itemsize
+    # slabs partition the first axis (on the source's chunk boundaries where possible); one more row is read
+    # as halo when the first axis itself is analysed
+    base = slab_plan(shape, 1 if len(shape) > 1 else 0, itemsize, slab_bytes, _chunk_edges_axis0(source)) \
+        if len(shape) > 1 else slab_plan(shape, 0, itemsize, slab_bytes)
+    if len(shape) == 1:  # only axis 0 exists
+        return [bitinformation_streamed(source, 0, slab_bytes, masked_value, set_zero_insignificant, confidence,
+                                        device, return_counts) for _ in axes]
+    halo_wanted = 0 in axes
+    plan = [(lo, hi, 1 if (halo_wanted and hi < n0) else 0) for lo, hi, _ in base]
+    return _stream(source, axes, plan, masked_value, set_zero_insignificant, confidence, device, return_counts)
+
+
+def _stream(source, axes, plan, masked_value, set_zero_insignificant, confidence, device, return_counts):
+    """Slabs ``[(lo, hi, halo)]`` of the first axis: pinned host buffer -> device (double buffered on two
+    streams) -> K1 per analysed axis.  With one axis the plan of ``slab_plan`` applies as is (rows
+    ``lo..hi+halo`` counted along it).  With several, the slab's own rows ``lo..hi`` are counted along the
+    axes other than the first and rows ``lo..hi+halo`` along the first."""
+    shape = tuple(int(s) for s in source.shape)
     dtype = np.dtype(source.dtype)
     nat.dtype_code(dtype)  # ValueError for unsupported dtypes
     tdtype = _TORCH_OF_NP[dtype.name]
     dev = torch.device("cuda", torch.cuda.current_device() if device is None else device)
-    plan = slab_plan(shape, axis, dtype.itemsize, slab_bytes, _chunk_edges_axis0(source))
+    single = len(axes) == 1
     inner_elems = int(np.prod(shape[1:], dtype=np.int64))
     max_rows = max((hi - lo + halo for lo, hi, halo in plan), default=0)
-    counters = [PairCounter(tdtype, dev) for _ in range(2)]
-    if max_rows == 0 or shape[axis] < 2:
-        mi = counters[0].information(set_zero_insignificant, confidence).cpu().numpy()
-        return (mi, counters[0].counts.cpu().numpy()) if return_counts else mi
+    counters = [[PairCounter(tdtype, dev) for _ in axes] for _ in range(2)]
+
+    def results():
+        out = []
+        for k in range(len(axes)):
+            counters[0][k].counts += counters[1][k].counts
+            mi = counters[0][k].information(set_zero_insignificant, confidence).cpu().numpy()
+            out.append((mi, counters[0][k].counts.cpu().numpy()) if return_counts else mi)
+        return out
+
+    if max_rows == 0:
+        return results()
     pinned = [torch.empty(max_rows * inner_elems, dtype=tdtype).pin_memory() for _ in range(2)]
     staged = [torch.empty(max_rows * inner_elems, dtype=tdtype, device=dev) for _ in range(2)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
@@ -119,14 +166,15 @@ def bitinformation_streamed(source, axis: int, slab_bytes: int = 1 << 30, masked
         with torch.cuda.stream(streams[b]):
             staged[b][:n].copy_(pinned[b][:n], non_blocking=True)
             x = staged[b][:n].view((rows,) + shape[1:])
-            counters[b].add(x, axis, masked_value=masked_value)
+            for k, axis in enumerate(axes):
+                if single or axis == 0:
+                    if shape[axis] >= 2 and rows >= (2 if axis == 0 else 1):
+                        counters[b][k].add(x, axis, masked_value=masked_value)
+                elif shape[axis] >= 2:
+                    counters[b][k].add(x[: hi - lo], axis, masked_value=masked_value)
             ev = torch.cuda.Event()
             ev.record(streams[b])
         done[b] = ev
     for s in streams:
         s.synchronize()
-    counters[0].counts += counters[1].counts
-    mi = counters[0].information(set_zero_insignificant, confidence).cpu().numpy()
-    if return_counts:
-        return mi, counters[0].counts.cpu().numpy()
-    return mi
+    return results()
