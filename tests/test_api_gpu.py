@@ -473,6 +473,31 @@ def test_lazy_arrays_are_read_once_for_all_dimensions():
     assert lazy.rows_read <= 50 + len(lazy.reads)
 
 
+def test_bitround_streamed_between_two_files(tmp_path):
+    """Out-of-core rounding: file-backed input and output (np.memmap), slab by slab."""
+    from xbitinfo_b200.streaming import bitround_streamed
+
+    rng = np.random.default_rng(19)
+    x = smooth_field(rng, (101, 40, 30), "float32", axis=0, scale=0.4)
+    x.tofile(tmp_path / "in.dat")
+    src = np.memmap(tmp_path / "in.dat", dtype="float32", mode="r", shape=x.shape)
+    dst = np.memmap(tmp_path / "out.dat", dtype="float32", mode="w+", shape=x.shape)
+    lazy = _LazyChunked(src, chunk_rows=8)
+    bitround_streamed(lazy, 7, dst, slab_bytes=20 * 40 * 30 * 4)
+    dst.flush()
+    assert lazy.rows_read == 101 and all(lo % 8 == 0 for lo, _ in lazy.reads) and len(lazy.reads) == 7
+    got = np.fromfile(tmp_path / "out.dat", dtype="float32").reshape(x.shape)
+    assert np.array_equal(got.view("u4"), bro.bitround(x, 7).view("u4"))
+    y = smooth_field(rng, (1000,), "float64", axis=0)
+    out = np.empty_like(y)
+    assert bitround_streamed(y, 30, out, slab_bytes=800) is out
+    assert np.array_equal(out.view("u8"), bro.bitround(y, 30).view("u8"))
+    with pytest.raises(ValueError):
+        bitround_streamed(y, 30, np.empty(999))
+    with pytest.raises(TypeError):
+        bitround_streamed(np.arange(10), 3, np.empty(10, dtype="int64"))
+
+
 def test_bitround_by_chunks_equals_the_per_block_loop_of_the_chunking_notebook():
     from xbitinfo_b200.chunked import bitround_by_chunks, slices_from_chunks, normalize_chunks
 

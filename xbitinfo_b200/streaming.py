@@ -178,3 +178,28 @@ def _stream(source, axes, plan, masked_value, set_zero_insignificant, confidence
     for s in streams:
         s.synchronize()
     return results()
+
+
+def bitround_streamed(source, keepbits: int, out, slab_bytes: int = 1 << 30, device=None):
+    """Out-of-core ``xr_bitround``: ``out[lo:hi] = bitround(source[lo:hi], keepbits)`` slab by slab along the
+    first axis (on the source's chunk boundaries), so that neither the input nor the result has to fit in host
+    memory.  ``source``: anything sliceable (``np.memmap``, zarr / h5py / netCDF4 variables, dask arrays);
+    ``out``: anything that accepts slice assignment of numpy arrays (a ``np.memmap``, a zarr array, an h5py
+    dataset ...) with the shape and dtype of ``source``.  Every slab goes through ``xbi_bitround_host`` (pinned
+    ring + copy threads + K3).  Returns ``out``."""
+    from . import engine
+
+    shape = tuple(int(s) for s in source.shape)
+    if len(shape) == 0:
+        raise ValueError("cannot round a 0-d array")
+    dtype = np.dtype(source.dtype)
+    if dtype.kind != "f" or dtype.itemsize > 8:
+        raise TypeError("Only float arrays (16-64bit) can be bit-rounded")
+    if tuple(int(s) for s in out.shape) != shape or np.dtype(out.dtype) != dtype:
+        raise ValueError("`out` must have the shape and dtype of `source`")
+    plan = slab_plan(shape, 1, dtype.itemsize, slab_bytes, _chunk_edges_axis0(source)) if len(shape) > 1 else \
+        [(lo, min(lo + max(1, slab_bytes // dtype.itemsize), shape[0]), 0)
+         for lo in range(0, shape[0], max(1, slab_bytes // dtype.itemsize))]
+    for lo, hi, _ in plan:
+        out[lo:hi] = engine.bitround(np.asarray(source[lo:hi]), keepbits, device=device)
+    return out
