@@ -302,3 +302,31 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["config"]["workload"].startswith("configs[1]")
+
+
+def test_chunk_grid_descriptions():
+    """Host logic of the chunk-grid front end: dask-style chunk tuples -> what the batched kernels take."""
+    from xbitinfo_b200.chunked import _chunk_spec, keepbits_of_information, keepbits_of_information_batched, normalize_chunks
+    from xbitinfo_b200.device import chunk_grid_shape
+
+    grid = normalize_chunks((120, 25, 53), {1: 5, 2: 10})
+    assert _chunk_spec(grid) == (120, 5, 10)                      # regular: the last chunk may be shorter
+    assert _chunk_spec(((120,), (5, 7, 13), (53,))) == (120, (5, 7, 13), 53)
+    assert _chunk_spec(((4, 4, 5),)) == ((4, 4, 5),)              # a longer last chunk is not regular
+    assert chunk_grid_shape((120, 25, 53), (120, 5, 10)) == (1, 5, 6)
+    assert chunk_grid_shape((120, 25, 53), (120, (5, 7, 13), 53)) == (1, 3, 1)
+    assert chunk_grid_shape((0, 4), (2, 2)) == (0, 2)
+    assert chunk_grid_shape((7,), (100,)) == (1,)
+    with pytest.raises(ValueError):
+        chunk_grid_shape((7, 7), (3,))
+    with pytest.raises(ValueError):
+        chunk_grid_shape((7,), (0,))
+    rng = np.random.default_rng(3)
+    info = np.abs(rng.standard_normal((4, 5, 32))) ** 4
+    info[1, 2] = np.nan                                            # a chunk without valid pairs
+    batched = keepbits_of_information_batched(info, np.dtype("float32"), 0.99)
+    for idx in np.ndindex(4, 5):
+        assert batched[idx] == keepbits_of_information(info[idx], np.dtype("float32"), 0.99)
+        if idx != (1, 2):
+            assert batched[idx] == ko.keepbits_from_info(info[idx], "float32", 0.99)
+    assert (keepbits_of_information_batched(info, np.dtype("float32"), 1.0) == 23).all()
