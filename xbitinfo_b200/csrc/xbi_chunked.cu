@@ -206,9 +206,9 @@ k_pairs_chunked(const void* __restrict__ x, const __grid_constant__ ChunkGrid g,
         auto flush = [&]() {
 #pragma unroll
             for (int k = 0; k < NW; ++k) {
-                accA[k] += A[k].warp_totals(lane, it);
-                accB[k] += B[k].warp_totals(lane, it);
-                accAB[k] += AB[k].warp_totals(lane, it);
+                accA[k] += A[k].warp_totals_bounded(lane, it);
+                accB[k] += B[k].warp_totals_bounded(lane, it);
+                accAB[k] += AB[k].warp_totals_bounded(lane, it);
                 A[k].clear(); B[k].clear(); AB[k].clear();
             }
             nvalid_total += nvalid;

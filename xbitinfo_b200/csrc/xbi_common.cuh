@@ -207,6 +207,28 @@ struct Ladder {
             if ((it >> l) & 1u) ripple_add(n, LOGC + l, kPlanes + 1, Q[l]);
         return butterfly_totals(n, kPlanes + 1, lane);
     }
+    // The same for a counter that has seen only `it` >= 1 chunks (uniform across the warp): a lane's count per
+    // bit position is at most it * 2^LOGC < 2^(LOGC + bits(it)), so only that many digit planes can be non-zero
+    // and the butterfly (whose cost is proportional to the number of planes) runs on those.  For work items
+    // of a tile or two (small chunks of a chunk grid) this is 2-3 times cheaper than the full extraction.
+    __device__ __forceinline__ uint32_t warp_totals_bounded(uint32_t lane, uint32_t it) const {
+        constexpr int W = kPlanes + 6;
+        uint32_t n[W];
+#pragma unroll
+        for (int i = 0; i < LOGC; ++i) n[i] = p[i];
+#pragma unroll
+        for (int i = 0; i < DYN; ++i) n[LOGC + i] = P[i];
+#pragma unroll
+        for (int i = 0; i < UP; ++i) n[LOGC + DYN + i] = U[i];
+#pragma unroll
+        for (int i = kPlanes; i < W; ++i) n[i] = 0;
+        int planes = LOGC + (32 - __clz((int)it));
+        if (planes > kPlanes + 1) planes = kPlanes + 1;
+#pragma unroll
+        for (int l = 0; l < DYN; ++l)
+            if ((it >> l) & 1u) ripple_add(n, LOGC + l, planes, Q[l]);
+        return butterfly_totals(n, planes, lane);
+    }
 };
 
 // ---------------------------------------------------------------------------------
