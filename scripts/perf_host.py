@@ -32,6 +32,18 @@ def timed(fn, reps=3):
 
 
 gb = x.nbytes / 1e9
+# the pageable route (pinned ring + copy threads) must give what the direct route gives, also beyond 2^32 bytes
+mi_a, c_a = engine.bitinformation(x, -1, return_counts=True)
+mi_b, c_b = engine.bitinformation(pinned, -1, return_counts=True)
+assert np.array_equal(c_a, c_b) and np.array_equal(mi_a, mi_b), "pageable and pinned routes disagree"
+r_a, r_b = engine.bitround(x, 7), engine.bitround(pinned, 7)
+assert np.array_equal(r_a.view("u4"), r_b.view("u4")), "bitround: pageable and pinned routes disagree"
+probe = slice(0, x.shape[0], max(1, x.shape[0] // 7))
+import importlib
+bro = importlib.import_module("oracle.bitround_oracle")
+assert np.array_equal(r_a[probe].view("u4"), bro.bitround(x[probe], 7).view("u4")), "bitround differs from the oracle"
+del r_a, r_b
+print(f"routes agree on {gb:.2f} GB ({x.nbytes} bytes)")
 for name, arr in (("pageable", x), ("pinned", pinned)):
     t = timed(lambda: engine.bitinformation(arr, -1))
     print(f"bitinformation {name:9s} {gb:.2f} GB: {t*1e3:8.1f} ms = {gb/t:6.1f} GB/s")
