@@ -127,3 +127,25 @@ def test_header_is_plain_c_and_links(tmp_path):
     assert r.returncode == 0, r.stderr
     r = subprocess.run([str(exe)], capture_output=True, text=True)
     assert r.returncode == 0 and "abi consumer ok" in r.stdout, (r.returncode, r.stdout, r.stderr)
+
+
+def test_host_copy_pool(tmp_path):
+    """The thread pool behind the pageable-memory route of the host entry points, on CPU: compiled from
+    tests/c/hostpool_check.cu against the object the library is linked from."""
+    import shutil
+    import subprocess
+
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    csrc = os.path.dirname(nat.LIB_PATH)
+    obj = os.path.join(csrc, "build", "xbi_hostpool.o")
+    if not os.path.exists(nvcc) or not os.path.exists(obj):
+        pytest.skip("nvcc or the built object is not available")
+    exe = tmp_path / "hostpool_check"
+    cmd = [nvcc, "-O2", "-std=c++17", "-I", csrc, os.path.join(ROOT, "tests", "c", "hostpool_check.cu"), obj,
+           "-o", str(exe), "-Xcompiler", "-pthread", "-lpthread", "-Wno-deprecated-gpu-targets"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for threads in ("1", "3", "8"):
+        r = subprocess.run([str(exe)], capture_output=True, text=True, env=dict(os.environ, XBI_HOST_THREADS=threads),
+                           timeout=300)
+        assert r.returncode == 0 and f"host pool ok ({threads} threads)" in r.stdout, (threads, r.returncode, r.stdout, r.stderr)
