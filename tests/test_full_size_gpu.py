@@ -125,8 +125,18 @@ def test_config1_era5_like_float32_longitude():
     assert torch.equal(counts_of(s, -1), counts_of(s, -1, force_generic=True))
     # reversal along the analysed axis transposes every table
     y = torch.flip(x, dims=(-1,)).contiguous()
-    del x
     assert torch.equal(counts_of(y, -1), whole.transpose(1, 2))
+    del y
+    # bit-exact at full size: the whole array back on the host, counted by the C restatement of the
+    # reference's algorithm (oracle/fast_count.c, pinned to the numpy oracle and the golden vectors)
+    import psutil
+
+    from oracle import fast_count as fc
+
+    if psutil.virtual_memory().available > 1.3 * x.numel() * 4:
+        xh = x.cpu().numpy()
+        del x
+        assert np.array_equal(fc.count_pairs(xh, 2), whole.cpu().numpy()), "device counts differ from the CPU oracle"
 
 
 @pytest.mark.parametrize("masked_value", [float("nan"), -999.0])
