@@ -177,6 +177,14 @@ def test_config2_ocean_float64_latitude_with_land_mask(masked_value):
         rows = min(hi + 1, 1080) - lo  # + halo row of the next slab, none after the last
         pc.add(v[lo: lo + rows], 0, masked_value=masked_value)
     assert torch.equal(pc.counts, counts_of(v, 0, masked_value=masked_value))
+    # bit-exact against the CPU oracle (oracle/fast_count.c) on one day of the field: all 75 levels at the
+    # full 1080 x 1440 grid with its land mask, along latitude (the configured axis) and along longitude
+    from oracle import fast_count as fc
+
+    day = x[:1].contiguous()
+    xh = day.cpu().numpy()
+    for axis in (2, 3):
+        assert np.array_equal(fc.count_pairs(xh, axis, masked_value), counts_of(day, axis, masked_value=masked_value).cpu().numpy()), axis
 
 
 def test_config3_multi_variable_float32_every_dim():
@@ -201,6 +209,13 @@ def test_config3_multi_variable_float32_every_dim():
     s = x[:2, :9].contiguous()
     for axis in range(4):
         assert torch.equal(counts_of(s, axis), counts_of(s, axis, force_generic=True)), axis
+    # bit-exact against the CPU oracle (oracle/fast_count.c) along every dimension of a 2.3 GB time slab
+    from oracle import fast_count as fc
+
+    slab = x[:32].contiguous()
+    xh = slab.cpu().numpy()
+    for axis in range(4):
+        assert np.array_equal(fc.count_pairs(xh, axis), counts_of(slab, axis).cpu().numpy()), axis
 
 
 @pytest.mark.parametrize("dtype", [torch.float16, torch.float32])
