@@ -171,6 +171,23 @@ def reference_step(x, threads):
     return bo.mutual_information_from_counts(counts, npairs)
 
 
+def fast_cpu_figure(rows=64):
+    """For scale only, NOT the reference's algorithm cost: the same counts from oracle/fast_count.c (bit planes by
+    64 x 64 transposes + popcounts, every host core) on a (rows,721,1440) slab of the workload."""
+    try:
+        from oracle import fast_count as fc
+
+        x = synth_host((rows,) + FULL_SHAPE[1:], 1234)
+        fc.count_pairs(x[:2], 2)  # loads (or builds) the library
+        t0 = time.perf_counter()
+        fc.count_pairs(x, 2)
+        dt = time.perf_counter() - t0
+        return {"value": x.nbytes / dt / 1e9, "unit": UNIT, "cores": os.cpu_count(),
+                "note": "oracle/fast_count.c on all host cores; a different (popcount) formulation, not the reference's"}
+    except Exception as e:  # never let the extra figure break the line
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def cpu_sample_rows(budget_s, per_step_steps, threads):
     """How many time steps of the workload one CPU step may cover so that
     ``per_step_steps`` steps fit in ``budget_s`` (calibrated on one time step)."""
@@ -379,6 +396,7 @@ def run_ours(args):
             "sample": f"({rows},{FULL_SHAPE[1]},{FULL_SHAPE[2]}) float32 time-slab of the workload, one pass, dim=longitude",
             "host_cores_available": os.cpu_count(),
         }
+        cpu_baseline["fast_cpu_popcount"] = fast_cpu_figure()
 
     if rank == 0:
         line = {
