@@ -1,4 +1,4 @@
-// K1 and K3 batched over a regular chunk grid: the per-chunk workflow of the reference's
+// K1 and K3 batched over a chunk grid (regular, or irregular through per-dimension offset tables): the per-chunk workflow of the reference's
 // docs/chunking.ipynb (cells 8-10: get_bitinformation -> get_keepbits -> xr_bitround on every
 // dask block on its own) in a constant number of launches, whatever the number of chunks.
 //

@@ -119,7 +119,7 @@ def bitround_(x: torch.Tensor, keepbits: int) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------------------
-# batched over a regular chunk grid (docs/chunking.ipynb workflow, csrc/xbi_chunked.cu)
+# batched over a chunk grid, regular or irregular (docs/chunking.ipynb workflow, csrc/xbi_chunked.cu)
 # --------------------------------------------------------------------------------------
 def _grid_tables(shape, chunk_shape, device):
     """None for a regular grid (every entry of ``chunk_shape`` an int), else ``(nchunks per dimension,
