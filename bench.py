@@ -5,11 +5,20 @@
 
 Workload (BASELINE.json configs[1]): one ERA5-like float32 variable of shape
 (8760, 721, 1440) (36.4 GB), get_bitinformation along ``longitude`` (the last axis).
-One *step* = one pass of the hot path over that array, resident in HBM:
-K1 pair counting (TMA fast path + edge/tail passes + combine), the NCCL all-reduce of the
-int64[32,2,2] counts when N > 1, and the K2 mutual-information epilogue.  ``value`` is GB/s
-of input for the whole job.  With N > 1 every rank holds its own (8760, 721, 1440) time slab
-of a global (N*8760, 721, 1440) array ("weak"; ``--scaling strong`` splits the one array).
+One *step* = one pass of the hot path over that array, resident in HBM: workspace clear, the
+K1 pair-counting kernel (TMA rows) and ONE finish kernel (leftover pairs, combine, the all-reduce
+of the int64[32,2,2] counts over NVLink peer memory when N > 1, K2 mutual information) --
+``xbi_bitinformation_dev[_allreduce]``.  ``value`` is GB/s of input for the whole job.  With N > 1
+the named array is split over time, 8760/N steps per GPU ("strong": BASELINE configs[1] "sharded
+over time to 8"; ``--scaling weak`` gives every rank its own (8760, 721, 1440) slab instead).
+The data is generated in 73-step blocks seeded by their position in the global array, so every N
+analyses the same array and the printed counts checksum must not depend on N.
+
+The same line carries ``configs.c2 / c3 / c4``: BASELINE configs[2..4] at sizes one GPU holds
+(float64 ocean field with a land mask along latitude; one float32 (720,137,256,512) variable along
+all four dimensions with the significance filter; float16 / float32 bitinfo -> keepbits -> bitround
+on 5e9-element shares), each with GB/s, fraction of the measured copy peak and an in-run bit-exact
+check of a slab against oracle/fast_count (outside the timed regions).
 
 ``--impl reference`` times the reference's CPU algorithm (the numpy restatement in
 oracle/, the reference package itself cannot be imported in this image) on a bounded
@@ -42,7 +51,11 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"])
+    ap.add_argument("--collective", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N > 1: all-reduce inside the finish kernel over NVLink peer memory, or NCCL (auto: the faster of a short trial)")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[2..4] sub-benchmarks")
+    ap.add_argument("--config-steps", type=int, default=10)
     ap.add_argument("--time-steps", type=int, default=FULL_SHAPE[0], help="override the length of the time axis (debug)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -54,17 +67,33 @@ def parse_args():
 # --------------------------------------------------------------------------------------
 # synthetic data: base + cumulative sum of noise along longitude
 # --------------------------------------------------------------------------------------
-def synth_device(shape, seed, device):
+BLOCK_ROWS = 73  # 8760 = 120 x 73; the shards of 2, 4 and 8 ranks are whole blocks
+
+
+def synth_rows(lo, hi, device, seed=1234):
+    """Time steps [lo, hi) of THE global workload array: block b (steps 73 b .. 73 b + 72) is drawn from a
+    generator seeded with seed + b, whoever generates it -- 1 GPU or a shard of 8."""
     import torch
 
-    g = torch.Generator(device=device).manual_seed(seed)
-    x = torch.empty(shape, dtype=torch.float32, device=device)
-    step = max(1, (256 << 20) // (shape[1] * shape[2] * 4))
-    for lo in range(0, shape[0], step):
-        blk = x[lo: lo + step]
+    x = torch.empty((hi - lo,) + FULL_SHAPE[1:], dtype=torch.float32, device=device)
+    g = torch.Generator(device=device)
+    tmp = None
+    for b in range(lo // BLOCK_ROWS, -(-hi // BLOCK_ROWS)):
+        b_lo, b_hi = b * BLOCK_ROWS, (b + 1) * BLOCK_ROWS
+        g.manual_seed(seed + b)
+        whole = lo <= b_lo and b_hi <= hi
+        if whole:
+            blk = x[b_lo - lo: b_hi - lo]
+        else:
+            if tmp is None:
+                tmp = torch.empty((BLOCK_ROWS,) + FULL_SHAPE[1:], dtype=torch.float32, device=device)
+            blk = tmp
         blk.normal_(0.0, 0.35, generator=g)
         torch.cumsum(blk, dim=-1, out=blk)
         blk += 287.0
+        if not whole:
+            s_lo, s_hi = max(lo, b_lo), min(hi, b_hi)
+            x[s_lo - lo: s_hi - lo] = tmp[s_lo - b_lo: s_hi - b_lo]
     return x
 
 
@@ -233,14 +262,38 @@ def run_reference(args):
 
 def workload_config(args, world):
     shape = (args.time_steps,) + FULL_SHAPE[1:]
+    strong = args.scaling == "strong"
+    per_gpu = [-(-shape[0] // world) if strong else shape[0], shape[1], shape[2]]
     return {
         "workload": "configs[1]: ERA5-like float32 (8760,721,1440), get_bitinformation dim='longitude' "
                     "(masked_value=None, set_zero_insignificant=False: the reference python path's semantics)",
-        "per_gpu_shape": list(shape if args.scaling == "weak" else (shape[0] // world,) + shape[1:]),
-        "global_shape": [shape[0] * world if args.scaling == "weak" else shape[0], shape[1], shape[2]],
-        "sharding": "time axis, one slab per GPU, one all-reduce of int64[32,2,2] counts" if world > 1 else "none",
+        "per_gpu_shape": per_gpu,
+        "global_shape": [shape[0] if strong else shape[0] * world, shape[1], shape[2]],
+        "sharding": ("time axis, one slab per GPU (the named array split N ways), one all-reduce of int64[32,2,2] counts"
+                     if world > 1 else "none"),
         "l2": "input per GPU is far larger than the 126 MB L2 (no flush needed)",
     }
+
+
+def _time_steps(fn, steps, sync_all, dist_max):
+    """ms per call of fn over `steps` calls: CUDA events on the current stream, barrier + synchronize on both
+    sides, max over ranks."""
+    import torch
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    sync_all()
+    return dist_max(e0.elapsed_time(e1)) / steps
+
+
+def _checksum(counts_np):
+    import hashlib
+
+    return hashlib.sha256(counts_np.astype("<i8").tobytes()).hexdigest()[:16]
 
 
 # --------------------------------------------------------------------------------------
@@ -251,10 +304,6 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from xbitinfo_b200 import _native as nat
-    from xbitinfo_b200 import distributed as xdist
-    from xbitinfo_b200.device import PairCounter
-
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -262,6 +311,13 @@ def run_ours(args):
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    # one staging-thread pool per rank, sized to its share of the host cores (read when the library starts its pool)
+    os.environ.setdefault("XBI_HOST_THREADS", str(max(1, min(8, (os.cpu_count() or 8) // max(world, 1)))))
+
+    from xbitinfo_b200 import _native as nat
+    from xbitinfo_b200 import distributed as xdist
+    from xbitinfo_b200.device import PairCounter
+
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     numa_node = None
@@ -270,21 +326,63 @@ def run_ours(args):
         numa_node = xdist.bind_to_gpu_numa_node(local_rank)
         dist.init_process_group("nccl", device_id=dev)
 
-    shape = (args.time_steps,) + FULL_SHAPE[1:]
-    if args.scaling == "strong" and world > 1:
-        lo, hi = xdist.shard_bounds(shape[0], world, rank)
-        shape = (hi - lo,) + shape[1:]
-    x = synth_device(shape, 1234 + rank, dev)
+    def dist_max(v):
+        if world == 1:
+            return float(v)
+        t = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    T = args.time_steps
+    if args.scaling == "strong":
+        lo, hi = xdist.shard_bounds(T, world, rank)
+        global_rows = T
+    else:
+        lo, hi = rank * T, (rank + 1) * T
+        global_rows = T * world
+    x = synth_rows(lo, hi, dev)
     nbytes_local = x.numel() * 4
+    total_bytes = global_rows * FULL_SHAPE[1] * FULL_SHAPE[2] * 4
     pc = PairCounter(x.dtype, dev)
     sync_all = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
 
-    def step():
-        pc.reset()
-        pc.add(x, -1, masked_value=None)  # K1
-        if world > 1:
-            xdist.allreduce_counts(pc.counts)  # the path's one collective
-        return pc.information(False)  # K2
+    # ---- the step: K1 + finish kernel (+ the all-reduce inside it) ----
+    peers, peer_error = None, None
+    if world > 1 and args.collective in ("auto", "peer"):
+        try:
+            peers = xdist.PeerExchange(dev)
+        except Exception as e:  # IPC not permitted in this container, ...: NCCL takes over, and the line says so
+            peer_error = f"{type(e).__name__}: {e}"
+
+    def step_local():
+        return pc.bitinformation(x, -1, masked_value=None)
+
+    def step_peer():
+        return pc.bitinformation(x, -1, masked_value=None, peers=peers)
+
+    def step_nccl():
+        pc.bitinformation(x, -1, masked_value=None, with_information=False)  # K1 -> per-rank table
+        xdist.allreduce_counts(pc.counts)                                     # the path's one collective
+        return pc.information(False)                                          # K2
+
+    collective = {"kind": "none"}
+    step = step_local
+    if world > 1:
+        trials = {}
+        for _ in range(max(args.warmup, 3)):
+            step_nccl()
+        trials["nccl_ms_per_step"] = _time_steps(step_nccl, 10, sync_all, dist_max)
+        if peers is not None:
+            for _ in range(max(args.warmup, 3)):
+                step_peer()
+            trials["peer_ms_per_step"] = _time_steps(step_peer, 10, sync_all, dist_max)
+        use_peer = peers is not None and (args.collective == "peer" or trials["peer_ms_per_step"] <= trials["nccl_ms_per_step"])
+        step = step_peer if use_peer else step_nccl
+        collective = {
+            "kind": ("push over NVLink peer memory inside the finish kernel (xbi_bitinformation_dev_allreduce)" if use_peer
+                     else "torch.distributed.all_reduce (NCCL) on int64[32,2,2] + separate K2 launch"),
+            "trial_10_steps": trials, "peer_unavailable": peer_error,
+        }
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -299,20 +397,41 @@ def run_ours(args):
             mi_dev = step()
         e1.record()
         sync_all()
-    elapsed_ms = e0.elapsed_time(e1)
+    elapsed_local = e0.elapsed_time(e1)
     kern_ms, kern_n, kern_bytes = nat.profile_collect()
     nat.profile_enable(False)
     launches = nat.kernel_launches() - launches0
-    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    elapsed_ms = float(t.item())
+    elapsed_ms = dist_max(elapsed_local)
     ms_per_step = elapsed_ms / args.steps
-    total_bytes = nbytes_local * world
     value = total_bytes / (ms_per_step * 1e-3) / 1e9
     mi = mi_dev.cpu().numpy()
+    counts_np = pc.counts.cpu().numpy()
 
-    # roofline of the dominant kernel (TMA row kernel), timed with events on its own stream
+    # ---- in-run verification of what was timed (outside the timed region) ----
+    npairs_global = global_rows * FULL_SHAPE[1] * (FULL_SHAPE[2] - 1)
+    verify = {
+        "pairs_expected": int(npairs_global),
+        "cells_sum_to_pairs": bool((counts_np.reshape(32, 4).sum(axis=1) == npairs_global).all()),
+        "counts_checksum": _checksum(counts_np),  # the same for every N (strong scaling analyses one array)
+    }
+    if world > 1:
+        # the all-reduced table must equal the sum of the per-rank tables, summed here once more with NCCL
+        ref = PairCounter(x.dtype, dev)
+        ref.bitinformation(x, -1, masked_value=None, with_information=False)
+        local_sum_ok = bool((ref.counts.cpu().numpy().reshape(32, 4).sum(axis=1) == (hi - lo) * FULL_SHAPE[1] * (FULL_SHAPE[2] - 1)).all())
+        dist.all_reduce(ref.counts, op=dist.ReduceOp.SUM)
+        same = torch.tensor([int(torch.equal(ref.counts, pc.counts)) & int(local_sum_ok)], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        verify["allreduce_equals_nccl_sum_on_every_rank"] = bool(same.item())
+        if peers is not None:
+            failed = torch.tensor([peers.failed_epoch()], device=dev)
+            dist.all_reduce(failed, op=dist.ReduceOp.MAX)
+            verify["peer_wait_timeouts"] = int(failed.item() != 0)
+        del ref
+    if not verify["cells_sum_to_pairs"] or verify.get("allreduce_equals_nccl_sum_on_every_rank") is False:
+        raise SystemExit(f"bench.py: counts verification failed: {verify}")
+
+    # ---- roofline of the dominant kernel (TMA row kernel), timed with events on its own stream ----
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -328,7 +447,8 @@ def run_ours(args):
         "kernel": "k_pairs_rows_tma<f32,unmasked>", "launches_timed": kern_n,
         "algorithmic_bytes_per_launch": (kern_bytes / kern_n) if kern_n else None,
         "kernel_ms_avg": (kern_ms / kern_n) if kern_n else None,
-        "kernel_share_of_step": (kern_ms / elapsed_ms) if kern_n else None,
+        "kernel_share_of_step": (kern_ms / elapsed_local) if kern_n else None,
+        "step_minus_kernel_us": (1e3 * (elapsed_local - kern_ms) / args.steps) if kern_n else None,  # this rank
         "traffic": None,  # dram__bytes per launch from ncu --set full: see profiles/
     }
     traffic_file = os.path.join(ROOT, "profiles", "k1_rows_f32_dram_bytes.json")
@@ -340,49 +460,57 @@ def run_ours(args):
         except Exception:
             pass
 
-    # K3 on the same array (second half of the headline metric)
+    # ---- the same step replayed from a CUDA graph (launch gaps out of the picture; informational, 1 GPU) ----
+    graph_ms = None
+    if world == 1:
+        try:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                step()
+            for _ in range(3):
+                g.replay()
+            graph_ms = _time_steps(g.replay, args.steps, sync_all, dist_max)
+            del g
+        except Exception as e:
+            graph_ms = f"unavailable: {type(e).__name__}: {e}"
+
+    # ---- K3 on the same array (second half of the headline metric) ----
     bitround_gbs = None
     if rank == 0:
         from xbitinfo_b200.device import bitround_
 
-        y = x[: min(shape[0], 2048)].clone()
+        y = x[: min(x.shape[0], 2048)].clone()
         for _ in range(3):
             bitround_(y, 7)
-        torch.cuda.synchronize()
-        b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        b0.record()
-        for _ in range(10):
-            bitround_(y, 7)
-        b1.record()
-        torch.cuda.synchronize()
-        bitround_gbs = y.numel() * 4 / (b0.elapsed_time(b1) / 10 * 1e-3) / 1e9
+        bitround_gbs = y.numel() * 4 / (_time_steps(lambda: bitround_(y, 7), 10, torch.cuda.synchronize, float) * 1e-3) / 1e9
         del y
 
-    # the same step with the public API's default keyword (masked_value=NaN: pairs holding a NaN
-    # are dropped; the data has none, the probe in the kernel has to find that out)
+    # the same step with the public API's default keywords (masked_value=NaN: pairs holding a NaN are dropped;
+    # the data has none, the probe in the kernel has to find that out; significance filter on)
     nan_masked_gbs = None
     if rank == 0:
         def masked_step():
-            pc.reset()
-            pc.add(x, -1, masked_value=float("nan"))
-            return pc.information(True, 0.99)
+            return pc.bitinformation(x, -1, masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99)
 
         for _ in range(3):
             masked_step()
-        torch.cuda.synchronize()
-        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        m0.record()
-        for _ in range(10):
-            masked_step()
-        m1.record()
-        torch.cuda.synchronize()
-        nan_masked_gbs = nbytes_local / (m0.elapsed_time(m1) / 10 * 1e-3) / 1e9
+        nan_masked_gbs = nbytes_local / (_time_steps(masked_step, 10, torch.cuda.synchronize, float) * 1e-3) / 1e9
 
-    # end to end through the public API with host buffers (H2D inside the timed region)
+    # ---- end to end through the public API with host buffers (H2D inside the timed region) ----
     e2e = None
     if not args.no_e2e:
-        e2e = run_e2e(args, x, rank, world, dev, sync_all)
+        e2e = run_e2e(args, x, rank, world, dev, sync_all, dist_max)
         e2e["numa_node_of_rank0"] = numa_node
+        e2e["host_copy_threads_per_rank"] = int(os.environ["XBI_HOST_THREADS"])
+    if peers is not None:
+        peers.close()
+    del x, pc
+    torch.cuda.empty_cache()
+
+    # ---- BASELINE configs[2..4] at sizes one GPU holds ----
+    configs = None
+    if world == 1 and not args.no_configs:
+        configs = run_configs(args, dev, peak)
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -406,9 +534,12 @@ def run_ours(args):
             "config": workload_config(args, world),
             "pct_hbm_peak_nominal": 100.0 * value / (HBM_NOMINAL_GBS * world),
             "pct_hbm_peak_measured": 100.0 * value / (peak * world),
+            "launches_per_step": launches / args.steps,
+            "collective": collective, "verify": verify,
+            "graph_replay_ms_per_step": graph_ms,
             "xr_bitround_input_GBps": bitround_gbs,
             "default_kwargs_step_GBps": nan_masked_gbs,  # masked_value=NaN, set_zero_insignificant=True (1 GPU)
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "configs": configs,
             "gpu_launches": int(launches), "clocks": clocks.summary(),
             "info_bits_preview": [float(v) for v in mi[:12]],
         }
@@ -417,11 +548,12 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
-def run_e2e(args, x_dev, rank, world, dev, sync_all):
-    """Same metric through the public host-buffer API: numpy array in pinned host memory ->
-    sharded_bitinformation (xbi_bitinformation_host: slabs H2D + K1, then all-reduce + K2)
-    -> 32 doubles back.  The host array is the largest time-slab of the workload that fits
-    comfortably in host RAM."""
+def run_e2e(args, x_dev, rank, world, dev, sync_all, dist_max):
+    """Same metric through the public host-buffer API: this rank's slab as a numpy array in pinned host memory ->
+    sharded_bitinformation (xbi_bitinformation_host: slabs H2D + K1, then all-reduce + K2) -> 32 doubles back.
+    Also: the same call on a pageable numpy array (what a numpy / xarray user passes), every rank's own H2D rate,
+    and -- N > 1 -- a plain pinned -> device copy of 1 GiB per rank, each rank alone and all ranks together, to tell
+    the host's share of an e2e number that does not scale from the library's."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -435,7 +567,7 @@ def run_e2e(args, x_dev, rank, world, dev, sync_all):
     except Exception:
         avail = 64 << 30
     full = x_dev.numel() * 4
-    budget = int(avail * 0.35 / max(world, 1))
+    budget = int(avail * 0.35 / max(world if args.scaling == "weak" else 1, 1))
     rows = x_dev.shape[0] if full <= budget else max(1, int(x_dev.shape[0] * budget / full))
     rows = min(rows, x_dev.shape[0])
     try:
@@ -450,22 +582,241 @@ def run_e2e(args, x_dev, rank, world, dev, sync_all):
     steps = max(1, min(args.e2e_steps, args.steps))
     xdist.sharded_bitinformation(xh, -1, masked_value=None, device=dev.index)  # warm (staging buffers)
     sync_all()
+    own = 0.0
     t0 = time.perf_counter()
     for _ in range(steps):
-        mi = xdist.sharded_bitinformation(xh, -1, masked_value=None, device=dev.index)
+        t1 = time.perf_counter()
+        xdist.sharded_bitinformation(xh, -1, masked_value=None, device=dev.index)
+        own += time.perf_counter() - t1
     torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / steps
-    t = torch.tensor([dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dt = float(t.item())
-    return {
+    dt = dist_max((time.perf_counter() - t0) / steps)
+    out = {
         "value": xh.nbytes * world / dt / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(xh.nbytes),
         "d2h_bytes_per_step": int(32 * 8 + 32 * 4 * 8), "steps": steps, "pinned": pinned,
         "sample": f"({rows},{x_dev.shape[1]},{x_dev.shape[2]}) float32 per GPU"
                   + ("" if rows == x_dev.shape[0] else " (host RAM bound: time-slab of the workload)"),
         "api": "xbitinfo_b200.distributed.sharded_bitinformation(numpy) -> xbi_bitinformation_host (C ABI)",
     }
+    rate = xh.nbytes * steps / own / 1e9
+    if world > 1:
+        rates = [None] * world
+        dist.all_gather_object(rates, rate)
+        out["h2d_GBps_per_rank"] = [round(float(r), 2) for r in rates]
+    else:
+        out["h2d_GBps_per_rank"] = [round(rate, 2)]
+
+    # pageable input: an ordinary numpy array (up to 4 GiB of the same slab), through the pinned ring + copy threads
+    prow = max(1, min(rows, (4 << 30) // (x_dev.shape[1] * x_dev.shape[2] * 4)))
+    xp = np.empty((prow,) + tuple(x_dev.shape[1:]), dtype=np.float32)
+    np.copyto(xp, xh[:prow])
+    xdist.sharded_bitinformation(xp, -1, masked_value=None, device=dev.index)
+    sync_all()
+    t0 = time.perf_counter()
+    xdist.sharded_bitinformation(xp, -1, masked_value=None, device=dev.index)
+    torch.cuda.synchronize()
+    dtp = dist_max(time.perf_counter() - t0)
+    out["pageable"] = {"value": xp.nbytes * world / dtp / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(xp.nbytes),
+                       "sample": f"({prow},{x_dev.shape[1]},{x_dev.shape[2]}) float32 per GPU, ordinary (pageable) numpy memory"}
+    del xp
+
+    if world > 1:
+        # where does a flat e2e curve come from?  1 GiB pinned -> device per rank, alone and together
+        n = min(host.numel(), (1 << 30) // 4)
+        src, dst = host.view(-1)[:n], torch.empty(n, dtype=torch.float32, device=dev)
+
+        def copy_rate():
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                dst.copy_(src, non_blocking=True)
+            torch.cuda.synchronize()
+            return 3 * n * 4 / (time.perf_counter() - t0) / 1e9
+
+        copy_rate()
+        alone = 0.0
+        for r in range(world):
+            dist.barrier()
+            if r == rank:
+                alone = copy_rate()
+        dist.barrier()
+        together = copy_rate()
+        a, t = [None] * world, [None] * world
+        dist.all_gather_object(a, alone)
+        dist.all_gather_object(t, together)
+        out["h2d_probe_1GiB_pinned"] = {"alone_GBps": [round(float(v), 1) for v in a],
+                                        "together_GBps": [round(float(v), 1) for v in t],
+                                        "together_sum_GBps": round(float(sum(t)), 1)}
+    return out
+
+
+# --------------------------------------------------------------------------------------
+# BASELINE configs[2], [3], [4] on one GPU
+# --------------------------------------------------------------------------------------
+def _synth_nd(shape, dtype, axis, seed, device, piece_bytes=1 << 30):
+    """base + cumulative sum of float32 noise along `axis` (not the first one), generated in pieces along the
+    first axis, cast to `dtype`."""
+    import torch
+
+    g = torch.Generator(device=device).manual_seed(seed)
+    x = torch.empty(shape, dtype=dtype, device=device)
+    per = max(1, piece_bytes // max(1, x[0].numel() * 4))
+    for lo in range(0, shape[0], per):
+        k = min(per, shape[0] - lo)
+        blk = torch.empty((k,) + tuple(shape[1:]), dtype=torch.float32, device=device)
+        blk.normal_(0.0, 0.3, generator=g)
+        torch.cumsum(blk, dim=axis, out=blk)
+        blk += 12.0
+        x[lo: lo + k] = blk.to(dtype)
+    return x
+
+
+def run_configs(args, dev, peak):
+    import numpy as np
+    import torch
+
+    from oracle import fast_count as fc  # the checker, outside every timed region
+    from xbitinfo_b200 import _native as nat
+    from xbitinfo_b200.chunked import keepbits_of_information
+    from xbitinfo_b200.device import PairCounter, bitround
+
+    K = max(3, args.config_steps)
+    sync = torch.cuda.synchronize
+    out = {}
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        return _time_steps(fn, K, sync, float)
+
+    # ---- c2: float64 ocean field, land mask, dim='latitude' (strided adjacency) ----
+    try:
+        days = 24
+        shape = (days, 75, 1080, 1440)
+        x = _synth_nd(shape, torch.float64, 2, 77, dev, piece_bytes=1 << 29)
+        land = torch.rand((1080, 1440), generator=torch.Generator(device=dev).manual_seed(5), device=dev)
+        # ~30 % land in blobs: a smooth random field thresholded (coast lines, not salt and pepper)
+        land = torch.nn.functional.avg_pool2d(land[None, None], 31, stride=1, padding=15)[0, 0]
+        land = land < torch.quantile(land.flatten()[::7], 0.30)
+        res = {}
+        for name, mv in (("nan", float("nan")), ("minus999", -999.0)):
+            x.masked_fill_(land, mv)
+            pc = PairCounter(x.dtype, dev)
+            nat.profile_enable(True)
+            ms = timed(lambda: pc.bitinformation(x, 2, masked_value=mv, set_zero_insignificant=True, confidence=0.99))
+            kms, kn, kb = nat.profile_collect()
+            nat.profile_enable(False)
+            day = x[:1].contiguous()
+            pd = PairCounter(x.dtype, dev)
+            pd.bitinformation(day, 2, masked_value=mv)
+            exact = bool(np.array_equal(pd.counts.cpu().numpy(), fc.count_pairs(day.cpu().numpy(), 2, masked_value=mv)))
+            gbs = x.numel() * 8 / (ms * 1e-3) / 1e9
+            res[name] = {"value": gbs, "unit": UNIT, "ms_per_step": ms, "frac_of_measured_peak": gbs / peak,
+                         "kernel_GBps": (kb / (kms * 1e-3) / 1e9) if kn else None,
+                         "bit_exact_vs_fast_count": exact, "checked": "first day (75,1080,1440)"}
+            del pc, pd, day
+        out["c2"] = {
+            "workload": f"configs[2]: float64 ocean field, {days} of 365 days resident ({days},75,1080,1440) = "
+                        f"{x.numel() * 8 / 1e9:.1f} GB (the full 340 GB field streams through the same accumulate-only "
+                        "counts in time slabs), ~30 % land mask constant over time/level, dim='latitude' (inner = 1440), "
+                        "masked_value + set_zero_insignificant=True, confidence=0.99",
+            "land_fraction": float(land.float().mean()), "kernel": "k_pairs_cols<f64, masked sparse flavour>",
+            "masked_value_nan": res["nan"], "masked_value_minus999": res["minus999"],
+        }
+        del x, land
+    except Exception as e:
+        out["c2"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+
+    # ---- c3: one float32 (720,137,256,512) variable along all four dims, significance filter on ----
+    try:
+        shape = (720, 137, 256, 512)
+        x = _synth_nd(shape, torch.float32, 3, 91, dev)
+        pc = [PairCounter(x.dtype, dev) for _ in range(4)]
+
+        def all_dims():
+            for a in range(4):
+                pc[a].bitinformation(x, a, masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99)
+
+        ms = timed(all_dims)
+        per_axis = []
+        for a in range(4):
+            m = timed(lambda a=a: pc[a].bitinformation(x, a, masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99))
+            per_axis.append({"axis": a, "ms": m, "GBps": x.numel() * 4 / (m * 1e-3) / 1e9})
+        slab = x[:8].contiguous()
+        hs = slab.cpu().numpy()
+        exact = True
+        for a in range(4):
+            p = PairCounter(x.dtype, dev)
+            p.bitinformation(slab, a, masked_value=float("nan"))
+            exact &= bool(np.array_equal(p.counts.cpu().numpy(), fc.count_pairs(hs, a, masked_value=float("nan"))))
+        nb = x.numel() * 4
+        out["c3"] = {
+            "workload": "configs[3]: one of the 10 float32 variables, (720,137,256,512) = 51.7 GB resident, analysed along "
+                        "every dim (get_bitinformation(ds) with dim=None), masked_value=NaN (API default), "
+                        "set_zero_insignificant=True, confidence=0.99",
+            "ms_all_dims": ms, "array_GBps": nb / (ms * 1e-3) / 1e9,       # the array's bytes once per all-dims job
+            "value": 4 * nb / (ms * 1e-3) / 1e9, "unit": UNIT,              # (variable, dim) passes x bytes, SURVEY 8(d)
+            "frac_of_measured_peak": 4 * nb / (ms * 1e-3) / 1e9 / peak,
+            "passes_equivalent": ms / min(p_["ms"] for p_ in per_axis),
+            "per_axis": per_axis, "bit_exact_vs_fast_count": exact, "checked": "first 8 time steps, all four axes",
+        }
+        del x, pc, slab
+    except Exception as e:
+        out["c3"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+
+    # ---- c4: bitinfo -> keepbits -> bitround on one GPU's share (5e9 elements), float16 and float32 ----
+    try:
+        res = {}
+        n = 5_000_000_000
+        for name, tdt, ndt in (("float16", torch.float16, "float16"), ("float32", torch.float32, "float32")):
+            rows = n // 100_000
+            x = _synth_nd((rows, 100_000), tdt, 1, 13, dev).view(-1)
+            y = torch.empty_like(x)
+            pc = PairCounter(tdt, dev)
+            state = {}
+
+            def pipeline():
+                mi = pc.bitinformation(x, 0, masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99)
+                info = mi.cpu().numpy()                                   # 16 / 32 doubles back: the host decides
+                keep = max(0, keepbits_of_information(info, np.dtype(ndt), 0.99))
+                bitround(x, keep, out=y)                                  # new array, input untouched
+                state["keep"] = keep
+
+            ms = timed(pipeline)
+            m_count = timed(lambda: pc.bitinformation(x, 0, masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99))
+            m_round = timed(lambda: bitround(x, state["keep"], out=y))
+            # checks on a 2^24-element slab: counts vs fast_count, rounded bits vs the bitround oracle
+            from oracle import bitround_oracle as bro
+
+            k = 1 << 24
+            hs = x[:k].cpu().numpy()
+            p = PairCounter(tdt, dev)
+            p.bitinformation(x[:k], 0, masked_value=float("nan"))
+            u = f"u{np.dtype(ndt).itemsize}"
+            exact = bool(np.array_equal(p.counts.cpu().numpy(), fc.count_pairs(hs, 0, masked_value=float("nan"))))
+            exact_round = bool(np.array_equal(y[:k].cpu().numpy().view(u), bro.bitround(hs, state["keep"]).view(u)))
+            isz = x.element_size()
+            res[name] = {
+                "ms_pipeline": ms, "elements_per_s": n / (ms * 1e-3), "keepbits": state["keep"],
+                "value": 3 * n * isz / (ms * 1e-3) / 1e9, "unit": UNIT,  # 1x read (count) + read + write (round), SURVEY 8(d)
+                "frac_of_measured_peak": 3 * n * isz / (ms * 1e-3) / 1e9 / peak,
+                "count_GBps": n * isz / (m_count * 1e-3) / 1e9, "bitround_GBps_read_plus_write": 2 * n * isz / (m_round * 1e-3) / 1e9,
+                "bit_exact_counts_vs_fast_count": exact, "bit_exact_rounding_vs_oracle": exact_round,
+                "checked": "first 2^24 elements",
+            }
+            del x, y, pc, p
+            torch.cuda.empty_cache()
+        out["c4"] = {
+            "workload": "configs[4]: bitinfo -> get_keepbits(0.99) -> bitround on ONE GPU's share of the 4e10-element arrays "
+                        "(5e9 elements: float16 10 GB, float32 20 GB), API default keywords; the 8-GPU job runs this on "
+                        "every rank with the all-reduce of the counts before the keepbits decision",
+            "float16": res["float16"], "float32": res["float32"],
+        }
+    except Exception as e:
+        out["c4"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():

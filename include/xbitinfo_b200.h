@@ -61,7 +61,7 @@ enum xbi_dtype {
 /* error codes */
 #define XBI_OK 0
 #define XBI_ERR_ARG 1
-#define XBI_ERR_UNSUPPORTED 2
+#define XBI_ERR_UNSUPPORTED 2 /* also: the TMA fast path cannot run on this driver (never a silent slow path) */
 #define XBI_ERR_NO_DEVICE 3
 #define XBI_ERR_CUDA_BASE 1000 /* + cudaError_t */
 
@@ -110,6 +110,49 @@ int xbi_mutual_information(const unsigned long long* counts_dev, int nbits,
                            int set_zero_insignificant, double confidence, double* mi_dev,
                            void* stream);
 
+/*
+ * K1 + K2 of one device-resident variable along one axis in ONE call: what the backend function
+ * _py_get_bitinformation (xbitinfo/xbitinfo.py:337-370: transform, cast, pb.bitinformation(X, axis).compute())
+ * does for an array that already lives in HBM.  counts_dev (nbits*4) is OVERWRITTEN with the pair histogram
+ * (layout as for xbi_count_pairs) and mi_dev (nbits doubles; NULL: counts only) receives the information per
+ * bit (semantics of xbi_mutual_information).  Two or three launches in all: workspace clear, the counting
+ * kernel, and one finish kernel that counts the few pairs the fast kernel leaves over, combines the raw sums
+ * and runs K2.  No pairs along the axis: counts 0, information NaN.
+ */
+int xbi_bitinformation_dev(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner,
+                           unsigned flags, uint64_t mask_bits, int set_zero_insignificant, double confidence,
+                           unsigned long long* counts_dev, double* mi_dev, void* workspace_dev,
+                           size_t workspace_bytes, void* stream);
+
+/*
+ * The same across the GPUs of one node, one process per GPU (every rank counts its slab, the
+ * int64[nbits,2,2] tables are summed over the ranks, K2 runs on every rank): the all-reduce is part of the
+ * finish kernel.  Each rank owns an exchange buffer (xbi_peer_create: xbi_peer_bytes() of device memory plus
+ * a CUDA IPC handle of xbi_peer_handle_bytes() bytes to hand to the other ranks by whatever means the host
+ * program has -- torch.distributed.all_gather_object in this package); a rank maps the buffers of the others
+ * with xbi_peer_open.  peer_buffers[p] is rank p's buffer as addressable by THIS process (own buffer at
+ * [rank]).  The finish kernel stores the rank's table into its slot of every peer's buffer over NVLink, raises
+ * a flag there, waits for the flags of all peers in its own buffer, sums the slots: counts_dev and mi_dev then
+ * hold the GLOBAL result on every rank.
+ *   epoch: 1 for the first call, +1 for every later call, the same sequence on every rank.
+ *   timeout_s: a rank that does not see its peers within this time stops waiting (no hung GPU); the call's
+ *   results are then invalid and xbi_peer_error_epoch() returns the epoch of the failed wait (0: none so far).
+ *   <= 0: 20 s.
+ * All ranks must call it the same number of times; world <= 8.
+ */
+size_t xbi_peer_bytes(void);
+size_t xbi_peer_handle_bytes(void);
+int xbi_peer_create(void** buffer_dev, void* handle_out);
+int xbi_peer_open(const void* handle, void** mapped_dev);
+int xbi_peer_close(void* mapped_dev);
+int xbi_peer_destroy(void* buffer_dev);
+int xbi_peer_error_epoch(const void* own_buffer_dev, unsigned long long* epoch_out);
+int xbi_bitinformation_dev_allreduce(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner,
+                                     unsigned flags, uint64_t mask_bits, int set_zero_insignificant,
+                                     double confidence, unsigned long long* counts_dev, double* mi_dev,
+                                     void* workspace_dev, size_t workspace_bytes, void* stream, int world, int rank,
+                                     uint64_t epoch, void* const* peer_buffers, double timeout_s);
+
 /* K2 on `nbatch` consecutive (nbits,2,2) tables: mi_dev receives nbatch*nbits doubles. */
 int xbi_mutual_information_batched(const unsigned long long* counts_dev, int nbits, int64_t nbatch,
                                    int set_zero_insignificant, double confidence, double* mi_dev, void* stream);
@@ -155,6 +198,12 @@ int xbi_bitround_chunked_v(void* x_dev, int dtype, int ndim, const int64_t* shap
  * keepbits < 0 or > mantissa bits -> XBI_ERR_ARG (numcodecs raises ValueError).
  */
 int xbi_bitround_inplace(void* x_dev, int dtype, int64_t numel, int keepbits, void* stream);
+/*
+ * The same into a second array: dst = bitround(src), src untouched -- _np_bitround's contract (it copies its
+ * input first, xbitinfo/bitround.py:10) in one read and one write instead of a copy plus an in-place pass.
+ * src_dev == dst_dev is the in-place call; otherwise the arrays must not overlap.
+ */
+int xbi_bitround(const void* src_dev, void* dst_dev, int dtype, int64_t numel, int keepbits, void* stream);
 
 /*
  * K4: the lossless-compression pre-filters that follow bitround on the reference's save path

@@ -143,3 +143,34 @@ def test_bitround_along_dim(air_temperature):
     # Test error when neither keepbits nor inflevels are provided
     with pytest.raises(ValueError):
         bi.bitround_along_dim(ds, info_per_bit, dim="lat", inflevels=None)
+
+
+@pytest.mark.parametrize("dtype", ["float16", "float32", "float64"])
+def test_out_of_place_bitround_leaves_the_input_alone(dtype):
+    """xbi_bitround (src -> dst): one read, one write, the `_np_bitround` contract (bitround.py:10) without a copy;
+    also from / to addresses that sit differently inside their 16-byte vectors, and the identity."""
+    import torch
+
+    from oracle import bitround_oracle as bro
+    from xbitinfo_b200 import device
+
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(100003) * 50).astype(dtype)
+    u = f"u{np.dtype(dtype).itemsize}"
+    mant = {"float16": 10, "float32": 23, "float64": 52}[dtype]
+    t = torch.from_numpy(x).cuda()
+    for keep in (0, 3, mant - 1, mant):
+        out = device.bitround(t, keep)
+        assert np.array_equal(t.cpu().numpy().view(u), x.view(u))
+        assert np.array_equal(out.cpu().numpy().view(u), bro.bitround(x, keep).view(u))
+    big = torch.zeros(100010, dtype=t.dtype, device="cuda")
+    out = device.bitround(t[1:], 5, out=big[3:3 + t.numel() - 1])  # different alignment inside a 16-byte vector
+    assert np.array_equal(out.cpu().numpy().view(u), bro.bitround(x[1:], 5).view(u))
+    assert float(big[:3].abs().sum()) == 0.0 and float(big[3 + t.numel() - 1:].abs().sum()) == 0.0
+    with pytest.raises(ValueError):
+        device.bitround(t[:-1], 5, out=t[1:])  # overlap
+    # engine.bitround on a tensor: new tensor, input untouched
+    from xbitinfo_b200 import engine
+
+    r = engine.bitround(t, 4)
+    assert r.data_ptr() != t.data_ptr() and np.array_equal(r.cpu().numpy().view(u), bro.bitround(x, 4).view(u))

@@ -282,3 +282,17 @@ def test_arrays_of_more_than_2_to_32_elements_use_64_bit_offsets():
         for j in range(2):
             got_rows = x[::977, 64 * i:64 * (i + 1), 128 * j:128 * (j + 1)]
             assert torch.equal(got_rows.view(torch.int16), ref_blocks[2 * i + j].view(torch.int16)), (i, j)
+
+
+def test_ragged_chunk_of_extent_one_along_the_axis_is_left_unrounded():
+    """101 rows cut in chunks of 50 leave a last chunk of ONE row along the analysed axis: it has no pairs, its
+    information is NaN, and it must come back unrounded (with a warning) -- not rounded to 0 mantissa bits."""
+    rng = np.random.default_rng(11)
+    x = (280.0 + np.cumsum(rng.standard_normal((101, 64)) * 0.3, axis=0)).astype("float32")
+    for batched in (True, False):
+        with pytest.warns(RuntimeWarning, match="no valid pair"):
+            rounded, keep = bitround_by_chunks(x, {0: 50}, 0, inflevel=0.99, masked_value=None,
+                                                       set_zero_insignificant=False, batched=batched)
+        assert keep.shape == (3, 1) and keep[2, 0] == 23 and 0 <= keep[0, 0] < 23
+        assert np.array_equal(rounded[100].view("u4"), x[100].view("u4"))
+        assert np.array_equal(rounded[:50].view("u4"), bro.bitround(x[:50], int(keep[0, 0])).view("u4"))

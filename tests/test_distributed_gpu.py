@@ -1,5 +1,5 @@
-"""N>1 on real GPUs (skipped on a single-GPU box): per-rank K1 + one NCCL all-reduce must give
-exactly the 1-GPU / oracle counts."""
+"""N>1 on real GPUs (skipped on a single-GPU box): per-rank K1 + one all-reduce -- NCCL, and the push over
+NVLink peer memory inside the finish kernel -- must give exactly the 1-GPU / oracle counts."""
 import os
 import socket
 
@@ -51,6 +51,24 @@ def _worker(rank, world, port, out_dir):
             mi2, counts2 = distributed.sharded_bitinformation(np.ascontiguousarray(x[tuple(sl)]), axis, masked_value=mv,
                                                               return_counts=True, device=rank)
             ok &= int(np.array_equal(counts2, ref_counts))
+        # the all-reduce inside the finish kernel (NVLink peer memory, CUDA IPC): same global table on every rank
+        from xbitinfo_b200.device import PairCounter
+
+        peers = distributed.PeerExchange(torch.device("cuda", rank))
+        try:
+            for axis, mv in ((2, None), (1, float("nan")), (0, None), (2, float("nan"))):
+                plan = distributed.plan_shard(x.shape, axis, world, rank)
+                sl = [slice(None)] * x.ndim
+                sl[plan.split_axis] = plan.read_slice
+                slab = torch.from_numpy(np.ascontiguousarray(x[tuple(sl)])).cuda()
+                pc = PairCounter(slab.dtype, slab.device)
+                mi = pc.bitinformation(slab, axis, masked_value=mv, peers=peers).cpu().numpy()
+                ref_counts, _, ref_mi = bo.bitinformation(x, axis, masked_value=mv)
+                ok &= int(np.array_equal(pc.counts.cpu().numpy(), ref_counts))
+                ok &= int(np.allclose(mi, ref_mi, rtol=1e-12, atol=1e-12 * np.nanmax(np.abs(ref_mi))))
+            ok &= int(peers.failed_epoch() == 0)
+        finally:
+            peers.close()
         np.save(os.path.join(out_dir, f"ok_{rank}.npy"), np.array([ok]))
     finally:
         dist.destroy_process_group()

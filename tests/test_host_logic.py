@@ -330,3 +330,14 @@ def test_chunk_grid_descriptions():
         if idx != (1, 2):
             assert batched[idx] == ko.keepbits_from_info(info[idx], "float32", 0.99)
     assert (keepbits_of_information_batched(info, np.dtype("float32"), 1.0) == 23).all()
+    # what K3 is fed: negatives clamped to 0, but a chunk WITHOUT any valid pair (all-NaN information) is left
+    # unrounded with a warning instead of being rounded to 0 mantissa bits
+    from xbitinfo_b200.chunked import chunk_keepbits
+
+    assert batched[1, 2] < 0
+    with pytest.warns(RuntimeWarning, match="no valid pair"):
+        fed = chunk_keepbits(info, np.dtype("float32"), 0.99)
+    assert fed[1, 2] == 23 and fed.min() >= 0
+    rest = np.ones((4, 5), bool)
+    rest[1, 2] = False
+    assert np.array_equal(fed[rest], np.clip(batched, 0, 23)[rest])

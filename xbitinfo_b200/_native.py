@@ -78,6 +78,25 @@ def lib() -> C.CDLL:
     L.xbi_count_pairs.argtypes = [vp, i32, i64, i64, i64, u32, u64, vp, vp, C.c_size_t, vp]
     L.xbi_mutual_information.restype = i32
     L.xbi_mutual_information.argtypes = [vp, i32, i32, dbl, vp, vp]
+    L.xbi_bitinformation_dev.restype = i32
+    L.xbi_bitinformation_dev.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, vp, C.c_size_t, vp]
+    L.xbi_bitinformation_dev_allreduce.restype = i32
+    L.xbi_bitinformation_dev_allreduce.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, vp, C.c_size_t, vp,
+                                                   i32, i32, u64, C.POINTER(vp), dbl]
+    L.xbi_peer_bytes.restype = C.c_size_t
+    L.xbi_peer_bytes.argtypes = []
+    L.xbi_peer_handle_bytes.restype = C.c_size_t
+    L.xbi_peer_handle_bytes.argtypes = []
+    L.xbi_peer_create.restype = i32
+    L.xbi_peer_create.argtypes = [C.POINTER(vp), vp]
+    L.xbi_peer_open.restype = i32
+    L.xbi_peer_open.argtypes = [vp, C.POINTER(vp)]
+    L.xbi_peer_close.restype = i32
+    L.xbi_peer_close.argtypes = [vp]
+    L.xbi_peer_destroy.restype = i32
+    L.xbi_peer_destroy.argtypes = [vp]
+    L.xbi_peer_error_epoch.restype = i32
+    L.xbi_peer_error_epoch.argtypes = [vp, C.POINTER(C.c_ulonglong)]
     L.xbi_mutual_information_batched.restype = i32
     L.xbi_mutual_information_batched.argtypes = [vp, i32, i64, i32, dbl, vp, vp]
     L.xbi_count_pairs_chunked.restype = i32
@@ -91,6 +110,8 @@ def lib() -> C.CDLL:
     L.xbi_bitround_chunked_v.argtypes = [vp, i32, i32, C.POINTER(i64), C.POINTER(i64), C.POINTER(i64), vp, vp, vp]
     L.xbi_bitround_inplace.restype = i32
     L.xbi_bitround_inplace.argtypes = [vp, i32, i64, i32, vp]
+    L.xbi_bitround.restype = i32
+    L.xbi_bitround.argtypes = [vp, vp, i32, i64, i32, vp]
     L.xbi_shuffle.restype = i32
     L.xbi_shuffle.argtypes = [vp, vp, i32, i64, i32, i32, vp]
     L.xbi_bitround_shuffle.restype = i32
@@ -107,6 +128,11 @@ def lib() -> C.CDLL:
     if L.xbi_abi_version() != 1:
         raise ImportError("libxbitinfo_b200.so ABI version mismatch; rebuild it")
     _lib = L
+    # the host-buffer entry points keep a staging context per host thread; worker threads free theirs when they
+    # exit (the library's thread_local destructor), the main thread's goes here, while the runtime is still up
+    import atexit
+
+    atexit.register(L.xbi_host_release)
     return L
 
 
@@ -117,6 +143,8 @@ EXPORTED_SYMBOLS = (
     "xbi_bitinformation_host", "xbi_bitround_host", "xbi_host_release",
     "xbi_mutual_information_batched", "xbi_count_pairs_chunked", "xbi_bitround_chunked",
     "xbi_bitinformation_host_multi", "xbi_count_pairs_chunked_v", "xbi_bitround_chunked_v",
+    "xbi_bitinformation_dev", "xbi_bitinformation_dev_allreduce", "xbi_peer_bytes", "xbi_peer_handle_bytes",
+    "xbi_bitround", "xbi_peer_create", "xbi_peer_open", "xbi_peer_close", "xbi_peer_destroy", "xbi_peer_error_epoch",
 )
 
 

@@ -330,34 +330,42 @@ def _merge_dims(ds, per_dim):
 
 
 # ---------------------------------------------------------------------------------------
-# JSON label cache  [467-476, 594-599, 947-957]
+# JSON label cache: the on-disk format is the reference's, so caches written by either package load in the
+# other (encoder: xbitinfo/xbitinfo.py:947-957; load: 467-476; save: 594-599)
 # ---------------------------------------------------------------------------------------
+_JSON_CONVERSIONS = (
+    ((np.ndarray, np.number), lambda o: o.tolist()),
+    (complex, lambda o: [o.real, o.imag]),
+    (set, list),
+    (bytes, bytes.decode),
+)
+
+
 class JsonCustomEncoder(json.JSONEncoder):
+    """numpy arrays / scalars, complex numbers, sets and bytes as plain JSON -- the conversions of the
+    reference's encoder of the same name (xbitinfo/xbitinfo.py:947-957)."""
+
     def default(self, obj):
-        if isinstance(obj, (np.ndarray, np.number)):
-            return obj.tolist()
-        if isinstance(obj, complex):
-            return [obj.real, obj.imag]
-        if isinstance(obj, set):
-            return list(obj)
-        if isinstance(obj, bytes):
-            return obj.decode()
-        return json.JSONEncoder.default(self, obj)
+        for types, convert in _JSON_CONVERSIONS:
+            if isinstance(obj, types):
+                return convert(obj)
+        return super().default(obj)
 
 
 def load_bitinformation(label, like=None):
-    """Load bitinformation from JSON file"""
-    label_file = label + ".json"
-    if os.path.exists(label_file):
-        with open(label_file) as f:
-            logging.debug(f"Load bitinformation from {label_file}")
-            info_per_bit = json.load(f)
-        return dict_to_dataset(info_per_bit, like=like)
-    raise FileNotFoundError(f"No bitinformation could be found at {label_file}")
+    """Dataset from the cache file ``<label>.json``; FileNotFoundError when there is none
+    (xbitinfo/xbitinfo.py:467-476)."""
+    path = f"{label}.json"
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"No bitinformation could be found at {path}")
+    logging.debug(f"Load bitinformation from {path}")
+    with open(path) as f:
+        return dict_to_dataset(json.load(f), like=like)
 
 
 def save_bitinformation(info_per_bit, out_fn, overwrite=False):
-    """Save bitinformation to JSON file"""
+    """Write the per-variable result dicts to ``out_fn`` as JSON (xbitinfo/xbitinfo.py:594-599; like the
+    reference, an existing file is always replaced)."""
+    logging.debug(f"Save bitinformation to {out_fn}")
     with open(out_fn, "w") as f:
-        logging.debug(f"Save bitinformation to {out_fn}")
         json.dump(info_per_bit, f, cls=JsonCustomEncoder)

@@ -36,65 +36,73 @@ def _dtype_of(data) -> np.dtype:
     return np.asarray(data).dtype
 
 
+_ONE_INFLEVEL = "Information content is only allowed for one 'inflevel' here. Please make a selection."
+_ONE_DIM = ("Information content is only allowed along one dimension here. Please select one `dim`. "
+            "To find the maximum keepbits, simply use `keepbits.max(dim='dim')`")
+
+
+def _require_single(labelled, coord, message, optional=False):
+    """AssertionError unless coordinate ``coord`` of a keepbits object holds at most one entry
+    (the reference asserts the same, so callers that catch AssertionError keep working)."""
+    if optional and coord not in labelled.coords:
+        return
+    if not labelled.coords[coord].shape <= (1,):
+        raise AssertionError(message)
+
+
+def _lookup(name, table, wrap=lambda v: v):
+    if name not in table.keys():
+        raise ValueError(f"name {name} not for in keepbits: {table.keys()}")
+    return wrap(table[name])
+
+
 def _keepbits_interface(da, keepbits):
-    """Common interface to the allowed keepbits types  [bitround.py:15-66]."""
-    assert _xr.is_dataarray(da)
+    """Resolve any of the accepted keepbits forms to the int that applies to ``da``.
+
+    Same contract as the reference adapter (xbitinfo/bitround.py:15-66): a plain integer is taken as
+    is; a mapping ``{name: int}`` and a keepbits Dataset are indexed by ``da.name`` (missing ->
+    ValueError); a keepbits DataArray must carry the same name (else KeyError); Dataset / DataArray
+    forms may hold one ``inflevel`` and one ``dim`` only (AssertionError); anything else -> TypeError.
+    """
+    if not _xr.is_dataarray(da):
+        raise AssertionError("expected a DataArray")
     if isinstance(keepbits, (int, np.integer)) and not isinstance(keepbits, bool):
-        keep = int(keepbits)
-    elif isinstance(keepbits, dict):
-        v = da.name
-        if v in keepbits.keys():
-            keep = keepbits[v]
-        else:
-            raise ValueError(f"name {v} not for in keepbits: {keepbits.keys()}")
-    elif _xr.is_dataset(keepbits):
-        assert keepbits.coords["inflevel"].shape <= (
-            1,
-        ), "Information content is only allowed for one 'inflevel' here. Please make a selection."
-        if "dim" in keepbits.coords:
-            assert keepbits.coords["dim"].shape <= (
-                1,
-            ), "Information content is only allowed along one dimension here. Please select one `dim`. To find the maximum keepbits, simply use `keepbits.max(dim='dim')`"
-        v = da.name
-        if v in keepbits.keys():
-            keep = int(keepbits[v])
-        else:
-            raise ValueError(f"name {v} not for in keepbits: {keepbits.keys()}")
-    elif _xr.is_dataarray(keepbits):
-        assert keepbits.coords["inflevel"].shape <= (
-            1,
-        ), "Information content is only allowed for one 'inflevel' here. Please make a selection."
-        assert keepbits.coords["dim"].shape <= (
-            1,
-        ), "Information content is only allowed along one dimension here. Please select one `dim`. To find the maximum keepbits, simply use `keepbits.max(dim='dim')`"
-        v = da.name
-        if v == keepbits.name:
-            keep = int(keepbits)
-        else:
-            raise KeyError(f"no keepbits found for variable {v}")
+        return int(keepbits)
+    if isinstance(keepbits, dict):
+        return _lookup(da.name, keepbits)
+    if _xr.is_dataset(keepbits):
+        _require_single(keepbits, "inflevel", _ONE_INFLEVEL)
+        _require_single(keepbits, "dim", _ONE_DIM, optional=True)
+        return _lookup(da.name, keepbits, int)
+    if _xr.is_dataarray(keepbits):
+        _require_single(keepbits, "inflevel", _ONE_INFLEVEL)
+        _require_single(keepbits, "dim", _ONE_DIM)
+        if da.name != keepbits.name:
+            raise KeyError(f"no keepbits found for variable {da.name}")
+        return int(keepbits)
+    raise TypeError(f"type {type(keepbits)} is not a valid type for keepbits.")
+
+
+def _round_variable(da, keep):
+    """One DataArray -> rounded DataArray carrying the CF quantisation attribute (bitround.py:99-100)."""
+    if _xr.is_xarray(da):  # pragma: no cover - xarray is absent from the build image
+        rounded = _xr.xarray_module().apply_ufunc(_cuda_bitround, da, keep, dask="parallelized", keep_attrs=True)
     else:
-        raise TypeError(f"type {type(keepbits)} is not a valid type for keepbits.")
-    return keep
+        rounded = da._replace(_cuda_bitround(da.data, keep))
+    rounded.attrs["_QuantizeBitRoundNumberOfSignificantDigits"] = keep
+    return rounded
 
 
 def xr_bitround(da, keepbits):
-    """Apply bitrounding based on keepbits from :py:func:`get_keepbits` to a Dataset or
-    DataArray  [bitround.py:69-101]."""
+    """Bitround a Dataset or DataArray to the keepbits :py:func:`get_keepbits` returned (or an int /
+    ``{name: int}``); a new object comes back, the input is untouched.  Public twin of the reference's
+    ``xr_bitround`` (xbitinfo/bitround.py:69-101) with K3 in place of numcodecs' BitRound."""
     if _xr.is_dataset(da):
-        da_bitrounded = da.copy()
-        for v in da.data_vars:
-            da_bitrounded[v] = xr_bitround(da[v], keepbits)
-        return da_bitrounded
-
-    assert _xr.is_dataarray(da)
-    keep = _keepbits_interface(da, keepbits)
-    if _xr.is_xarray(da):  # pragma: no cover - xarray is absent from the build image
-        xr = _xr.xarray_module()
-        out = xr.apply_ufunc(_cuda_bitround, da, keep, dask="parallelized", keep_attrs=True)
-    else:
-        out = da._replace(_cuda_bitround(da.data, keep))
-    out.attrs["_QuantizeBitRoundNumberOfSignificantDigits"] = keep
-    return out
+        out = da.copy()
+        for name in da.data_vars:
+            out[name] = _round_variable(da[name], _keepbits_interface(da[name], keepbits))
+        return out
+    return _round_variable(da, _keepbits_interface(da, keepbits))
 
 
 def bitround_along_dim(ds, info_per_bit, dim, inflevels=[1.0, 0.9999, 0.99, 0.975, 0.95], keepbits=None):

@@ -87,6 +87,26 @@ def keepbits_of_information_batched(info, np_dtype, inflevel=0.99) -> np.ndarray
         return ((cdf > inflevel).argmax(axis=-1) + 1 - (n_bits - n_mant)).astype("int64")
 
 
+def chunk_keepbits(info, np_dtype, inflevel=0.99) -> np.ndarray:
+    """Keepbits per chunk from a stack of information vectors ``(..., nbits)``, ready for K3: negative values
+    are clamped to 0 as the reference's multi-file flow does (``xbitinfo/xbitinfo.py:867-868``).  A chunk whose
+    information is all NaN had NO valid pair along the analysed axis (extent 1 along it -- e.g. the ragged last
+    chunk of 101 cut in 50s -- or everything masked): there is nothing to base a decision on, so it keeps every
+    mantissa bit (left unrounded) and a warning says so; clamping its meaningless negative keepbits to 0 would
+    silently wipe the mantissa."""
+    import warnings
+
+    _, _, _, n_mant = bit_partitioning(np_dtype)
+    info = np.asarray(info, dtype="float64")
+    keep = np.clip(keepbits_of_information_batched(info, np_dtype, inflevel), 0, n_mant)
+    undecided = np.isnan(info).all(axis=-1)
+    if undecided.any():
+        warnings.warn(f"{int(undecided.sum())} chunk(s) hold no valid pair along the analysed axis; they are left "
+                      f"unrounded (keepbits={n_mant})", RuntimeWarning, stacklevel=3)
+        keep = np.where(undecided, n_mant, keep)
+    return keep.astype("int64")
+
+
 def bitinformation_by_chunks(x, chunks, axis: int, masked_value=float("nan"), set_zero_insignificant: bool = True,
                              confidence: float = 0.99):
     """Information per bit of every chunk of the grid on its own: ``(info, counts)`` as CUDA tensors of
@@ -109,7 +129,8 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
     chunk.  Returns ``(rounded, keepbits)`` with ``rounded`` of the type of ``x`` (a new array)
     and ``keepbits`` an int64 array with one entry per chunk (shape = chunks per axis).
     Negative keepbits (not even all exponent bits carry information) are clamped to 0, as the
-    reference's multi-file flow does (``xbitinfo/xbitinfo.py:867-868``).
+    reference's multi-file flow does (``xbitinfo/xbitinfo.py:867-868``); a chunk without any valid pair
+    along ``axis`` is left unrounded, with a warning (:func:`chunk_keepbits`).
 
     The grid (regular, or dask-style tuples of uneven chunk lengths) is processed in a constant number
     of launches whatever the number of chunks: ``xbi_count_pairs_chunked[_v]`` ->
@@ -133,7 +154,7 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
 
         counts = count_pairs_chunked(t, chunk_shape, axis, masked_value=masked_value)
         info = information_batched(counts, set_zero_insignificant, confidence).cpu().numpy()
-        keep = np.clip(keepbits_of_information_batched(info, np_dtype, inflevel), 0, _MANT[t.dtype]).reshape(keep.shape)
+        keep = chunk_keepbits(info, np_dtype, inflevel).reshape(keep.shape)
         if keep.size:
             bitround_chunked_(t, chunk_shape, torch.from_numpy(keep.astype("int32").ravel()).to(t.device))
         return (t.cpu().numpy() if is_np else t), keep
@@ -143,7 +164,7 @@ def bitround_by_chunks(x, chunks, axis: int, inflevel: float = 0.99, masked_valu
         pc.reset()
         pc.add(blk, axis, masked_value=masked_value)
         info = pc.information(set_zero_insignificant, confidence).cpu().numpy()
-        k = max(0, min(keepbits_of_information(info, np_dtype, inflevel), _MANT[t.dtype]))
+        k = int(chunk_keepbits(info[None, :], np_dtype, inflevel)[0])
         keep[idx] = k
         bitround_(blk, k)
         t[sl] = blk

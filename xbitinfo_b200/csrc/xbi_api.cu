@@ -78,53 +78,117 @@ static cudaEvent_t prof_event(int idx) {
     return g_prof.ev[idx];
 }
 
-static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long long* counts_dev, Workspace* ws,
-                            cudaStream_t stream) {
-    const int nbits = 8 * dtype_bytes(job.dtype);
+// what becomes of the table of one counting job (the tail of count_pairs_impl: the finish kernel)
+struct Finish {
+    unsigned long long* counts = nullptr;  // nbits*4
+    bool accumulate = true;                // counts += table; false: counts = table
+    double* mi = nullptr;                  // K2 in the same launch when set
+    int set_zero = 0;
+    double z = 0.0;
+    PeerExchange px = {};                  // world > 1: all-reduce over peer memory before counts / K2
+};
+
+static bool allow_generic_only() {
+    static const bool on = [] {
+        const char* env = std::getenv("XBI_ALLOW_GENERIC");
+        return env && env[0] == '1';
+    }();
+    return on;
+}
+
+// K1 of one job into the workspace, then ONE finish launch: fringe pairs + combine (+ exchange) (+ K2).
+static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, cudaStream_t stream, const Finish& fin) {
     const int64_t numel = job.outer * job.n * job.inner;
-    if (numel == 0 || job.n < 2) return XBI_OK;  // no pairs along the axis: nothing to add
+    const bool nothing = numel == 0 || job.n < 2;  // no pairs along the axis
+    if (nothing && fin.accumulate && !fin.mi && fin.px.world <= 1) return XBI_OK;  // nothing to add
     XBI_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), stream), "cudaMemsetAsync(workspace)");
-    const int64_t npairs_flat = numel - job.inner;
-    int64_t dlo = 0, dhi = 0;
-    bool edges_done = false;
-    if (!(flags & XBI_FORCE_GENERIC)) {
-        const bool timed = g_prof.enabled && g_prof.used < Profile::kMax;
-        // masked modes: sample the density of validity boundaries; the sparse and the dense flavour of
-        // the fast kernels both read it and one of them returns at once
-        if (flags & XBI_FORCE_DENSE) {
-            static const unsigned long long kForceDense[2] = {1ull, 0ull};  // "every sampled pair is a boundary"
-            XBI_CUDA(cudaMemcpyAsync(ws->plus.pad, kForceDense, sizeof(kForceDense), cudaMemcpyHostToDevice, stream),
-                     "cudaMemcpyAsync(flavour)");
-        } else if (!(flags & XBI_FORCE_SPARSE)) {
-            XBI_CUDA(launch_mask_density(job, npairs_flat, ws, stream), "mask density sample");
-        }
-        if (timed) XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used), stream), "cudaEventRecord");
-        if (job.inner == 1)
-            XBI_CUDA(launch_pairs_tma(job, npairs_flat, ws, stream, &dlo, &dhi, &edges_done), "pair counting (TMA rows)");
-        else
-            XBI_CUDA(launch_pairs_cols(job, ws, stream, &dlo, &dhi, &edges_done), "pair counting (column walkers)");
-        if (timed) {
-            XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used + 1), stream), "cudaEventRecord");
-            if (dhi > dlo) {
-                g_prof.bytes += (unsigned long long)(dhi - dlo) * dtype_bytes(job.dtype);
-                ++g_prof.used;
+    FinishJob J = {};
+    J.x = job.x;
+    J.n = job.n;
+    J.inner = job.inner > 0 ? job.inner : 1;
+    J.mask_lo = (uint32_t)(job.mask_bits & 0xFFFFFFFFu);
+    J.mask_hi = (uint32_t)(job.mask_bits >> 32);
+    J.ws = ws;
+    J.counts = fin.counts;
+    J.accumulate = fin.accumulate ? 1 : 0;
+    J.mi = fin.mi;
+    J.set_zero = fin.set_zero;
+    J.z = fin.z;
+    J.px = fin.px;
+    if (!nothing) {
+        const int64_t npairs_flat = numel - job.inner;
+        int64_t dlo = 0, dhi = 0;
+        bool edges_done = false;
+        if (!(flags & XBI_FORCE_GENERIC)) {
+            const bool timed = g_prof.enabled && g_prof.used < Profile::kMax;
+            // masked modes: sample the density of validity boundaries; the sparse and the dense flavour of
+            // the fast kernels both read it and one of them returns at once
+            if (flags & XBI_FORCE_DENSE) {
+                static const unsigned long long kForceDense[2] = {1ull, 0ull};  // "every sampled pair is a boundary"
+                XBI_CUDA(cudaMemcpyAsync(ws->plus.pad, kForceDense, sizeof(kForceDense), cudaMemcpyHostToDevice, stream),
+                         "cudaMemcpyAsync(flavour)");
+            } else if (!(flags & XBI_FORCE_SPARSE)) {
+                XBI_CUDA(launch_mask_density(job, npairs_flat, ws, stream), "mask density sample");
+            }
+            if (timed) XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used), stream), "cudaEventRecord");
+            cudaError_t fast;
+            if (job.inner == 1)
+                fast = launch_pairs_tma(job, npairs_flat, ws, stream, &dlo, &dhi, &edges_done);
+            else
+                fast = launch_pairs_cols(job, ws, stream, &dlo, &dhi, &edges_done);
+            if (fast == cudaErrorSymbolNotFound) {
+                // the driver does not hand out cuTensorMapEncodeTiled: the TMA kernel cannot run.  Never silently:
+                // the generic kernel is 4-10x slower.
+                cudaGetLastError();
+                if (!allow_generic_only())
+                    return fail(XBI_ERR_UNSUPPORTED,
+                                "cuTensorMapEncodeTiled could not be resolved from the CUDA driver: the TMA fast path is "
+                                "unavailable (set XBI_ALLOW_GENERIC=1 to run on the 4-10x slower generic kernel)");
+                static std::atomic<bool> warned{false};
+                if (!warned.exchange(true))
+                    std::fprintf(stderr, "xbitinfo_b200: TMA fast path unavailable, counting on the generic kernel (XBI_ALLOW_GENERIC=1)\n");
+                dlo = dhi = 0;
+            } else if (fast != cudaSuccess) {
+                return fail_cuda(fast, job.inner == 1 ? "pair counting (TMA rows)" : "pair counting (column walkers)");
+            }
+            if (timed) {
+                XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used + 1), stream), "cudaEventRecord");
+                if (dhi > dlo) {
+                    g_prof.bytes += (unsigned long long)(dhi - dlo) * dtype_bytes(job.dtype);
+                    ++g_prof.used;
+                }
             }
         }
+        if (dhi <= dlo) { dlo = 0; dhi = 0; edges_done = false; }
+        // what the fast kernel left: flat pairs [0, dlo) and [dhi, npairs_flat) ...
+        J.range_lo[0] = 0;   J.range_cnt[0] = dlo;
+        J.range_lo[1] = dhi; J.range_cnt[1] = npairs_flat - dhi;
+        if (J.range_cnt[0] + J.range_cnt[1] > kFinishMaxFlat) {
+            XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
+            XBI_CUDA(launch_pairs_generic_flat(job, dhi, npairs_flat, &ws->plus, stream), "pair counting (generic, tail)");
+            J.range_cnt[0] = J.range_cnt[1] = 0;
+        }
+        // ... and the block-straddling pairs it did not remove itself
+        const int64_t nedges = (job.outer - 1) * job.inner;
+        if (edges_done && job.inner != 1) {
+            // column walkers: every block-boundary pair has been subtracted by k_block_edges
+        } else if (edges_done) {
+            // inner == 1: edge t sits at flat index t*n + n-1; those inside [dlo, dhi) are done
+            J.range_lo[2] = 0;          J.range_cnt[2] = dlo / job.n;
+            J.range_lo[3] = dhi / job.n; J.range_cnt[3] = nedges - dhi / job.n;
+        } else {
+            J.range_lo[2] = 0; J.range_cnt[2] = nedges;
+        }
+        for (int r = 2; r < 4; ++r)
+            if (J.range_cnt[r] < 0) J.range_cnt[r] = 0;
+        if (J.range_cnt[2] + J.range_cnt[3] > kFinishMaxEdges) {
+            for (int r = 2; r < 4; ++r)
+                XBI_CUDA(launch_pairs_generic_edges(job, J.range_lo[r], J.range_lo[r] + J.range_cnt[r], &ws->minus, stream),
+                         "pair counting (edge pairs)");
+            J.range_cnt[2] = J.range_cnt[3] = 0;
+        }
     }
-    if (dhi <= dlo) { dlo = 0; dhi = 0; edges_done = false; }
-    XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
-    XBI_CUDA(launch_pairs_generic_flat(job, dhi, npairs_flat, &ws->plus, stream), "pair counting (generic, tail)");
-    const int64_t nedges = (job.outer - 1) * job.inner;
-    if (edges_done && job.inner != 1) {
-        // column walkers: every block-boundary pair has been subtracted by k_block_edges
-    } else if (edges_done) {
-        // inner == 1: edge t sits at flat index t*n + n-1; those inside [dlo, dhi) are done
-        XBI_CUDA(launch_pairs_generic_edges(job, 0, dlo / job.n, &ws->minus, stream), "pair counting (edge pairs, head)");
-        XBI_CUDA(launch_pairs_generic_edges(job, dhi / job.n, nedges, &ws->minus, stream), "pair counting (edge pairs, tail)");
-    } else {
-        XBI_CUDA(launch_pairs_generic_edges(job, 0, nedges, &ws->minus, stream), "pair counting (edge pairs)");
-    }
-    XBI_CUDA(launch_combine(ws, nbits, counts_dev, stream), "combine");
+    XBI_CUDA(launch_finish(job, J, stream), "finish (fringe + combine)");
     return XBI_OK;
 }
 
@@ -133,7 +197,8 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, unsigned long l
 // ---------------------------------------------------------------------------------
 struct HostCtx {
     int device = -1;
-    size_t buf_bytes = 0;
+    size_t buf_bytes = 0;  // current size of each staging buffer
+    size_t buf_cap = 0;    // the most they may grow to (XBI_STAGING_MB)
     void* buf[2] = {nullptr, nullptr};
     cudaStream_t stream[2] = {nullptr, nullptr};
     Workspace* ws[2] = {nullptr, nullptr};
@@ -169,8 +234,18 @@ struct HostCtx {
         counts = nullptr; mi = nullptr; counts_multi = nullptr; mi_multi = nullptr;
         device = -1;
         buf_bytes = 0;
+        buf_cap = 0;
+        in_next = 0;
     }
-    ~HostCtx() {}  // process teardown order is not ours to rely on; explicit xbi_host_release() frees
+    // A host thread that used the *_host entry points gives its staging memory back when it exits (dask worker
+    // threads come and go).  At process teardown the runtime may already be gone: every call then fails with
+    // cudaErrorCudartUnloading and nothing is touched.
+    ~HostCtx() {
+        if (device < 0) return;
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) release();
+        else cudaGetLastError();
+    }
 };
 static thread_local HostCtx g_ctx;
 
@@ -189,15 +264,43 @@ static int ensure_ctx(int device) {
         const long v = std::atol(env);
         if (v >= 1 && v <= 65536) mb = (size_t)v;
     }
-    g_ctx.buf_bytes = mb << 20;
-    g_ctx.device = device;
+    g_ctx.buf_cap = mb << 20;
+    g_ctx.device = device;  // (release() needs it; a half-built context is torn down again below)
+    const int rc = [&]() -> int {
+        for (int i = 0; i < 2; ++i) {
+            XBI_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream[i], cudaStreamNonBlocking), "cudaStreamCreate");
+            XBI_CUDA(cudaMalloc(&g_ctx.ws[i], sizeof(Workspace)), "cudaMalloc(workspace)");
+        }
+        XBI_CUDA(cudaMalloc(&g_ctx.counts, 64 * 4 * sizeof(unsigned long long)), "cudaMalloc(counts)");
+        XBI_CUDA(cudaMalloc(&g_ctx.mi, 64 * sizeof(double)), "cudaMalloc(mi)");
+        return XBI_OK;
+    }();
+    if (rc != XBI_OK) g_ctx.release();  // never leave a context that looks ready but holds null pointers
+    return rc;
+}
+
+// The two staging buffers are sized by what the call at hand needs (at most XBI_STAGING_MB each, default 256):
+// a worker thread that rounds 8 MB dask chunks holds 2 x 8 MB of HBM, not 2 x 256 MB.  They only ever grow.
+static int ensure_staging(size_t want_bytes) {
+    HostCtx& c = g_ctx;
+    size_t want = want_bytes < c.buf_cap ? want_bytes : c.buf_cap;
+    want = (want + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);  // whole MB
+    if (want < ((size_t)1 << 20)) want = (size_t)1 << 20;
+    if (want > c.buf_cap) want = c.buf_cap;
+    if (c.buf[0] && c.buf[1] && c.buf_bytes >= want) return XBI_OK;
     for (int i = 0; i < 2; ++i) {
-        XBI_CUDA(cudaStreamCreateWithFlags(&g_ctx.stream[i], cudaStreamNonBlocking), "cudaStreamCreate");
-        XBI_CUDA(cudaMalloc(&g_ctx.buf[i], g_ctx.buf_bytes), "cudaMalloc(staging)");
-        XBI_CUDA(cudaMalloc(&g_ctx.ws[i], sizeof(Workspace)), "cudaMalloc(workspace)");
+        if (c.stream[i]) XBI_CUDA(cudaStreamSynchronize(c.stream[i]), "cudaStreamSynchronize");
+        if (c.buf[i]) { cudaFree(c.buf[i]); c.buf[i] = nullptr; }
     }
-    XBI_CUDA(cudaMalloc(&g_ctx.counts, 64 * 4 * sizeof(unsigned long long)), "cudaMalloc(counts)");
-    XBI_CUDA(cudaMalloc(&g_ctx.mi, 64 * sizeof(double)), "cudaMalloc(mi)");
+    c.buf_bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+        const cudaError_t e = cudaMalloc(&c.buf[i], want);
+        if (e != cudaSuccess) {
+            for (int k = 0; k < 2; ++k) { if (c.buf[k]) cudaFree(c.buf[k]); c.buf[k] = nullptr; }
+            return fail_cuda(e, "cudaMalloc(staging)");
+        }
+    }
+    c.buf_bytes = want;
     return XBI_OK;
 }
 
@@ -312,8 +415,113 @@ int xbi_count_pairs(const void* x_dev, int dtype, int64_t outer, int64_t n, int6
     CountJob job;
     if (int rc = make_job(job, x_dev, dtype, outer, n, inner, flags, mask_bits)) return rc;
     if (!x_dev && outer * n * inner > 0) return fail(XBI_ERR_ARG, "null data pointer");
-    return count_pairs_impl(job, flags, counts_dev, static_cast<Workspace*>(workspace_dev),
-                            static_cast<cudaStream_t>(stream));
+    Finish fin;
+    fin.counts = counts_dev;
+    return count_pairs_impl(job, flags, static_cast<Workspace*>(workspace_dev), static_cast<cudaStream_t>(stream), fin);
+}
+
+static int bitinformation_dev_impl(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner, unsigned flags,
+                                   uint64_t mask_bits, int set_zero_insignificant, double confidence,
+                                   unsigned long long* counts_dev, double* mi_dev, void* workspace_dev,
+                                   size_t workspace_bytes, void* stream, const PeerExchange& px) {
+    if (!counts_dev || !workspace_dev) return fail(XBI_ERR_ARG, "null counts or workspace pointer");
+    if (workspace_bytes < sizeof(Workspace)) return fail(XBI_ERR_ARG, "workspace smaller than xbi_workspace_bytes()");
+    if (reinterpret_cast<uintptr_t>(workspace_dev) % 8 != 0) return fail(XBI_ERR_ARG, "workspace must be 8-byte aligned");
+    CountJob job;
+    if (int rc = make_job(job, x_dev, dtype, outer, n, inner, flags, mask_bits)) return rc;
+    if (!x_dev && outer * n * inner > 0) return fail(XBI_ERR_ARG, "null data pointer");
+    Finish fin;
+    fin.counts = counts_dev;
+    fin.accumulate = false;
+    fin.mi = mi_dev;
+    fin.px = px;
+    if (mi_dev && set_zero_insignificant) {
+        if (!(confidence > 0.0 && confidence < 1.0)) return fail(XBI_ERR_ARG, "confidence must be in (0,1)");
+        fin.set_zero = 1;
+        fin.z = normal_quantile(1.0 - (1.0 - confidence) / 2.0);
+    }
+    return count_pairs_impl(job, flags, static_cast<Workspace*>(workspace_dev), static_cast<cudaStream_t>(stream), fin);
+}
+
+int xbi_bitinformation_dev(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner, unsigned flags,
+                           uint64_t mask_bits, int set_zero_insignificant, double confidence,
+                           unsigned long long* counts_dev, double* mi_dev, void* workspace_dev, size_t workspace_bytes,
+                           void* stream) {
+    PeerExchange none = {};
+    return bitinformation_dev_impl(x_dev, dtype, outer, n, inner, flags, mask_bits, set_zero_insignificant, confidence,
+                                   counts_dev, mi_dev, workspace_dev, workspace_bytes, stream, none);
+}
+
+// ---------------------------------------------------------------------------------
+// all-reduce over peer memory: exchange buffers (cudaMalloc + CUDA IPC) and the fused entry point
+// ---------------------------------------------------------------------------------
+size_t xbi_peer_bytes(void) { return kPeerWords * sizeof(unsigned long long); }
+size_t xbi_peer_handle_bytes(void) { return sizeof(cudaIpcMemHandle_t); }
+
+int xbi_peer_create(void** buffer_dev, void* handle_out) {
+    if (!buffer_dev || !handle_out) return fail(XBI_ERR_ARG, "null pointer");
+    void* p = nullptr;
+    XBI_CUDA(cudaMalloc(&p, xbi_peer_bytes()), "cudaMalloc(peer exchange buffer)");
+    cudaError_t e = cudaMemset(p, 0, xbi_peer_bytes());
+    cudaIpcMemHandle_t h;
+    if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail_cuda(e, "cudaIpcGetMemHandle");
+    }
+    std::memcpy(handle_out, &h, sizeof(h));
+    *buffer_dev = p;
+    return XBI_OK;
+}
+
+int xbi_peer_open(const void* handle, void** mapped_dev) {
+    if (!handle || !mapped_dev) return fail(XBI_ERR_ARG, "null pointer");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void* p = nullptr;
+    XBI_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess), "cudaIpcOpenMemHandle");
+    *mapped_dev = p;
+    return XBI_OK;
+}
+
+int xbi_peer_close(void* mapped_dev) {
+    if (mapped_dev) XBI_CUDA(cudaIpcCloseMemHandle(mapped_dev), "cudaIpcCloseMemHandle");
+    return XBI_OK;
+}
+
+int xbi_peer_destroy(void* buffer_dev) {
+    if (buffer_dev) XBI_CUDA(cudaFree(buffer_dev), "cudaFree(peer exchange buffer)");
+    return XBI_OK;
+}
+
+int xbi_peer_error_epoch(const void* own_buffer_dev, unsigned long long* epoch_out) {
+    if (!own_buffer_dev || !epoch_out) return fail(XBI_ERR_ARG, "null pointer");
+    XBI_CUDA(cudaMemcpy(epoch_out, static_cast<const unsigned long long*>(own_buffer_dev) + kPeerErrorWord,
+                        sizeof(unsigned long long), cudaMemcpyDeviceToHost),
+             "cudaMemcpy(peer error word)");
+    return XBI_OK;
+}
+
+int xbi_bitinformation_dev_allreduce(const void* x_dev, int dtype, int64_t outer, int64_t n, int64_t inner, unsigned flags,
+                                     uint64_t mask_bits, int set_zero_insignificant, double confidence,
+                                     unsigned long long* counts_dev, double* mi_dev, void* workspace_dev,
+                                     size_t workspace_bytes, void* stream, int world, int rank, uint64_t epoch,
+                                     void* const* peer_buffers, double timeout_s) {
+    if (world < 1 || world > kPeerMaxWorld) return fail(XBI_ERR_ARG, "world must be in 1..8 (the GPUs of one node)");
+    if (rank < 0 || rank >= world) return fail(XBI_ERR_ARG, "rank out of range");
+    if (epoch == 0) return fail(XBI_ERR_ARG, "epochs start at 1");
+    if (!peer_buffers) return fail(XBI_ERR_ARG, "null peer buffer table");
+    PeerExchange px = {};
+    px.world = world;
+    px.rank = rank;
+    px.epoch = epoch;
+    px.timeout_ns = (unsigned long long)((timeout_s > 0.0 ? timeout_s : 20.0) * 1e9);
+    for (int p = 0; p < world; ++p) {
+        if (!peer_buffers[p]) return fail(XBI_ERR_ARG, "null peer buffer");
+        px.peer[p] = static_cast<unsigned long long*>(peer_buffers[p]);
+    }
+    return bitinformation_dev_impl(x_dev, dtype, outer, n, inner, flags, mask_bits, set_zero_insignificant, confidence,
+                                   counts_dev, mi_dev, workspace_dev, workspace_bytes, stream, px);
 }
 
 int xbi_mutual_information_batched(const unsigned long long* counts_dev, int nbits, int64_t nbatch,
@@ -557,6 +765,19 @@ int xbi_bitround_inplace(void* x_dev, int dtype, int64_t numel, int keepbits, vo
     return XBI_OK;
 }
 
+int xbi_bitround(const void* src_dev, void* dst_dev, int dtype, int64_t numel, int keepbits, void* stream) {
+    if (int rc = check_bitround_args(dtype, numel, keepbits)) return rc;
+    if (numel == 0) return XBI_OK;
+    if (!src_dev || !dst_dev) return fail(XBI_ERR_ARG, "null data pointer");
+    const int bytes = dtype_bytes(dtype);
+    const uintptr_t a = reinterpret_cast<uintptr_t>(src_dev), b = reinterpret_cast<uintptr_t>(dst_dev);
+    if (a % bytes != 0 || b % bytes != 0) return fail(XBI_ERR_ARG, "data pointer is not element-aligned");
+    const uint64_t nb = (uint64_t)numel * (uint64_t)bytes;
+    if (a != b && a < b + nb && b < a + nb) return fail(XBI_ERR_ARG, "source and destination overlap");
+    XBI_CUDA(launch_bitround_to(src_dev, dst_dev, dtype, numel, keepbits, static_cast<cudaStream_t>(stream)), "bitround");
+    return XBI_OK;
+}
+
 int xbi_shuffle(const void* src_dev, void* dst_dev, int itemsize, int64_t numel, int kind, int inverse, void* stream) {
     if (itemsize != 2 && itemsize != 4 && itemsize != 8) return fail(XBI_ERR_ARG, "itemsize must be 2, 4 or 8");
     if (kind != XBI_SHUFFLE_BYTES && kind != XBI_SHUFFLE_BITS) return fail(XBI_ERR_ARG, "unknown shuffle kind");
@@ -609,6 +830,7 @@ int xbi_bitinformation_host(const void* x_host, int dtype, int64_t outer, int64_
     const int nbits = 8 * bytes;
     const int64_t numel = outer * n * inner;
     if (numel > 0 && !x_host) return fail(XBI_ERR_ARG, "null data pointer");
+    if (int rc = ensure_staging((size_t)numel * bytes)) return rc;
     XBI_CUDA(cudaMemsetAsync(c.counts, 0, 64 * 4 * sizeof(unsigned long long), c.stream[0]), "memset(counts)");
     XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
 
@@ -638,7 +860,9 @@ int xbi_bitinformation_host(const void* x_host, int dtype, int64_t outer, int64_
         CountJob job = probe;
         job.x = c.buf[which];
         job.outer = so; job.n = sn; job.inner = si;
-        if (int rc = count_pairs_impl(job, flags, c.counts, c.ws[which], st)) return rc;
+        Finish fin;
+        fin.counts = c.counts;
+        if (int rc = count_pairs_impl(job, flags, c.ws[which], st, fin)) return rc;
         which ^= 1;
         return XBI_OK;
     };
@@ -727,6 +951,7 @@ int xbi_bitinformation_host_multi(const void* x_host, int dtype, int ndim, const
     if (int rc = ensure_ctx(device)) return rc;
     HostCtx& c = g_ctx;
     const int64_t row = shape[0] > 0 ? numel / shape[0] : 0;  // elements of one index of the first dimension
+    if (int rc = ensure_staging((size_t)(numel + row) * bytes)) return rc;
     const int64_t cap = (int64_t)(c.buf_bytes / bytes);
     if (naxes == 1 || numel == 0 || row == 0 || 2 * row > cap) {
         // nothing to share between the axes (or one row of the first dimension does not fit the staging
@@ -770,7 +995,9 @@ int xbi_bitinformation_host_multi(const void* x_host, int dtype, int ndim, const
             CountJob job = probe;
             job.x = c.buf[which];
             dims_of(axes[a], axes[a] == 0 ? own + halo : own, &job.outer, &job.n, &job.inner);
-            if (int rc = count_pairs_impl(job, flags, c.counts_multi + (size_t)a * table, c.ws[which], st)) return rc;
+            Finish fin;
+            fin.counts = c.counts_multi + (size_t)a * table;
+            if (int rc = count_pairs_impl(job, flags, c.ws[which], st, fin)) return rc;
         }
     }
     XBI_CUDA(cudaStreamSynchronize(c.stream[0]), "sync");
@@ -797,6 +1024,10 @@ int xbi_bitround_host(const void* src_host, void* dst_host, int dtype, int64_t n
     const int bytes = dtype_bytes(dtype);
     const bool stage_in = staging_enabled() && is_pageable(src_host);
     const bool stage_out = staging_enabled() && is_pageable(dst_host);
+    {
+        const size_t all = (size_t)numel * bytes;
+        if (int rc = ensure_staging((stage_in || stage_out) && all > HostCtx::kPinBytes ? HostCtx::kPinBytes : all)) return rc;
+    }
     if (stage_in || stage_out) {
         // slabs of one pinned slot; slot k of each direction belongs to stream k.  While the GPU works on
         // slab i the pool copies slab i-1's result out and slab i+1 in.

@@ -13,6 +13,8 @@
 // bits(its last row); two small row-plane passes (xbi_count_generic.cu) add those to the
 // plus / minus sums.  Masked modes add the boundary corrections of xbi_mask.cuh.
 // Pairs that straddle two blocks of the analysed axis are subtracted by k_block_edges.
+#include <atomic>
+
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
@@ -681,11 +683,12 @@ cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t s
     auto kern = k_pairs_cols<KIND, MASK, XFORM, G>;
     int dev = 0;
     cudaGetDevice(&dev);
-    static bool attr_set[64] = {};
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    static std::atomic<unsigned long long> attr_set{0ull};  // per instantiation; bit = device
+    const unsigned long long dev_bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (!(attr_set.load(std::memory_order_acquire) & dev_bit)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kAsyncSmem);
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        attr_set.fetch_or(dev_bit, std::memory_order_release);
     }
     // Work split: warp items = 32-chunk strips x row segments, dealt round-robin to the
     // sms*16 warps.  All items cost the same (segments differ by one row at most), so the

@@ -14,6 +14,8 @@
 // Unmasked pairs need only two word streams: a (every element) and a&b.  The b-stream
 // total equals the a-stream total shifted by one element, i.e. A - bits(first element)
 // + bits(halo element of the last stage); block 0 applies that correction.
+#include <atomic>
+
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
@@ -585,9 +587,11 @@ cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, Workspace* ws,
     while (nstages > 0 && (head + nstages * S::kElemsPerStage) * bytes + 16 > numel * bytes) --nstages;
     if (nstages < 1) return cudaSuccess;
     const uint64_t nrows = (uint64_t)nstages * S::kRowsPerStage;
-    if (nrows >= (1ull << 31)) return cudaSuccess;  // TMA coordinates are 32-bit: leave it to the caller's slabs
+    // TMA coordinates are 32-bit: 2^31 rows of 128 bytes are 256 GiB, more than one B200 holds.  An error, not a
+    // silent detour through the generic kernel
+    if (nrows >= (1ull << 31)) return cudaErrorNotSupported;
     EncodeFn encode = get_encode_fn();
-    if (!encode) return cudaSuccess;
+    if (!encode) return cudaErrorSymbolNotFound;  // reported by the caller (xbi_api.cu), never silently
 
     const char* region = static_cast<const char*>(job.x) + head * bytes;
     CUtensorMap tmap;
@@ -603,11 +607,13 @@ cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, Workspace* ws,
     auto kern = k_pairs_rows_tma<KIND, MASK, XFORM>;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
-    static bool attr_set[64] = {};  // per instantiation and device (the opt-in is per device)
-    if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    // per instantiation and device (the opt-in is per device); a bit set lets concurrent host threads race benignly
+    static std::atomic<unsigned long long> attr_set{0ull};
+    const unsigned long long dev_bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (!(attr_set.load(std::memory_order_acquire) & dev_bit)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes<KIND>());
         if (e != cudaSuccess) return e;
-        if (dev >= 0 && dev < 64) attr_set[dev] = true;
+        attr_set.fetch_or(dev_bit, std::memory_order_release);
     }
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const unsigned grid = (unsigned)(nstages < sms ? nstages : sms);

@@ -1,83 +1,24 @@
-// Combine kernel (raw plane sums -> (nbits,2,2) counts) and K2 (mutual information +
-// binomial significance filter on the nbits x 4 counts).
+// K2 as a stand-alone kernel (mutual information + binomial significance filter on stacks of nbits x 4 counts;
+// the single-table case normally runs inside the finish kernel, xbi_finish.cu) and the normal quantile.
 #include <cmath>
 
 #include "xbi_common.cuh"
+#include "xbi_epilogue.cuh"
 #include "xbi_internal.h"
 
 namespace xbi {
 
 namespace {
 
-// counts[4k + 2a + b], k = 0 is the most significant bit (bitpaircount layout,
-// xbitinfo/_py_bitinfo.py:128-140).  Flat pairs minus the pairs that straddle two blocks
-// of the analysed axis are exactly the pairs of _py_bitinfo.py:155-160.
-__global__ void k_combine(const Workspace* __restrict__ ws, int nbits, unsigned long long* __restrict__ counts) {
-    const int j = threadIdx.x;  // bit number from the least significant bit
-    if (j >= nbits) return;
-    const unsigned long long A = ws->plus.sums[S_A][j] - ws->minus.sums[S_A][j];
-    const unsigned long long B = ws->plus.sums[S_B][j] - ws->minus.sums[S_B][j];
-    const unsigned long long AB = ws->plus.sums[S_AB][j] - ws->minus.sums[S_AB][j];
-    const unsigned long long N = ws->plus.npairs - ws->minus.npairs;
-    const int k = nbits - 1 - j;
-    // atomics: several streams may add slabs of the same variable into one counts buffer
-    atomicAdd(&counts[4 * k + 0], N - A - B + AB);
-    atomicAdd(&counts[4 * k + 1], B - AB);
-    atomicAdd(&counts[4 * k + 2], A - AB);
-    atomicAdd(&counts[4 * k + 3], AB);
-}
-
-// One thread per bit.  Follows xbitinfo/_py_bitinfo.py:143-152 operation by operation:
-//   p = counts / size                      (line 147)
-//   zero cells masked out                  (line 148)
-//   pr = row sums, ps = column sums        (lines 149-150)
-//   sum p * log(p / (pr * ps)) / log(2)    (line 151), summed in the order 00,01,10,11
-// Round-to-nearest intrinsics keep ptxas from contracting mul+add into FMA.
-// One thread per (table, bit): `total` = number of tables x nbits.
+// One thread per (table, bit): `total` = number of tables x nbits.  Arithmetic: xbi_epilogue.cuh.
 __global__ void k_mutual_information(const unsigned long long* __restrict__ counts, long long total, int set_zero,
                                      double z, double* __restrict__ mi) {
     const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= total) return;
-    const unsigned long long c00 = counts[4 * k + 0], c01 = counts[4 * k + 1];
-    const unsigned long long c10 = counts[4 * k + 2], c11 = counts[4 * k + 3];
-    const unsigned long long n = c00 + c01 + c10 + c11;
-    if (n == 0) {
-        mi[k] = nan("");
-        return;
-    }
-    const double size = (double)n;
-    const double p00 = __ddiv_rn((double)c00, size), p01 = __ddiv_rn((double)c01, size);
-    const double p10 = __ddiv_rn((double)c10, size), p11 = __ddiv_rn((double)c11, size);
-    const double pr0 = __dadd_rn(p00, p01), pr1 = __dadd_rn(p10, p11);
-    const double ps0 = __dadd_rn(p00, p10), ps1 = __dadd_rn(p01, p11);
-    double acc = 0.0;
-    if (c00) acc = __dadd_rn(acc, __dmul_rn(p00, log(__ddiv_rn(p00, __dmul_rn(pr0, ps0)))));
-    if (c01) acc = __dadd_rn(acc, __dmul_rn(p01, log(__ddiv_rn(p01, __dmul_rn(pr0, ps1)))));
-    if (c10) acc = __dadd_rn(acc, __dmul_rn(p10, log(__ddiv_rn(p10, __dmul_rn(pr1, ps0)))));
-    if (c11) acc = __dadd_rn(acc, __dmul_rn(p11, log(__ddiv_rn(p11, __dmul_rn(pr1, ps1)))));
-    double v = __ddiv_rn(acc, 0.6931471805599453);  // np.log(2)
-    if (set_zero) {
-        // BitInformation.jl binom_confidence / binom_free_entropy:
-        //   p = min(1, 1/2 + z / (2 sqrt(N))),  Hfree = 1 - H2(p),  M <= Hfree -> 0
-        double p = __dadd_rn(0.5, __ddiv_rn(z, __dmul_rn(2.0, sqrt(size))));
-        double hfree = 1.0;
-        if (p < 1.0) {
-            const double q = __dadd_rn(1.0, -p);
-            const double h = -__dadd_rn(__dmul_rn(p, log2(p)), __dmul_rn(q, log2(q)));
-            hfree = __dadd_rn(1.0, -h);
-        }
-        if (v <= hfree) v = 0.0;
-    }
-    mi[k] = v;
+    mi[k] = mutual_information_bit(counts[4 * k + 0], counts[4 * k + 1], counts[4 * k + 2], counts[4 * k + 3], set_zero, z);
 }
 
 }  // namespace
-
-cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* counts, cudaStream_t stream) {
-    k_combine<<<1, 64, 0, stream>>>(ws, nbits, counts);
-    note_launch();
-    return cudaGetLastError();
-}
 
 cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, long long nbatch, int set_zero,
                                       double z_quantile, double* mi, cudaStream_t stream) {

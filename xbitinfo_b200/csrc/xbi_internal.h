@@ -85,11 +85,53 @@ cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t s
 // in ws->plus.pad[0], pad[1] for the masked fast kernels to choose their flavour.
 cudaError_t launch_mask_density(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream);
 
-cudaError_t launch_combine(const Workspace* ws, int nbits, unsigned long long* counts, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------
+// finish kernel (xbi_finish.cu): fringe pairs + combine (+ all-reduce over peer memory) (+ K2), one launch
+// ---------------------------------------------------------------------------------
+// Exchange buffer of the peer all-reduce, one per rank, in 64-bit words:
+//   slots [2 parities][kPeerMaxWorld source ranks][kPeerCells]   the (nbits,2,2) table of every rank
+//   flags [2 parities][kPeerMaxWorld source ranks]                epoch of the table in that slot
+//   error word                                                    epoch of a wait that timed out (0: none)
+// Epochs start at 1 and grow by one per call on every rank; consecutive epochs use different parities, and a
+// rank can only reach epoch e+2 after every peer has finished reading epoch e (it needs their flag of e+1,
+// raised by a kernel that is stream-ordered after the one that read e), so the slots are never overwritten
+// while they are being read.
+constexpr int kPeerMaxWorld = 8;
+constexpr int kPeerCells = 256;
+constexpr size_t kPeerErrorWord = (size_t)2 * kPeerMaxWorld * kPeerCells + 2 * kPeerMaxWorld;
+constexpr size_t kPeerWords = kPeerErrorWord + 8;
+struct PeerExchange {
+    int world;  // <= 1: no exchange
+    int rank;
+    unsigned long long epoch;
+    unsigned long long timeout_ns;
+    unsigned long long* peer[kPeerMaxWorld];  // exchange buffer of every rank as mapped into this process (own included)
+};
+struct FinishJob {
+    const void* x;
+    long long n, inner;
+    // fringe: [0], [1] ranges of flat pairs (f, f+inner), f in [lo, lo+cnt) -> added;
+    //         [2], [3] ranges of edge indices t = o*inner + i (pair f = (o*n + n-1)*inner + i) -> subtracted
+    long long range_lo[4], range_cnt[4];
+    uint32_t mask_lo, mask_hi;
+    const Workspace* ws;
+    unsigned long long* counts;  // nbits*4
+    int accumulate;              // counts += table (atomics) instead of counts = table
+    double* mi;                  // nbits doubles, or nullptr: no K2
+    int set_zero;
+    double z;
+    PeerExchange px;
+};
+// up to this many fringe pairs go through the finish kernel; larger leftovers keep their own generic launches
+constexpr long long kFinishMaxFlat = 16384, kFinishMaxEdges = 4096;
+cudaError_t launch_finish(const CountJob& job, const FinishJob& J, cudaStream_t stream);
 // K2 on `nbatch` consecutive (nbits,2,2) tables -> mi[nbatch][nbits]
 cudaError_t launch_mutual_information(const unsigned long long* counts, int nbits, long long nbatch, int set_zero,
                                       double z_quantile, double* mi, cudaStream_t stream);
 cudaError_t launch_bitround(void* x, int dtype, int64_t numel, int keepbits, cudaStream_t stream);
+// dst = bitround(src); src == dst: in place, otherwise the arrays must not overlap
+cudaError_t launch_bitround_to(const void* src, void* dst, int dtype, int64_t numel, int keepbits, cudaStream_t stream);
 // K4: byte (bits == false) or bit (bits == true) shuffle of numel elements of itemsize bytes,
 // forward or inverse; src and dst must not overlap.  drop_bits > 0 (forward only): the elements are
 // bitrounded (K3's arithmetic, that many trailing mantissa bits dropped) on their way through.

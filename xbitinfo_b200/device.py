@@ -98,6 +98,39 @@ class PairCounter:
                 self.workspace.data_ptr(), self.workspace.numel(), _stream_ptr(x.device))
         nat.check(rc)
 
+    def bitinformation(self, x: torch.Tensor, axis: int = -1, *, transform: bool = True, masked_value=None,
+                       set_zero_insignificant: bool = False, confidence: float = 0.99, dims=None,
+                       with_information: bool = True, peers=None, flavour: str | None = None):
+        """K1 + K2 in ONE call of the C ABI (``xbi_bitinformation_dev``): ``counts`` is OVERWRITTEN with the pair
+        histogram of ``x`` along ``axis`` and the information per bit lands in ``mi`` (returned; ``None`` with
+        ``with_information=False``).  Three launches: workspace clear, counting kernel, finish kernel.
+
+        ``peers`` (a :class:`xbitinfo_b200.distributed.PeerExchange`): ``x`` is this rank's slab of a sharded
+        variable and the finish kernel all-reduces the table over NVLink peer memory before K2
+        (``xbi_bitinformation_dev_allreduce``); ``counts`` and ``mi`` then hold the global result on every rank."""
+        require_cuda_tensor(x)
+        if torch_dtype_code(x.dtype) != self.code:
+            raise ValueError("dtype differs from the counter's dtype")
+        outer, n, inner = dims if dims is not None else split_axis(tuple(x.shape), axis)
+        np_dtype = numpy_dtype_of(x)
+        flags, bits = nat.mask_spec(np_dtype, masked_value)
+        if np_dtype.kind == "f" and transform:
+            flags |= nat.SIGNED_EXPONENT
+        if flavour is not None:
+            flags |= {"sparse": nat.FORCE_SPARSE, "dense": nat.FORCE_DENSE, "generic": nat.FORCE_GENERIC}[flavour]
+        mi_ptr = self.mi.data_ptr() if with_information else None
+        with torch.cuda.device(x.device):
+            common = (x.data_ptr(), self.code, outer, n, inner, flags, bits, int(bool(set_zero_insignificant)),
+                      float(confidence), self.counts.data_ptr(), mi_ptr, self.workspace.data_ptr(),
+                      self.workspace.numel(), _stream_ptr(x.device))
+            if peers is None or peers.world == 1:
+                rc = nat.lib().xbi_bitinformation_dev(*common)
+            else:
+                rc = nat.lib().xbi_bitinformation_dev_allreduce(*common, peers.world, peers.rank, peers.next_epoch(),
+                                                                peers.table, float(peers.timeout_s))
+        nat.check(rc)
+        return self.mi if with_information else None
+
     def information(self, set_zero_insignificant: bool = False, confidence: float = 0.99) -> torch.Tensor:
         """K2 on the current counts -> float64[nbits] on the device."""
         with torch.cuda.device(self.device):
@@ -116,6 +149,23 @@ def bitround_(x: torch.Tensor, keepbits: int) -> torch.Tensor:
         rc = nat.lib().xbi_bitround_inplace(x.data_ptr(), code, x.numel(), int(keepbits), _stream_ptr(x.device))
     nat.check(rc)
     return x
+
+
+def bitround(x: torch.Tensor, keepbits: int, out: torch.Tensor | None = None) -> torch.Tensor:
+    """K3 into a second tensor (``xbi_bitround``): ``x`` is read once and left untouched, the rounded values are
+    written once -- the "new array, input not modified" contract of ``_np_bitround`` without a clone."""
+    require_cuda_tensor(x)
+    code = torch_dtype_code(x.dtype)
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        require_cuda_tensor(out)
+        if out.dtype != x.dtype or out.numel() != x.numel() or out.device != x.device:
+            raise ValueError("`out` must match the input in dtype, size and device")
+    with torch.cuda.device(x.device):
+        rc = nat.lib().xbi_bitround(x.data_ptr(), out.data_ptr(), code, x.numel(), int(keepbits), _stream_ptr(x.device))
+    nat.check(rc)
+    return out
 
 
 # --------------------------------------------------------------------------------------

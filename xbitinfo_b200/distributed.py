@@ -115,6 +115,97 @@ def allreduce_counts(counts, group=None):
     return counts
 
 
+class PeerExchange:
+    """Exchange buffers of the fused all-reduce (``xbi_bitinformation_dev_allreduce``): one small device buffer
+    per rank, allocated by the library, shared with the other ranks of the node through CUDA IPC handles that
+    travel over ``torch.distributed.all_gather_object`` (plumbing), and mapped into this process.  The finish
+    kernel of every counting call then pushes the rank's ``int64[nbits,2,2]`` table into the peers' buffers over
+    NVLink and sums what the peers pushed -- no NCCL call, no extra launch.
+
+    Raises (``XbiError`` / ``RuntimeError``) where the ranks are not GPUs of one node or IPC is not permitted;
+    callers fall back to :func:`allreduce_counts` (NCCL) and say so."""
+
+    def __init__(self, device, group=None, timeout_s: float = 20.0):
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _native as nat
+
+        if not is_initialized():
+            raise RuntimeError("PeerExchange needs an initialised torch.distributed process group")
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        if self.world > 8:
+            raise RuntimeError("the peer all-reduce spans the GPUs of one node (world <= 8)")
+        self.timeout_s = float(timeout_s)
+        self.device = torch.device(device)
+        self._epoch = 0
+        self._lib = nat.lib()
+        self._own = C.c_void_p()
+        self._mapped = []
+        handle = C.create_string_buffer(int(self._lib.xbi_peer_handle_bytes()))
+        with torch.cuda.device(self.device):
+            nat.check(self._lib.xbi_peer_create(C.byref(self._own), handle))
+            gathered = [None] * self.world
+            dist.all_gather_object(gathered, (self.rank, bytes(handle.raw)), group=group)
+            ptrs = [None] * self.world
+            failure = None
+            for r, raw in gathered:
+                if r == self.rank:
+                    ptrs[r] = self._own.value
+                    continue
+                mapped = C.c_void_p()
+                rc = self._lib.xbi_peer_open(C.create_string_buffer(raw, len(raw)), C.byref(mapped))
+                if rc != 0:
+                    failure = self._lib.xbi_last_error().decode("utf-8", "replace")
+                    break
+                self._mapped.append(mapped)
+                ptrs[r] = mapped.value
+            # every rank must know whether every rank succeeded, or some would wait for flags that never come
+            ok = [None] * self.world
+            dist.all_gather_object(ok, failure, group=group)
+            if any(f is not None for f in ok):
+                self.close()
+                raise RuntimeError("CUDA IPC mapping of the peer exchange buffers failed: "
+                                   + "; ".join(f"rank {i}: {f}" for i, f in enumerate(ok) if f is not None))
+        self.table = (C.c_void_p * self.world)(*ptrs)
+
+    def next_epoch(self) -> int:
+        self._epoch += 1
+        return self._epoch
+
+    def failed_epoch(self) -> int:
+        """Epoch of a wait that timed out (0: none): results from that call on are invalid."""
+        import ctypes as C
+
+        out = C.c_ulonglong(0)
+        from . import _native as nat
+
+        nat.check(self._lib.xbi_peer_error_epoch(self._own, C.byref(out)))
+        return int(out.value)
+
+    def close(self) -> None:
+        import torch
+
+        with torch.cuda.device(self.device):
+            torch.cuda.synchronize()
+            if is_initialized():  # a peer may still be pushing into this rank's buffer
+                import torch.distributed as dist
+
+                try:
+                    dist.barrier()
+                except Exception:
+                    pass
+            for m in self._mapped:
+                self._lib.xbi_peer_close(m)
+            self._mapped = []
+            if self._own:
+                self._lib.xbi_peer_destroy(self._own)
+                self._own = None
+
+
 def sharded_bitinformation(local_slab, axis: int, masked_value=None, set_zero_insignificant: bool = False,
                            confidence: float = 0.99, return_counts: bool = False, device=None):
     """Information per bit of the GLOBAL array whose rank-local slab (as cut by

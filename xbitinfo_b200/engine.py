@@ -138,12 +138,17 @@ def _bitinformation_device(x, axis, masked_value, set_zero, confidence, return_c
     if not x.is_contiguous():
         x = x.contiguous()
     pc = PairCounter(x.dtype, x.device)
-    pc.add(x, axis, masked_value=masked_value)
     if sharded:
         from .distributed import allreduce_counts
 
+        # per-rank table (counts only), one all-reduce, K2 on every rank
+        pc.bitinformation(x, axis, masked_value=masked_value, with_information=False)
         allreduce_counts(pc.counts)
-    mi = pc.information(set_zero, confidence).cpu().numpy()
+        mi = pc.information(set_zero, confidence).cpu().numpy()
+    else:
+        # K1 + K2 in one call of the C ABI (workspace clear, counting kernel, finish kernel)
+        mi = pc.bitinformation(x, axis, masked_value=masked_value, set_zero_insignificant=set_zero,
+                               confidence=confidence).cpu().numpy()
     if return_counts:
         return mi, pc.counts.cpu().numpy()
     return mi
@@ -153,9 +158,9 @@ def bitround(data, keepbits: int, device: int | None = None):
     """New array rounded to ``keepbits`` mantissa bits (K3); the input is not modified
     (``xbitinfo/bitround.py:10``).  numpy in -> numpy out, CUDA tensor in -> CUDA tensor out."""
     if _is_torch_tensor(data):
-        from .device import bitround_
+        from .device import bitround as bitround_to
 
-        return bitround_(data.contiguous().clone(), keepbits)
+        return bitround_to(data.contiguous(), keepbits)  # one read, one write; the input is left as it is
     x = np.asarray(data)
     if x.dtype.kind != "f" or x.dtype.itemsize > 8:
         raise TypeError("Only float arrays (16-64bit) can be bit-rounded")

@@ -153,6 +153,13 @@ def _stream(source, axes, plan, masked_value, set_zero_insignificant, confidence
     pinned = [torch.empty(max_rows * inner_elems, dtype=tdtype).pin_memory() for _ in range(2)]
     staged = [torch.empty(max_rows * inner_elems, dtype=tdtype, device=dev) for _ in range(2)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    # the counters were zero-filled and the staging buffers allocated on the current stream: the side streams
+    # are not ordered after it unless told to be
+    for s_ in streams:
+        s_.wait_stream(torch.cuda.current_stream(dev))
+    for buf in staged:
+        for s_ in streams:
+            buf.record_stream(s_)
     done = [None, None]
     for i, (lo, hi, halo) in enumerate(plan):
         b = i & 1
