@@ -365,23 +365,38 @@ def run_ours(args):
         xdist.allreduce_counts(pc.counts)                                     # the path's one collective
         return pc.information(False)                                          # K2
 
+    def trial(fn, steps=15):
+        """ms per step (max over ranks) and the per-step time outside the counting kernel (events around that kernel on
+        its own stream; max over ranks) -- the second is what the collectives differ in, the first drifts with clocks."""
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        sync_all()
+        nat.profile_enable(True)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        sync_all()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        sync_all()
+        el = e0.elapsed_time(e1)
+        kms, kn, _ = nat.profile_collect()
+        nat.profile_enable(False)
+        return {"ms_per_step": dist_max(el) / steps, "step_minus_kernel_us": dist_max(1e3 * (el - kms) / steps)}
+
     collective = {"kind": "none"}
     step = step_local
     if world > 1:
-        trials = {}
-        for _ in range(max(args.warmup, 3)):
-            step_nccl()
-        trials["nccl_ms_per_step"] = _time_steps(step_nccl, 10, sync_all, dist_max)
+        trials = {"nccl": trial(step_nccl)}
         if peers is not None:
-            for _ in range(max(args.warmup, 3)):
-                step_peer()
-            trials["peer_ms_per_step"] = _time_steps(step_peer, 10, sync_all, dist_max)
-        use_peer = peers is not None and (args.collective == "peer" or trials["peer_ms_per_step"] <= trials["nccl_ms_per_step"])
+            trials["peer"] = trial(step_peer)
+        use_peer = peers is not None and (
+            args.collective == "peer" or trials["peer"]["step_minus_kernel_us"] <= trials["nccl"]["step_minus_kernel_us"])
         step = step_peer if use_peer else step_nccl
         collective = {
             "kind": ("push over NVLink peer memory inside the finish kernel (xbi_bitinformation_dev_allreduce)" if use_peer
                      else "torch.distributed.all_reduce (NCCL) on int64[32,2,2] + separate K2 launch"),
-            "trial_10_steps": trials, "peer_unavailable": peer_error,
+            "trial_15_steps": trials, "peer_unavailable": peer_error,
         }
 
     for _ in range(max(args.warmup, 3)):

@@ -119,6 +119,7 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, 
         const int64_t npairs_flat = numel - job.inner;
         int64_t dlo = 0, dhi = 0;
         bool edges_done = false;
+        RowsLeftovers left;  // what the TMA kernel's producer warps counted on top of [dlo, dhi)
         if (!(flags & XBI_FORCE_GENERIC)) {
             const bool timed = g_prof.enabled && g_prof.used < Profile::kMax;
             // masked modes: sample the density of validity boundaries; the sparse and the dense flavour of
@@ -133,7 +134,7 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, 
             if (timed) XBI_CUDA(cudaEventRecord(prof_event(2 * g_prof.used), stream), "cudaEventRecord");
             cudaError_t fast;
             if (job.inner == 1)
-                fast = launch_pairs_tma(job, npairs_flat, ws, stream, &dlo, &dhi, &edges_done);
+                fast = launch_pairs_tma(job, npairs_flat, ws, stream, &dlo, &dhi, &edges_done, &left);
             else
                 fast = launch_pairs_cols(job, ws, stream, &dlo, &dhi, &edges_done);
             if (fast == cudaErrorSymbolNotFound) {
@@ -148,6 +149,7 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, 
                 if (!warned.exchange(true))
                     std::fprintf(stderr, "xbitinfo_b200: TMA fast path unavailable, counting on the generic kernel (XBI_ALLOW_GENERIC=1)\n");
                 dlo = dhi = 0;
+                left = RowsLeftovers{};
             } else if (fast != cudaSuccess) {
                 return fail_cuda(fast, job.inner == 1 ? "pair counting (TMA rows)" : "pair counting (column walkers)");
             }
@@ -159,10 +161,11 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, 
                 }
             }
         }
-        if (dhi <= dlo) { dlo = 0; dhi = 0; edges_done = false; }
+        if (dhi <= dlo) { dlo = 0; dhi = 0; edges_done = false; left = RowsLeftovers{}; }
         // what the fast kernel left: flat pairs [0, dlo) and [dhi, npairs_flat) ...
         J.range_lo[0] = 0;   J.range_cnt[0] = dlo;
         J.range_lo[1] = dhi; J.range_cnt[1] = npairs_flat - dhi;
+        if (left.flat) J.range_cnt[0] = J.range_cnt[1] = 0;  // (the TMA kernel's producer warps took them along)
         if (J.range_cnt[0] + J.range_cnt[1] > kFinishMaxFlat) {
             XBI_CUDA(launch_pairs_generic_flat(job, 0, dlo, &ws->plus, stream), "pair counting (generic, head)");
             XBI_CUDA(launch_pairs_generic_flat(job, dhi, npairs_flat, &ws->plus, stream), "pair counting (generic, tail)");
@@ -180,7 +183,7 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, 
             J.range_lo[2] = 0; J.range_cnt[2] = nedges;
         }
         for (int r = 2; r < 4; ++r)
-            if (J.range_cnt[r] < 0) J.range_cnt[r] = 0;
+            if (J.range_cnt[r] < 0 || left.edges) J.range_cnt[r] = 0;
         if (J.range_cnt[2] + J.range_cnt[3] > kFinishMaxEdges) {
             for (int r = 2; r < 4; ++r)
                 XBI_CUDA(launch_pairs_generic_edges(job, J.range_lo[r], J.range_lo[r] + J.range_cnt[r], &ws->minus, stream),

@@ -32,6 +32,7 @@ constexpr int kCountWarps = kCountThreads / 32;
 constexpr int kThreads = kCountThreads + 32;  // + producer warp
 constexpr int kRowBytes = 128;
 constexpr int kBoxRows = 240;  // rows per TMA box (<= 256)
+constexpr long long kRowsFringeMax = 32768;  // leftover pairs (and row ends) the producer warps take along
 
 template <int KIND>
 struct Seg {
@@ -90,11 +91,84 @@ __device__ __forceinline__ void lds_elem(uint32_t addr, uint32_t (&w)[BYTES == 8
     }
 }
 
+// What the TMA ranges leave over -- the elements before the first 16-byte boundary, the ragged tail shorter
+// than one stage, and the row ends among them -- is a few thousand pairs at most.  Counted after the kernel by a
+// single CTA they cost 25-40 us per call (round 1: a (1,1,1)-grid generic kernel; then the finish kernel); here
+// the PRODUCER warps take them, 32 pairs per CTA and round, once all their TMA loads are issued and while the
+// counting warps are still busy with the last stages: per-bit __ballot_sync + __popc on the three explicit
+// streams (a, b, a&b) of the pairs' transformed words, lane k keeping the totals of bit k.  Nothing is left for
+// the critical path.
+struct RowsFringe {
+    const void* x;  // element 0 of the array
+    long long n;    // length of the analysed (last) axis
+    // [0], [1]: flat pairs (f, f+1), f in [lo, lo+cnt) -> plus sums;
+    // [2], [3]: row ends t in [lo, lo+cnt), pair (t*n + n-1, t*n + n) -> minus sums
+    long long lo[4], cnt[4];
+};
+
+template <int KIND, int MT, bool XFORM>
+static __device__ __noinline__ void count_fringe(const RowsFringe& fr, uint32_t mask_lo, uint32_t mask_hi, uint32_t lane,
+                                                 RawSums* __restrict__ plus, RawSums* __restrict__ minus) {
+    using E = Elem<KIND>;
+    constexpr int NW = E::kWords;
+#pragma unroll 1
+    for (int kind = 0; kind < 2; ++kind) {
+        const long long c0 = fr.cnt[2 * kind], total = c0 + fr.cnt[2 * kind + 1];
+        if (total <= 0) continue;
+        unsigned long long accA[NW], accB[NW], accAB[NW], nvalid = 0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) { accA[w] = 0; accB[w] = 0; accAB[w] = 0; }
+#pragma unroll 1
+        for (long long base = (long long)blockIdx.x * 32; base < total; base += (long long)gridDim.x * 32) {
+            const long long idx = base + lane;
+            uint32_t a[NW], b[NW];
+#pragma unroll
+            for (int w = 0; w < NW; ++w) { a[w] = 0; b[w] = 0; }
+            bool ok = false;
+            if (idx < total) {
+                long long f = idx < c0 ? fr.lo[2 * kind] + idx : fr.lo[2 * kind + 1] + (idx - c0);
+                if (kind == 1) f = f * fr.n + (fr.n - 1);
+                E::load(fr.x, f, a);
+                E::load(fr.x, f + 1, b);
+                ok = true;
+                if (MT == kMaskNaN) ok = !(E::is_nan(a) || E::is_nan(b));
+                if (MT == kMaskValue) ok = !(E::equals(a, mask_lo, mask_hi) || E::equals(b, mask_lo, mask_hi));
+                if (XFORM) { E::transform(a); E::transform(b); }
+                if (!ok) {
+#pragma unroll
+                    for (int w = 0; w < NW; ++w) { a[w] = 0; b[w] = 0; }
+                }
+            }
+            nvalid += (unsigned long long)__popc(__ballot_sync(0xFFFFFFFFu, ok));
+#pragma unroll
+            for (int w = 0; w < NW; ++w) {
+                const uint32_t ab = a[w] & b[w];
+#pragma unroll
+                for (int bit = 0; bit < 32; ++bit) {
+                    const uint32_t ca = __popc(__ballot_sync(0xFFFFFFFFu, (a[w] >> bit) & 1u));
+                    const uint32_t cb = __popc(__ballot_sync(0xFFFFFFFFu, (b[w] >> bit) & 1u));
+                    const uint32_t cab = __popc(__ballot_sync(0xFFFFFFFFu, (ab >> bit) & 1u));
+                    if (lane == (uint32_t)bit) { accA[w] += ca; accB[w] += cb; accAB[w] += cab; }
+                }
+            }
+        }
+        RawSums* dst = kind == 0 ? plus : minus;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+            const int j = w * 32 + (int)lane;
+            if (accA[w]) atomicAdd(&dst->sums[S_A][j], accA[w]);
+            if (accB[w]) atomicAdd(&dst->sums[S_B][j], accB[w]);
+            if (accAB[w]) atomicAdd(&dst->sums[S_AB][j], accAB[w]);
+        }
+        if (lane == 0 && nvalid) atomicAdd(&dst->npairs, nvalid);
+    }
+}
+
 template <int KIND, int MASK, bool XFORM>
 __global__ void __launch_bounds__(kThreads, 1)
 k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restrict__ region, long long nstages,
                  uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst, RawSums* __restrict__ dst_minus,
-                 long long row_len, long long region_phase) {
+                 long long row_len, long long region_phase, const __grid_constant__ RowsFringe fringe) {
     using S = Seg<KIND>;
     constexpr int BYTES = S::kBytes;
     constexpr int NL = S::kLaddersPerStream;
@@ -271,6 +345,8 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
             for (int o = 16; o > 0; o >>= 1) nsum += __shfl_xor_sync(0xFFFFFFFFu, nsum, o);
             if (lane == 0 && nsum) atomicAdd(&dst_minus->npairs, nsum);
         }
+        // the leftovers of the TMA ranges (see RowsFringe), while the counting warps finish the last stages
+        count_fringe<KIND, MT, XFORM>(fringe, mask_lo, mask_hi, lane, dst, dst_minus);
         return;
     }
 
@@ -575,7 +651,7 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
 // ---------------------------------------------------------------------------------
 template <int KIND, int MASK, bool XFORM>
 cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
-                        int64_t* done_hi, bool* edges_done) {
+                        int64_t* done_hi, bool* edges_done, RowsLeftovers* left) {
     using S = Seg<KIND>;
     const int bytes = S::kBytes;
     const uintptr_t addr = reinterpret_cast<uintptr_t>(job.x);
@@ -620,35 +696,65 @@ cudaError_t launch_rows(const CountJob& job, int64_t npairs_flat, Workspace* ws,
     // rows long enough that a stage holds fewer than 32 row ends: the producer warp removes the
     // row-straddling pairs in shared memory (one per lane); shorter rows go to the edge pass
     const bool in_kernel_edges = !S::k64 && job.n > S::kElemsPerStage / 32 && job.outer > 1;
+    // the leftovers the producer warps take along (both flavours of a masked mode get the same plan; only the
+    // one that runs counts them)
+    const int64_t dlo = head, dhi = head + nstages * S::kElemsPerStage;
+    RowsFringe fr = {};
+    fr.x = job.x;
+    fr.n = job.n;
+    RowsLeftovers lv = {};
+    if (dlo + (npairs_flat - dhi) <= kRowsFringeMax) {
+        fr.lo[0] = 0;   fr.cnt[0] = dlo;
+        fr.lo[1] = dhi; fr.cnt[1] = npairs_flat - dhi;
+        lv.flat = true;
+    }
+    {
+        // row ends: t in [0, outer-1) sits at flat index t*n + n-1; with in-kernel edges those inside [dlo, dhi) are
+        // done by the producer warps from shared memory
+        const int64_t nedges = job.outer - 1;
+        int64_t e_lo[2] = {0, 0}, e_cnt[2] = {nedges, 0};
+        if (in_kernel_edges) {
+            e_cnt[0] = dlo / job.n;
+            e_lo[1] = dhi / job.n;
+            e_cnt[1] = nedges - dhi / job.n;
+        }
+        for (int i = 0; i < 2; ++i)
+            if (e_cnt[i] < 0) e_cnt[i] = 0;
+        if (e_cnt[0] + e_cnt[1] <= kRowsFringeMax) {
+            for (int i = 0; i < 2; ++i) { fr.lo[2 + i] = e_lo[i]; fr.cnt[2 + i] = e_cnt[i]; }
+            lv.edges = true;
+        }
+    }
     kern<<<grid, kThreads, smem_bytes<KIND>(), stream>>>(tmap, region, (long long)nstages, (uint32_t)job.mask_bits,
                                                           (uint32_t)(job.mask_bits >> 32), &ws->plus, &ws->minus,
                                                           in_kernel_edges ? (long long)job.n : 0ll,
-                                                          (long long)(head % job.n));
+                                                          (long long)(head % job.n), fr);
     *edges_done = in_kernel_edges;
+    *left = lv;
     note_fast_launch();
-    *done_lo = head;
-    *done_hi = head + nstages * S::kElemsPerStage;
+    *done_lo = dlo;
+    *done_hi = dhi;
     return cudaGetLastError();
 }
 
 template <int KIND>
 cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, Workspace* dst, cudaStream_t stream, int64_t* lo,
-                          int64_t* hi, bool* ed) {
+                          int64_t* hi, bool* ed, RowsLeftovers* lv) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (job.transform) {
         if constexpr (isf) {
             switch (job.mask_mode) {
-                case kMaskNone: return launch_rows<KIND, kMaskNone, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                case kMaskNone: return launch_rows<KIND, kMaskNone, true>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
                 // masked: both flavours are launched, one of them returns at once (see xbi_internal.h)
                 case kMaskNaN: {
-                    const cudaError_t e = launch_rows<KIND, kMaskNaN, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                    const cudaError_t e = launch_rows<KIND, kMaskNaN, true>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
                     if (e != cudaSuccess || *hi <= *lo) return e;
-                    return launch_rows<KIND, kMaskNaNDense, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                    return launch_rows<KIND, kMaskNaNDense, true>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
                 }
                 default: {
-                    const cudaError_t e = launch_rows<KIND, kMaskValue, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                    const cudaError_t e = launch_rows<KIND, kMaskValue, true>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
                     if (e != cudaSuccess || *hi <= *lo) return e;
-                    return launch_rows<KIND, kMaskValueDense, true>(job, npairs_flat, dst, stream, lo, hi, ed);
+                    return launch_rows<KIND, kMaskValueDense, true>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
                 }
             }
         }
@@ -658,28 +764,29 @@ cudaError_t dispatch_rows(const CountJob& job, int64_t npairs_flat, Workspace* d
     // mask without the transform is rare enough to stay on the generic kernel
     if (job.mask_mode == kMaskNaN) return cudaSuccess;
     constexpr int UK = (KIND == kF16) ? kU16 : (KIND == kF32) ? kU32 : (KIND == kF64) ? kU64 : KIND;
-    if (job.mask_mode == kMaskNone) return launch_rows<UK, kMaskNone, false>(job, npairs_flat, dst, stream, lo, hi, ed);
-    const cudaError_t e = launch_rows<UK, kMaskValue, false>(job, npairs_flat, dst, stream, lo, hi, ed);
+    if (job.mask_mode == kMaskNone) return launch_rows<UK, kMaskNone, false>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
+    const cudaError_t e = launch_rows<UK, kMaskValue, false>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
     if (e != cudaSuccess || *hi <= *lo) return e;
-    return launch_rows<UK, kMaskValueDense, false>(job, npairs_flat, dst, stream, lo, hi, ed);
+    return launch_rows<UK, kMaskValueDense, false>(job, npairs_flat, dst, stream, lo, hi, ed, lv);
 }
 
 }  // namespace
 
 cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, Workspace* dst, cudaStream_t stream,
-                             int64_t* done_lo, int64_t* done_hi, bool* edges_done) {
+                             int64_t* done_lo, int64_t* done_hi, bool* edges_done, RowsLeftovers* leftovers) {
     *done_lo = 0;
     *done_hi = 0;
     *edges_done = false;
+    *leftovers = RowsLeftovers{};
     if (job.inner != 1) return cudaSuccess;  // strided adjacency: see xbi_count_cols.cu
     switch (job.dtype) {
-        case XBI_U8: return dispatch_rows<kU8>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
-        case XBI_U16: return dispatch_rows<kU16>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
-        case XBI_U32: return dispatch_rows<kU32>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
-        case XBI_U64: return dispatch_rows<kU64>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
-        case XBI_F16: return dispatch_rows<kF16>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
-        case XBI_F32: return dispatch_rows<kF32>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
-        case XBI_F64: return dispatch_rows<kF64>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done);
+        case XBI_U8: return dispatch_rows<kU8>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done, leftovers);
+        case XBI_U16: return dispatch_rows<kU16>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done, leftovers);
+        case XBI_U32: return dispatch_rows<kU32>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done, leftovers);
+        case XBI_U64: return dispatch_rows<kU64>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done, leftovers);
+        case XBI_F16: return dispatch_rows<kF16>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done, leftovers);
+        case XBI_F32: return dispatch_rows<kF32>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done, leftovers);
+        case XBI_F64: return dispatch_rows<kF64>(job, npairs_flat, dst, stream, done_lo, done_hi, edges_done, leftovers);
         default: return cudaErrorInvalidValue;
     }
 }

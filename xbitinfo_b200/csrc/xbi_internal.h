@@ -73,8 +73,14 @@ cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, R
 // allow, reports the flat range it covered in [*done_lo, *done_hi) (empty if none), and
 // leaves the rest to the generic kernel.
 // *edges_done: the kernel also removed the row-straddling pairs inside [*done_lo, *done_hi).
+// *leftovers: what else the kernel counted itself (its producer warps, see RowsFringe in xbi_count_tma.cu):
+//   flat  -- the flat pairs outside [*done_lo, *done_hi) as well, i.e. every flat pair of the job;
+//   edges -- every row-straddling pair that *edges_done does not cover, i.e. all of them.
+struct RowsLeftovers {
+    bool flat = false, edges = false;
+};
 cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream,
-                             int64_t* done_lo, int64_t* done_hi, bool* edges_done);
+                             int64_t* done_lo, int64_t* done_hi, bool* edges_done, RowsLeftovers* leftovers);
 
 // Column walkers for inner > 1 (16-byte aligned rows); covers flat pairs [*done_lo, *done_hi).
 // *edges_done: the block-boundary pairs have been subtracted as well (all of them).
