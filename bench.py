@@ -709,8 +709,10 @@ def run_configs(args, dev, peak):
         shape = (days, 75, 1080, 1440)
         x = _synth_nd(shape, torch.float64, 2, 77, dev, piece_bytes=1 << 29)
         land = torch.rand((1080, 1440), generator=torch.Generator(device=dev).manual_seed(5), device=dev)
-        # ~30 % land in blobs: a smooth random field thresholded (coast lines, not salt and pepper)
-        land = torch.nn.functional.avg_pool2d(land[None, None], 31, stride=1, padding=15)[0, 0]
+        # ~30 % land as a few continents: white noise box-filtered twice at 255 points and thresholded (a handful of
+        # coast-line crossings per column, like a real 1/4-degree ocean grid; not salt and pepper)
+        for _ in range(2):
+            land = torch.nn.functional.avg_pool2d(land[None, None], 255, stride=1, padding=127)[0, 0]
         land = land < torch.quantile(land.flatten()[::7], 0.30)
         res = {}
         for name, mv in (("nan", float("nan")), ("minus999", -999.0)):
@@ -734,7 +736,8 @@ def run_configs(args, dev, peak):
                         f"{x.numel() * 8 / 1e9:.1f} GB (the full 340 GB field streams through the same accumulate-only "
                         "counts in time slabs), ~30 % land mask constant over time/level, dim='latitude' (inner = 1440), "
                         "masked_value + set_zero_insignificant=True, confidence=0.99",
-            "land_fraction": float(land.float().mean()), "kernel": "k_pairs_cols<f64, masked sparse flavour>",
+            "land_fraction": float(land.float().mean()),
+            "coast_crossings_per_column": float((land[1:] != land[:-1]).float().sum(0).mean()), "kernel": "k_pairs_cols<f64, masked sparse flavour>",
             "masked_value_nan": res["nan"], "masked_value_minus999": res["minus999"],
         }
         del x, land
@@ -746,36 +749,39 @@ def run_configs(args, dev, peak):
     try:
         shape = (720, 137, 256, 512)
         x = _synth_nd(shape, torch.float32, 3, 91, dev)
-        pc = [PairCounter(x.dtype, dev) for _ in range(4)]
+        from xbitinfo_b200.device import MultiAxisCounter
 
-        def all_dims():
-            for a in range(4):
-                pc[a].bitinformation(x, a, masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99)
-
-        ms = timed(all_dims)
+        kw = dict(masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99)
+        mc = MultiAxisCounter(x.dtype, 4, dev)
+        ms = timed(lambda: mc.bitinformation(x, [0, 1, 2, 3], **kw))       # xbi_bitinformation_dev_multi
+        pc = PairCounter(x.dtype, dev)
         per_axis = []
         for a in range(4):
-            m = timed(lambda a=a: pc[a].bitinformation(x, a, masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99))
+            m = timed(lambda a=a: pc.bitinformation(x, a, **kw))            # one single-axis pass, for scale
             per_axis.append({"axis": a, "ms": m, "GBps": x.numel() * 4 / (m * 1e-3) / 1e9})
+        m_xy = timed(lambda: mc2.bitinformation(x, [2, 3], **kw)) if (mc2 := MultiAxisCounter(x.dtype, 2, dev)) else None
         slab = x[:8].contiguous()
         hs = slab.cpu().numpy()
-        exact = True
-        for a in range(4):
-            p = PairCounter(x.dtype, dev)
-            p.bitinformation(slab, a, masked_value=float("nan"))
-            exact &= bool(np.array_equal(p.counts.cpu().numpy(), fc.count_pairs(hs, a, masked_value=float("nan"))))
+        ms_slab = MultiAxisCounter(x.dtype, 4, dev)
+        ms_slab.bitinformation(slab, [0, 1, 2, 3], masked_value=float("nan"))
+        got = ms_slab.counts.cpu().numpy()
+        exact = all(bool(np.array_equal(got[a], fc.count_pairs(hs, a, masked_value=float("nan")))) for a in range(4))
         nb = x.numel() * 4
         out["c3"] = {
             "workload": "configs[3]: one of the 10 float32 variables, (720,137,256,512) = 51.7 GB resident, analysed along "
-                        "every dim (get_bitinformation(ds) with dim=None), masked_value=NaN (API default), "
+                        "every dim in one call (get_bitinformation(ds) with dim=None -> xbi_bitinformation_dev_multi: the two "
+                        "innermost dims in one read, the outer two one pass each), masked_value=NaN (API default), "
                         "set_zero_insignificant=True, confidence=0.99",
             "ms_all_dims": ms, "array_GBps": nb / (ms * 1e-3) / 1e9,       # the array's bytes once per all-dims job
             "value": 4 * nb / (ms * 1e-3) / 1e9, "unit": UNIT,              # (variable, dim) passes x bytes, SURVEY 8(d)
             "frac_of_measured_peak": 4 * nb / (ms * 1e-3) / 1e9 / peak,
-            "passes_equivalent": ms / min(p_["ms"] for p_ in per_axis),
+            "passes_equivalent": ms / min(p_["ms"] for p_ in per_axis),  # in units of the fastest single-axis pass
+            "ms_one_pass_per_axis": sum(p_["ms"] for p_ in per_axis),
+            "two_innermost_axes_in_one_read": {"ms": m_xy, "array_GBps": x.numel() * 4 / (m_xy * 1e-3) / 1e9,
+                                               "kernel": "k_pairs_cols_xy<f32>"},
             "per_axis": per_axis, "bit_exact_vs_fast_count": exact, "checked": "first 8 time steps, all four axes",
         }
-        del x, pc, slab
+        del x, pc, mc, mc2, ms_slab, slab
     except Exception as e:
         out["c3"] = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.empty_cache()

@@ -125,6 +125,24 @@ int xbi_bitinformation_dev(const void* x_dev, int dtype, int64_t outer, int64_t 
                            size_t workspace_bytes, void* stream);
 
 /*
+ * Several analysed dimensions of ONE device-resident array: get_bitinformation(ds) with dim=None, which the
+ * reference serves by looping the dimensions and running the backend once per dimension
+ * (xbitinfo/xbitinfo.py:373-406).  The C-contiguous array has `ndim` extents `shape`; counts_dev receives
+ * naxes*nbits*4 counters and mi_dev (may be NULL) naxes*nbits doubles in the order of `axes`; results are
+ * identical to naxes calls of xbi_bitinformation_dev.  When the two innermost dimensions are both asked for
+ * (4-byte element types, rows a multiple of 16 bytes) they are counted in ONE read of the array by a
+ * two-axis kernel; the remaining dimensions take one pass each.  With a mask flag the two-axis kernel counts
+ * as if nothing were masked and looks for masked elements on the way: the call then waits for the stream
+ * once, and if there are any recounts the two dimensions with the masked single-axis kernels.
+ * workspace: xbi_workspace_bytes_multi(naxes) bytes of device scratch.
+ */
+size_t xbi_workspace_bytes_multi(int naxes);
+int xbi_bitinformation_dev_multi(const void* x_dev, int dtype, int ndim, const int64_t* shape, int naxes,
+                                 const int* axes, unsigned flags, uint64_t mask_bits, int set_zero_insignificant,
+                                 double confidence, unsigned long long* counts_dev, double* mi_dev,
+                                 void* workspace_dev, size_t workspace_bytes, void* stream);
+
+/*
  * The same across the GPUs of one node, one process per GPU (every rank counts its slab, the
  * int64[nbits,2,2] tables are summed over the ranks, K2 runs on every rank): the all-reduce is part of the
  * finish kernel.  Each rank owns an exchange buffer (xbi_peer_create: xbi_peer_bytes() of device memory plus

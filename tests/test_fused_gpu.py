@@ -206,3 +206,82 @@ def test_peer_allreduce_protocol_on_one_gpu():
         torch.cuda.synchronize()
         for b in bufs:
             lib.xbi_peer_destroy(b)
+
+
+# ---------------------------------------------------------------------------------------
+# several dimensions of one device-resident array in one call (the two innermost in ONE read)
+# ---------------------------------------------------------------------------------------
+from xbitinfo_b200 import engine  # noqa: E402
+from xbitinfo_b200.device import MultiAxisCounter  # noqa: E402
+
+
+def _multi(x, axes, **kw):
+    t = x if isinstance(x, torch.Tensor) else _torch_view(np.ascontiguousarray(x))
+    return engine.bitinformation_multi(t, axes, return_counts=True, **kw)
+
+
+@pytest.mark.parametrize("shape", [(3, 70, 64), (5, 9, 33, 128), (2, 300, 8), (4, 97, 132), (1, 1, 130, 520), (70, 36)])
+@pytest.mark.parametrize("dtype", ["float32", "int32", "uint32"])
+def test_all_axes_in_one_call(shape, dtype):
+    """xbi_bitinformation_dev_multi == one single-axis call per axis == the oracle; the shapes walk through ragged
+    strips (rows that are not a multiple of 512 bytes), single-strip rows, tail groups and block boundaries."""
+    rng = np.random.default_rng(len(shape) * 1000 + shape[-1])
+    if dtype == "float32":
+        x = smooth_field(rng, shape, dtype, axis=-1, scale=0.2, base=3.0)
+    else:
+        info = np.iinfo(dtype)
+        x = rng.integers(info.min, info.max, size=shape, dtype=dtype, endpoint=True)
+    axes = list(range(len(shape)))
+    launches0 = nat.fast_path_launches()
+    got = _multi(x, axes)
+    for a, (mi, counts) in zip(axes, got):
+        if shape[a] < 2:
+            assert (counts == 0).all()
+            continue
+        ref_counts, npairs, ref_mi = bo.bitinformation(x, a)
+        assert np.array_equal(counts, ref_counts), (shape, dtype, a)
+        assert_mi_close(mi, ref_mi)
+    assert nat.fast_path_launches() > launches0
+    # a subset and a different order of the axes
+    got = _multi(x, axes[::-1][:2])
+    for a, (mi, counts) in zip(axes[::-1][:2], got):
+        assert np.array_equal(counts, bo.bitinformation(x, a)[0] if shape[a] >= 2 else np.zeros_like(counts))
+
+
+@pytest.mark.parametrize("masked_value", [float("nan"), -999.0])
+def test_all_axes_masked_clean_and_dirty(masked_value):
+    """With a mask the two-axis kernel counts optimistically and looks for masked elements: clean data takes the
+    one-read route, data that holds masked elements is recounted by the masked kernels -- same answers."""
+    rng = np.random.default_rng(17)
+    x = smooth_field(rng, (6, 80, 256), "float32", axis=2, scale=0.3, base=5.0)
+    for dirty in (False, True):
+        if dirty:
+            x[:, rng.random((80, 256)) < 0.3] = masked_value
+            x[3, 40, 100] = np.nan  # a NaN that is not the masked value in the -999 variant
+        got = _multi(x, [0, 1, 2], masked_value=masked_value, set_zero_insignificant=True, confidence=0.99)
+        for a, (mi, counts) in enumerate(got):
+            ref_counts, _, ref_mi = bo.bitinformation(x, a, masked_value=masked_value)
+            assert np.array_equal(counts, ref_counts), (masked_value, dirty, a)
+            single = engine.bitinformation(_torch_view(x), a, masked_value=masked_value, set_zero_insignificant=True)
+            assert np.array_equal(mi, single, equal_nan=True)
+
+
+def test_multi_axis_counter_reuse_and_errors():
+    rng = np.random.default_rng(2)
+    x = smooth_field(rng, (40, 50, 64), "float32", axis=1, scale=0.2)
+    t = torch.from_numpy(x).cuda()
+    mc = MultiAxisCounter(t.dtype, 3, t.device)
+    a = mc.bitinformation(t, [0, 1, 2]).clone()
+    c = mc.counts.clone()
+    b = mc.bitinformation(t, [0, 1, 2])
+    assert torch.equal(c, mc.counts) and torch.equal(a, b)
+    with pytest.raises(ValueError):
+        mc.bitinformation(t, [0, 1, 1])
+    with pytest.raises(ValueError):
+        mc.bitinformation(t, [0, 1])
+    # other widths fall back to one pass per axis inside the same call
+    for dtype in ("float64", "float16", "uint8"):
+        y = smooth_field(rng, (9, 30, 64), dtype, axis=1, scale=0.2, base=40.0) if dtype != "uint8" else \
+            rng.integers(0, 255, size=(9, 30, 64), dtype="uint8")
+        for a, (mi, counts) in enumerate(_multi(y, [0, 1, 2])):
+            assert np.array_equal(counts, bo.bitinformation(y, a)[0]), (dtype, a)

@@ -80,6 +80,11 @@ def lib() -> C.CDLL:
     L.xbi_mutual_information.argtypes = [vp, i32, i32, dbl, vp, vp]
     L.xbi_bitinformation_dev.restype = i32
     L.xbi_bitinformation_dev.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, vp, C.c_size_t, vp]
+    L.xbi_workspace_bytes_multi.restype = C.c_size_t
+    L.xbi_workspace_bytes_multi.argtypes = [i32]
+    L.xbi_bitinformation_dev_multi.restype = i32
+    L.xbi_bitinformation_dev_multi.argtypes = [vp, i32, i32, C.POINTER(i64), i32, C.POINTER(i32), u32, u64, i32, dbl, vp, vp,
+                                               vp, C.c_size_t, vp]
     L.xbi_bitinformation_dev_allreduce.restype = i32
     L.xbi_bitinformation_dev_allreduce.argtypes = [vp, i32, i64, i64, i64, u32, u64, i32, dbl, vp, vp, vp, C.c_size_t, vp,
                                                    i32, i32, u64, C.POINTER(vp), dbl]
@@ -144,7 +149,7 @@ EXPORTED_SYMBOLS = (
     "xbi_mutual_information_batched", "xbi_count_pairs_chunked", "xbi_bitround_chunked",
     "xbi_bitinformation_host_multi", "xbi_count_pairs_chunked_v", "xbi_bitround_chunked_v",
     "xbi_bitinformation_dev", "xbi_bitinformation_dev_allreduce", "xbi_peer_bytes", "xbi_peer_handle_bytes",
-    "xbi_bitround", "xbi_peer_create", "xbi_peer_open", "xbi_peer_close", "xbi_peer_destroy", "xbi_peer_error_epoch",
+    "xbi_bitround", "xbi_workspace_bytes_multi", "xbi_bitinformation_dev_multi", "xbi_peer_create", "xbi_peer_open", "xbi_peer_close", "xbi_peer_destroy", "xbi_peer_error_epoch",
 )
 
 

@@ -96,13 +96,8 @@ static bool allow_generic_only() {
     return on;
 }
 
-// K1 of one job into the workspace, then ONE finish launch: fringe pairs + combine (+ exchange) (+ K2).
-static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, cudaStream_t stream, const Finish& fin) {
-    const int64_t numel = job.outer * job.n * job.inner;
-    const bool nothing = numel == 0 || job.n < 2;  // no pairs along the axis
-    if (nothing && fin.accumulate && !fin.mi && fin.px.world <= 1) return XBI_OK;  // nothing to add
-    XBI_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), stream), "cudaMemsetAsync(workspace)");
-    FinishJob J = {};
+static FinishJob finish_job(const CountJob& job, const Workspace* ws, const Finish& fin) {
+    FinishJob J = {};  // (no leftover ranges)
     J.x = job.x;
     J.n = job.n;
     J.inner = job.inner > 0 ? job.inner : 1;
@@ -115,6 +110,16 @@ static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, 
     J.set_zero = fin.set_zero;
     J.z = fin.z;
     J.px = fin.px;
+    return J;
+}
+
+// K1 of one job into the workspace, then ONE finish launch: fringe pairs + combine (+ exchange) (+ K2).
+static int count_pairs_impl(const CountJob& job, unsigned flags, Workspace* ws, cudaStream_t stream, const Finish& fin) {
+    const int64_t numel = job.outer * job.n * job.inner;
+    const bool nothing = numel == 0 || job.n < 2;  // no pairs along the axis
+    if (nothing && fin.accumulate && !fin.mi && fin.px.world <= 1) return XBI_OK;  // nothing to add
+    XBI_CUDA(cudaMemsetAsync(ws, 0, sizeof(Workspace), stream), "cudaMemsetAsync(workspace)");
+    FinishJob J = finish_job(job, ws, fin);
     if (!nothing) {
         const int64_t npairs_flat = numel - job.inner;
         int64_t dlo = 0, dhi = 0;
@@ -453,6 +458,93 @@ int xbi_bitinformation_dev(const void* x_dev, int dtype, int64_t outer, int64_t 
     PeerExchange none = {};
     return bitinformation_dev_impl(x_dev, dtype, outer, n, inner, flags, mask_bits, set_zero_insignificant, confidence,
                                    counts_dev, mi_dev, workspace_dev, workspace_bytes, stream, none);
+}
+
+size_t xbi_workspace_bytes_multi(int naxes) {
+    return (size_t)(naxes > 0 ? naxes : 1) * sizeof(Workspace) + 64;  // one workspace per axis + the "masked element seen" flag
+}
+
+int xbi_bitinformation_dev_multi(const void* x_dev, int dtype, int ndim, const int64_t* shape, int naxes, const int* axes,
+                                 unsigned flags, uint64_t mask_bits, int set_zero_insignificant, double confidence,
+                                 unsigned long long* counts_dev, double* mi_dev, void* workspace_dev, size_t workspace_bytes,
+                                 void* stream) {
+    if (ndim < 1 || ndim > XBI_MAX_DIMS) return fail(XBI_ERR_ARG, "ndim must be in 1..XBI_MAX_DIMS");
+    if (naxes < 1 || naxes > XBI_MAX_DIMS) return fail(XBI_ERR_ARG, "naxes must be in 1..XBI_MAX_DIMS");
+    if (!shape || !axes) return fail(XBI_ERR_ARG, "null shape / axes pointer");
+    if (!counts_dev || !workspace_dev) return fail(XBI_ERR_ARG, "null counts or workspace pointer");
+    if (workspace_bytes < xbi_workspace_bytes_multi(naxes)) return fail(XBI_ERR_ARG, "workspace smaller than xbi_workspace_bytes_multi(naxes)");
+    if (reinterpret_cast<uintptr_t>(workspace_dev) % 8 != 0) return fail(XBI_ERR_ARG, "workspace must be 8-byte aligned");
+    int64_t numel = 1;
+    for (int d = 0; d < ndim; ++d) {
+        if (shape[d] < 0) return fail(XBI_ERR_ARG, "negative extent");
+        numel *= shape[d];
+    }
+    int pos_y = -1, pos_x = -1;  // where the two innermost axes sit in `axes`
+    for (int a = 0; a < naxes; ++a) {
+        if (axes[a] < 0 || axes[a] >= ndim) return fail(XBI_ERR_ARG, "axis out of range");
+        for (int b = 0; b < a; ++b)
+            if (axes[b] == axes[a]) return fail(XBI_ERR_ARG, "an axis is listed twice");
+        if (axes[a] == ndim - 2) pos_y = a;
+        if (axes[a] == ndim - 1) pos_x = a;
+    }
+    CountJob probe;
+    if (int rc = make_job(probe, x_dev, dtype, 0, 0, 0, flags, mask_bits)) return rc;
+    if (!x_dev && numel > 0) return fail(XBI_ERR_ARG, "null data pointer");
+    const int nbits = 8 * dtype_bytes(dtype);
+    const size_t table = (size_t)nbits * 4;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Workspace* ws = static_cast<Workspace*>(workspace_dev);
+    unsigned int* dirty_flag = reinterpret_cast<unsigned int*>(ws + naxes);
+    double z = 0.0;
+    if (mi_dev && set_zero_insignificant) {
+        if (!(confidence > 0.0 && confidence < 1.0)) return fail(XBI_ERR_ARG, "confidence must be in (0,1)");
+        z = normal_quantile(1.0 - (1.0 - confidence) / 2.0);
+    }
+    auto job_of = [&](int axis) {
+        CountJob j = probe;
+        j.outer = 1; j.inner = 1;
+        for (int d = 0; d < axis; ++d) j.outer *= shape[d];
+        j.n = shape[axis];
+        for (int d = axis + 1; d < ndim; ++d) j.inner *= shape[d];
+        return j;
+    };
+    auto fin_of = [&](int a) {
+        Finish fin;
+        fin.counts = counts_dev + (size_t)a * table;
+        fin.accumulate = false;
+        fin.mi = mi_dev ? mi_dev + (size_t)a * nbits : nullptr;
+        fin.set_zero = (mi_dev && set_zero_insignificant) ? 1 : 0;
+        fin.z = z;
+        return fin;
+    };
+    bool fused = false;
+    if (pos_y >= 0 && pos_x >= 0 && numel > 0 && !(flags & XBI_FORCE_GENERIC)) {
+        const CountJob jy = job_of(ndim - 2);
+        if (pairs_xy_eligible(jy)) {
+            // the two innermost axes in ONE read (xbi_count_xy.cu)
+            XBI_CUDA(cudaMemsetAsync(ws, 0, xbi_workspace_bytes_multi(naxes), st), "cudaMemsetAsync(workspace)");
+            XBI_CUDA(launch_pairs_xy(jy, ws + pos_y, ws + pos_x, dirty_flag, st), "pair counting (two axes)");
+            fused = true;
+            if (jy.mask_mode != kMaskNone) {
+                // the kernel counted as if nothing were masked and only looked for masked elements: if there
+                // are any, both axes are recounted by the masked single-axis kernels
+                unsigned int seen = 0;
+                XBI_CUDA(cudaMemcpyAsync(&seen, dirty_flag, sizeof(seen), cudaMemcpyDeviceToHost, st), "cudaMemcpyAsync(flag)");
+                XBI_CUDA(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+                if (seen) fused = false;
+            }
+            if (fused) {
+                const CountJob jx = job_of(ndim - 1);
+                XBI_CUDA(launch_finish(jy, finish_job(jy, ws + pos_y, fin_of(pos_y)), st), "finish (combine)");
+                XBI_CUDA(launch_finish(jx, finish_job(jx, ws + pos_x, fin_of(pos_x)), st), "finish (combine)");
+            }
+        }
+    }
+    for (int a = 0; a < naxes; ++a) {
+        if (fused && (a == pos_y || a == pos_x)) continue;
+        if (int rc = count_pairs_impl(job_of(axes[a]), flags, ws + a, st, fin_of(a))) return rc;
+    }
+    return XBI_OK;
 }
 
 // ---------------------------------------------------------------------------------

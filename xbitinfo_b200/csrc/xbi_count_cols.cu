@@ -872,6 +872,37 @@ k_block_edges(const uint4* __restrict__ x, long long chunks_per_row, long long n
     }
 }
 
+// What follows the walkers: the a-stream correction (row planes) and, for 16-byte aligned rows, the pairs that
+// straddle two blocks of the analysed axis.
+template <int KIND, int MASK, bool XFORM>
+cudaError_t cols_followups(const CountJob& job, Workspace* ws, cudaStream_t stream, bool aligned, int64_t chunks,
+                           int64_t pair_rows, int sms) {
+    {
+        // a-stream correction: + planes(first row) - planes(row after the last pair row)
+        // (masked elements contribute nothing, as in the walkers; the dense flavour forms its
+        // a-stream explicitly, so these passes return at once when it is the one that ran)
+        const RawSums* flavour = (MASK != kMaskNone && aligned) ? &ws->plus : nullptr;
+        cudaError_t e = launch_elem_planes(job, 0, job.inner, &ws->plus, stream, flavour, kColsDenseOneIn);
+        if (e != cudaSuccess) return e;
+        e = launch_elem_planes(job, pair_rows * job.inner, job.inner, &ws->minus, stream, flavour, kColsDenseOneIn);
+        if (e != cudaSuccess) return e;
+    }
+    if (job.outer > 1 && aligned) {
+        const int64_t nbound = job.outer - 1;
+        const int64_t items = ((nbound + 3) / 4) * chunks;
+        // the end-of-kernel flush costs a warp ~10 items' worth of instructions: give every
+        // warp at least 16 items before adding more blocks
+        int64_t eblocks = (items + (int64_t)kThreads * 16 - 1) / ((int64_t)kThreads * 16);
+        if (eblocks > (int64_t)sms * 8) eblocks = (int64_t)sms * 8;
+        if (eblocks < 1) eblocks = 1;
+        k_block_edges<KIND, MASK, XFORM><<<(unsigned)eblocks, kThreads, 0, stream>>>(
+            static_cast<const uint4*>(job.x), (long long)chunks, (long long)job.n, (long long)nbound,
+            (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), &ws->minus);
+        note_launch();
+    }
+    return cudaGetLastError();
+}
+
 template <int KIND, int MASK, bool XFORM>
 cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo, int64_t* done_hi,
                         bool* edges_done) {
@@ -902,29 +933,7 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
         }
         if (e != cudaSuccess) return e;
     }
-    {
-        // a-stream correction: + planes(first row) - planes(row after the last pair row)
-        // (masked elements contribute nothing, as in the walkers; the dense flavour forms its
-        // a-stream explicitly, so these passes return at once when it is the one that ran)
-        const RawSums* flavour = (MASK != kMaskNone && aligned) ? &ws->plus : nullptr;
-        cudaError_t e = launch_elem_planes(job, 0, job.inner, &ws->plus, stream, flavour, kColsDenseOneIn);
-        if (e != cudaSuccess) return e;
-        e = launch_elem_planes(job, pair_rows * job.inner, job.inner, &ws->minus, stream, flavour, kColsDenseOneIn);
-        if (e != cudaSuccess) return e;
-    }
-    if (job.outer > 1 && aligned) {
-        const int64_t nbound = job.outer - 1;
-        const int64_t items = ((nbound + 3) / 4) * chunks;
-        // the end-of-kernel flush costs a warp ~10 items' worth of instructions: give every
-        // warp at least 16 items before adding more blocks
-        int64_t eblocks = (items + (int64_t)kThreads * 16 - 1) / ((int64_t)kThreads * 16);
-        if (eblocks > (int64_t)sms * 8) eblocks = (int64_t)sms * 8;
-        if (eblocks < 1) eblocks = 1;
-        k_block_edges<KIND, MASK, XFORM><<<(unsigned)eblocks, kThreads, 0, stream>>>(
-            static_cast<const uint4*>(job.x), (long long)chunks, (long long)job.n, (long long)nbound,
-            (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32), &ws->minus);
-        note_launch();
-    }
+    if (cudaError_t e = cols_followups<KIND, MASK, XFORM>(job, ws, stream, aligned, chunks, pair_rows, sms)) return e;
     *edges_done = aligned;  // otherwise the caller runs the generic edge pass
     note_fast_launch();
     *done_lo = 0;
@@ -952,6 +961,16 @@ cudaError_t dispatch_cols(const CountJob& job, Workspace* ws, cudaStream_t strea
 }
 
 }  // namespace
+
+cudaError_t launch_cols_followups(const CountJob& job, Workspace* ws, cudaStream_t stream) {
+    // 4-byte element types, unmasked, 16-byte aligned rows (the two-axis kernel of xbi_count_xy.cu)
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int64_t chunks = job.inner * 4 / 16, pair_rows = job.outer * job.n - 1;
+    if (job.transform) return cols_followups<kF32, kMaskNone, true>(job, ws, stream, true, chunks, pair_rows, sms);
+    return cols_followups<kU32, kMaskNone, false>(job, ws, stream, true, chunks, pair_rows, sms);
+}
 
 cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
                               int64_t* done_hi, bool* edges_done) {

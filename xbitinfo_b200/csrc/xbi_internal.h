@@ -69,6 +69,10 @@ cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int
 cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream,
                                const RawSums* dense_probe = nullptr, unsigned long long dense_one_in = 0);
 
+// the same for every stride-th element (f = lo + t*stride, t < count), added to dst->sums[stream_sel]; unmasked jobs
+cudaError_t launch_elem_planes_strided(const CountJob& job, int64_t lo, int64_t count, int64_t stride, RawSums* dst,
+                                       int stream_sel, cudaStream_t stream);
+
 // TMA fast paths.  Each consumes as much of [0, numel-inner) as its alignment rules
 // allow, reports the flat range it covered in [*done_lo, *done_hi) (empty if none), and
 // leaves the rest to the generic kernel.
@@ -86,6 +90,15 @@ cudaError_t launch_pairs_tma(const CountJob& job, int64_t npairs_flat, Workspace
 // *edges_done: the block-boundary pairs have been subtracted as well (all of them).
 cudaError_t launch_pairs_cols(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t* done_lo,
                               int64_t* done_hi, bool* edges_done);
+
+// The follow-up passes of the walkers alone (row planes, block-boundary pairs) for an unmasked job of a 4-byte type
+// with 16-byte aligned rows.
+cudaError_t launch_cols_followups(const CountJob& job, Workspace* ws, cudaStream_t stream);
+
+// Two innermost axes in one read (xbi_count_xy.cu).  jy = the job of the second-to-last axis.
+bool pairs_xy_eligible(const CountJob& jy);
+cudaError_t launch_pairs_xy(const CountJob& jy, Workspace* ws_y, Workspace* ws_x, unsigned int* dirty_flag,
+                            cudaStream_t stream);
 
 // Samples ~2^18 flat pairs and leaves (#pairs whose two elements differ in validity, #pairs sampled)
 // in ws->plus.pad[0], pad[1] for the masked fast kernels to choose their flavour.

@@ -141,6 +141,59 @@ class PairCounter:
         return self.mi
 
 
+class MultiAxisCounter:
+    """Reusable device state for the analysis of several dimensions of one array in one call
+    (``xbi_bitinformation_dev_multi``): ``counts`` ``(naxes, nbits, 2, 2)`` int64 and ``mi`` ``(naxes, nbits)``
+    float64, both overwritten by every call, plus the scratch workspace."""
+
+    def __init__(self, dtype: torch.dtype, naxes: int, device):
+        self.code = torch_dtype_code(dtype)
+        self.nbits = 8 * torch.empty((), dtype=dtype).element_size()
+        self.naxes = int(naxes)
+        self.device = torch.device(device)
+        self.counts = torch.zeros((self.naxes, self.nbits, 2, 2), dtype=torch.int64, device=self.device)
+        self.mi = torch.empty((self.naxes, self.nbits), dtype=torch.float64, device=self.device)
+        self.workspace = torch.empty(nat.lib().xbi_workspace_bytes_multi(self.naxes), dtype=torch.uint8, device=self.device)
+
+    def bitinformation(self, x: torch.Tensor, axes, *, transform: bool = True, masked_value=None,
+                       set_zero_insignificant: bool = False, confidence: float = 0.99, flavour: str | None = None):
+        """Information per bit along each of ``axes`` (distinct) -> ``mi`` (device tensor ``(naxes, nbits)``)."""
+        require_cuda_tensor(x)
+        if torch_dtype_code(x.dtype) != self.code:
+            raise ValueError("dtype differs from the counter's dtype")
+        nd = x.dim()
+        axes = [int(a) % nd for a in axes]
+        if len(axes) != self.naxes or len(set(axes)) != len(axes):
+            raise ValueError("`axes` must name naxes distinct dimensions")
+        np_dtype = numpy_dtype_of(x)
+        flags, bits = nat.mask_spec(np_dtype, masked_value)
+        if np_dtype.kind == "f" and transform:
+            flags |= nat.SIGNED_EXPONENT
+        if flavour is not None:
+            flags |= {"sparse": nat.FORCE_SPARSE, "dense": nat.FORCE_DENSE, "generic": nat.FORCE_GENERIC}[flavour]
+        with torch.cuda.device(x.device):
+            rc = nat.lib().xbi_bitinformation_dev_multi(
+                x.data_ptr(), self.code, nd, nat.int64_array(x.shape), self.naxes, (nat.C.c_int * self.naxes)(*axes),
+                flags, bits, int(bool(set_zero_insignificant)), float(confidence), self.counts.data_ptr(),
+                self.mi.data_ptr(), self.workspace.data_ptr(), self.workspace.numel(), _stream_ptr(x.device))
+        nat.check(rc)
+        return self.mi
+
+
+def bitinformation_multi_device(x: torch.Tensor, axes, masked_value=None, set_zero_insignificant: bool = False,
+                                confidence: float = 0.99, return_counts: bool = False):
+    """list of float64[nbits] (with ``return_counts``: of ``(mi, counts)``) in the order of ``axes``."""
+    if not x.is_contiguous():
+        x = x.contiguous()
+    mc = MultiAxisCounter(x.dtype, len(axes), x.device)
+    mi = mc.bitinformation(x, axes, masked_value=masked_value, set_zero_insignificant=set_zero_insignificant,
+                           confidence=confidence).cpu().numpy()
+    if return_counts:
+        counts = mc.counts.cpu().numpy()
+        return [(mi[i], counts[i]) for i in range(len(axes))]
+    return [mi[i] for i in range(len(axes))]
+
+
 def bitround_(x: torch.Tensor, keepbits: int) -> torch.Tensor:
     """K3 in place on a CUDA tensor."""
     require_cuda_tensor(x)

@@ -78,7 +78,8 @@ def bitinformation_multi(data, axes, masked_value=None, set_zero_insignificant: 
     """Information per bit along several axes of one array: list of float64[nbits] in the order of
     ``axes`` (with ``return_counts`` a list of ``(mi, counts)``).  A host numpy array crosses PCIe once for
     all the axes (``xbi_bitinformation_host_multi``), a lazy array (dask / zarr / h5py) is read slab by slab
-    from its source once for all the axes; device tensors are analysed axis by axis (the data is resident)."""
+    from its source once for all the axes; a device tensor goes through ``xbi_bitinformation_dev_multi`` (the two
+    innermost axes in one read of the array, the others one pass each)."""
     from .streaming import is_lazy_array
 
     axes = [int(a) for a in axes]
@@ -89,6 +90,13 @@ def bitinformation_multi(data, axes, masked_value=None, set_zero_insignificant: 
         return bitinformation_streamed_multi(data, axes, masked_value=masked_value,
                                              set_zero_insignificant=set_zero_insignificant, confidence=confidence,
                                              device=device, return_counts=return_counts)
+    if _is_torch_tensor(data) and len(axes) >= 2 and 0 < data.dim() <= 8 and len(set(a % data.dim() for a in axes)) == len(axes):
+        # device-resident: one call of the C ABI; the two innermost axes share one read of the array
+        from .device import bitinformation_multi_device
+
+        return bitinformation_multi_device(data, axes, masked_value=masked_value,
+                                           set_zero_insignificant=set_zero_insignificant, confidence=confidence,
+                                           return_counts=return_counts)
     if _is_torch_tensor(data) or is_lazy_array(data) or len(axes) < 2:
         return [bitinformation(data, a, masked_value=masked_value, set_zero_insignificant=set_zero_insignificant,
                                confidence=confidence, device=device, return_counts=return_counts) for a in axes]
