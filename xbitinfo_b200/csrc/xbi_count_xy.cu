@@ -12,14 +12,16 @@
 //   x pairs   (e, e+1) inside every `cur` row.  The right neighbour of a lane's last word is the first word of the
 //             next lane's chunk: read from the warp's slice of the shared-memory ring (every lane copies its own
 //             16 bytes with cp.async; lane 31 copies one word more) after a __syncwarp, and transformed once more.
-//             With S = sum of x' over the cur rows: A_x = S - (last column), B_x = S - (first column); the two
-//             columns are summed by a strided element pass, row 0 of the matrix by the generic kernel.
+//             With S = sum of x' over the cur rows: A_x = S - (last column), B_x = S - (first column); the one lane
+//             per row that holds a column end sums it in a small counter of its own (a strided pass over the two
+//             columns cost 13 % of the call), row 0 of the matrix goes through the generic kernel.
 //
 // Masked modes: the kernel runs the unmasked formulation and only PROBES for masked elements (x*0 on the FMA pipe,
 // xbi_mask.cuh); when it finds one it raises a flag and the caller recounts the two axes one by one with the
 // masked kernels.  Data without masked elements -- the API's default NaN mask on NaN-free data -- pays one pass.
 // 4-byte element types; everything else is counted axis by axis.
 #include <atomic>
+#include <type_traits>
 
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
@@ -79,15 +81,43 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
     const long long warps_total = (long long)gridDim.x * kWarpsXY;
     const long long groups = seg_min >> 2;
 
+    // block totals (flushes are rare: they add straight into shared memory, no per-lane 64-bit accumulators)
+    __shared__ unsigned long long s_sum[5][32];  // sum x' (cur rows), x' & above, x' & right, first column, last column
+    for (int i = threadIdx.x; i < 5 * 32; i += kThreadsXY) (&s_sum[0][0])[i] = 0;
+    __syncthreads();
+
     L Bl, ABy, ABx;
     Bl.clear(); ABy.clear(); ABx.clear();
-    unsigned long long accB = 0, accABy = 0, accABx = 0;
     uint32_t it = 0;
     bool dirty = false;
+    // first / last column of the rows (A_x = S - last column, B_x = S - first column): the one lane of a row that
+    // holds it feeds one word per row into a small counter of its own (4 rows = one chunk); warps whose strip
+    // touches neither end of the row skip it altogether
+    using LC = Ladder<3, 5, 2>;
+    LC Col;
+    Col.clear();
+    uint32_t cit = 0, role = 0;  // role of this lane in the current item: 1 first column, 2 last column
+    auto flush_col = [&]() {
+        if (cit == 0) return;  // (warp-uniform)
+        LC t = Col;
+        if (role != 1u) t.clear();
+        const uint32_t f = t.warp_totals(lane, cit);
+        if (f) atomicAdd(&s_sum[3][lane], (unsigned long long)f);
+        t = Col;
+        if (role != 2u) t.clear();
+        const uint32_t l = t.warp_totals(lane, cit);
+        if (l) atomicAdd(&s_sum[4][lane], (unsigned long long)l);
+        Col.clear();
+        cit = 0;
+    };
     auto flush = [&](bool keep) {
         // (an idle lane's counters hold zeros: its words were neutral or never added)
         const uint32_t b = Bl.warp_totals(lane, it), y = ABy.warp_totals(lane, it), xx = ABx.warp_totals(lane, it);
-        if (keep) { accB += b; accABy += y; accABx += xx; }
+        if (keep) {
+            if (b) atomicAdd(&s_sum[0][lane], (unsigned long long)b);
+            if (y) atomicAdd(&s_sum[1][lane], (unsigned long long)y);
+            if (xx) atomicAdd(&s_sum[2][lane], (unsigned long long)xx);
+        }
         Bl.clear(); ABy.clear(); ABx.clear();
         it = 0;
     };
@@ -98,6 +128,10 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
         const long long chunk = strip * 32 + lane;
         const bool live = chunk < cpr;
         const bool has_right_word = lane == 31u && chunk + 1 < cpr;  // lane 31 fetches the word after the strip
+        const uint32_t new_role = (live && chunk == 0) ? 1u : (live && chunk == cpr - 1) ? 2u : 0u;
+        if (__any_sync(0xFFFFFFFFu, new_role != role)) flush_col();
+        role = new_role;
+        const bool col_warp = __any_sync(0xFFFFFFFFu, role != 0u);
         const long long row_begin = seg * seg_min + (seg < seg_extra ? seg : seg_extra);
         const int tail_rows = (int)(seg_min + (seg < seg_extra ? 1 : 0) - (groups << 2));  // 0..4, warp-uniform
         const long long ngroups = groups + (tail_rows > 0 ? 1 : 0);
@@ -117,14 +151,22 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
         auto issue = [&]() {
             if (issued < ngroups && live) {
                 const uint32_t dst = my0 + slot_w * kTileXY;
+                if (issued < groups) {
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                    for (int r = 0; r < 4; ++r) {
+                        cpa16(dst + r * kRowPitch, q + r * row_bytes);
+                        if (has_right_word) cpa4(dst + r * kRowPitch + 16, q + r * row_bytes + 16);
+                    }
+                    q += 4 * row_bytes;
+                } else {
                     // the tail group re-reads an in-bounds row for its absent rows (they are masked out below)
-                    const long long rr = (issued < groups || r < tail_rows) ? r : (long long)tail_rows - 1;
-                    cpa16(dst + r * kRowPitch, q + rr * row_bytes);
-                    if (has_right_word) cpa4(dst + r * kRowPitch + 16, q + rr * row_bytes + 16);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const long long rr = (r < tail_rows) ? r : (long long)tail_rows - 1;
+                        cpa16(dst + r * kRowPitch, q + rr * row_bytes);
+                        if (has_right_word) cpa4(dst + r * kRowPitch + 16, q + rr * row_bytes + 16);
+                    }
                 }
-                if (issued < groups) q += 4 * row_bytes;
             }
             cpa_commit();
             slot_w = (slot_w + 1 == kRingXY) ? 0 : slot_w + 1;
@@ -157,29 +199,42 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
             __syncwarp();  // everybody has read this slot before anybody's next copies overwrite it
             slot_r = (slot_r + 1 == kRingXY) ? 0 : slot_r + 1;
             if (MT != kMaskNone) dirty |= may_contain_masked<KIND, MT>(raw, mask_lo, mask_hi);
-            const int nrows = g < groups ? 4 : tail_rows;
-            uint32_t wb[16], wy[16], wx[16];
+            // (two instantiations: in a full group every `present` test folds away)
+            auto fold = [&](auto full, int nrows) {
+                constexpr bool FULL = decltype(full)::value;
+                uint32_t wb[16], wy[16], wx[16];
 #pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                const bool present = r < nrows;
-                uint32_t c[5];
+                for (int r = 0; r < 4; ++r) {
+                    const bool present = FULL || r < nrows;
+                    uint32_t c[5];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) c[i] = present ? xf<KIND, XFORM>(raw[4 * r + i]) : 0u;
-                c[4] = xf<KIND, XFORM>(nb[r]);
+                    for (int i = 0; i < 4; ++i) c[i] = present ? xf<KIND, XFORM>(raw[4 * r + i]) : 0u;
+                    c[4] = xf<KIND, XFORM>(nb[r]);
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    wb[4 * r + i] = c[i];
-                    wy[4 * r + i] = c[i] & prev[i];
-                    wx[4 * r + i] = c[i] & c[i + 1];
+                    for (int i = 0; i < 4; ++i) {
+                        wb[4 * r + i] = c[i];
+                        wy[4 * r + i] = c[i] & prev[i];
+                        wx[4 * r + i] = c[i] & c[i + 1];
+                    }
+                    if (present) {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) prev[i] = c[i];
+                    }
                 }
-                if (present) {
+                Bl.add16(wb, it);
+                ABy.add16(wy, it);
+                ABx.add16(wx, it);
+                if (col_warp) {
+                    uint32_t cw[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) prev[i] = c[i];
+                    for (int r = 0; r < 4; ++r) cw[r] = role == 1u ? wb[4 * r] : role == 2u ? wb[4 * r + 3] : 0u;
+                    Col.add_chunk(cw, cit);
+                    ++cit;
+                    if (cit == LC::kFlushChunks) flush_col();
                 }
-            }
-            Bl.add16(wb, it);
-            ABy.add16(wy, it);
-            ABx.add16(wx, it);
+            };
+            if (g < groups) fold(std::true_type{}, 4);
+            else fold(std::false_type{}, tail_rows);
             ++it;
             if (it == L::kFlushChunks) flush(true);
         }
@@ -187,17 +242,15 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
     }
     cpa_wait<0>();
     flush(true);
+    flush_col();
 
-    // block reduction, one atomic per non-zero counter and block
-    __shared__ unsigned long long s_sum[3][32];
-    for (int i = threadIdx.x; i < 3 * 32; i += kThreadsXY) (&s_sum[0][0])[i] = 0;
-    __syncthreads();
-    if (accB) atomicAdd(&s_sum[0][lane], accB);
-    if (accABy) atomicAdd(&s_sum[1][lane], accABy);
-    if (accABx) atomicAdd(&s_sum[2][lane], accABx);
+    // one global atomic per non-zero counter and block
     __syncthreads();
     if (threadIdx.x < 32) {
         const unsigned long long b = s_sum[0][lane], y = s_sum[1][lane], xx = s_sum[2][lane];
+        // x axis: the first column is never a b, the last never an a
+        if (s_sum[3][lane]) atomicAdd(&ws_x->minus.sums[S_B][lane], s_sum[3][lane]);
+        if (s_sum[4][lane]) atomicAdd(&ws_x->minus.sums[S_A][lane], s_sum[4][lane]);
         // y axis: a-stream = b-stream shifted up one row (the launcher adds the first row, subtracts the last)
         if (b) { atomicAdd(&ws_y->plus.sums[S_A][lane], b); atomicAdd(&ws_y->plus.sums[S_B][lane], b); }
         if (y) atomicAdd(&ws_y->plus.sums[S_AB][lane], y);
@@ -300,12 +353,8 @@ cudaError_t launch_pairs_xy(const CountJob& jy, Workspace* ws_y, Workspace* ws_x
     // the kernel's x pairs cover rows 1 .. rows-1; row 0: explicit three streams
     CountJob row0 = jx;
     row0.outer = 1;
-    e = launch_pairs_generic_flat(row0, 0, nx - 1, &ws_x->plus, stream);
-    if (e != cudaSuccess) return e;
-    // A_x = S - (last column), B_x = S - (first column), S = sum over rows 1 .. rows-1
-    e = launch_elem_planes_strided(jx, nx + (nx - 1), rows - 1, nx, &ws_x->minus, S_A, stream);
-    if (e != cudaSuccess) return e;
-    return launch_elem_planes_strided(jx, nx, rows - 1, nx, &ws_x->minus, S_B, stream);
+    // (A_x = S - last column, B_x = S - first column over rows 1 .. rows-1: the kernel summed the two columns itself)
+    return launch_pairs_generic_flat(row0, 0, nx - 1, &ws_x->plus, stream);
 }
 
 }  // namespace xbi
