@@ -18,6 +18,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libxbitinfo_b200.so")
 U8, U16, U32, U64, F16, F32, F64 = range(7)
 # flags
 SIGNED_EXPONENT, MASK_NAN, MASK_VALUE, FORCE_GENERIC = 1, 2, 4, 8
+FORCE_WALK = 64  # testing: the walker kernel of the chunk-grid entry points (FORCE_GENERIC: the odometer kernel)
 FORCE_SPARSE, FORCE_DENSE = 16, 32  # testing: flavour of the masked fast kernels (default: sampled on the device)
 # xbi_shuffle kinds
 SHUFFLE_BYTES, SHUFFLE_BITS = 0, 1

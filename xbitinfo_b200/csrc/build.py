@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libxbitinfo_b200.so")
-SOURCES = ["xbi_api.cu", "xbi_count_generic.cu", "xbi_count_tma.cu", "xbi_count_cols.cu", "xbi_count_xy.cu", "xbi_epilogue.cu", "xbi_finish.cu", "xbi_bitround.cu", "xbi_shuffle.cu", "xbi_chunked.cu", "xbi_hostpool.cu"]
+SOURCES = ["xbi_api.cu", "xbi_count_generic.cu", "xbi_count_tma.cu", "xbi_count_cols.cu", "xbi_count_xy.cu", "xbi_epilogue.cu", "xbi_finish.cu", "xbi_bitround.cu", "xbi_shuffle.cu", "xbi_chunked.cu", "xbi_chunked_walk.cu", "xbi_hostpool.cu"]
 HEADERS = ["xbi_common.cuh", "xbi_elem.cuh", "xbi_mask.cuh", "xbi_epilogue.cuh", "xbi_tma.cuh", "xbi_tmap.h", "xbi_internal.h", "../../include/xbitinfo_b200.h"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

@@ -790,7 +790,7 @@ static int count_pairs_grid(const void* x_dev, int dtype, int ndim, const int64_
     if (empty) return XBI_OK;
     if (!x_dev) return fail(XBI_ERR_ARG, "null data pointer");
     XBI_CUDA(launch_pairs_chunked(x_dev, dtype, g, (unsigned)nchunks, job.transform, job.mask_mode, job.mask_bits,
-                                  counts_dev, st),
+                                  counts_dev, st, flags),
              "pair counting (chunk grid)");
     return XBI_OK;
 }

@@ -14,6 +14,7 @@
 // three word streams a, b, a&b of the valid pairs go into vertical counters (xbi_common.cuh) as
 // in the generic kernel, and each item ends with one warp butterfly, a block reduction and one
 // atomic per counter into the chunk's table.
+#include <cstdlib>
 #include <type_traits>
 
 #include "xbi_common.cuh"
@@ -415,9 +416,22 @@ cudaError_t launch_count_kind(const void* x, const ChunkGrid& g, bool transform,
 }  // namespace
 
 cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
-                                 int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream) {
-    cudaError_t e;
-    switch (dtype) {
+                                 int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream,
+                                 unsigned flags) {
+    cudaError_t e = cudaSuccess;
+    // the walkers of xbi_chunked_walk.cu (one load per element, warp-level indexing) where the grid gives them
+    // enough columns / runs; the per-element odometers below otherwise (tiny chunks, very short rows)
+    bool walked = false;
+    static const bool allow_walk = [] {
+        const char* env = std::getenv("XBI_CHUNKED_WALK");
+        return !(env && env[0] == '0');
+    }();
+    if ((allow_walk || (flags & XBI_FORCE_WALK)) && !(flags & XBI_FORCE_GENERIC)) {
+        e = launch_pairs_chunked_walk(x, dtype, g, nchunks, transform, mask_mode, mask_bits, counts, stream,
+                                      (flags & XBI_FORCE_WALK) != 0, &walked);
+        if (e != cudaSuccess) return e;
+    }
+    if (!walked) switch (dtype) {
         case XBI_U8: e = launch_count_kind<kU8>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
         case XBI_U16: e = launch_count_kind<kU16>(x, g, transform, mask_mode, mask_bits, counts, stream); break;
         case XBI_U32: e = launch_count_kind<kU32>(x, g, transform, mask_mode, mask_bits, counts, stream); break;

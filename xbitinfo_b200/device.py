@@ -268,7 +268,7 @@ def chunk_grid_shape(shape, chunk_shape):
 
 
 def count_pairs_chunked(x: torch.Tensor, chunk_shape, axis: int, *, transform: bool = True,
-                        masked_value=None) -> torch.Tensor:
+                        masked_value=None, flavour: str | None = None) -> torch.Tensor:
     """K1 on every chunk of a grid on its own, one launch: int64 tensor of shape
     ``chunks-per-dimension + (nbits, 2, 2)`` (chunks in C order of the grid).  ``chunk_shape``: one int
     (regular) or one tuple of chunk lengths (dask's ``.chunks``) per dimension."""
@@ -286,6 +286,8 @@ def count_pairs_chunked(x: torch.Tensor, chunk_shape, axis: int, *, transform: b
     flags, bits = nat.mask_spec(np_dtype, masked_value)
     if np_dtype.kind == "f" and transform:
         flags |= nat.SIGNED_EXPONENT
+    if flavour is not None:  # testing: pin one of the two chunk-grid kernels
+        flags |= {"walk": nat.FORCE_WALK, "odometer": nat.FORCE_GENERIC}[flavour]
     with torch.cuda.device(x.device):
         if tables is None:
             rc = nat.lib().xbi_count_pairs_chunked(

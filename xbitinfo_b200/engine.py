@@ -174,10 +174,39 @@ def bitround(data, keepbits: int, device: int | None = None):
         raise TypeError("Only float arrays (16-64bit) can be bit-rounded")
     code = nat.dtype_code(x.dtype)
     src = _native_contiguous(x)
-    out = np.empty_like(src)
+    out = _new_output_like(src)
     if device is None:
         device = _current_device()
     rc = nat.lib().xbi_bitround_host(src.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), code,
                                      src.size, int(keepbits), int(device))
     nat.check(rc)
     return out
+
+
+def _pinned_output_cap_bytes() -> int:
+    import os
+
+    try:
+        return int(float(os.environ.get("XBI_PINNED_OUTPUT_MB", "8192")) * (1 << 20))
+    except ValueError:
+        return 8192 << 20
+
+
+def _new_output_like(src: np.ndarray) -> np.ndarray:
+    """The array ``bitround`` returns.  A fresh ``np.empty_like`` is first touched while the result is copied out: its
+    page faults cap the call at ~20 GB/s however many threads copy (profiles/r01_host_path.md).  Outputs from 1 MB up
+    to ``XBI_PINNED_OUTPUT_MB`` (default 8192; 0 disables) are therefore taken from torch's caching page-locked host
+    allocator -- the DMA engine writes the rounded slabs straight into them, no staging copy, no faults -- and given
+    back to that cache when the caller drops the array (the numpy array owns a reference to the storage).  It is an
+    ordinary numpy array in every other respect."""
+    cap = _pinned_output_cap_bytes()
+    if (1 << 20) <= src.nbytes <= cap:
+        try:
+            import torch
+
+            if torch.cuda.is_available():
+                buf = torch.empty(src.nbytes, dtype=torch.uint8, pin_memory=True)
+                return buf.numpy().view(src.dtype).reshape(src.shape)
+        except Exception:  # torch is plumbing: any trouble here and the plain allocation serves
+            pass
+    return np.empty_like(src)
