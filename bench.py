@@ -517,15 +517,18 @@ def run_ours(args):
         e2e = run_e2e(args, x, rank, world, dev, sync_all, dist_max)
         e2e["numa_node_of_rank0"] = numa_node
         e2e["host_copy_threads_per_rank"] = int(os.environ["XBI_HOST_THREADS"])
-    if peers is not None:
-        peers.close()
     del x, pc
     torch.cuda.empty_cache()
 
-    # ---- BASELINE configs[2..4] at sizes one GPU holds ----
+    # ---- BASELINE configs[2..4] at sizes one GPU holds; N > 1: configs[4], the sharded pipeline ----
     configs = None
-    if world == 1 and not args.no_configs:
-        configs = run_configs(args, dev, peak)
+    if not args.no_configs:
+        if world == 1:
+            configs = run_configs(args, dev, peak)
+        else:
+            configs = {"c4": run_pipeline_sharded(args, dev, peak, rank, world, peers, sync_all, dist_max)}
+    if peers is not None:
+        peers.close()
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -838,6 +841,79 @@ def run_configs(args, dev, peak):
         out["c4"] = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.empty_cache()
     return out
+
+
+def run_pipeline_sharded(args, dev, peak, rank, world, peers, sync_all, dist_max):
+    """configs[4] across the GPUs of the node: every rank holds 5e9 elements of the (world x 5e9) array; one step =
+    count the local share -> all-reduce the int64[nbits,2,2] counts (inside the finish kernel when the peer exchange
+    is up, else NCCL) -> K2 on every rank -> 16 / 32 doubles to the host -> get_keepbits(0.99) -> bitround the
+    local share into a second array.  Timed with CUDA events, barrier on both sides, max over ranks."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from oracle import bitround_oracle as bro
+    from oracle import fast_count as fc
+    from xbitinfo_b200 import distributed as xdist
+    from xbitinfo_b200.chunked import keepbits_of_information
+    from xbitinfo_b200.device import PairCounter, bitround
+
+    K = max(3, args.config_steps)
+    n = 5_000_000_000
+    res = {}
+    try:
+        for name, tdt in (("float16", torch.float16), ("float32", torch.float32)):
+            x = _synth_nd((n // 100_000, 100_000), tdt, 1, 13 + rank, dev).view(-1)
+            y = torch.empty_like(x)
+            pc = PairCounter(tdt, dev)
+            kw = dict(masked_value=float("nan"), set_zero_insignificant=True, confidence=0.99)
+            state = {}
+
+            def pipeline():
+                if peers is not None:
+                    mi = pc.bitinformation(x, 0, peers=peers, **kw)
+                else:
+                    pc.bitinformation(x, 0, masked_value=float("nan"), with_information=False)
+                    xdist.allreduce_counts(pc.counts)
+                    mi = pc.information(True, 0.99)
+                keep = max(0, keepbits_of_information(mi.cpu().numpy(), np.dtype(name), 0.99))  # the same on every rank
+                bitround(x, keep, out=y)
+                state["keep"] = keep
+
+            for _ in range(3):
+                pipeline()
+            ms = _time_steps(pipeline, K, sync_all, dist_max)
+            # checks (outside the timed region): the global table = sum of per-rank tables of fast_count on a slab is not
+            # affordable at 5e9 elements per rank; the local slab's counts and the rounded bits are checked instead, and
+            # every rank must have taken the same keepbits decision
+            k = 1 << 24
+            hs = x[:k].cpu().numpy()
+            p = PairCounter(tdt, dev)
+            p.bitinformation(x[:k], 0, masked_value=float("nan"))
+            u = f"u{np.dtype(name).itemsize}"
+            ok = np.array_equal(p.counts.cpu().numpy(), fc.count_pairs(hs, 0, masked_value=float("nan"))) and \
+                np.array_equal(y[:k].cpu().numpy().view(u), bro.bitround(hs, state["keep"]).view(u))
+            pairs_ok = int(pc.counts[0].sum().item()) == world * (n - 1)
+            flags = torch.tensor([int(ok and pairs_ok), state["keep"], -state["keep"]], device=dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            isz = x.element_size()
+            res[name] = {
+                "ms_pipeline": ms, "elements_per_s": world * n / (ms * 1e-3), "keepbits": state["keep"],
+                "value": 3 * world * n * isz / (ms * 1e-3) / 1e9, "unit": UNIT,
+                "frac_of_measured_peak": 3 * n * isz / (ms * 1e-3) / 1e9 / peak,
+                "bit_exact_slab_on_every_rank": bool(flags[0].item()),
+                "same_keepbits_on_every_rank": bool(flags[1].item() == -flags[2].item()),
+                "global_pairs_ok": pairs_ok,
+            }
+            del x, y, pc, p
+            torch.cuda.empty_cache()
+        res["workload"] = (f"configs[4]: bitinfo -> all-reduce -> get_keepbits(0.99) -> bitround on a ({world} x 5e9)-element "
+                           f"array, one 5e9-element share per GPU ({world * 5e9:.1e} elements in all), float16 and float32, "
+                           "API default keywords")
+        res["collective"] = "peer exchange in the finish kernel" if peers is not None else "NCCL all_reduce"
+    except Exception as e:
+        res["error"] = f"{type(e).__name__}: {e}"
+    return res
 
 
 def main():
