@@ -1,27 +1,21 @@
 // K1 over a chunk grid, fast formulation (docs/chunking.ipynb cells 8-10: get_bitinformation on every dask block on
 // its own).  The first chunk-grid kernel (k_pairs_chunked, xbi_chunked.cu) is the generic formulation batched: every
-// thread steps a mixed-radix odometer per ELEMENT and loads both elements of every pair -- 81 instructions per
-// element, 0.9-1.25 TB/s.  Here a WARP owns the indexing and a lane owns a column:
-//
-//   analysed axis is not the innermost dimension (kWalk)
-//       a lane takes one column of the chunk -- fixed coordinates in every dimension but the analysed one, 32
-//       neighbouring lanes = 32 neighbouring elements of the innermost dimension -- and walks down the analysed
-//       axis 16 rows per step, the previous row in registers: ONE load per element, one address add per row.
-//       The column's offset is worked out once per column (divisions by the chunk's extents), not per element.
-//   analysed axis is the innermost dimension (kRun)
-//       a warp takes one run of the chunk (its contiguous innermost extent) at a time, 32 consecutive elements per
-//       step; the position (run, step) is warp-uniform and advanced by a uniform odometer once per step; a lane
-//       reads its element and the next one (the second read hits the same line in L1).
+// thread steps a mixed-radix odometer per ELEMENT and loads both elements of every pair -- 0.9-1.25 TB/s.  Here a
+// lane owns a COLUMN of a chunk: fixed coordinates in every dimension but the analysed one, worked out once per
+// column (divisions by the chunk's extents), then one address add per row.  The columns of a chunk, flattened over
+// all its other dimensions, are cut into tiles of 32 (one per warp); a lane walks down the analysed axis 8 rows per
+// fold with the previous row in registers: ONE load per element.  When the analysed axis is not the innermost
+// dimension, neighbouring lanes are neighbouring elements in memory (coalesced rows); when it is, they sit on
+// neighbouring runs and each lane uses up its own 32-byte sectors as it goes.
 //
 // 4- and 8-byte element types do not load into registers (16 scalar loads per lane = 2 KB per warp in flight: the
 // kernel was latency-bound at 1.3-1.5 TB/s) but through a per-warp shared-memory ring filled with element-sized
-// cp.async copies four 16-row steps ahead of the fold (RING): 8-10 KB per warp in flight, no registers tied up.  In the
-// column walkers a lane reads back only what it copied (no barrier at all); in the run variant it also reads its right
-// neighbour's element (one __syncwarp per step).
+// cp.async copies seven 8-row steps ahead of the fold (RING): 7 KB per warp in flight, no registers tied up; a lane
+// reads back only what it copied, so there is no barrier at all.
 //
 // Three explicit word streams a, b, a&b of the valid pairs go into the bit-sliced counters of xbi_common.cuh.  A
-// warp works through a CONTIGUOUS range of (chunk, group) items, so it changes chunk a few times in its whole life
-// and only then (and at the end) pays the butterfly flush and the atomics into that chunk's table.
+// CTA works through a CONTIGUOUS range of tiles dealt to its warps in turn, so a warp changes chunk a few times in
+// its whole life and only then (and at the end) pays the butterfly flush and the atomics into that chunk's table.
 #include <atomic>
 
 #include "xbi_common.cuh"
@@ -85,60 +79,19 @@ __device__ __forceinline__ void lds_elem_w(uint32_t addr, uint32_t (&w)[NW]) {
 }
 __device__ __forceinline__ uint32_t smem_addr_w(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
-// uniform cursor over the (run, 32-element step) sequence of a range of runs of one chunk
-struct RunCursor {
-    unsigned c[kD - 1];
-    long long roff;
-    unsigned long long runs_left;
-    unsigned j0;
-    __device__ __forceinline__ void init(const ChunkBox& box, const ChunkGrid& g, unsigned long long r_lo, unsigned long long count);
-    // the current step (offset of its run, first element, whether it exists), then on to the next
-    __device__ __forceinline__ void step(const ChunkBox& box, const ChunkGrid& g, unsigned e4, long long& ro, unsigned& jj, bool& act);
-};
-
-__device__ __forceinline__ void RunCursor::init(const ChunkBox& box, const ChunkGrid& g, unsigned long long r_lo,
-                                                unsigned long long count) {
-    roff = box.base;
-    unsigned long long rr = r_lo;
-#pragma unroll
-    for (int d = kD - 2; d >= 0; --d) {
-        c[d] = (unsigned)(rr % box.e[d]);
-        rr /= box.e[d];
-        roff += (long long)c[d] * g.stride[d];
-    }
-    runs_left = count;
-    j0 = 0;
-}
-__device__ __forceinline__ void RunCursor::step(const ChunkBox& box, const ChunkGrid& g, unsigned e4, long long& ro,
-                                                unsigned& jj, bool& act) {
-    ro = roff;
-    jj = j0;
-    act = runs_left > 0;
-    j0 += 32;
-    if (j0 + 1 >= e4 && runs_left > 0) {  // no pair starts in the next 32 elements: next run
-        j0 = 0;
-        --runs_left;
-#pragma unroll
-        for (int d = kD - 2; d >= 0; --d) {
-            if (d >= g.lo) {
-                roff += g.stride[d];
-                if (++c[d] < box.e[d]) break;
-                roff -= (long long)box.e[d] * g.stride[d];
-                c[d] = 0;
-            }
-        }
-    }
-}
-
-template <int KIND, int MASK, bool XFORM, bool RUN, bool RING>
+template <int KIND, int MASK, bool XFORM, bool RING, bool LASTAX>
 __global__ void __launch_bounds__(kWThreads, Elem<KIND>::kWords == 1 ? 2 : 1)
 k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
                      unsigned long long* __restrict__ counts, unsigned long long items, unsigned groups) {
     constexpr int BYTES = Elem<KIND>::kBytes;
     static_assert(!RING || BYTES >= 4, "cp.async moves 4 bytes at least");
-    // the warp's ring: kSlots steps of kRows rows x 32 lanes (column walkers) or kRows steps x 33 elements (runs)
-    constexpr uint32_t kRowElems = RUN ? 33u : 32u;
-    constexpr uint32_t kSlotBytes = (uint32_t)kRows * kRowElems * (uint32_t)BYTES;
+    // the warp's ring, kSlots steps of kRows rows x 32 lanes.  Row-major ([row][lane], element-sized copies, coalesced
+    // rows) when the analysed axis is not the innermost dimension; LASTAX: lane-major ([lane][row]) so that a lane
+    // whose run starts on a 16-byte boundary copies 16 bytes (kRows * BYTES / 16 copies per step instead of kRows)
+    // and reads them back with 128-bit loads -- lane pitch 48 / 80 bytes keeps those conflict-free
+    constexpr uint32_t kLanePitch = LASTAX ? (uint32_t)(kRows * BYTES + 16) : (uint32_t)BYTES;
+    constexpr uint32_t kRowPitch = LASTAX ? (uint32_t)BYTES : 32u * (uint32_t)BYTES;
+    constexpr uint32_t kSlotBytes = LASTAX ? 32u * kLanePitch : (uint32_t)kRows * 32u * (uint32_t)BYTES;
     extern __shared__ uint8_t smem_ring[];
     const uint32_t ring0 = RING ? ((smem_addr_w(smem_ring) + 15u) & ~15u) + (threadIdx.x >> 5) * (kSlots * kSlotBytes) : 0u;
     uint32_t slot_w = 0, slot_r = 0;
@@ -236,28 +189,28 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
         asm volatile("" : "+r"(ea));
         if (ea < 2) continue;  // no pairs in this chunk
 
-        if constexpr (!RUN) {
-            // ---------------- column walkers ----------------
+        {
+            // column walkers: the chunk's columns (every dimension but the analysed one, flattened) in tiles of 32
             unsigned long long O = 1, I = 1;
 #pragma unroll
             for (int d = 0; d < kD; ++d) {
                 if (d < axis) O *= box.e[d];
                 if (d > axis) I *= box.e[d];
             }
-            const unsigned long long tiles_per_o = (I + 31) / 32, tiles = O * tiles_per_o;
+            const unsigned long long ncols = O * I, tiles = (ncols + 31) / 32;
             const unsigned long long t_lo = tiles * grp / groups, t_hi = tiles * (grp + 1) / groups;
             long long step_bytes = astride * BYTES;
             asm volatile("" : "+l"(step_bytes));
             for (unsigned long long tile = t_lo; tile < t_hi; ++tile) {
-                const unsigned long long o = tile / tiles_per_o, ti = tile - o * tiles_per_o;
-                const unsigned long long i = ti * 32 + lane;
-                unsigned live_u = i < I ? 1u : 0u;
+                const unsigned long long col = tile * 32 + lane;
+                unsigned live_u = col < ncols ? 1u : 0u;
                 asm volatile("" : "+r"(live_u));  // (else re-derived from the extents in every step)
                 const bool live = live_u != 0u;
                 // offset of this lane's column at row 0 of the chunk
                 long long off = box.base;
                 {
-                    unsigned long long ro = o, ri = live ? i : 0;
+                    const unsigned long long cc = live ? col : 0;
+                    unsigned long long ro = cc / I, ri = cc - ro * I;
 #pragma unroll
                     for (int d = kD - 1; d >= 0; --d) {
                         if (d > axis) { off += (long long)(ri % box.e[d]) * g.stride[d]; ri /= box.e[d]; }
@@ -265,30 +218,35 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
                     }
                 }
                 const char* p = static_cast<const char*>(x) + off * BYTES;  // row 0 of the column
+                // the walk starts AT row 0 with "no row above" (pk = 0): the first row is a current row like the others
                 uint32_t prev[NW], pk = 0u;  // previous row (transformed) and its keep-mask (0: masked or no such row)
 #pragma unroll
                 for (int k = 0; k < NW; ++k) prev[k] = 0;
-                if (live) {
-                    E::load(p, 0, prev);
-                    pk = keep_of(prev);
-                    if (XFORM) E::transform(prev);
-                }
-                unsigned nsteps = (ea - 1 + kRows - 1) / kRows;
+                unsigned nsteps = (ea + kRows - 1) / kRows;
                 asm volatile("" : "+r"(nsteps));
-                const char* q = p + step_bytes;  // row 1; advanced by the copies (RING) or the loads
+                // LASTAX: 16-byte copies when every lane's run starts on a 16-byte boundary (warp-uniform)
+                const bool vec = LASTAX && RING && __all_sync(0xFFFFFFFFu, !live || (reinterpret_cast<uintptr_t>(p) & 15u) == 0u);
+                const char* q = p;  // advanced by the copies (RING) or the loads
                 unsigned issued = 0;
-                // RING: copy step `issued` (16 rows of this lane's column) into the ring; a lane reads back only its own cells
+                // RING: copy step `issued` (kRows rows of this lane's column) into the ring; a lane reads back only its own cells
                 auto issue = [&]() {
                     if (issued < nsteps && live) {
-                        const uint32_t dst = ring0 + slot_w * kSlotBytes + lane * BYTES;
-                        const unsigned left = ea - 1 - kRows * issued;  // rows from this step on
+                        const uint32_t dst = ring0 + slot_w * kSlotBytes + lane * kLanePitch;
+                        const unsigned left = ea - kRows * issued;  // rows from this step on
                         if (left >= (unsigned)kRows) {
+                            if (LASTAX && vec) {
 #pragma unroll
-                            for (int u = 0; u < kRows; ++u) { cpa_elem<BYTES>(dst + u * 32 * BYTES, q); q += step_bytes; }
+                                for (int v = 0; v < kRows * BYTES / 16; ++v)
+                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * v), "l"(q + 16 * v) : "memory");
+                                q += kRows * BYTES;
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < kRows; ++u) { cpa_elem<BYTES>(dst + u * kRowPitch, q); q += step_bytes; }
+                            }
                         } else {
 #pragma unroll
                             for (int u = 0; u < kRows; ++u)
-                                if ((unsigned)u < left) { cpa_elem<BYTES>(dst + u * 32 * BYTES, q); q += step_bytes; }
+                                if ((unsigned)u < left) { cpa_elem<BYTES>(dst + u * kRowPitch, q); q += step_bytes; }
                         }
                     }
                     cpa_commit_w();
@@ -301,19 +259,34 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
                 }
 #pragma unroll 1
                 for (unsigned s = 0; s < nsteps; ++s) {
-                    const unsigned left = live ? ea - 1 - kRows * s : 0u;  // rows this lane has from this step on
+                    const unsigned left = live ? ea - kRows * s : 0u;  // rows this lane has from this step on
                     uint32_t raw[NW][kRows];
                     if constexpr (RING) {
                         issue();
                         cpa_wait_w<kAheadW>();
-                        const uint32_t src = ring0 + slot_r * kSlotBytes + lane * BYTES;
+                        const uint32_t src = ring0 + slot_r * kSlotBytes + lane * kLanePitch;
                         slot_r = (slot_r + 1 == kSlots) ? 0 : slot_r + 1;
+                        if constexpr (LASTAX) {
+                            // lane-major: the lane's kRows elements are contiguous (absent rows: stale cells, zeroed below)
+                            uint32_t flat[kRows * NW];
 #pragma unroll
-                        for (int u = 0; u < kRows; ++u) {
-                            uint32_t w[NW];
-                            lds_elem_w<NW>(src + u * 32 * BYTES, w);  // (absent rows: stale cells, zeroed below)
+                            for (int v = 0; v < kRows * BYTES / 16; ++v) {
+                                asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                             : "=r"(flat[4 * v]), "=r"(flat[4 * v + 1]), "=r"(flat[4 * v + 2]), "=r"(flat[4 * v + 3])
+                                             : "r"(src + 16 * v));
+                            }
 #pragma unroll
-                            for (int k = 0; k < NW; ++k) raw[k][u] = w[k];
+                            for (int u = 0; u < kRows; ++u)
+#pragma unroll
+                                for (int k = 0; k < NW; ++k) raw[k][u] = flat[u * NW + k];
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < kRows; ++u) {
+                                uint32_t w[NW];
+                                lds_elem_w<NW>(src + u * kRowPitch, w);  // (absent rows: stale cells, zeroed below)
+#pragma unroll
+                                for (int k = 0; k < NW; ++k) raw[k][u] = w[k];
+                            }
                         }
                     } else {
 #pragma unroll
@@ -327,8 +300,9 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
                         }
                     }
                     uint32_t wa[NW][kRows], wb[NW][kRows];
-                    if (__all_sync(0xFFFFFFFFu, left >= (unsigned)kRows)) {
-                        // every lane has all kRows rows (the common case): no "does the row exist" tests
+                    if (s > 0 && __all_sync(0xFFFFFFFFu, left >= (unsigned)kRows)) {
+                        // every lane has all kRows rows and a row above the first of them (the common case): no
+                        // "does the row exist" tests
                         uint32_t vbits = 0;
 #pragma unroll
                         for (int u = 0; u < kRows; ++u) {
@@ -375,114 +349,18 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
                 }
                 if constexpr (RING) slot_r = slot_w;  // the kAheadW groups committed past the end of the column were empty
             }
-        } else {
-            // ---------------- runs along the innermost dimension ----------------
-            unsigned long long R = 1;
-#pragma unroll
-            for (int d = 0; d < kD - 1; ++d) R *= box.e[d];
-            const unsigned long long r_lo = R * grp / groups, r_hi = R * (grp + 1) / groups;
-            if (r_hi <= r_lo) continue;
-            const unsigned e4 = box.e[kD - 1];
-            {
-                RunCursor cons;  // (uniform) where the fold is
-                cons.init(box, g, r_lo, r_hi - r_lo);
-                RunCursor prod = cons;  // RING: where the copies are, kAheadW folds of 16 steps ahead
-                auto issue = [&]() {
-                    const uint32_t dst = ring0 + slot_w * kSlotBytes;
-#pragma unroll
-                    for (int u = 0; u < kRows; ++u) {
-                        long long ro;
-                        unsigned jj;
-                        bool act;
-                        prod.step(box, g, e4, ro, jj, act);
-                        const unsigned j = jj + lane;
-                        const char* src = static_cast<const char*>(x) + (ro + j) * BYTES;
-                        if (act && j < e4) cpa_elem<BYTES>(dst + (u * 33 + lane) * BYTES, src);
-                        if (act && lane == 0 && jj + 32 < e4)  // the partner of lane 31's element
-                            cpa_elem<BYTES>(dst + (u * 33 + 32) * BYTES, src + 32 * BYTES);
-                    }
-                    cpa_commit_w();
-                    slot_w = (slot_w + 1 == kSlots) ? 0 : slot_w + 1;
-                };
-                if constexpr (RING) {
-#pragma unroll 1
-                    for (int k = 0; k < kAheadW; ++k) issue();
-                }
-#pragma unroll 1
-                while (cons.runs_left > 0) {
-                    uint32_t wa[NW][kRows], wb[NW][kRows], pairs = 0;  // pairs: bit u = this lane's pair of step u exists
-                    if constexpr (RING) {
-                        issue();
-                        cpa_wait_w<kAheadW>();
-                        __syncwarp();  // the neighbours' copies have landed as well
-                        const uint32_t src = ring0 + slot_r * kSlotBytes;
-                        slot_r = (slot_r + 1 == kSlots) ? 0 : slot_r + 1;
-#pragma unroll
-                        for (int u = 0; u < kRows; ++u) {
-                            long long ro;
-                            unsigned jj;
-                            bool act;
-                            cons.step(box, g, e4, ro, jj, act);
-                            pairs |= ((act && jj + lane + 1 < e4) ? 1u : 0u) << u;
-                            uint32_t a[NW], b[NW];
-                            lds_elem_w<NW>(src + (u * 33 + lane) * BYTES, a);
-                            lds_elem_w<NW>(src + (u * 33 + lane + 1) * BYTES, b);
-#pragma unroll
-                            for (int k = 0; k < NW; ++k) { wa[k][u] = a[k]; wb[k][u] = b[k]; }
-                        }
-                        __syncwarp();  // everybody has read this slot before the next copies overwrite it
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < kRows; ++u) {
-                            long long ro;
-                            unsigned jj;
-                            bool act;
-                            cons.step(box, g, e4, ro, jj, act);
-                            const bool pair = act && jj + lane + 1 < e4;
-                            pairs |= (pair ? 1u : 0u) << u;
-                            uint32_t a[NW], b[NW];
-#pragma unroll
-                            for (int k = 0; k < NW; ++k) { a[k] = 0; b[k] = 0; }
-                            if (pair) {
-                                E::load(x, ro + jj + lane, a);
-                                E::load(x, ro + jj + lane + 1, b);
-                            }
-#pragma unroll
-                            for (int k = 0; k < NW; ++k) { wa[k][u] = a[k]; wb[k][u] = b[k]; }
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < kRows; ++u) {
-                        uint32_t a[NW], b[NW];
-#pragma unroll
-                        for (int k = 0; k < NW; ++k) { a[k] = wa[k][u]; b[k] = wb[k][u]; }
-                        uint32_t m = ((pairs >> u) & 1u) ? 0xFFFFFFFFu : 0u;
-                        if (MASK != kMaskNone) m &= keep_of(a) & keep_of(b);
-                        if (XFORM) { E::transform(a); E::transform(b); }
-                        nvalid += m & 1u;
-#pragma unroll
-                        for (int k = 0; k < NW; ++k) { wa[k][u] = a[k] & m; wb[k][u] = b[k] & m; }
-                    }
-                    fold(wa, wb);
-                }
-                if constexpr (RING) {
-                    cpa_wait_w<0>();
-                    __syncwarp();
-                    slot_r = slot_w = 0;
-                }
-            }
         }
     }
     if (cur_chunk != 0xFFFFFFFFu) flush_chunk(cur_chunk);
 }
 
-template <int KIND, int MASK, bool XFORM, bool RUN>
-cudaError_t launch_walk_variant(const void* x, const ChunkGrid& g, uint32_t mlo, uint32_t mhi, unsigned long long* counts,
-                                unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream) {
+template <int KIND, int MASK, bool XFORM, bool LASTAX>
+cudaError_t launch_walk_ax(const void* x, const ChunkGrid& g, uint32_t mlo, uint32_t mhi, unsigned long long* counts,
+                           unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream) {
     constexpr int BYTES = Elem<KIND>::kBytes;
     constexpr bool RING = BYTES >= 4;
-    constexpr size_t smem = RING ? 16 + (size_t)kWWarps * kSlots * kRows * (RUN ? 33 : 32) * BYTES : 0;
-    auto kern = k_pairs_chunked_walk<KIND, MASK, XFORM, RUN, RING>;
+    constexpr size_t smem = RING ? 16 + (size_t)kWWarps * kSlots * 32 * (LASTAX ? kRows * BYTES + 16 : kRows * BYTES) : 0;
+    auto kern = k_pairs_chunked_walk<KIND, MASK, XFORM, RING, LASTAX>;
     if (smem > 48 * 1024) {
         int dev = 0;
         cudaGetDevice(&dev);
@@ -501,8 +379,10 @@ cudaError_t launch_walk_variant(const void* x, const ChunkGrid& g, uint32_t mlo,
 template <int KIND, int MASK, bool XFORM>
 cudaError_t launch_walk(const void* x, const ChunkGrid& g, uint32_t mlo, uint32_t mhi, unsigned long long* counts,
                         unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream) {
-    if (g.axis == kD - 1) return launch_walk_variant<KIND, MASK, XFORM, true>(x, g, mlo, mhi, counts, items, groups, grid, stream);
-    return launch_walk_variant<KIND, MASK, XFORM, false>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+    if constexpr (Elem<KIND>::kBytes >= 4) {
+        if (g.axis == kD - 1) return launch_walk_ax<KIND, MASK, XFORM, true>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+    }
+    return launch_walk_ax<KIND, MASK, XFORM, false>(x, g, mlo, mhi, counts, items, groups, grid, stream);
 }
 
 template <int KIND>
@@ -543,25 +423,18 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = dtype_bytes(dtype) == 8 ? 1 : 2;
     const unsigned long long warps = (unsigned long long)sms * per_sm * kWWarps;
-    // the work inside a (full) chunk that the warps share: column tiles, or runs
-    unsigned long long units = 1;
-    if (g.axis == kD - 1) {
-        // the run variant is correct but not yet faster than the odometer kernel (0.7-1.0 TB/s against 1.1: two
-        // uniform cursors and two transforms per pair); it runs when asked for (tests), the planner does not pick it
-        if (!force) return cudaSuccess;
-        for (int d = 0; d < kD - 1; ++d) units *= g.chunk[d];
-    } else {
-        unsigned long long O = 1, I = 1;
-        for (int d = 0; d < kD; ++d) {
-            if (d < g.axis) O *= g.chunk[d];
-            if (d > g.axis) I *= g.chunk[d];
-        }
-        units = O * ((I + 31) / 32);
-    }
-    if (units * nchunks < 2 * warps && !force) return cudaSuccess;  // too few columns / runs to occupy the GPU this way
-    // items per chunk: one column tile, or one block of 16 runs, each (edge chunks: some items stay empty)
-    unsigned long long groups = g.axis == kD - 1 ? (units + 15) / 16 : units;
-    if (groups < 1) groups = 1;
+    // the work inside a (full) chunk that the warps share: tiles of 32 columns
+    unsigned long long cols = 1;
+    for (int d = 0; d < kD; ++d)
+        if (d != g.axis) cols *= g.chunk[d];
+    const unsigned long long units = (cols + 31) / 32;
+    if (units * nchunks < 2 * warps && !force) return cudaSuccess;  // too few columns to occupy the GPU this way
+    // the innermost dimension as analysed axis: lanes sit on neighbouring RUNS, each copy instruction touches 32
+    // different sectors; worth it only while a lane uses up its sectors, i.e. runs of at least a sector or two
+    if (g.axis == kD - 1 && ((unsigned long long)g.chunk[kD - 1] * dtype_bytes(dtype) < 64 || dtype_bytes(dtype) < 4) && !force)
+        return cudaSuccess;
+    // items per chunk: one column tile each (edge chunks: some items stay empty)
+    unsigned long long groups = units;
     if (groups > 0xFFFFFFFFull) return cudaSuccess;
     const unsigned long long items = groups * nchunks;
     const unsigned grid = (unsigned)(sms * per_sm);
