@@ -73,11 +73,16 @@ while time.time() < t_end:
         print("case", n_cases, shape, dtype, "axis", axis, "spec", spec, "mv", mv, flush=True)
     t = torch.from_numpy(x).cuda()
     got = count_pairs_chunked(t, spec, axis, masked_value=mv).cpu().numpy()
+    # both chunk-grid kernels whatever the planner picks: the column walkers and the per-element odometers
+    got_walk = count_pairs_chunked(t, spec, axis, masked_value=mv, flavour="walk").cpu().numpy()
+    got_odo = count_pairs_chunked(t, spec, axis, masked_value=mv, flavour="odometer").cpu().numpy()
     grid = normalize_chunks(shape, spec)
     gshape = tuple(len(c) for c in grid)
     for idx, sl in zip(np.ndindex(*gshape), slices_from_chunks(grid)):
         want = bo.bitinformation(x[sl], axis, masked_value=mv)[0]
         assert np.array_equal(got[idx], want), ("counts", shape, dtype, spec, axis, mv, idx)
+        assert np.array_equal(got_walk[idx], want), ("counts (walkers)", shape, dtype, spec, axis, mv, idx)
+        assert np.array_equal(got_odo[idx], want), ("counts (odometers)", shape, dtype, spec, axis, mv, idx)
     if np.dtype(dtype).kind == "f":
         mant = {"float16": 10, "float32": 23, "float64": 52}[dtype]
         keep = rng.integers(0, mant, size=gshape, endpoint=True).astype("int32")

@@ -17,7 +17,7 @@ sys.path.insert(0, "tests")
 from oracle import bitinfo_oracle as bo
 from oracle import bitround_oracle as bro
 from xbitinfo_b200 import engine
-from xbitinfo_b200.device import PairCounter, bitround_
+from xbitinfo_b200.device import MultiAxisCounter, PairCounter, bitround, bitround_
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--seconds", type=float, default=60.0)
@@ -77,7 +77,22 @@ while time.time() < t_end:
         pc.reset()
         pc.add(t, axis, masked_value=mv, **kw)
         assert np.array_equal(pc.counts.cpu().numpy(), want_c), ("K1", shape, dtype, axis, mv, offset, kw)
+    # the fused entry point (xbi_bitinformation_dev: counts overwritten, K2 in the finish kernel) ...
+    pc.counts.fill_(-7)
+    mi_f = pc.bitinformation(t, axis, masked_value=mv).cpu().numpy()
+    assert np.array_equal(pc.counts.cpu().numpy(), want_c), ("fused", shape, dtype, axis, mv, offset)
+    # ... and every axis of the array in one call (the two innermost share one read where the kernel applies)
+    if nd >= 2 and rng.random() < 0.5:
+        axes = [int(a) for a in rng.permutation(nd)[: int(rng.integers(2, nd + 1))]]
+        mc = MultiAxisCounter(t.dtype, len(axes), t.device)
+        mc.bitinformation(t, axes, masked_value=mv)
+        got = mc.counts.cpu().numpy()
+        for i, a in enumerate(axes):
+            assert np.array_equal(got[i], bo.bitinformation(x, a, masked_value=mv)[0]), ("multi", shape, dtype, axes, a, mv, offset)
+    pc.reset()
+    pc.add(t, axis, masked_value=mv)
     mi = pc.information(False).cpu().numpy()
+    assert np.array_equal(mi, mi_f, equal_nan=True), ("fused K2", shape, dtype, axis, mv)
     if np.isnan(want_mi).all():
         assert np.isnan(mi).all()
     else:
@@ -98,6 +113,10 @@ while time.time() < t_end:
         else:
             bitround_(r, kb)
         assert np.array_equal(r.cpu().numpy().view(u), want_r), ("K3", shape, dtype, kb, offset)
+        t.copy_(torch.from_numpy(x))
+        o = bitround(t, kb)  # out of place: the input stays as it is
+        assert np.array_equal(o.cpu().numpy().view(u), want_r) and np.array_equal(t.cpu().numpy().view(u), x.view(u)), \
+            ("K3 out of place", shape, dtype, kb, offset)
         assert np.array_equal(engine.bitround(x, kb).view(u), want_r), ("K3 host", shape, dtype, kb)
     n_cases += 1
 print(f"fuzz ok: {n_cases} random cases in {args.seconds:.0f} s (seed {args.seed})")
