@@ -23,7 +23,7 @@ template <int KIND, int MASK, bool XFORM, int MODE>
 __global__ void __launch_bounds__(kThreads)
 k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long long n, long long inner,
                 uint32_t mask_lo, uint32_t mask_hi, RawSums* __restrict__ dst, const RawSums* dense_probe,
-                unsigned long long dense_one_in, long long stride, int stream_sel) {
+                unsigned long long dense_one_in) {
     using E = Elem<KIND>;
     if (MODE == 2 && dense_probe != nullptr && sampled_mask_is_dense(dense_probe, dense_one_in)) return;
     constexpr int NW = E::kWords;
@@ -79,7 +79,7 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
                         while (ei >= inner) { ei -= inner; ++eo; }
                     }
                 } else {
-                    f = lo + (MODE == 2 ? t * stride : t);  // (MODE 2: every stride-th element, e.g. one column)
+                    f = lo + t;
                 }
                 E::load(x, f, a);
                 if (MODE != 2) E::load(x, f + inner, b);
@@ -120,7 +120,7 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
 #pragma unroll
     for (int w = 0; w < NW; ++w) {
         const int j = w * 32 + lane;
-        if (accA[w]) atomicAdd(&s_sum[MODE == 2 ? stream_sel : (int)S_A][j], accA[w]);  // (MODE 2: the planes go where asked)
+        if (accA[w]) atomicAdd(&s_sum[S_A][j], accA[w]);
         if (accB[w]) atomicAdd(&s_sum[S_B][j], accB[w]);
         if (accAB[w]) atomicAdd(&s_sum[S_AB][j], accAB[w]);
     }
@@ -178,7 +178,7 @@ cudaError_t launch_density_kind(const CountJob& job, long long nsamples, long lo
 
 template <int KIND, int MASK, bool XFORM, int MODE>
 cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream,
-                       const RawSums* dense_probe, unsigned long long dense_one_in, long long stride = 1, int stream_sel = S_A) {
+                       const RawSums* dense_probe, unsigned long long dense_one_in) {
     if (count <= 0) return cudaSuccess;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -188,47 +188,46 @@ cudaError_t launch_one(const CountJob& job, long long lo, long long count, RawSu
     if (grid > tiles) grid = tiles;
     k_pairs_generic<KIND, MASK, XFORM, MODE><<<(unsigned)grid, kThreads, 0, stream>>>(
         job.x, lo, count, job.n, job.inner, (uint32_t)(job.mask_bits & 0xFFFFFFFFu),
-        (uint32_t)(job.mask_bits >> 32), dst, dense_probe, dense_one_in, stride, stream_sel);
+        (uint32_t)(job.mask_bits >> 32), dst, dense_probe, dense_one_in);
     note_launch();
     return cudaGetLastError();
 }
 
 template <int KIND, int MODE>
 cudaError_t dispatch_mask(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream,
-                          const RawSums* dense_probe, unsigned long long dense_one_in, long long stride, int stream_sel) {
+                          const RawSums* dense_probe, unsigned long long dense_one_in) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (job.transform) {
         if constexpr (isf) {
             switch (job.mask_mode) {
-                case kMaskNone: return launch_one<KIND, kMaskNone, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-                case kMaskNaN: return launch_one<KIND, kMaskNaN, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-                default: return launch_one<KIND, kMaskValue, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
+                case kMaskNone: return launch_one<KIND, kMaskNone, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+                case kMaskNaN: return launch_one<KIND, kMaskNaN, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+                default: return launch_one<KIND, kMaskValue, true, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
             }
         } else {
             return cudaErrorInvalidValue;
         }
     }
     switch (job.mask_mode) {
-        case kMaskNone: return launch_one<KIND, kMaskNone, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
+        case kMaskNone: return launch_one<KIND, kMaskNone, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
         case kMaskNaN:
-            if constexpr (isf) return launch_one<KIND, kMaskNaN, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
+            if constexpr (isf) return launch_one<KIND, kMaskNaN, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
             return cudaErrorInvalidValue;
-        default: return launch_one<KIND, kMaskValue, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
+        default: return launch_one<KIND, kMaskValue, false, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
     }
 }
 
 template <int MODE>
 cudaError_t dispatch_kind(const CountJob& job, long long lo, long long count, RawSums* dst, cudaStream_t stream,
-                          const RawSums* dense_probe = nullptr, unsigned long long dense_one_in = 0, long long stride = 1,
-                          int stream_sel = S_A) {
+                          const RawSums* dense_probe = nullptr, unsigned long long dense_one_in = 0) {
     switch (job.dtype) {
-        case XBI_U8: return dispatch_mask<kU8, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-        case XBI_U16: return dispatch_mask<kU16, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-        case XBI_U32: return dispatch_mask<kU32, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-        case XBI_U64: return dispatch_mask<kU64, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-        case XBI_F16: return dispatch_mask<kF16, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-        case XBI_F32: return dispatch_mask<kF32, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
-        case XBI_F64: return dispatch_mask<kF64, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in, stride, stream_sel);
+        case XBI_U8: return dispatch_mask<kU8, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_U16: return dispatch_mask<kU16, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_U32: return dispatch_mask<kU32, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_U64: return dispatch_mask<kU64, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_F16: return dispatch_mask<kF16, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_F32: return dispatch_mask<kF32, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
+        case XBI_F64: return dispatch_mask<kF64, MODE>(job, lo, count, dst, stream, dense_probe, dense_one_in);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -270,11 +269,6 @@ cudaError_t launch_mask_density(const CountJob& job, int64_t npairs_flat, Worksp
 cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream,
                                const RawSums* dense_probe, unsigned long long dense_one_in) {
     return dispatch_kind<2>(job, lo, count, dst, stream, dense_probe, dense_one_in);
-}
-
-cudaError_t launch_elem_planes_strided(const CountJob& job, int64_t lo, int64_t count, int64_t stride, RawSums* dst,
-                                       int stream_sel, cudaStream_t stream) {
-    return dispatch_kind<2>(job, lo, count, dst, stream, nullptr, 0, stride, stream_sel);
 }
 
 }  // namespace xbi

@@ -69,10 +69,6 @@ cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int
 cudaError_t launch_elem_planes(const CountJob& job, int64_t lo, int64_t count, RawSums* dst, cudaStream_t stream,
                                const RawSums* dense_probe = nullptr, unsigned long long dense_one_in = 0);
 
-// the same for every stride-th element (f = lo + t*stride, t < count), added to dst->sums[stream_sel]; unmasked jobs
-cudaError_t launch_elem_planes_strided(const CountJob& job, int64_t lo, int64_t count, int64_t stride, RawSums* dst,
-                                       int stream_sel, cudaStream_t stream);
-
 // TMA fast paths.  Each consumes as much of [0, numel-inner) as its alignment rules
 // allow, reports the flat range it covered in [*done_lo, *done_hi) (empty if none), and
 // leaves the rest to the generic kernel.
