@@ -670,7 +670,7 @@ def run_e2e(args, x_dev, rank, world, dev, sync_all, dist_max):
         out["h2d_probe_1GiB_pinned"] = {"alone_GBps": [round(float(v), 1) for v in a],
                                         "together_GBps": [round(float(v), 1) for v in t],
                                         "together_sum_GBps": round(float(sum(t)), 1)}
-        del dst
+        del src, dst
         spread = max(t) / max(min(t), 1e-9)
         if os.environ.get("XBI_BENCH_FORCE_WEIGHTED") == "1":  # (exercise the weighted path on a box with equal links)
             t = [v * (1.0 + 0.5 * (i % 2)) for i, v in enumerate(t)]
