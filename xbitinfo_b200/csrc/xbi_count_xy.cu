@@ -79,7 +79,10 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
 
     const long long n_items = spr * nseg;
     const long long warps_total = (long long)gridDim.x * kWarpsXY;
-    const long long groups = seg_min >> 2;
+    // 32-bit loop counters and opaque loop invariants: left alone, ptxas re-derives `groups` from the kernel
+    // parameters and compares 64-bit counters in every group (a dozen uniform-pipe instructions per iteration)
+    unsigned groups = (unsigned)(seg_min >> 2);
+    asm volatile("" : "+r"(groups));
 
     // block totals (flushes are rare: they add straight into shared memory, no per-lane 64-bit accumulators)
     __shared__ unsigned long long s_sum[5][32];  // sum x' (cur rows), x' & above, x' & right, first column, last column
@@ -133,8 +136,9 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
         role = new_role;
         const bool col_warp = __any_sync(0xFFFFFFFFu, role != 0u);
         const long long row_begin = seg * seg_min + (seg < seg_extra ? seg : seg_extra);
-        const int tail_rows = (int)(seg_min + (seg < seg_extra ? 1 : 0) - (groups << 2));  // 0..4, warp-uniform
-        const long long ngroups = groups + (tail_rows > 0 ? 1 : 0);
+        int tail_rows = (int)(seg_min + (seg < seg_extra ? 1 : 0) - ((long long)groups << 2));  // 0..4, warp-uniform
+        unsigned ngroups = groups + (tail_rows > 0 ? 1u : 0u);
+        asm volatile("" : "+r"(tail_rows), "+r"(ngroups));
 
         // cells the copies of this item will never write: neutral value in every slot of the ring
         // (nothing of the previous item is in flight any more)
@@ -147,7 +151,7 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
         }
         const char* q0 = x + row_begin * row_bytes + (live ? chunk : 0) * 16;
         const char* q = q0 + row_bytes;
-        long long issued = 0;
+        unsigned issued = 0;
         auto issue = [&]() {
             if (issued < ngroups && live) {
                 const uint32_t dst = my0 + slot_w * kTileXY;
@@ -184,7 +188,7 @@ k_pairs_cols_xy(const char* __restrict__ x, long long row_bytes, long long cpr, 
             for (int i = 0; i < 4; ++i) prev[i] = xf<KIND, XFORM>(raw[i]);
         }
 #pragma unroll 1
-        for (long long g = 0; g < ngroups; ++g) {
+        for (unsigned g = 0; g < ngroups; ++g) {
             issue();
             cpa_wait<kAheadXY>();
             __syncwarp();  // the neighbour's copies have landed as well
