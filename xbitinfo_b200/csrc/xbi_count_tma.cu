@@ -192,7 +192,14 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31u;
 
+    // block totals; the boundary corrections of the masked modes are added to s_minus as they occur
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_minus[2][64];  // boundary corrections of the a and b streams
+    __shared__ unsigned long long s_ninvalid;
+    for (int i = threadIdx.x; i < 3 * 64; i += kThreads) (&s_sum[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < 2 * 64; i += kThreads) (&s_minus[0][0])[i] = 0;
     if (threadIdx.x == 0) {
+        s_ninvalid = 0;
         for (int s = 0; s < S::kStages; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, kCountWarps + ((!S::k64 && row_len > 0) ? 1 : 0));
@@ -376,8 +383,7 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     // sparse flavour: pairs with a masked element; dense flavour: valid pairs (this thread, since the last flush)
     uint32_t ninvalid = 0;
     unsigned long long ninvalid_total = 0;
-    BoundaryEvents<(MASKED && !DENSE) ? Elem<KIND>::kWords : 1> ev;
-    ev.init();
+    constexpr uint32_t kEvFold = S::kBits < 32 ? S::kBits : 32;  // (boundary corrections: see warp_event_push)
     uint32_t it = 0;
 
     auto flush = [&]() {
@@ -475,14 +481,14 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                         ninvalid += count_fields<BYTES>(~(keep[i] & ks));
                         bnd |= keep[i] ^ ks;
                     }
-                    if (bnd) {  // validity changes inside this thread's words: rare
-                        ev.touch();
+                    if (__any_sync(0xFFFFFFFFu, bnd != 0u)) {  // validity changes inside some thread's words: rare
 #pragma unroll
                         for (int i = 0; i < 16; ++i) {
                             const uint32_t ks = successor_word<BYTES>(keep[i], keep[i + 1]);
-                            const uint32_t va = keep[i] & ~ks, vb = ~keep[i] & ks;
-                            if (va) ev.add_a(0, tw[i] & va);
-                            if (vb) ev.add_b(0, successor_word<BYTES>(tw[i], tw[i + 1]) & vb);
+                            const uint32_t va[1] = {tw[i] & keep[i] & ~ks};
+                            const uint32_t vb[1] = {successor_word<BYTES>(tw[i], tw[i + 1]) & ~keep[i] & ks};
+                            warp_event_push<0>((keep[i] & ~ks) != 0u, va, lane, s_minus, kEvFold);
+                            warp_event_push<1>((~keep[i] & ks) != 0u, vb, lane, s_minus, kEvFold);
                         }
                     }
                 }
@@ -508,46 +514,51 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
                     if (__all_sync(0xFFFFFFFFu, all_masked_quick<KIND, MT>(w, mask_lo, mask_hi))) {
                         ninvalid += 16u;
                         skip = true;
-                    } else if (tdirty) {
-                        uint32_t m = 0u;  // bit e: element e (0..16) is masked
+                    } else {
+                        uint32_t m = 0u, bnd = 0u;  // bit e: element e (0..16) is masked / differs in validity from e+1
+                        if (tdirty) {
 #pragma unroll
-                        for (int e = 0; e < 17; ++e) {
-                            if (masked_elem<KIND, MT>(w[WPE * e], w[WPE * e + WPE - 1], mask_lo, mask_hi)) {
-                                m |= 1u << e;
-                                // overwritten with the value whose transform is 0: drops out of every sum
+                            for (int e = 0; e < 17; ++e) {
+                                if (masked_elem<KIND, MT>(w[WPE * e], w[WPE * e + WPE - 1], mask_lo, mask_hi)) {
+                                    m |= 1u << e;
+                                    // overwritten with the value whose transform is 0: drops out of every sum
 #pragma unroll
-                                for (int k = 0; k < WPE; ++k) w[WPE * e + k] = neutral_word<KIND, XFORM>(k);
+                                    for (int k = 0; k < WPE; ++k) w[WPE * e + k] = neutral_word<KIND, XFORM>(k);
+                                }
                             }
+                            ninvalid += __popc((m | (m >> 1)) & 0xFFFFu);
+                            bnd = (m ^ (m >> 1)) & 0xFFFFu;
                         }
-                        ninvalid += __popc((m | (m >> 1)) & 0xFFFFu);
-                        uint32_t bnd = (m ^ (m >> 1)) & 0xFFFFu;
-                        if (bnd) ev.touch();
-                        // validity changes between elements e and e+1: the valid one of the two is
-                        // re-read from the stage buffer (still ours) and rippled into the corrections
+                        // validity changes between elements e and e+1: the valid one of the two is re-read from
+                        // the stage buffer (still ours), transformed, and handed to the warp (WarpEvents), one
+                        // boundary per lane and round
 #pragma unroll 1
-                        while (bnd) {
-                            const uint32_t e = (uint32_t)__ffs((int)bnd) - 1u;
-                            bnd &= bnd - 1u;
-                            const bool a_masked = (m >> e) & 1u;
-                            const uint32_t ve = a_masked ? e + 1u : e;
-                            const uint32_t wi = ve * WPE;  // word index inside the thread's segment
-                            const uint32_t addr = (ve == 16u)
-                                                      ? (nb_halo ? (halo0 + 16 * s) : (sbase + nb_off))
-                                                      : (sbase + row * kRowBytes + (((cbase + (wi >> 2)) ^ swz) << 4) + ((wi & 3u) << 2));
+                        while (__any_sync(0xFFFFFFFFu, bnd != 0u)) {
+                            const bool have = bnd != 0u;
+                            bool a_masked = false;
                             uint32_t v[Elem<KIND>::kWords];
-                            if constexpr (S::k64) {
-                                const uint2 q = lds64(addr);
-                                v[0] = q.x;
-                                v[1] = q.y;
-                            } else {
-                                v[0] = lds32(addr);
-                            }
-                            if (XFORM) Elem<KIND>::transform(v);
 #pragma unroll
-                            for (int k = 0; k < WPE; ++k) {
-                                if (a_masked) ev.add_b(k, v[k]);
-                                else ev.add_a(k, v[k]);
+                            for (int k = 0; k < WPE; ++k) v[k] = 0u;
+                            if (have) {
+                                const uint32_t e = (uint32_t)__ffs((int)bnd) - 1u;
+                                bnd &= bnd - 1u;
+                                a_masked = (m >> e) & 1u;
+                                const uint32_t ve = a_masked ? e + 1u : e;
+                                const uint32_t wi = ve * WPE;  // word index inside the thread's segment
+                                const uint32_t addr = (ve == 16u)
+                                                          ? (nb_halo ? (halo0 + 16 * s) : (sbase + nb_off))
+                                                          : (sbase + row * kRowBytes + (((cbase + (wi >> 2)) ^ swz) << 4) + ((wi & 3u) << 2));
+                                if constexpr (S::k64) {
+                                    const uint2 q = lds64(addr);
+                                    v[0] = q.x;
+                                    v[1] = q.y;
+                                } else {
+                                    v[0] = lds32(addr);
+                                }
+                                if (XFORM) Elem<KIND>::transform(v);
                             }
+                            warp_event_push<0>(have && !a_masked, v, lane, s_minus, kEvFold);
+                            warp_event_push<1>(have && a_masked, v, lane, s_minus, kEvFold);
                         }
                     }
                 }
@@ -587,15 +598,7 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     flush();
 
     // ---- block reduction over the 15 counting warps (named barrier 1, producer not involved)
-    __shared__ unsigned long long s_sum[3][64];
-    __shared__ unsigned long long s_minus[2][64];  // boundary corrections of the a and b streams
-    __shared__ unsigned long long s_ninvalid;
-    for (int i = t; i < 3 * 64; i += kCountThreads) (&s_sum[0][0])[i] = 0;
-    if (MASKED) {
-        for (int i = t; i < 2 * 64; i += kCountThreads) (&s_minus[0][0])[i] = 0;
-        if (t == 0) s_ninvalid = 0;
-    }
-    asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
+    // (s_sum, s_minus, s_ninvalid were zeroed before the first barrier of the kernel)
 #pragma unroll
     for (int i = 0; i < NL; ++i) {
         const int j = S::k64 ? (i * 32 + (int)lane) : ((int)lane % S::kBits);
@@ -609,7 +612,6 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
     }
     if (MASKED) {
         if (ninvalid_total) atomicAdd(&s_ninvalid, ninvalid_total);
-        if (!DENSE) ev.drain(s_minus, S::kBits, lane);
     }
     asm volatile("bar.sync 1, %0;" ::"n"(kCountThreads) : "memory");
     for (int i = t; i < 3 * 64; i += kCountThreads) {

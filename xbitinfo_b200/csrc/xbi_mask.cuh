@@ -15,8 +15,9 @@
 //      ALU pipe where possible (x*0 accumulated with FFMA/HFMA2: NaN iff a NaN/Inf went in);
 //   2. take the plain unmasked code when a whole warp is clean;
 //   3. otherwise build the keep-masks, zero the masked elements, count the invalid pairs
-//      and, at validity boundaries only, ripple the correction words into a rare-event
-//      vertical counter kept in local memory (-> the `minus` sums of the workspace).
+//      and, at validity boundaries only, add the correction words to small counters (rows kernel:
+//      broadcast over the warp, WarpEvents; column walkers: register bit planes, EventPlanes)
+//      (-> the `minus` sums of the workspace).
 // The probe may report false positives (Inf, doubles >= 2^1017, ...), never false negatives:
 // step 3 always uses the exact test.
 #pragma once
@@ -206,84 +207,28 @@ __device__ __forceinline__ bool all_masked_quick(const uint32_t (&w)[N], uint32_
 }
 
 // ---------------------------------------------------------------------------------
-// rare-event vertical counter: 32 bit planes in local memory (one array per stream and
-// word), rippled with early exit; capacity 2^32-1 events per lane and bit -- more than a
-// thread can see in one launch.
+// Boundary corrections of the rows kernel, warp-cooperative: a correction word is broadcast to the warp
+// (__shfl_sync) and every lane L whose bit L of it is set bumps the block's shared total of bit position L.
+// No bit planes, no registers, no local memory, no butterfly at the end; an event costs the whole warp a
+// shuffle, a test and (for about half the lanes) one shared-memory atomic.  (The per-thread rippled planes in
+// local memory this replaces cost land-masked arrays a tenth to a third of their throughput: every event was a
+// chain of dependent local loads and stores that 31 lanes waited for.)  All calls warp-converged.
+//   s_minus: shared [2][64] totals (stream a, stream b), bit number from the least significant bit, zeroed
+//   before the first event; fold = min(bits per element, 32): packed types fold their fields onto one another.
 // ---------------------------------------------------------------------------------
-static __device__ __noinline__ void event_add(uint32_t* n, uint32_t w) {
-#pragma unroll 1
-    for (int j = 0; j < 32 && w != 0u; ++j) {
-        const uint32_t t = n[j] & w;
-        n[j] ^= w;
-        w = t;
+template <int STREAM, int NW>
+__device__ __forceinline__ void warp_event_push(bool have, const uint32_t (&v)[NW], uint32_t lane,
+                                                unsigned long long (*s_minus)[64], uint32_t fold) {
+    // STREAM 0: a valid / b masked (a-stream correction), 1: a masked / b valid
+    unsigned hv = __ballot_sync(0xFFFFFFFFu, have);
+    while (hv) {
+        const int src = __ffs((int)hv) - 1;
+        hv &= hv - 1u;
+#pragma unroll
+        for (int k = 0; k < NW; ++k)
+            if ((__shfl_sync(0xFFFFFFFFu, v[k], src) >> lane) & 1u) atomicAdd(&s_minus[STREAM][k * 32 + (int)(lane % fold)], 1ull);
     }
 }
-static __device__ __noinline__ void event_clear(uint32_t* n, int words) {
-#pragma unroll 1
-    for (int j = 0; j < words; ++j) n[j] = 0u;
-}
-// Warp-collective drain (all 32 lanes call): the 32 planes of every lane that used its
-// counter are summed over the warp with the butterfly of xbi_common.cuh; lane L ends up with
-// the warp's count of bit position L and adds it to dst[L % nbits] (shared-memory totals).
-static __device__ __noinline__ void event_drain_warp(const uint32_t* planes, bool used, uint32_t lane,
-                                                     unsigned long long* dst, int nbits) {
-    constexpr int P = 32;
-    uint32_t n[P + 6];
-#pragma unroll 1
-    for (int j = 0; j < P; ++j) n[j] = used ? planes[j] : 0u;
-#pragma unroll 1
-    for (int j = P; j < P + 6; ++j) n[j] = 0u;
-    for (int step = 0; step < 5; ++step) {
-        const int d = 16 >> step;
-        const uint32_t hi_sel = (d == 16) ? 0xFFFF0000u : (d == 8) ? 0xFF00FF00u : (d == 4) ? 0xF0F0F0F0u
-                               : (d == 2) ? 0xCCCCCCCCu : 0xAAAAAAAAu;
-        const uint32_t keep = (lane & d) ? hi_sel : ~hi_sel;
-        uint32_t carry = 0;
-        const int np = P + step;
-#pragma unroll 1
-        for (int j = 0; j < np; ++j) {
-            const uint32_t mine = n[j] & keep;
-            const uint32_t give = n[j] & ~keep;
-            const uint32_t got = __shfl_xor_sync(0xFFFFFFFFu, give, d);
-            uint32_t hi, lo;
-            csa(hi, lo, mine, got, carry);
-            n[j] = lo;
-            carry = hi;
-        }
-        n[np] = carry;
-    }
-    unsigned long long total = 0;
-#pragma unroll 1
-    for (int j = 0; j < P + 5; ++j) total |= (unsigned long long)((n[j] >> lane) & 1u) << j;
-    if (total) atomicAdd(&dst[lane % nbits], total);
-}
-
-// Per-thread state of the boundary corrections: [stream a/b][word lo/hi][32 planes].
-template <int NW>
-struct BoundaryEvents {
-    uint32_t planes[2][NW][32];
-    bool used;
-    __device__ __forceinline__ void init() { used = false; }
-    __device__ __forceinline__ void touch() {
-        if (!used) {
-            event_clear(&planes[0][0][0], 2 * NW * 32);
-            used = true;
-        }
-    }
-    // a-stream correction ("a valid, b masked"): word `wi` of the a element, fields selected
-    __device__ __forceinline__ void add_a(int wi, uint32_t word) { event_add(planes[0][wi], word); }
-    __device__ __forceinline__ void add_b(int wi, uint32_t word) { event_add(planes[1][wi], word); }
-    // s_minus: shared [2][64] totals (stream a, stream b), bit number from the least significant bit
-    // warp-collective: every lane of the warp must call
-    __device__ __forceinline__ void drain(unsigned long long (*s_minus)[64], int nbits, uint32_t lane) {
-        if (!__any_sync(0xFFFFFFFFu, used)) return;
-#pragma unroll 1
-        for (int s = 0; s < 2; ++s)
-#pragma unroll 1
-            for (int wi = 0; wi < NW; ++wi)
-                event_drain_warp(planes[s][wi], used, lane, &s_minus[s][wi * 32], nbits < 32 ? nbits : 32);
-    }
-};
 
 // ---------------------------------------------------------------------------------
 // Boundary-correction counters: P bit planes per stream and element word, in registers.  A
