@@ -763,6 +763,10 @@ def run_configs(args, dev, peak):
             land = torch.nn.functional.avg_pool2d(land[None, None], 255, stride=1, padding=127)[0, 0]
         land = land < torch.quantile(land.flatten()[::7], 0.30)
         res = {}
+        pc0 = PairCounter(x.dtype, dev)
+        ms0 = timed(lambda: pc0.bitinformation(x, 2, masked_value=None))  # the same field before the land goes in
+        no_mask_gbs = x.numel() * 8 / (ms0 * 1e-3) / 1e9
+        del pc0
         for name, mv in (("nan", float("nan")), ("minus999", -999.0)):
             x.masked_fill_(land, mv)
             pc = PairCounter(x.dtype, dev)
@@ -787,6 +791,7 @@ def run_configs(args, dev, peak):
             "land_fraction": float(land.float().mean()),
             "coast_crossings_per_column": float((land[1:] != land[:-1]).float().sum(0).mean()), "kernel": "k_pairs_cols<f64, masked sparse flavour>",
             "masked_value_nan": res["nan"], "masked_value_minus999": res["minus999"],
+            "same_field_without_mask_GBps": no_mask_gbs,
         }
         del x, land
     except Exception as e:
