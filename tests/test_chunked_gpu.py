@@ -63,6 +63,12 @@ CASES = [
     ((3, 4, 5, 6, 7), (2, 3, 2, 4, 3), 2),    # five chunked dimensions
     ((2, 3, 4, 5, 6, 7), (1, 3, 4, 2, 6, 7), 3),  # six dimensions, three groups after merging
     ((9, 2), (4, 2), 1),                      # two elements along the axis: one pair per row
+    # rows made of whole 16-byte vectors: the walkers take 16 bytes per lane along the outer axes
+    ((40, 24, 64), (40, 8, 16), 0),
+    ((40, 24, 64), (10, 24, 32), 1),
+    ((33, 6, 72), (33, 4, 20), 0),             # ... ragged edge chunk (12 columns) and a single row group left over
+    ((19, 5, 3, 16), (19, 2, 3, 8), 0),        # ... inner dimensions flattened into the vector columns
+    ((40, 24, 64), (40, 8, 16), 2),            # the same grid along the innermost axis (lane-major ring)
     # irregular grids (dask-style tuples of chunk lengths), alone and mixed with regular dimensions
     ((120, 25, 53), (120, (5, 7, 13), (53,)), 1),
     ((120, 25, 53), ((100, 20), (5, 7, 13), (1, 30, 2, 20)), 2),
@@ -91,6 +97,10 @@ def test_counts_per_chunk_every_width(dtype):
         x = rng.integers(info.min, info.max, size=(40, 23, 37), dtype=dtype, endpoint=True)
     check(x, (16, 8, 10), 1)
     check(x, (40, 23, 5), 2)
+    # rows of whole 16-byte vectors for every width (8-byte types: two columns per lane, 4-byte types: four)
+    y = np.ascontiguousarray(np.concatenate([x, x[:, :, :3]], axis=2))  # (40, 23, 40)
+    check(y, (40, 8, 8), 0)
+    check(y, (10, 23, 16), 1)
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64", "float16"])

@@ -735,6 +735,7 @@ static int plan_chunk_grid(int ndim, const int64_t* shape, const int64_t* chunk_
         g.shape[i] = 1; g.stride[i] = 0; g.chunk[i] = 1; g.nchunk[i] = 1; g.bounds[i] = nullptr; g.scale[i] = 1;
     }
     g.axis = -1;
+    g.vec16 = 0;  // (set by the walkers' planner, xbi_chunked_walk.cu)
     g.lo = kMaxChunkDims - m;
     for (int i = 0; i < m; ++i) {  // group i (innermost first) -> slot kMaxChunkDims-1-i
         const int slot = kMaxChunkDims - 1 - i;

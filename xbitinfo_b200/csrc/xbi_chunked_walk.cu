@@ -17,6 +17,7 @@
 // CTA works through a CONTIGUOUS range of tiles dealt to its warps in turn, so a warp changes chunk a few times in
 // its whole life and only then (and at the end) pays the butterfly flush and the atomics into that chunk's table.
 #include <atomic>
+#include <type_traits>
 
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
@@ -189,27 +190,36 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
         asm volatile("" : "+r"(ea));
         if (ea < 2) continue;  // no pairs in this chunk
 
-        {
-            // column walkers: the chunk's columns (every dimension but the analysed one, flattened) in tiles of 32
-            unsigned long long O = 1, I = 1;
+        // column walkers: the chunk's columns (every dimension but the analysed one, flattened) in tiles of 32 lanes.
+        // A lane takes EPV neighbouring columns: 1, or -- outer axes, when the chunk's rows are whole 16-byte vectors
+        // (`vec_allowed` from the planner, and this chunk's innermost extent a multiple of EPV) -- 16 bytes' worth:
+        // 16-byte copies and 128-bit reads, a warp's row 512 contiguous bytes instead of 128.
+        unsigned long long O = 1, I = 1;
 #pragma unroll
-            for (int d = 0; d < kD; ++d) {
-                if (d < axis) O *= box.e[d];
-                if (d > axis) I *= box.e[d];
-            }
-            const unsigned long long ncols = O * I, tiles = (ncols + 31) / 32;
+        for (int d = 0; d < kD; ++d) {
+            if (d < axis) O *= box.e[d];
+            if (d > axis) I *= box.e[d];
+        }
+        long long step_bytes = astride * BYTES;
+        asm volatile("" : "+l"(step_bytes));
+
+        auto walk = [&](auto epv_tag) {
+            constexpr int EPV = decltype(epv_tag)::value;   // columns per lane
+            constexpr int RS = kRows / EPV;                  // rows per fold
+            constexpr bool V16 = EPV * BYTES == 16 && !LASTAX;
+            constexpr uint32_t kCell = LASTAX ? kLanePitch : (uint32_t)(EPV * BYTES);           // a lane's cell
+            constexpr uint32_t kRowP = LASTAX ? (uint32_t)BYTES : 32u * (uint32_t)(EPV * BYTES);  // a row of the step
+            const unsigned long long ncols = O * I / EPV, tiles = (ncols + 31) / 32;
             const unsigned long long t_lo = tiles * grp / groups, t_hi = tiles * (grp + 1) / groups;
-            long long step_bytes = astride * BYTES;
-            asm volatile("" : "+l"(step_bytes));
             for (unsigned long long tile = t_lo; tile < t_hi; ++tile) {
                 const unsigned long long col = tile * 32 + lane;
                 unsigned live_u = col < ncols ? 1u : 0u;
                 asm volatile("" : "+r"(live_u));  // (else re-derived from the extents in every step)
                 const bool live = live_u != 0u;
-                // offset of this lane's column at row 0 of the chunk
+                // offset of this lane's (first) column at row 0 of the chunk
                 long long off = box.base;
                 {
-                    const unsigned long long cc = live ? col : 0;
+                    const unsigned long long cc = (live ? col : 0) * EPV;
                     unsigned long long ro = cc / I, ri = cc - ro * I;
 #pragma unroll
                     for (int d = kD - 1; d >= 0; --d) {
@@ -217,36 +227,40 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
                         if (d < axis) { off += (long long)(ro % box.e[d]) * g.stride[d]; ro /= box.e[d]; }
                     }
                 }
-                const char* p = static_cast<const char*>(x) + off * BYTES;  // row 0 of the column
+                const char* p = static_cast<const char*>(x) + off * BYTES;  // row 0 of the column(s)
                 // the walk starts AT row 0 with "no row above" (pk = 0): the first row is a current row like the others
-                uint32_t prev[NW], pk = 0u;  // previous row (transformed) and its keep-mask (0: masked or no such row)
+                uint32_t prev[EPV][NW], pk[EPV];  // previous row (transformed), its keep-masks (0: masked / no such row)
 #pragma unroll
-                for (int k = 0; k < NW; ++k) prev[k] = 0;
-                unsigned nsteps = (ea + kRows - 1) / kRows;
+                for (int e = 0; e < EPV; ++e) {
+                    pk[e] = 0u;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) prev[e][k] = 0;
+                }
+                unsigned nsteps = (ea + RS - 1) / RS;
                 asm volatile("" : "+r"(nsteps));
                 // LASTAX: 16-byte copies when every lane's run starts on a 16-byte boundary (warp-uniform)
                 const bool vec = LASTAX && RING && __all_sync(0xFFFFFFFFu, !live || (reinterpret_cast<uintptr_t>(p) & 15u) == 0u);
                 const char* q = p;  // advanced by the copies (RING) or the loads
                 unsigned issued = 0;
-                // RING: copy step `issued` (kRows rows of this lane's column) into the ring; a lane reads back only its own cells
+                // RING: copy step `issued` (RS rows of this lane's columns) into the ring; a lane reads back only its own cells
                 auto issue = [&]() {
                     if (issued < nsteps && live) {
-                        const uint32_t dst = ring0 + slot_w * kSlotBytes + lane * kLanePitch;
-                        const unsigned left = ea - kRows * issued;  // rows from this step on
-                        if (left >= (unsigned)kRows) {
-                            if (LASTAX && vec) {
+                        const uint32_t dst = ring0 + slot_w * kSlotBytes + lane * kCell;
+                        const unsigned left = ea - RS * issued;  // rows from this step on
+                        if (LASTAX && vec && left >= (unsigned)RS) {
 #pragma unroll
-                                for (int v = 0; v < kRows * BYTES / 16; ++v)
-                                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * v), "l"(q + 16 * v) : "memory");
-                                q += kRows * BYTES;
-                            } else {
-#pragma unroll
-                                for (int u = 0; u < kRows; ++u) { cpa_elem<BYTES>(dst + u * kRowPitch, q); q += step_bytes; }
-                            }
+                            for (int v = 0; v < kRows * BYTES / 16; ++v)
+                                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * v), "l"(q + 16 * v) : "memory");
+                            q += kRows * BYTES;
                         } else {
 #pragma unroll
-                            for (int u = 0; u < kRows; ++u)
-                                if ((unsigned)u < left) { cpa_elem<BYTES>(dst + u * kRowPitch, q); q += step_bytes; }
+                            for (int u = 0; u < RS; ++u) {
+                                if (left >= (unsigned)RS || (unsigned)u < left) {
+                                    if constexpr (V16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * kRowP), "l"(q) : "memory");
+                                    else cpa_elem<BYTES>(dst + u * kRowP, q);
+                                    q += step_bytes;
+                                }
+                            }
                         }
                     }
                     cpa_commit_w();
@@ -259,21 +273,22 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
                 }
 #pragma unroll 1
                 for (unsigned s = 0; s < nsteps; ++s) {
-                    const unsigned left = live ? ea - kRows * s : 0u;  // rows this lane has from this step on
-                    uint32_t raw[NW][kRows];
+                    const unsigned left = live ? ea - RS * s : 0u;  // rows this lane has from this step on
+                    uint32_t raw[NW][kRows];  // [word][row * EPV + column]
                     if constexpr (RING) {
                         issue();
                         cpa_wait_w<kAheadW>();
-                        const uint32_t src = ring0 + slot_r * kSlotBytes + lane * kLanePitch;
+                        const uint32_t src = ring0 + slot_r * kSlotBytes + lane * kCell;
                         slot_r = (slot_r + 1 == kSlots) ? 0 : slot_r + 1;
-                        if constexpr (LASTAX) {
-                            // lane-major: the lane's kRows elements are contiguous (absent rows: stale cells, zeroed below)
+                        if constexpr (LASTAX || V16) {
+                            // 128-bit reads: LASTAX -- the lane's kRows elements are contiguous; V16 -- one row's EPV
+                            // elements are (absent rows: stale cells, zeroed below)
                             uint32_t flat[kRows * NW];
 #pragma unroll
                             for (int v = 0; v < kRows * BYTES / 16; ++v) {
                                 asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                              : "=r"(flat[4 * v]), "=r"(flat[4 * v + 1]), "=r"(flat[4 * v + 2]), "=r"(flat[4 * v + 3])
-                                             : "r"(src + 16 * v));
+                                             : "r"(src + (LASTAX ? 16u * v : (uint32_t)v * kRowP)));
                             }
 #pragma unroll
                             for (int u = 0; u < kRows; ++u)
@@ -283,7 +298,7 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
 #pragma unroll
                             for (int u = 0; u < kRows; ++u) {
                                 uint32_t w[NW];
-                                lds_elem_w<NW>(src + u * kRowPitch, w);  // (absent rows: stale cells, zeroed below)
+                                lds_elem_w<NW>(src + u * kRowP, w);  // (absent rows: stale cells, zeroed below)
 #pragma unroll
                                 for (int k = 0; k < NW; ++k) raw[k][u] = w[k];
                             }
@@ -300,56 +315,61 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
                         }
                     }
                     uint32_t wa[NW][kRows], wb[NW][kRows];
-                    if (s > 0 && __all_sync(0xFFFFFFFFu, left >= (unsigned)kRows)) {
-                        // every lane has all kRows rows and a row above the first of them (the common case): no
+                    if (s > 0 && __all_sync(0xFFFFFFFFu, left >= (unsigned)RS)) {
+                        // every lane has all RS rows and a row above the first of them (the common case): no
                         // "does the row exist" tests
                         uint32_t vbits = 0;
 #pragma unroll
                         for (int u = 0; u < kRows; ++u) {
+                            const int e = u % EPV;
                             uint32_t w[NW];
 #pragma unroll
                             for (int k = 0; k < NW; ++k) w[k] = raw[k][u];
                             if (MASK != kMaskNone) {
                                 const uint32_t kk = keep_of(w);
                                 if (XFORM) E::transform(w);
-                                const uint32_t m = kk & pk;  // the pair (row above, this row) counts
+                                const uint32_t m = kk & pk[e];  // the pair (row above, this row) counts
                                 vbits |= m & (1u << u);
 #pragma unroll
-                                for (int k = 0; k < NW; ++k) { wa[k][u] = prev[k] & m; wb[k][u] = w[k] & m; }
-                                pk = kk;
+                                for (int k = 0; k < NW; ++k) { wa[k][u] = prev[e][k] & m; wb[k][u] = w[k] & m; }
+                                pk[e] = kk;
                             } else {
                                 if (XFORM) E::transform(w);
 #pragma unroll
-                                for (int k = 0; k < NW; ++k) { wa[k][u] = prev[k]; wb[k][u] = w[k]; }
+                                for (int k = 0; k < NW; ++k) { wa[k][u] = prev[e][k]; wb[k][u] = w[k]; }
                             }
 #pragma unroll
-                            for (int k = 0; k < NW; ++k) prev[k] = w[k];
+                            for (int k = 0; k < NW; ++k) prev[e][k] = w[k];
                         }
                         nvalid += (MASK != kMaskNone) ? (uint32_t)__popc(vbits) : (uint32_t)kRows;
                     } else {
 #pragma unroll
                         for (int u = 0; u < kRows; ++u) {
+                            const int e = u % EPV;
                             uint32_t w[NW];
 #pragma unroll
                             for (int k = 0; k < NW; ++k) w[k] = raw[k][u];
-                            uint32_t kk = ((unsigned)u < left) ? 0xFFFFFFFFu : 0u;  // the row exists ...
-                            if (MASK != kMaskNone) kk &= keep_of(w);                 // ... and is not masked
+                            uint32_t kk = ((unsigned)(u / EPV) < left) ? 0xFFFFFFFFu : 0u;  // the row exists ...
+                            if (MASK != kMaskNone) kk &= keep_of(w);                         // ... and is not masked
                             if (XFORM) E::transform(w);
-                            const uint32_t m = kk & pk;                             // the pair (row above, this row) counts
+                            const uint32_t m = kk & pk[e];                                  // the pair (row above, this row) counts
                             nvalid += m & 1u;
 #pragma unroll
-                            for (int k = 0; k < NW; ++k) { wa[k][u] = prev[k] & m; wb[k][u] = w[k] & m; }
+                            for (int k = 0; k < NW; ++k) { wa[k][u] = prev[e][k] & m; wb[k][u] = w[k] & m; }
                             // (past the end of the column nothing follows: prev may take anything there)
 #pragma unroll
-                            for (int k = 0; k < NW; ++k) prev[k] = w[k];
-                            pk = kk;
+                            for (int k = 0; k < NW; ++k) prev[e][k] = w[k];
+                            pk[e] = kk;
                         }
                     }
                     fold(wa, wb);
                 }
                 if constexpr (RING) slot_r = slot_w;  // the kAheadW groups committed past the end of the column were empty
             }
-        }
+        };
+        constexpr int kVecCols = (RING && !LASTAX) ? 16 / BYTES : 1;
+        if (kVecCols > 1 && g.vec16 && box.e[kD - 1] % kVecCols == 0) walk(std::integral_constant<int, kVecCols>{});
+        else walk(std::integral_constant<int, 1>{});
     }
     if (cur_chunk != 0xFFFFFFFFu) flush_chunk(cur_chunk);
 }
@@ -423,10 +443,29 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = dtype_bytes(dtype) == 8 ? 1 : 2;
     const unsigned long long warps = (unsigned long long)sms * per_sm * kWWarps;
-    // the work inside a (full) chunk that the warps share: tiles of 32 columns
+    // outer axes, 4- / 8-byte types: a lane takes 16 bytes of a row when every row of every chunk is made of whole,
+    // aligned 16-byte vectors -- base pointer, every stride and the (regular) chunk length along the innermost
+    // dimension multiples of 16 bytes (ragged edge chunks fall back to one column per lane inside the kernel)
+    ChunkGrid gg = g;
+    gg.vec16 = 0;
+    const int bytes = dtype_bytes(dtype);
+    if (bytes >= 4 && g.axis != kD - 1 && g.bounds[kD - 1] == nullptr && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+        const long long epv = 16 / bytes;
+        bool ok = g.chunk[kD - 1] % epv == 0;
+        for (int d = g.lo; d < kD - 1; ++d) ok = ok && (g.stride[d] % epv == 0);
+        // ... and a chunk has enough columns to fill the lanes of a tile or two that way (4x4-column chunks: 4 live
+        // lanes of 32, 0.3 TB/s instead of 1.1)
+        unsigned long long c = 1;
+        for (int d = 0; d < kD; ++d)
+            if (d != g.axis) c *= g.chunk[d];
+        ok = ok && c / (unsigned long long)epv >= 64;
+        gg.vec16 = ok ? 1 : 0;
+    }
+    // the work inside a (full) chunk that the warps share: tiles of 32 lanes
     unsigned long long cols = 1;
     for (int d = 0; d < kD; ++d)
         if (d != g.axis) cols *= g.chunk[d];
+    if (gg.vec16) cols /= (unsigned long long)(16 / bytes);
     const unsigned long long units = (cols + 31) / 32;
     if (units * nchunks < 2 * warps && !force) return cudaSuccess;  // too few columns to occupy the GPU this way
     // the innermost dimension as analysed axis: lanes sit on neighbouring RUNS, each copy instruction touches 32
@@ -441,13 +480,13 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
     const uint32_t mlo = (uint32_t)(mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(mask_bits >> 32);
     cudaError_t e;
     switch (dtype) {
-        case XBI_U8: e = dispatch_walk<kU8>(x, g, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_U16: e = dispatch_walk<kU16>(x, g, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_U32: e = dispatch_walk<kU32>(x, g, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_U64: e = dispatch_walk<kU64>(x, g, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_F16: e = dispatch_walk<kF16>(x, g, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_F32: e = dispatch_walk<kF32>(x, g, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_F64: e = dispatch_walk<kF64>(x, g, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_U8: e = dispatch_walk<kU8>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_U16: e = dispatch_walk<kU16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_U32: e = dispatch_walk<kU32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_U64: e = dispatch_walk<kU64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_F16: e = dispatch_walk<kF16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_F32: e = dispatch_walk<kF32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_F64: e = dispatch_walk<kF64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
         default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

@@ -173,6 +173,7 @@ struct ChunkGrid {
     unsigned groups;                  // work items per chunk
     unsigned tiles_per_group;         // 4096-element tiles per work item
     unsigned items;                   // nchunks * groups
+    int vec16;                        // (walkers) every row of every chunk is made of whole, aligned 16-byte vectors
 };
 // counts[nchunks][nbits][4] must be zero on entry and holds the 2x2 tables on completion
 cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
