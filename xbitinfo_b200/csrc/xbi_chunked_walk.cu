@@ -458,7 +458,7 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
         unsigned long long c = 1;
         for (int d = 0; d < kD; ++d)
             if (d != g.axis) c *= g.chunk[d];
-        ok = ok && c / (unsigned long long)epv >= 64;
+        ok = ok && (force || c / (unsigned long long)epv >= 64);  // (force: the tests pin this path on small grids)
         gg.vec16 = ok ? 1 : 0;
     }
     // the work inside a (full) chunk that the warps share: tiles of 32 lanes
