@@ -360,7 +360,7 @@ def test_masked_zero_matches_bit_pattern_only():
 def test_strided_rows_that_are_only_element_aligned(dtype, mask):
     """Adjacency along non-last axes when a row is not a multiple of 16 bytes (and the base
     is not 16-byte aligned either): whole-word element types still take the column walkers,
-    with short copies and a last chunk per row that is padded with the neutral value.
+    with element-sized copies; lane slots beyond the end of a row hold the neutral value.
     'neutral' masks exactly that padding value (1.0 / 0)."""
     import torch
 
@@ -393,6 +393,67 @@ def test_strided_rows_that_are_only_element_aligned(dtype, mask):
             ref_counts, npairs, _ = bo.bitinformation(x, axis, masked_value=masked_value)
             assert np.array_equal(pc.counts.cpu().numpy(), ref_counts), (dtype, mask, off, axis)
             assert int(pc.counts[0].sum()) == npairs
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64", "uint32"])
+@pytest.mark.parametrize("mask", [None, "nan_or_value"])
+def test_element_aligned_rows_strips_and_side_by_side_segments(dtype, mask):
+    """The element-aligned column walkers give a warp a strip of 128 (64 for 8-byte types) columns and, when a whole
+    row is at most half a strip, walk 2..32 row segments side by side in one warp.  Row lengths on both sides of
+    every strip / power-of-two fraction of a strip x row counts with and without a tail group; the base address is
+    one element past a 16-byte boundary, so that row lengths that ARE a multiple of 16 bytes take this kernel too."""
+    import torch
+
+    from xbitinfo_b200.device import PairCounter
+
+    isfloat = np.dtype(dtype).kind == "f"
+    rng = np.random.default_rng(77)
+    mv = None
+    if mask is not None:
+        mv = float("nan") if isfloat else 3
+    for inner in (2, 3, 31, 32, 33, 50, 64, 65, 96, 97, 128, 129, 161, 193, 257, 513):
+        for rows in (2, 3, 4, 5, 6, 8, 9, 23, 70):
+            n = rows * inner
+            if isfloat:
+                flat = smooth_field(rng, (n + 1,), dtype, axis=0, scale=0.2, base=1.0)
+            else:
+                flat = rng.integers(0, 5, size=n + 1, dtype=dtype)
+            if mv is not None:
+                flat[rng.random(n + 1) < 0.2] = mv
+            x = flat[1:].reshape(rows, inner)
+            t = torch.from_numpy(flat).cuda()[1:].view(rows, inner)
+            pc = PairCounter(t.dtype, t.device)
+            before = nat.fast_path_launches()
+            pc.add(t, 0, masked_value=mv)
+            assert nat.fast_path_launches() > before, "fast path was not taken"
+            ref_counts, npairs, _ = bo.bitinformation(x, 0, masked_value=mv)
+            assert np.array_equal(pc.counts.cpu().numpy(), ref_counts), (dtype, mask, rows, inner)
+            assert int(pc.counts[0].sum()) == npairs
+
+
+@pytest.mark.parametrize("dtype", ["float32", "float64"])
+def test_element_aligned_rows_many_segments_fast_equals_generic(dtype):
+    """Tall matrices with 513 / 161 / 1441 columns (many row segments per strip, segment lengths that differ by one,
+    a last strip with few columns) and with 13 / 33 / 3 columns (several segments side by side in a warp).  The
+    checker at this size is the generic kernel."""
+    import torch
+
+    from xbitinfo_b200.device import PairCounter
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    for rows, cols in ((40_001, 513), (90_003, 161), (20_002, 1441), (300_001, 13), (200_003, 33), (1_000_001, 3)):
+        x = torch.empty((rows, cols), dtype=torch.float32, device="cuda").normal_(0.0, 0.3, generator=g)
+        x = (torch.cumsum(x, dim=0) + 3.0).to(getattr(torch, dtype))
+        x[torch.rand((rows, cols), device="cuda", generator=g) < 0.05] = float("nan")
+        for mv in (None, float("nan")):
+            pc = PairCounter(x.dtype, x.device)
+            before = nat.fast_path_launches()
+            pc.add(x, 0, masked_value=mv)
+            assert nat.fast_path_launches() > before
+            fast = pc.counts.clone()
+            pc.reset()
+            pc.add(x, 0, masked_value=mv, force_generic=True)
+            assert torch.equal(fast, pc.counts), (dtype, rows, cols, mv)
 
 
 @pytest.mark.parametrize("dtype", ["float32", "float64", "float16", "int32", "uint8"])

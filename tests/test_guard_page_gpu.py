@@ -110,8 +110,10 @@ CASES = [
     # column walkers: 4-row groups + tails, one strip / several strips / ragged strips, segments
     ("float32", (2, 70, 128), 1), ("float32", (1, 261, 132), 1), ("float32", (3, 66, 8), 1), ("float64", (2, 130, 66), 1),
     ("float16", (1, 200, 72), 1), ("float32", (700, 4, 36), 0), ("int64", (5, 9, 34), 1),
-    # element-aligned rows (short copies, padded last chunk)
+    # element-aligned rows (element-sized copies, a lane owns single columns)
     ("float32", (2, 130, 13), 1), ("float32", (3, 67, 65), 1), ("float64", (2, 70, 33), 1), ("int32", (1, 300, 7), 1),
+    # ... a last strip with few columns, rows of a few columns (row segments side by side in a warp)
+    ("float32", (2, 71, 161), 1), ("float64", (1, 67, 65), 1), ("float32", (1, 3, 513), 1), ("float32", (1, 135, 513), 1),
     # packed types on unaligned rows: generic kernel
     ("float16", (2, 50, 13), 1), ("uint8", (3, 40, 7), 1),
 ]

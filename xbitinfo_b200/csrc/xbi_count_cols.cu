@@ -523,36 +523,15 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
 __device__ __forceinline__ void cp_async8(uint32_t dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(src) : "memory");
 }
-// one 16-byte column chunk of which the first `vb` bytes exist, copied in pieces of G bytes
-template <int G>
-__device__ __forceinline__ void copy_chunk(uint32_t dst, const char* src, int vb) {
-    if constexpr (G == 16) {
-        cp_async16(dst, src);
-    } else if constexpr (G == 8) {
-        cp_async8(dst, src);
-        if (vb > 8) cp_async8(dst + 8, src + 8);
-    } else {
-        cp_async4(dst, src);
-        if (vb > 4) cp_async4(dst + 4, src + 4);
-        if (vb > 8) cp_async4(dst + 8, src + 8);
-        if (vb > 12) cp_async4(dst + 12, src + 12);
-    }
-}
-
-// G = 16: rows are 16-byte aligned and a multiple of 16 bytes long.  G = 8 / 4 (element types of
-// that size): rows are only element aligned; chunks are still 16 bytes of a row, the last one
-// of a row may be short, and what does not exist is filled with the value whose transform is 0.
-template <int KIND, int MASK, bool XFORM, int G>
+// Rows are 16-byte aligned and a multiple of 16 bytes long (k_pairs_cols_elem below takes the others).
+template <int KIND, int MASK, bool XFORM>
 __global__ void __launch_bounds__(kAsyncThreads, 1)
 k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_per_row, long long nseg,
              long long seg_min, long long seg_extra, uint32_t mask_lo, uint32_t mask_hi,
              unsigned long long flat_pairs, Workspace* __restrict__ ws) {
     using W = ColWalker<KIND, MASK, XFORM>;
-    constexpr int BYTES = W::BYTES;
-    static_assert(G == 16 || G == BYTES, "short copies are element sized");
     // sparse and dense flavours are both launched; the sampled boundary density picks one
-    // (element-aligned rows exist in the sparse flavour only: it knows about the padded last chunk)
-    if (W::MASKED && G == 16 && sampled_mask_is_dense(&ws->plus, kColsDenseOneIn) != W::DENSE) return;
+    if (W::MASKED && sampled_mask_is_dense(&ws->plus, kColsDenseOneIn) != W::DENSE) return;
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
@@ -593,26 +572,6 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
         const long long ngroups = groups + (any_tail ? 1 : 0);
 
         const char* q0 = x + row_begin * row_bytes + chunk * 16;
-        int vb = 16;  // bytes of this chunk that exist
-        if constexpr (G != 16) {
-            const long long left = row_bytes - chunk * 16;
-            vb = left < 16 ? (int)left : 16;
-            const uint32_t ve = (uint32_t)vb / BYTES;  // elements that exist
-            constexpr uint32_t kRep = ((1u << (4 * W::EPC)) - 1u) / ((1u << W::EPC) - 1u);  // 1 + 2^EPC + 2^2EPC + 2^3EPC
-            cw.vrep = ((1u << ve) - 1u) * kRep;
-            if (vb < 16) {
-                // nothing of the previous item is in flight any more: fill what the copies will
-                // never write with the neutral value, in every slot of this lane's ring
-#pragma unroll 1
-                for (int c = 0; c < kAsyncRing * 4; ++c) {
-                    const uint32_t cell = my0 + (c >> 2) * kTileBytes + (c & 3) * kStripBytes;
-                    for (int wdx = vb >> 2; wdx < 4; ++wdx) {
-                        const uint32_t nv = neutral_word<KIND, XFORM>(BYTES == 8 ? (wdx & 1) : 0);
-                        asm volatile("st.shared.u32 [%0], %1;" ::"r"(cell + 4 * wdx), "r"(nv) : "memory");
-                    }
-                }
-            }
-        }
         const char* q = q0 + stride;  // first b-row; advanced by issue()
         long long issued = 0;
         // issue group `issued` (4 rows; the tail group re-reads an in-bounds row for absent rows)
@@ -621,13 +580,13 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
                 const uint32_t dst = my0 + slot_w * kTileBytes;
                 if (issued < groups) {
 #pragma unroll
-                    for (int r = 0; r < 4; ++r) copy_chunk<G>(dst + r * kStripBytes, q + r * stride, vb);
+                    for (int r = 0; r < 4; ++r) cp_async16(dst + r * kStripBytes, q + r * stride);
                     q += 4 * stride;
                 } else {
 #pragma unroll
                     for (int r = 0; r < 4; ++r) {
                         const long long rr = (r < tail_rows) ? r : (long long)tail_rows - 1;  // -1: last full-group row
-                        copy_chunk<G>(dst + r * kStripBytes, q + rr * stride, vb);
+                        cp_async16(dst + r * kStripBytes, q + rr * stride);
                     }
                 }
             }
@@ -637,21 +596,7 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
         };
 #pragma unroll 1
         for (int k = 0; k < kAhead; ++k) issue();
-        {
-            uint4 first;
-            if constexpr (G == 16) {
-                first = ldg_stream(reinterpret_cast<const uint4*>(q0));
-            } else {
-                uint32_t fw[4];
-#pragma unroll
-                for (int wdx = 0; wdx < 4; ++wdx) {
-                    fw[wdx] = neutral_word<KIND, XFORM>(BYTES == 8 ? (wdx & 1) : 0);
-                    if (4 * wdx < vb) fw[wdx] = __ldg(reinterpret_cast<const uint32_t*>(q0) + wdx);
-                }
-                first = make_uint4(fw[0], fw[1], fw[2], fw[3]);
-            }
-            cw.start(first, true, mask_lo, mask_hi);
-        }
+        cw.start(ldg_stream(reinterpret_cast<const uint4*>(q0)), true, mask_lo, mask_hi);
 #pragma unroll 1
         for (long long g = 0; g < ngroups; ++g) {
             issue();
@@ -677,10 +622,229 @@ k_pairs_cols(const char* __restrict__ x, long long row_bytes, long long chunks_p
     cw.finish(lane, kAsyncThreads, s_sum, &s_n, ws, flat_pairs);
 }
 
-template <int KIND, int MASK, bool XFORM, int G>
+
+// ---------------------------------------------------------------------------------
+// Rows that are only ELEMENT aligned (row length not a multiple of 16 bytes, or a base address that is not):
+// 4- and 8-byte element types.  No 16-byte piece of a row keeps its alignment from one row to the next, so a
+// lane owns single columns instead of a 16-byte chunk: a warp takes a strip of 32*EPC columns of one row
+// segment, lane l the columns l, l+32, (l+64, l+96) of it.  Every element-sized cp.async of the warp then
+// covers 32 consecutive elements (whole sectors but for the two ends), lands conflict-free in the lane's
+// cells of the ring, and comes back with conflict-free element-sized shared loads; the walker sees the same
+// "four rows of a 16-byte chunk" as in the aligned kernel -- which columns they are does not matter to it.
+//
+// The last strip of a row may hold few columns (513 = 4 x 128 + 1).  When half of a lane's element slots or
+// more would be idle there, the slots walk different ROW ranges of the segment side by side instead
+// (`split` sub-segments of Ls pair rows each; the < split rows that remain are walked by the last
+// sub-segment alone in one more group).  Slots without a column read the neutral value (transform 0) and
+// are excluded from the masked modes' bookkeeping through ColWalker::vrep.
+//
+// Measured alternatives: strips do not begin on sector boundaries, so neighbouring strips
+// fetch the 64 bytes around their common edge twice, and as warps drift apart the second fetch misses the L2 --
+// DRAM delivers 1.17x the array at 513 columns.  Walking the 16 warps of a block in lock step (a block barrier
+// every other group, no side-by-side ranges) brings that to 1.00x but costs more issue slots than it saves: this
+// kernel is bound by its instruction count (16 copies + 16 shared loads per group instead of 4 + 4).
+// ---------------------------------------------------------------------------------
+template <int KIND, int MASK, bool XFORM>
+__global__ void __launch_bounds__(kAsyncThreads, 1)
+k_pairs_cols_elem(const char* __restrict__ x, long long inner, long long strips, long long nseg, long long seg_min,
+                  long long seg_extra, uint32_t mask_lo, uint32_t mask_hi, unsigned long long flat_pairs,
+                  Workspace* __restrict__ ws) {
+    using W = ColWalker<KIND, MASK, XFORM>;
+    constexpr int BYTES = W::BYTES, EPC = W::EPC, WPE = W::WPE;
+    static_assert(BYTES >= 4 && !W::DENSE, "whole-word element types, sparse flavour");
+    constexpr int CW = 32 * EPC;           // columns of a strip
+    constexpr int kCell = 32 * BYTES;      // bytes of one element slot of a strip row (all 32 lanes)
+    constexpr uint32_t kAll = (1u << EPC) - 1u;
+    constexpr uint32_t kRep = ((1u << (4 * EPC)) - 1u) / kAll;  // replicate a row's bits for 4 rows
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem0 = (smem_addr(smem_raw) + 127u) & ~127u;
+    const uint32_t warp = __shfl_sync(0xFFFFFFFFu, threadIdx.x >> 5, 0);
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t my0 = smem0 + warp * (kAsyncRing * kTileBytes) + lane * BYTES;  // + slot*kTileBytes + r*512 + e*kCell
+
+    const long long n_witems = strips * nseg;
+    const long long warps_total = (long long)gridDim.x * kAsyncWarps;
+    const long long rounds = (n_witems + warps_total - 1) / warps_total;
+    const long long gw = (long long)blockIdx.x * kAsyncWarps + warp;
+    const long long stride = inner * BYTES;  // bytes between rows
+    const int rem = (int)(inner - (strips - 1) * CW);  // columns of a row's last strip: 1..CW
+    const int tail_w = (rem + 31) >> 5;                // element slots a lane needs there
+    const int tail_split = EPC / tail_w;               // 4, 2 or 1 sub-segments side by side
+
+    __shared__ unsigned long long s_sum[3][64];
+    __shared__ unsigned long long s_minus[2][64];
+    __shared__ unsigned long long s_n;
+    for (int i = threadIdx.x; i < 2 * 64; i += kAsyncThreads) (&s_minus[0][0])[i] = 0;
+    __syncthreads();
+
+    W cw;
+    cw.init(s_minus);
+    uint32_t slot_w = 0, slot_r = 0;  // ring positions (the same on every lane)
+    auto copy_elem = [](uint32_t dst, const char* src) {
+        if constexpr (BYTES == 8) cp_async8(dst, src);
+        else cp_async4(dst, src);
+    };
+
+#pragma unroll 1
+    for (long long round = 0; round < rounds; ++round) {
+        // a block takes 16 consecutive items per round; the start moves by one warp from round to round, so that
+        // no warp is dealt the (cheaper or dearer) last strip of a row every time
+        const long long wi = round * warps_total + (gw + round) % warps_total;
+        if (wi >= n_witems) continue;
+        const long long seg = wi / strips, strip = wi - seg * strips;
+        const long long row_begin = seg * seg_min + (seg < seg_extra ? seg : seg_extra);
+        const long long len = seg_min + (seg < seg_extra ? 1 : 0);  // pair rows of the segment
+        const bool last_strip = strip == strips - 1;
+        const int split = last_strip ? tail_split : 1;
+        const int sh = (split == 1) ? 31 : (split == EPC ? 0 : 1);  // slot e belongs to sub-segment e >> sh ...
+        const int wmask = (split == 1) ? (EPC - 1) : (EPC / split - 1);  // ... and to column block e & wmask
+        const long long Ls = len / split;                 // pair rows of a sub-segment
+        const int left = (int)(len - Ls * split);         // < split: walked by the last sub-segment alone
+        const long long full = Ls >> 2;
+        const int tail_rows = (int)(Ls & 3);
+        const long long ngroups = full + (tail_rows ? 1 : 0) + (left ? 1 : 0);
+
+        // slot e: its column, whether it exists, and the address of the first row of its walk
+        const char* p[EPC];
+        uint32_t em = 0u;       // bit e: slot e has a column
+        uint32_t em_last = 0u;  // ... and belongs to the last sub-segment
+#pragma unroll
+        for (int e = 0; e < EPC; ++e) {
+            const long long col = strip * CW + (long long)(e & wmask) * 32 + lane;
+            const int sub = e >> sh;
+            const bool have = col < inner;
+            if (have) em |= 1u << e;
+            if (have && sub == split - 1) em_last |= 1u << e;
+            p[e] = x + ((row_begin + sub * Ls) * inner + (have ? col : 0)) * BYTES;
+        }
+        cw.vrep = em * kRep;
+        if (em != kAll) {
+            // nothing of the previous item is in flight any more: the cells of the slots without a column are
+            // never written by a copy -- fill them with the neutral value in every slot of this lane's ring
+#pragma unroll 1
+            for (int c = 0; c < kAsyncRing * 4; ++c) {
+                const uint32_t cell = my0 + (c >> 2) * kTileBytes + (c & 3) * kStripBytes;
+#pragma unroll
+                for (int e = 0; e < EPC; ++e) {
+                    if (!((em >> e) & 1u)) {
+#pragma unroll
+                        for (int k = 0; k < WPE; ++k)
+                            asm volatile("st.shared.u32 [%0], %1;" ::"r"(cell + e * kCell + 4 * k), "r"(neutral_word<KIND, XFORM>(k)) : "memory");
+                    }
+                }
+            }
+        }
+        long long issued = 0;
+        long long roff = stride;  // byte offset of the first row of group `issued` from a slot's first row
+        // (warp-uniform) every lane has all its columns and walks one row range: no predicates, one address per row
+        const bool plain = !last_strip || rem == CW;
+        // issue group `issued` (4 rows; absent rows of a short group re-read an in-bounds row)
+        auto issue = [&]() {
+            if (issued < ngroups) {
+                const uint32_t dst = my0 + slot_w * kTileBytes;
+                if (plain && issued < full) {
+                    const char* q = p[0] + roff;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e) copy_elem(dst + r * kStripBytes + e * kCell, q + e * kCell);
+                        q += stride;
+                    }
+                    roff += 4 * stride;
+                } else {
+                    const bool is_left = issued >= full && !(tail_rows && issued == full);
+                    const int nr = issued < full ? 4 : (is_left ? left : tail_rows);
+                    const uint32_t who = is_left ? em_last : em;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        const long long at = roff + ((r < nr) ? r : nr - 1) * stride;
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e) {
+                            const char* a = p[e] + at;
+                            asm volatile("" : "+l"(a));  // (formed once, outside the predicate)
+                            if ((who >> e) & 1u) copy_elem(dst + r * kStripBytes + e * kCell, a);
+                        }
+                    }
+                    roff += (long long)nr * stride;
+                }
+            }
+            cp_async_commit();  // (possibly empty: keeps the group count uniform)
+            slot_w = (slot_w + 1 == kAsyncRing) ? 0 : slot_w + 1;
+            ++issued;
+        };
+#pragma unroll 1
+        for (int k = 0; k < kAhead; ++k) issue();
+        {
+            uint32_t fw[4];
+#pragma unroll
+            for (int e = 0; e < EPC; ++e) {
+#pragma unroll
+                for (int k = 0; k < WPE; ++k) {
+                    fw[WPE * e + k] = neutral_word<KIND, XFORM>(k);
+                    if ((em >> e) & 1u) fw[WPE * e + k] = __ldg(reinterpret_cast<const uint32_t*>(p[e]) + k);
+                }
+            }
+            cw.start(make_uint4(fw[0], fw[1], fw[2], fw[3]), true, mask_lo, mask_hi);
+        }
+#pragma unroll 1
+        for (long long g = 0; g < ngroups; ++g) {
+            issue();
+            cp_async_wait<kAhead>();  // group g has landed (kAhead younger ones may be in flight)
+            const uint32_t src = my0 + slot_r * kTileBytes;
+            uint4 buf[4];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                if constexpr (BYTES == 8) {
+                    const uint2 e0 = lds64(src + r * kStripBytes), e1 = lds64(src + r * kStripBytes + kCell);
+                    buf[r] = make_uint4(e0.x, e0.y, e1.x, e1.y);
+                } else {
+                    buf[r] = make_uint4(lds32(src + r * kStripBytes), lds32(src + r * kStripBytes + kCell),
+                                        lds32(src + r * kStripBytes + 2 * kCell), lds32(src + r * kStripBytes + 3 * kCell));
+                }
+            }
+            slot_r = (slot_r + 1 == kAsyncRing) ? 0 : slot_r + 1;
+            if (g < full) {
+                cw.process(buf, 4, mask_lo, mask_hi, lane);
+            } else {
+                int nr = tail_rows;
+                if (!(tail_rows && g == full)) {
+                    // the rows left over by the split: the slots of the other sub-segments are done (their cells
+                    // hold stale rows) -- neutral values, and out of the masked modes' bookkeeping
+                    nr = left;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        uint32_t w[4] = {buf[r].x, buf[r].y, buf[r].z, buf[r].w};
+#pragma unroll
+                        for (int e = 0; e < EPC; ++e)
+#pragma unroll
+                            for (int k = 0; k < WPE; ++k)
+                                if (!((em_last >> e) & 1u)) w[WPE * e + k] = neutral_word<KIND, XFORM>(k);
+                        buf[r] = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                    cw.vrep = em_last * kRep;
+                }
+                cw.process(buf, nr, mask_lo, mask_hi, lane);
+            }
+        }
+        // the kAhead groups committed past the end of the item are empty; the ring position
+        // moved with them, keep reader and writer aligned
+        slot_r = slot_w;
+    }
+    cp_async_wait<0>();
+
+    cw.finish(lane, kAsyncThreads, s_sum, &s_n, ws, flat_pairs);
+}
+
+// `chunks` = work items per row segment: 16-byte column chunks (32 of them make a warp item), or -- ELEM, rows that
+// are only element aligned -- strips of 32*EPC columns (a warp item each)
+template <int KIND, int MASK, bool XFORM, bool ELEM>
 cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t stream, int64_t row_bytes, int64_t chunks,
                               int64_t pair_rows, int sms) {
-    auto kern = k_pairs_cols<KIND, MASK, XFORM, G>;
+    auto kern = [] {
+        if constexpr (ELEM) return k_pairs_cols_elem<KIND, MASK, XFORM>;
+        else return k_pairs_cols<KIND, MASK, XFORM>;
+    }();
     int dev = 0;
     cudaGetDevice(&dev);
     static std::atomic<unsigned long long> attr_set{0ull};  // per instantiation; bit = device
@@ -697,8 +861,9 @@ cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t s
     // the least of the last round.  (With 4.3 items per warp 13 % of the SM time was idle.)
     const int64_t warps = (int64_t)sms * kAsyncWarps;
     const int64_t max_seg = pair_rows / 64 > 0 ? pair_rows / 64 : 1;
-    auto witems = [&](int64_t ns) { return (chunks * ns + 31) / 32; };
-    int64_t lo_seg = (4 * warps * 32 + chunks - 1) / chunks, hi_seg = (8 * warps * 32) / chunks;
+    constexpr int64_t per_warp = ELEM ? 1 : 32;  // items a warp takes at a time
+    auto witems = [&](int64_t ns) { return (chunks * ns + per_warp - 1) / per_warp; };
+    int64_t lo_seg = (4 * warps * per_warp + chunks - 1) / chunks, hi_seg = (8 * warps * per_warp) / chunks;
     if (lo_seg < 1) lo_seg = 1;
     if (hi_seg < lo_seg) hi_seg = lo_seg;
     if (lo_seg > max_seg) lo_seg = max_seg;
@@ -713,13 +878,20 @@ cudaError_t launch_cols_async(const CountJob& job, Workspace* ws, cudaStream_t s
     }
     const int64_t seg_min = pair_rows / nseg;
     const int64_t seg_extra = pair_rows - seg_min * nseg;
-    const int64_t total = chunks * nseg;
+    const int64_t total = witems(nseg) * 32;  // threads' worth of work
     int64_t blocks = (total + kAsyncThreads - 1) / kAsyncThreads;
     if (blocks > sms) blocks = sms;
-    kern<<<(unsigned)blocks, kAsyncThreads, kAsyncSmem, stream>>>(
-        static_cast<const char*>(job.x), (long long)row_bytes, (long long)chunks, (long long)nseg, (long long)seg_min,
-        (long long)seg_extra, (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32),
-        (unsigned long long)(pair_rows * job.inner), ws);
+    if constexpr (ELEM) {
+        kern<<<(unsigned)blocks, kAsyncThreads, kAsyncSmem, stream>>>(
+            static_cast<const char*>(job.x), (long long)job.inner, (long long)chunks, (long long)nseg,
+            (long long)seg_min, (long long)seg_extra, (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32),
+            (unsigned long long)(pair_rows * job.inner), ws);
+    } else {
+        kern<<<(unsigned)blocks, kAsyncThreads, kAsyncSmem, stream>>>(
+            static_cast<const char*>(job.x), (long long)row_bytes, (long long)chunks, (long long)nseg, (long long)seg_min,
+            (long long)seg_extra, (uint32_t)job.mask_bits, (uint32_t)(job.mask_bits >> 32),
+            (unsigned long long)(pair_rows * job.inner), ws);
+    }
     return cudaGetLastError();
 }
 
@@ -922,13 +1094,16 @@ cudaError_t launch_cols(const CountJob& job, Workspace* ws, cudaStream_t stream,
     {
         cudaError_t e;
         if (aligned) {
-            e = launch_cols_async<KIND, MASK, XFORM, 16>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
+            e = launch_cols_async<KIND, MASK, XFORM, false>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
             if constexpr (MASK != kMaskNone) {  // the other flavour; one of the two returns at once
                 if (e == cudaSuccess)
-                    e = launch_cols_async<KIND, MASK + 2, XFORM, 16>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
+                    e = launch_cols_async<KIND, MASK + 2, XFORM, false>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
             }
         } else {
-            if constexpr (BYTES >= 4) e = launch_cols_async<KIND, MASK, XFORM, BYTES>(job, ws, stream, row_bytes, chunks, pair_rows, sms);
+            constexpr int64_t kStripCols = 32 * (16 / BYTES);
+            if constexpr (BYTES >= 4)
+                e = launch_cols_async<KIND, MASK, XFORM, true>(job, ws, stream, row_bytes, (job.inner + kStripCols - 1) / kStripCols,
+                                                               pair_rows, sms);
             else e = cudaErrorInvalidValue;
         }
         if (e != cudaSuccess) return e;
