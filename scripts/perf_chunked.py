@@ -17,6 +17,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--shape", default="744,721,1440")
 ap.add_argument("--dtype", default="float32")
 ap.add_argument("--loop", action="store_true", help="also time the chunk-by-chunk route (slow for many chunks)")
+ap.add_argument("--compare", action="store_true", help="only K1: default kernel vs the three-stream walkers (walk3)")
+ap.add_argument("--nan", default=None, help="land: 30 %% NaN rectangle; a number: that fraction of NaNs at random")
 ap.add_argument("--chunk", default=None, help="only this chunk shape (comma separated), e.g. for an ncu capture")
 args = ap.parse_args()
 shape = tuple(int(v) for v in args.shape.split(","))
@@ -27,6 +29,10 @@ torch.cumsum(x, dim=-1, out=x)
 x += 287.0
 x = x.to(dt)
 nbytes = x.numel() * x.element_size()
+if args.nan == "land":
+    x[:, : int(shape[1] * 0.55), : int(shape[2] * 0.55)] = float("nan")
+elif args.nan:
+    x[torch.rand(shape, device="cuda", generator=g) < float(args.nan)] = float("nan")
 
 
 def timed(fn, reps=5):
@@ -54,6 +60,16 @@ if args.chunk:
 print(f"{args.dtype} {shape}: {nbytes/1e9:.2f} GB")
 for chunk in grids:
     for axis in (0, len(shape) - 1):
+        if args.compare:
+            ref = count_pairs_chunked(x, chunk, axis, masked_value=float("nan"), flavour="walk3")
+            new = count_pairs_chunked(x, chunk, axis, masked_value=float("nan"))
+            same = bool(torch.equal(ref, new))
+            t_new = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=float("nan")))
+            t_old = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=float("nan"), flavour="walk3"))
+            t_plain = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=None))
+            print(f"chunk {str(chunk):22s} axis {axis}: default {nbytes/t_new/1e6:6.0f} GB/s | three-stream walkers "
+                  f"{nbytes/t_old/1e6:6.0f} GB/s | no mask {nbytes/t_plain/1e6:6.0f} GB/s | equal {same}", flush=True)
+            continue
         counts = count_pairs_chunked(x, chunk, axis, masked_value=float("nan"))
         nchunks = counts.numel() // (counts.shape[-3] * 4)
         t_count = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=float("nan")))

@@ -22,6 +22,7 @@
 #include "xbi_common.cuh"
 #include "xbi_elem.cuh"
 #include "xbi_internal.h"
+#include "xbi_mask.cuh"
 
 namespace xbi {
 
@@ -374,58 +375,438 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
     if (cur_chunk != 0xFFFFFFFFu) flush_chunk(cur_chunk);
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// The walkers for 4- and 8-byte types, second formulation: TWO word streams and corrections at validity boundaries
+// (xbi_mask.cuh), 16 elements per lane and step.
+//
+// With x' = transform(x), zeroed where x is masked, S = sum of x' over every element of a column and rows -1 and
+// `ea` of a column taken as masked rows:
+//     AB = sum x'[r-1] & x'[r]                                   (no validity needed)
+//     A  = S - sum over {r-1 valid, r masked} of x'[r-1]         (includes the column's last row)
+//     B  = S - sum over {r-1 masked, r valid} of x'[r]           (includes the column's first row)
+// A step whose 16 x 32 elements all exist, follow a valid row and pass the masked-element probe (x * 0 on the FMA
+// pipe, may_contain_masked) is the unmasked two-stream step: transform, one AND, two ladders -- about 10 issued
+// instructions per element against 28 for the three explicit streams under keep-masks above.  Every other step
+// (the first and a ragged last step of a column, steps with masked elements) takes the exact per-element test and
+// feeds the correction words, where some lane has one, into small register bit planes (EventPlanes).  Lanes past
+// the last column of a tile read the value whose transform is 0 from cells they fill themselves, so partial tiles
+// (small chunks) stay on the fast step.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kLogR2 = 4;
+constexpr int kRows2 = 1 << kLogR2;  // elements per lane and step
+constexpr int kEvP = 6;              // planes of the correction counters: 63 events per lane between flushes
+
+template <bool LASTAX>
+struct Ring2 {
+    static constexpr int kSlots = LASTAX ? 5 : 6;
+};
+template <int BYTES, bool LASTAX>
+constexpr size_t ring2_bytes() {
+    return 16 + (size_t)kWWarps * Ring2<LASTAX>::kSlots * 32 * (LASTAX ? kRows2 * BYTES + 16 : kRows2 * BYTES);
+}
+
+template <int KIND, int MASK, bool XFORM, bool LASTAX>
+__global__ void __launch_bounds__(kWThreads, Elem<KIND>::kWords == 1 ? 2 : 1)
+k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
+                      unsigned long long* __restrict__ counts, unsigned long long items, unsigned groups) {
+    using E = Elem<KIND>;
+    constexpr int BYTES = E::kBytes;
+    constexpr int NW = E::kWords;
+    constexpr int NBITS = E::kBits;
+    static_assert(BYTES >= 4, "4- and 8-byte element types");
+    constexpr int kSlots = Ring2<LASTAX>::kSlots;
+    constexpr int kAhead = kSlots - 1;
+    constexpr uint32_t kLanePitch = (uint32_t)(kRows2 * BYTES + 16);  // LASTAX: a lane's 16 elements + 16 (conflict-free 128-bit reads)
+    constexpr uint32_t kSlotBytes = LASTAX ? 32u * kLanePitch : (uint32_t)kRows2 * 32u * (uint32_t)BYTES;
+    using L = Ladder<3, 8, kLogR2>;
+    using EP = EventPlanes<NW, kEvP>;
+
+    extern __shared__ uint8_t smem_ring[];
+    uint32_t lane = threadIdx.x & 31u;
+    uint32_t warp = threadIdx.x >> 5;
+    uint32_t ring0 = ((smem_addr_w(smem_ring) + 15u) & ~15u) + warp * (kSlots * kSlotBytes);
+    // (made opaque: under register pressure ptxas otherwise re-derives these in every step)
+    asm volatile("" : "+r"(lane), "+r"(warp), "+r"(ring0));
+    uint32_t slot_w = 0, slot_r = 0;
+
+    const unsigned long long item_lo = (unsigned long long)blockIdx.x * items / gridDim.x;
+    const unsigned long long item_hi = (unsigned long long)(blockIdx.x + 1) * items / gridDim.x;
+    const int axis = g.axis;
+    long long astride = 0;
+#pragma unroll
+    for (int d = 0; d < kD; ++d) if (d == axis) astride = g.stride[d];
+
+    L S[NW], AB[NW];
+    EP ev;
+    ev.init();
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { S[k].clear(); AB[k].clear(); }
+    uint32_t it = 0, nvalid = 0;
+    unsigned long long accS[NW], accAB[NW], accCA[NW], accCB[NW], nvalid_total = 0;
+#pragma unroll
+    for (int k = 0; k < NW; ++k) { accS[k] = 0; accAB[k] = 0; accCA[k] = 0; accCB[k] = 0; }
+
+    auto drain = [&]() {  // ladders -> per-lane totals (lane L: bit L)
+        if (it == 0) return;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            accS[k] += S[k].warp_totals_bounded(lane, it);
+            accAB[k] += AB[k].warp_totals_bounded(lane, it);
+            S[k].clear(); AB[k].clear();
+        }
+        nvalid_total += nvalid;
+        nvalid = 0;
+        it = 0;
+    };
+    auto ev_flush = [&]() {  // correction planes -> per-lane totals; warp-collective
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+#pragma unroll
+            for (int k = 0; k < NW; ++k) {
+                uint32_t n[kEvP + 6];
+#pragma unroll
+                for (int j = 0; j < kEvP; ++j) { n[j] = ev.r[s][k][j]; ev.r[s][k][j] = 0u; }
+#pragma unroll
+                for (int j = kEvP; j < kEvP + 6; ++j) n[j] = 0u;
+                const uint32_t total = butterfly_totals(n, kEvP, lane);
+                if (s == 0) accCA[k] += total;
+                else accCB[k] += total;
+            }
+        }
+        ev.ecnt = 0u;
+    };
+    auto ev_reserve = [&](uint32_t upcoming) {
+        if (__any_sync(0xFFFFFFFFu, ev.ecnt + upcoming > EP::kCap)) ev_flush();
+    };
+    auto flush_chunk = [&](unsigned cid) {  // per-lane totals -> the chunk's raw table (see k_chunk_finalize)
+        drain();
+        if (__any_sync(0xFFFFFFFFu, ev.ecnt != 0u)) ev_flush();
+        unsigned long long* dst = counts + (size_t)cid * NBITS * 4;
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int j = k * 32 + (int)lane;
+            const unsigned long long b = accS[k] - accCB[k], a = accS[k] - accCA[k];
+            if (b) atomicAdd(dst + 4 * (NBITS - 1 - j) + 1, b);
+            if (a) atomicAdd(dst + 4 * (NBITS - 1 - j) + 2, a);
+            if (accAB[k]) atomicAdd(dst + 4 * (NBITS - 1 - j) + 3, accAB[k]);
+            accS[k] = 0; accAB[k] = 0; accCA[k] = 0; accCB[k] = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) nvalid_total += __shfl_xor_sync(0xFFFFFFFFu, nvalid_total, o);
+        if (lane == 0 && nvalid_total) atomicAdd(dst, nvalid_total);
+        nvalid_total = 0;
+    };
+    // all-ones when the element is not masked
+    auto keep_of = [&](const uint32_t (&w)[NW]) -> uint32_t {
+        if (MASK == kMaskNaN) return E::is_nan(w) ? 0u : 0xFFFFFFFFu;
+        if (MASK == kMaskValue) return E::equals(w, mask_lo, mask_hi) ? 0u : 0xFFFFFFFFu;
+        return 0xFFFFFFFFu;
+    };
+
+    unsigned cur_chunk = 0xFFFFFFFFu;
+    ChunkBox box;
+    for (unsigned long long item = item_lo + warp; item < item_hi; item += kWWarps) {
+        const unsigned cid = (unsigned)(item / groups), grp = (unsigned)(item - (unsigned long long)cid * groups);
+        if (cid != cur_chunk) {
+            if (cur_chunk != 0xFFFFFFFFu) flush_chunk(cur_chunk);
+            cur_chunk = cid;
+            box.init(g, cid);
+        }
+        unsigned ea = 1;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) if (d == axis) ea = box.e[d];
+        asm volatile("" : "+r"(ea));
+        if (ea < 2) continue;  // no pairs in this chunk
+
+        unsigned long long O = 1, I = 1;
+#pragma unroll
+        for (int d = 0; d < kD; ++d) {
+            if (d < axis) O *= box.e[d];
+            if (d > axis) I *= box.e[d];
+        }
+        long long step_bytes = astride * BYTES;
+        asm volatile("" : "+l"(step_bytes));
+
+        auto walk = [&](auto epv_tag) {
+            constexpr int EPV = decltype(epv_tag)::value;   // columns per lane
+            constexpr int RS = kRows2 / EPV;                 // rows per step
+            constexpr bool V16 = EPV * BYTES == 16 && !LASTAX;
+            constexpr uint32_t kCell = LASTAX ? kLanePitch : (uint32_t)(EPV * BYTES);              // a lane's cell
+            constexpr uint32_t kRowP = LASTAX ? (uint32_t)BYTES : 32u * (uint32_t)(EPV * BYTES);   // a row of the step
+            const unsigned long long ncols = O * I / EPV, tiles = (ncols + 31) / 32;
+            const unsigned long long t_lo = tiles * grp / groups, t_hi = tiles * (grp + 1) / groups;
+            for (unsigned long long tile = t_lo; tile < t_hi; ++tile) {
+                const unsigned long long col = tile * 32 + lane;
+                unsigned live_u = col < ncols ? 1u : 0u;
+                asm volatile("" : "+r"(live_u));
+                const bool live = live_u != 0u;
+                uint32_t cell = ring0 + lane * kCell;
+                asm volatile("" : "+r"(cell));
+                if (!live) {
+                    // no column: the lane's cells hold the value whose transform is 0 (nothing is ever copied there
+                    // during this tile; what earlier tiles copied has landed, see the wait at the end of a tile)
+                    const uint32_t nw0 = neutral_word<KIND, XFORM>(0), nw1 = neutral_word<KIND, XFORM>(NW - 1);
+#pragma unroll 1
+                    for (int sl = 0; sl < kSlots; ++sl) {
+#pragma unroll
+                        for (int u = 0; u < kRows2; ++u) {
+                            const uint32_t a = cell + sl * kSlotBytes + (LASTAX ? (uint32_t)(u * BYTES) : (uint32_t)(u / EPV) * kRowP + (uint32_t)((u % EPV) * BYTES));
+                            if (NW == 2) asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(a), "r"(nw0), "r"(nw1) : "memory");
+                            else asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(nw0) : "memory");
+                        }
+                    }
+                }
+                // offset of this lane's (first) column at row 0 of the chunk
+                long long off = box.base;
+                {
+                    const unsigned long long cc = (live ? col : 0) * EPV;
+                    unsigned long long ro = cc / I, ri = cc - ro * I;
+#pragma unroll
+                    for (int d = kD - 1; d >= 0; --d) {
+                        if (d > axis) { off += (long long)(ri % box.e[d]) * g.stride[d]; ri /= box.e[d]; }
+                        if (d < axis) { off += (long long)(ro % box.e[d]) * g.stride[d]; ro /= box.e[d]; }
+                    }
+                }
+                const char* q = static_cast<const char*>(x) + off * BYTES;  // advanced by the copies
+                // previous row: transformed, zero where masked or absent; its keep-masks.  The walk starts at row 0
+                // with "row -1 masked"
+                uint32_t prev[EPV][NW], pk[EPV];
+#pragma unroll
+                for (int e = 0; e < EPV; ++e) {
+                    pk[e] = 0u;
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) prev[e][k] = 0;
+                }
+                bool pv_all = false;  // warp-uniform: every lane's previous row(s) valid
+                unsigned nsteps = (ea + RS - 1) / RS;
+                asm volatile("" : "+r"(nsteps));
+                const uint32_t nv_fast = live ? (uint32_t)kRows2 : 0u;
+                // LASTAX: 16-byte copies when every lane's run starts on a 16-byte boundary (warp-uniform)
+                const bool vec = LASTAX && __all_sync(0xFFFFFFFFu, !live || (reinterpret_cast<uintptr_t>(q) & 15u) == 0u);
+                unsigned issued = 0;
+                auto issue = [&]() {
+                    if (issued < nsteps) {
+                        const unsigned left = ea - RS * issued;  // rows from this step on (uniform)
+                        if (live) {
+                            const uint32_t dst = cell + slot_w * kSlotBytes;
+                            if (left >= (unsigned)RS) {
+                                if (LASTAX && vec) {
+#pragma unroll
+                                    for (int v = 0; v < kRows2 * BYTES / 16; ++v)
+                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * v), "l"(q + 16 * v) : "memory");
+                                    q += kRows2 * BYTES;
+                                } else {
+#pragma unroll
+                                    for (int u = 0; u < RS; ++u) {
+                                        if constexpr (V16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * kRowP), "l"(q) : "memory");
+                                        else cpa_elem<BYTES>(dst + u * kRowP, q);
+                                        q += step_bytes;
+                                    }
+                                }
+                            } else {
+#pragma unroll
+                                for (int u = 0; u < RS; ++u) {
+                                    if ((unsigned)u < left) {
+                                        if constexpr (V16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * kRowP), "l"(q) : "memory");
+                                        else cpa_elem<BYTES>(dst + u * kRowP, q);
+                                        q += step_bytes;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                    cpa_commit_w();
+                    slot_w = (slot_w + 1 == kSlots) ? 0 : slot_w + 1;
+                    ++issued;
+                };
+#pragma unroll 1
+                for (int k = 0; k < kAhead; ++k) issue();
+#pragma unroll 1
+                for (unsigned s = 0; s < nsteps; ++s) {
+                    issue();
+                    cpa_wait_w<kAhead>();
+                    const unsigned left = ea - RS * s;  // rows from this step on (uniform)
+                    const uint32_t src = cell + slot_r * kSlotBytes;
+                    slot_r = (slot_r + 1 == kSlots) ? 0 : slot_r + 1;
+                    uint32_t flat[kRows2 * NW];  // memory order: element u = row * EPV + column, NW words each
+                    if constexpr (LASTAX || V16) {
+#pragma unroll
+                        for (int v = 0; v < kRows2 * BYTES / 16; ++v) {
+                            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                                         : "=r"(flat[4 * v]), "=r"(flat[4 * v + 1]), "=r"(flat[4 * v + 2]), "=r"(flat[4 * v + 3])
+                                         : "r"(src + (LASTAX ? 16u * v : (uint32_t)v * kRowP)));
+                        }
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < kRows2; ++u) {
+                            uint32_t w[NW];
+                            lds_elem_w<NW>(src + u * kRowP, w);
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) flat[u * NW + k] = w[k];
+                        }
+                    }
+                    uint32_t sw[NW][kRows2], abw[NW][kRows2];
+                    bool fast = pv_all && left >= (unsigned)RS;
+                    if (MASK != kMaskNone && fast)
+                        fast = !__any_sync(0xFFFFFFFFu, may_contain_masked<KIND, MASK>(flat, mask_lo, mask_hi));
+                    if (fast) {
+#pragma unroll
+                        for (int u = 0; u < kRows2; ++u) {
+                            const int e = u % EPV;
+                            uint32_t w[NW];
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) w[k] = flat[u * NW + k];
+                            if (XFORM) E::transform(w);
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) { sw[k][u] = w[k]; abw[k][u] = prev[e][k] & w[k]; prev[e][k] = w[k]; }
+                        }
+                        nvalid += nv_fast;
+                    } else {
+                        ev_reserve((uint32_t)kRows2);
+                        uint32_t vbits = 0, pand = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int u = 0; u < kRows2; ++u) {
+                            const int e = u % EPV;
+                            uint32_t w[NW];
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) w[k] = flat[u * NW + k];
+                            uint32_t kk = ((unsigned)(u / EPV) < left) ? 0xFFFFFFFFu : 0u;  // the row exists ...
+                            if (MASK != kMaskNone) kk &= keep_of(w);                         // ... and is not masked
+                            if (XFORM) E::transform(w);
+                            uint32_t ca[NW], cb[NW], any_c = 0u;
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) {
+                                w[k] &= kk;
+                                ca[k] = prev[e][k] & ~kk;    // row above valid, this one masked / absent
+                                cb[k] = w[k] & ~pk[e];       // this row valid, the one above masked / absent
+                                any_c |= ca[k] | cb[k];
+                                sw[k][u] = w[k];
+                                abw[k][u] = prev[e][k] & w[k];
+                                prev[e][k] = w[k];
+                            }
+                            vbits |= (kk & pk[e]) & (1u << u);  // the pair (row above, this row) counts
+                            pk[e] = kk;
+                            if (__any_sync(0xFFFFFFFFu, any_c != 0u)) {
+                                ev.ecnt += any_c ? 1u : 0u;
+#pragma unroll
+                                for (int k = 0; k < NW; ++k) {
+                                    if (k == 0) { ev.template add<0, 0>(ca[0]); ev.template add<1, 0>(cb[0]); }
+                                    else { ev.template add<0, NW - 1>(ca[NW - 1]); ev.template add<1, NW - 1>(cb[NW - 1]); }
+                                }
+                            }
+                        }
+                        nvalid += live ? (uint32_t)__popc(vbits) : 0u;
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) pand &= pk[e];
+                        pv_all = __all_sync(0xFFFFFFFFu, pand == 0xFFFFFFFFu);
+                    }
+#pragma unroll
+                    for (int k = 0; k < NW; ++k) {
+                        S[k].add_chunk(sw[k], it);
+                        AB[k].add_chunk(abw[k], it);
+                    }
+                    ++it;
+                    if (it == L::kFlushChunks) drain();
+                }
+                // the row after the last one is "masked": the a-stream loses the last valid row of every column
+                // (prev is zero where a ragged last step has already dealt with it)
+                {
+                    uint32_t any_c = 0u;
+#pragma unroll
+                    for (int e = 0; e < EPV; ++e)
+#pragma unroll
+                        for (int k = 0; k < NW; ++k) any_c |= prev[e][k];
+                    if (__any_sync(0xFFFFFFFFu, any_c != 0u)) {
+                        ev_reserve((uint32_t)EPV);
+#pragma unroll
+                        for (int e = 0; e < EPV; ++e) {
+                            uint32_t c = 0u;
+#pragma unroll
+                            for (int k = 0; k < NW; ++k) c |= prev[e][k];
+                            ev.ecnt += c ? 1u : 0u;
+                            ev.template add<0, 0>(prev[e][0]);
+                            if (NW == 2) ev.template add<0, NW - 1>(prev[e][NW - 1]);
+                        }
+                    }
+                }
+                slot_r = slot_w;  // the kAhead groups committed past the end of the column were empty
+            }
+        };
+        constexpr int kVecCols = LASTAX ? 1 : 16 / BYTES;
+        if (kVecCols > 1 && g.vec16 && box.e[kD - 1] % kVecCols == 0) walk(std::integral_constant<int, kVecCols>{});
+        else walk(std::integral_constant<int, 1>{});
+    }
+    if (cur_chunk != 0xFFFFFFFFu) flush_chunk(cur_chunk);
+}
+
+template <typename K>
+cudaError_t set_smem_once(K kern, size_t smem, std::atomic<unsigned long long>& attr_set) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long dev_bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
+    if (!(attr_set.load(std::memory_order_acquire) & dev_bit)) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set.fetch_or(dev_bit, std::memory_order_release);
+    }
+    return cudaSuccess;
+}
+
 template <int KIND, int MASK, bool XFORM, bool LASTAX>
 cudaError_t launch_walk_ax(const void* x, const ChunkGrid& g, uint32_t mlo, uint32_t mhi, unsigned long long* counts,
-                           unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream) {
+                           unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream, bool three) {
     constexpr int BYTES = Elem<KIND>::kBytes;
     constexpr bool RING = BYTES >= 4;
-    constexpr size_t smem = RING ? 16 + (size_t)kWWarps * kSlots * 32 * (LASTAX ? kRows * BYTES + 16 : kRows * BYTES) : 0;
-    auto kern = k_pairs_chunked_walk<KIND, MASK, XFORM, RING, LASTAX>;
-    if (smem > 48 * 1024) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        static std::atomic<unsigned long long> attr_set{0ull};
-        const unsigned long long dev_bit = (dev >= 0 && dev < 64) ? (1ull << dev) : 0ull;
-        if (!(attr_set.load(std::memory_order_acquire) & dev_bit)) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            if (e != cudaSuccess) return e;
-            attr_set.fetch_or(dev_bit, std::memory_order_release);
+    if constexpr (RING) {
+        if (!three) {  // two streams + boundary corrections (the default for 4- and 8-byte types)
+            constexpr size_t smem2 = ring2_bytes<BYTES, LASTAX>();
+            auto kern2 = k_pairs_chunked_walk2<KIND, MASK, XFORM, LASTAX>;
+            static std::atomic<unsigned long long> attr_set2{0ull};
+            if (cudaError_t e = set_smem_once(kern2, smem2, attr_set2)) return e;
+            kern2<<<grid, kWThreads, smem2, stream>>>(x, g, mlo, mhi, counts, items, groups);
+            return cudaGetLastError();
         }
     }
+    constexpr size_t smem = RING ? 16 + (size_t)kWWarps * kSlots * 32 * (LASTAX ? kRows * BYTES + 16 : kRows * BYTES) : 0;
+    auto kern = k_pairs_chunked_walk<KIND, MASK, XFORM, RING, LASTAX>;
+    static std::atomic<unsigned long long> attr_set{0ull};
+    if (cudaError_t e = set_smem_once(kern, smem, attr_set)) return e;
     kern<<<grid, kWThreads, smem, stream>>>(x, g, mlo, mhi, counts, items, groups);
     return cudaGetLastError();
 }
 
 template <int KIND, int MASK, bool XFORM>
 cudaError_t launch_walk(const void* x, const ChunkGrid& g, uint32_t mlo, uint32_t mhi, unsigned long long* counts,
-                        unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream) {
+                        unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream, bool three) {
     if constexpr (Elem<KIND>::kBytes >= 4) {
-        if (g.axis == kD - 1) return launch_walk_ax<KIND, MASK, XFORM, true>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+        if (g.axis == kD - 1) return launch_walk_ax<KIND, MASK, XFORM, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
     }
-    return launch_walk_ax<KIND, MASK, XFORM, false>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+    return launch_walk_ax<KIND, MASK, XFORM, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
 }
 
 template <int KIND>
 cudaError_t dispatch_walk(const void* x, const ChunkGrid& g, bool transform, int mask_mode, uint32_t mlo, uint32_t mhi,
                           unsigned long long* counts, unsigned long long items, unsigned groups, unsigned grid,
-                          cudaStream_t stream) {
+                          cudaStream_t stream, bool three) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (transform) {
         if constexpr (isf) {
             switch (mask_mode) {
-                case kMaskNone: return launch_walk<KIND, kMaskNone, true>(x, g, mlo, mhi, counts, items, groups, grid, stream);
-                case kMaskNaN: return launch_walk<KIND, kMaskNaN, true>(x, g, mlo, mhi, counts, items, groups, grid, stream);
-                default: return launch_walk<KIND, kMaskValue, true>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+                case kMaskNone: return launch_walk<KIND, kMaskNone, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+                case kMaskNaN: return launch_walk<KIND, kMaskNaN, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+                default: return launch_walk<KIND, kMaskValue, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
             }
         }
         return cudaErrorInvalidValue;
     }
     switch (mask_mode) {
-        case kMaskNone: return launch_walk<KIND, kMaskNone, false>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+        case kMaskNone: return launch_walk<KIND, kMaskNone, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
         case kMaskNaN:
-            if constexpr (isf) return launch_walk<KIND, kMaskNaN, false>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+            if constexpr (isf) return launch_walk<KIND, kMaskNaN, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
             return cudaErrorInvalidValue;
-        default: return launch_walk<KIND, kMaskValue, false>(x, g, mlo, mhi, counts, items, groups, grid, stream);
+        default: return launch_walk<KIND, kMaskValue, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
     }
 }
 
@@ -435,7 +816,7 @@ cudaError_t dispatch_walk(const void* x, const ChunkGrid& g, bool transform, int
 // *taken = false leaves everything to the odometer kernel of xbi_chunked.cu.
 cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
                                       int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream,
-                                      bool force, bool* taken) {
+                                      bool force, bool three, bool* taken) {
     *taken = false;
     if (g.axis < 0 || nchunks == 0) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -480,13 +861,13 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
     const uint32_t mlo = (uint32_t)(mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(mask_bits >> 32);
     cudaError_t e;
     switch (dtype) {
-        case XBI_U8: e = dispatch_walk<kU8>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_U16: e = dispatch_walk<kU16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_U32: e = dispatch_walk<kU32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_U64: e = dispatch_walk<kU64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_F16: e = dispatch_walk<kF16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_F32: e = dispatch_walk<kF32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
-        case XBI_F64: e = dispatch_walk<kF64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream); break;
+        case XBI_U8: e = dispatch_walk<kU8>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
+        case XBI_U16: e = dispatch_walk<kU16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
+        case XBI_U32: e = dispatch_walk<kU32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
+        case XBI_U64: e = dispatch_walk<kU64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
+        case XBI_F16: e = dispatch_walk<kF16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
+        case XBI_F32: e = dispatch_walk<kF32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
+        case XBI_F64: e = dispatch_walk<kF64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
         default: return cudaErrorInvalidValue;
     }
     if (e != cudaSuccess) return e;

@@ -179,10 +179,12 @@ struct ChunkGrid {
 cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
                                  int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream,
                                  unsigned flags = 0);
-// the fast formulation (xbi_chunked_walk.cu); *taken = false: the grid does not suit it, nothing was launched
+// the fast formulation (xbi_chunked_walk.cu); *taken = false: the grid does not suit it, nothing was launched.
+// three: the walkers with three explicit streams under keep-masks also for 4- and 8-byte types (default: two
+// streams + boundary corrections)
 cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
                                       int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream,
-                                      bool force, bool* taken);
+                                      bool force, bool three, bool* taken);
 cudaError_t launch_bitround_chunked(void* x, int dtype, const ChunkGrid& g, const int* keepbits, cudaStream_t stream);
 
 // xbi_hostpool.cu: rows of row_bytes bytes copied host -> host by a small pool of threads
