@@ -58,7 +58,9 @@ enum xbi_dtype {
 #define XBI_FORCE_SPARSE 16u   /* testing: masked fast kernels in their boundary-correction flavour */
 #define XBI_FORCE_DENSE 32u    /* testing: ... in their three-stream flavour (default: sampled)     */
 #define XBI_FORCE_WALK 64u     /* testing (chunk grids): the walker kernel whatever the grid;
-                                  XBI_FORCE_GENERIC there: the per-element odometer kernel            */
+                                  XBI_FORCE_GENERIC there: the per-element odometer kernel;
+                                  XBI_FORCE_SPARSE / XBI_FORCE_DENSE there: the walkers of 4- / 8-byte types on
+                                  two streams + boundary corrections / on three explicit streams      */
 
 /* error codes */
 #define XBI_OK 0
@@ -187,8 +189,8 @@ int xbi_mutual_information_batched(const unsigned long long* counts_dev, int nbi
  *   shape[d] mean "not chunked").  Chunks are numbered in C order of the chunk grid.
  *   xbi_count_pairs_chunked: counts_dev[chunk][nbits][4] is OVERWRITTEN with the pair histogram of
  *   every chunk taken on its own along `axis` (pairs never cross a chunk boundary); flags and
- *   mask_bits as for xbi_count_pairs (of the XBI_FORCE_* flags only XBI_FORCE_WALK / XBI_FORCE_GENERIC
- *   mean something here: they pin one of the two chunk-grid kernels for the tests).
+ *   mask_bits as for xbi_count_pairs (the XBI_FORCE_* flags pin one of the chunk-grid kernels for the
+ *   tests, see their definitions).
  *   xbi_bitround_chunked: chunk c is rounded in place to keepbits_dev[c] mantissa bits (values are
  *   clamped to 0..mantissa bits; mantissa bits = unchanged).
  * XBI_ERR_UNSUPPORTED: more than 5 dimensions remain after merging unchunked neighbours, a chunk

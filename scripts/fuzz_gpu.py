@@ -75,6 +75,7 @@ while time.time() < t_end:
     got = count_pairs_chunked(t, spec, axis, masked_value=mv).cpu().numpy()
     # both chunk-grid kernels whatever the planner picks: the column walkers and the per-element odometers
     got_walk = count_pairs_chunked(t, spec, axis, masked_value=mv, flavour="walk").cpu().numpy()
+    got_walk2 = count_pairs_chunked(t, spec, axis, masked_value=mv, flavour="walk2").cpu().numpy()
     got_walk3 = count_pairs_chunked(t, spec, axis, masked_value=mv, flavour="walk3").cpu().numpy()
     got_odo = count_pairs_chunked(t, spec, axis, masked_value=mv, flavour="odometer").cpu().numpy()
     grid = normalize_chunks(shape, spec)
@@ -83,6 +84,7 @@ while time.time() < t_end:
         want = bo.bitinformation(x[sl], axis, masked_value=mv)[0]
         assert np.array_equal(got[idx], want), ("counts", shape, dtype, spec, axis, mv, idx)
         assert np.array_equal(got_walk[idx], want), ("counts (walkers)", shape, dtype, spec, axis, mv, idx)
+        assert np.array_equal(got_walk2[idx], want), ("counts (walkers, two streams)", shape, dtype, spec, axis, mv, idx)
         assert np.array_equal(got_walk3[idx], want), ("counts (walkers, three streams)", shape, dtype, spec, axis, mv, idx)
         assert np.array_equal(got_odo[idx], want), ("counts (odometers)", shape, dtype, spec, axis, mv, idx)
     if np.dtype(dtype).kind == "f":

@@ -65,9 +65,10 @@ for chunk in grids:
             new = count_pairs_chunked(x, chunk, axis, masked_value=float("nan"))
             same = bool(torch.equal(ref, new))
             t_new = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=float("nan")))
+            t_two = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=float("nan"), flavour="walk2"))
             t_old = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=float("nan"), flavour="walk3"))
             t_plain = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=None))
-            print(f"chunk {str(chunk):22s} axis {axis}: default {nbytes/t_new/1e6:6.0f} GB/s | three-stream walkers "
+            print(f"chunk {str(chunk):22s} axis {axis}: default {nbytes/t_new/1e6:6.0f} GB/s | two-stream walkers {nbytes/t_two/1e6:6.0f} GB/s | three-stream walkers "
                   f"{nbytes/t_old/1e6:6.0f} GB/s | no mask {nbytes/t_plain/1e6:6.0f} GB/s | equal {same}", flush=True)
             continue
         counts = count_pairs_chunked(x, chunk, axis, masked_value=float("nan"))

@@ -38,7 +38,7 @@ def check(x, chunk_shape, axis, masked_value=None, set_zero=False):
     assert np.array_equal(got.cpu().numpy(), want)
     # both chunk-grid kernels, whatever the planner would pick for this grid: the walkers (one load per element,
     # xbi_chunked_walk.cu) and the per-element odometers (xbi_chunked.cu)
-    for flavour in ("walk", "walk3", "odometer"):
+    for flavour in ("walk", "walk2", "walk3", "odometer"):
         pinned = count_pairs_chunked(t, chunk_shape, axis, masked_value=masked_value, flavour=flavour)
         assert np.array_equal(pinned.cpu().numpy(), want), flavour
     mi = information_batched(got, set_zero, 0.99).cpu().numpy()

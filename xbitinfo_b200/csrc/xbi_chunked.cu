@@ -428,7 +428,8 @@ cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, u
     }();
     if ((allow_walk || (flags & XBI_FORCE_WALK)) && !(flags & XBI_FORCE_GENERIC)) {
         e = launch_pairs_chunked_walk(x, dtype, g, nchunks, transform, mask_mode, mask_bits, counts, stream,
-                                      (flags & XBI_FORCE_WALK) != 0, (flags & XBI_FORCE_DENSE) != 0, &walked);
+                                      (flags & XBI_FORCE_WALK) != 0,
+                                      (flags & XBI_FORCE_DENSE) ? 2 : (flags & XBI_FORCE_SPARSE) ? 1 : 0, &walked);
         if (e != cudaSuccess) return e;
     }
     if (!walked) switch (dtype) {

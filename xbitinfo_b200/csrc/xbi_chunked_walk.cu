@@ -57,6 +57,18 @@ struct ChunkBox {
     }
 };
 
+// Masked modes, 4- and 8-byte types: a sampling kernel leaves (#pairs whose elements differ in validity, #pairs
+// sampled) in two scratch words of chunk 0's table (slot 0 of bits 1 and 2: unused until k_chunk_finalize overwrites
+// them); both walker kernels are launched and the one that does not suit the data returns at once.  More than one
+// boundary in kWalkOneIn pairs: masked elements are scattered, nearly every step of the two-stream walkers would
+// take the exact per-element path -- the three explicit streams are cheaper then.
+constexpr unsigned long long kWalkOneIn = 128;
+constexpr int kDensBnd = 4, kDensPairs = 8;  // word offsets into chunk 0's table
+__device__ __forceinline__ bool walk_density_is_scattered(const unsigned long long* dens) {
+    const volatile unsigned long long* p = dens;
+    return p[kDensBnd] * kWalkOneIn > p[kDensPairs];
+}
+
 constexpr int kLogR = 3;
 constexpr int kRows = 1 << kLogR;    // rows (column walkers) / 32-element steps (runs) folded at a time: 16 needed
                                      // ~30 registers more than the 128 a thread of a 2-CTA/SM kernel may have (spills)
@@ -84,7 +96,9 @@ __device__ __forceinline__ uint32_t smem_addr_w(const void* p) { return static_c
 template <int KIND, int MASK, bool XFORM, bool RING, bool LASTAX>
 __global__ void __launch_bounds__(kWThreads, Elem<KIND>::kWords == 1 ? 2 : 1)
 k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
-                     unsigned long long* __restrict__ counts, unsigned long long items, unsigned groups) {
+                     unsigned long long* __restrict__ counts, unsigned long long items, unsigned groups,
+                     const unsigned long long* dens) {
+    if (dens != nullptr && !walk_density_is_scattered(dens)) return;  // the two-stream walkers take this array
     constexpr int BYTES = Elem<KIND>::kBytes;
     static_assert(!RING || BYTES >= 4, "cp.async moves 4 bytes at least");
     // the warp's ring, kSlots steps of kRows rows x 32 lanes.  Row-major ([row][lane], element-sized copies, coalesced
@@ -406,10 +420,44 @@ constexpr size_t ring2_bytes() {
     return 16 + (size_t)kWWarps * Ring2<LASTAX>::kSlots * 32 * (LASTAX ? kRows2 * BYTES + 16 : kRows2 * BYTES);
 }
 
+// The correction planes live in LOCAL memory on purpose: they are touched at validity boundaries only, and the dozen
+// registers they would occupy are what the hot step needs to stay free of spills.  Handing their address to these
+// out-of-line functions is what pins them there.
+template <int NW>
+static __device__ __noinline__ void ev_add_words(EventPlanes<NW, kEvP>* ev, uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1) {
+    ev->ecnt += (a0 | a1 | b0 | b1) ? 1u : 0u;
+    ev->template add<0, 0>(a0);
+    ev->template add<1, 0>(b0);
+    if (NW == 2) {
+        ev->template add<0, NW - 1>(a1);
+        ev->template add<1, NW - 1>(b1);
+    }
+}
+static __device__ __noinline__ void acc_bump(unsigned long long* p, uint32_t v) { *p += v; }
+// warp-collective: planes -> per-lane totals (lane L: bit L) added to acc[stream][word]
+template <int NW>
+static __device__ __noinline__ void ev_flush_planes(EventPlanes<NW, kEvP>* ev, unsigned long long* acc, uint32_t lane) {
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            uint32_t n[kEvP + 6];
+#pragma unroll
+            for (int j = 0; j < kEvP; ++j) { n[j] = ev->r[s][k][j]; ev->r[s][k][j] = 0u; }
+#pragma unroll
+            for (int j = kEvP; j < kEvP + 6; ++j) n[j] = 0u;
+            acc[s * NW + k] += butterfly_totals(n, kEvP, lane);
+        }
+    }
+    ev->ecnt = 0u;
+}
+
 template <int KIND, int MASK, bool XFORM, bool LASTAX>
 __global__ void __launch_bounds__(kWThreads, Elem<KIND>::kWords == 1 ? 2 : 1)
 k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
-                      unsigned long long* __restrict__ counts, unsigned long long items, unsigned groups) {
+                      unsigned long long* __restrict__ counts, unsigned long long items, unsigned groups,
+                      const unsigned long long* dens) {
+    if (dens != nullptr && walk_density_is_scattered(dens)) return;  // the three-stream walkers take this array
     using E = Elem<KIND>;
     constexpr int BYTES = E::kBytes;
     constexpr int NW = E::kWords;
@@ -443,39 +491,26 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
 #pragma unroll
     for (int k = 0; k < NW; ++k) { S[k].clear(); AB[k].clear(); }
     uint32_t it = 0, nvalid = 0;
-    unsigned long long accS[NW], accAB[NW], accCA[NW], accCB[NW], nvalid_total = 0;
+    // per-lane totals since the last chunk change, in LOCAL memory (pinned there by acc_bump / ev_flush_planes):
+    // [0, 2NW) boundary corrections of streams a and b, then S, then AB, then the valid pairs
+    unsigned long long acc[4 * NW + 1];
+    unsigned long long* const accC = acc, * const accS = acc + 2 * NW, * const accAB = acc + 3 * NW;
 #pragma unroll
-    for (int k = 0; k < NW; ++k) { accS[k] = 0; accAB[k] = 0; accCA[k] = 0; accCB[k] = 0; }
+    for (int k = 0; k < 4 * NW + 1; ++k) acc[k] = 0;
 
     auto drain = [&]() {  // ladders -> per-lane totals (lane L: bit L)
         if (it == 0) return;
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
-            accS[k] += S[k].warp_totals_bounded(lane, it);
-            accAB[k] += AB[k].warp_totals_bounded(lane, it);
+            acc_bump(accS + k, S[k].warp_totals_bounded(lane, it));
+            acc_bump(accAB + k, AB[k].warp_totals_bounded(lane, it));
             S[k].clear(); AB[k].clear();
         }
-        nvalid_total += nvalid;
+        acc_bump(acc + 4 * NW, nvalid);
         nvalid = 0;
         it = 0;
     };
-    auto ev_flush = [&]() {  // correction planes -> per-lane totals; warp-collective
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-#pragma unroll
-            for (int k = 0; k < NW; ++k) {
-                uint32_t n[kEvP + 6];
-#pragma unroll
-                for (int j = 0; j < kEvP; ++j) { n[j] = ev.r[s][k][j]; ev.r[s][k][j] = 0u; }
-#pragma unroll
-                for (int j = kEvP; j < kEvP + 6; ++j) n[j] = 0u;
-                const uint32_t total = butterfly_totals(n, kEvP, lane);
-                if (s == 0) accCA[k] += total;
-                else accCB[k] += total;
-            }
-        }
-        ev.ecnt = 0u;
-    };
+    auto ev_flush = [&]() { ev_flush_planes<NW>(&ev, accC, lane); };  // warp-collective
     auto ev_reserve = [&](uint32_t upcoming) {
         if (__any_sync(0xFFFFFFFFu, ev.ecnt + upcoming > EP::kCap)) ev_flush();
     };
@@ -486,16 +521,17 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
 #pragma unroll
         for (int k = 0; k < NW; ++k) {
             const int j = k * 32 + (int)lane;
-            const unsigned long long b = accS[k] - accCB[k], a = accS[k] - accCA[k];
+            const unsigned long long b = accS[k] - accC[NW + k], a = accS[k] - accC[k];
             if (b) atomicAdd(dst + 4 * (NBITS - 1 - j) + 1, b);
             if (a) atomicAdd(dst + 4 * (NBITS - 1 - j) + 2, a);
             if (accAB[k]) atomicAdd(dst + 4 * (NBITS - 1 - j) + 3, accAB[k]);
-            accS[k] = 0; accAB[k] = 0; accCA[k] = 0; accCB[k] = 0;
+            accS[k] = 0; accAB[k] = 0; accC[k] = 0; accC[NW + k] = 0;
         }
+        unsigned long long nvalid_total = acc[4 * NW];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) nvalid_total += __shfl_xor_sync(0xFFFFFFFFu, nvalid_total, o);
         if (lane == 0 && nvalid_total) atomicAdd(dst, nvalid_total);
-        nvalid_total = 0;
+        acc[4 * NW] = 0;
     };
     // all-ones when the element is not masked
     auto keep_of = [&](const uint32_t (&w)[NW]) -> uint32_t {
@@ -559,7 +595,17 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                 }
                 // offset of this lane's (first) column at row 0 of the chunk
                 long long off = box.base;
-                {
+                if ((O * I) >> 32 == 0) {
+                    // (the chunk has fewer than 2^32 columns: 32-bit divisions, a fifth of the 64-bit routine's cost --
+                    // with short columns the set-up of a tile is a good part of its walk)
+                    const unsigned cc = (live ? (unsigned)col : 0u) * (unsigned)EPV, I32 = (unsigned)I;
+                    unsigned ro = cc / I32, ri = cc - ro * I32;
+#pragma unroll
+                    for (int d = kD - 1; d >= 0; --d) {
+                        if (d > axis) { off += (long long)(ri % box.e[d]) * g.stride[d]; ri /= box.e[d]; }
+                        if (d < axis) { off += (long long)(ro % box.e[d]) * g.stride[d]; ro /= box.e[d]; }
+                    }
+                } else {
                     const unsigned long long cc = (live ? col : 0) * EPV;
                     unsigned long long ro = cc / I, ri = cc - ro * I;
 #pragma unroll
@@ -571,10 +617,10 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                 const char* q = static_cast<const char*>(x) + off * BYTES;  // advanced by the copies
                 // previous row: transformed, zero where masked or absent; its keep-masks.  The walk starts at row 0
                 // with "row -1 masked"
-                uint32_t prev[EPV][NW], pk[EPV];
+                uint32_t prev[EPV][NW], pkb = 0u;  // pkb bit e: the row above in column e exists and is not masked
+                constexpr uint32_t kAllCols = (1u << EPV) - 1u;
 #pragma unroll
                 for (int e = 0; e < EPV; ++e) {
-                    pk[e] = 0u;
 #pragma unroll
                     for (int k = 0; k < NW; ++k) prev[e][k] = 0;
                 }
@@ -647,24 +693,82 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                         }
                     }
                     uint32_t sw[NW][kRows2], abw[NW][kRows2];
-                    bool fast = pv_all && left >= (unsigned)RS;
-                    if (MASK != kMaskNone && fast)
-                        fast = !__any_sync(0xFFFFFFFFu, may_contain_masked<KIND, MASK>(flat, mask_lo, mask_hi));
-                    if (fast) {
+                    const bool first = (s == 0), ragged = left < (unsigned)RS;  // uniform
+                    if (ragged) {
+                        // rows past the end of the column: stale cells -> the value whose transform is 0
 #pragma unroll
                         for (int u = 0; u < kRows2; ++u) {
-                            const int e = u % EPV;
-                            uint32_t w[NW];
+                            if ((unsigned)(u / EPV) >= left) {
 #pragma unroll
-                            for (int k = 0; k < NW; ++k) w[k] = flat[u * NW + k];
-                            if (XFORM) E::transform(w);
-#pragma unroll
-                            for (int k = 0; k < NW; ++k) { sw[k][u] = w[k]; abw[k][u] = prev[e][k] & w[k]; prev[e][k] = w[k]; }
+                                for (int k = 0; k < NW; ++k) flat[u * NW + k] = neutral_word<KIND, XFORM>(k == 0 ? 0 : NW - 1);
+                            }
                         }
-                        nvalid += nv_fast;
+                    }
+                    // Which step?  clean: no lane holds a masked element and every lane's row above is valid (or this is
+                    // row 0) -- the unmasked code.  lanes: some lanes hold nothing but masked elements, above and here
+                    // (columns inside a land mask); they are zeroed as a whole, no validity changes anywhere.  Anything
+                    // else: the exact per-element test.
+                    bool dirty = false, anyd = false, fast;
+                    uint32_t lm = 0xFFFFFFFFu;  // all-ones: this lane's elements count
+                    if (MASK != kMaskNone) {
+                        dirty = may_contain_masked<KIND, MASK>(flat, mask_lo, mask_hi);
+                        anyd = __any_sync(0xFFFFFFFFu, dirty);
+                    }
+                    if (!anyd) {
+                        fast = first || pv_all;
+                    } else {
+                        const bool allm = dirty && !ragged && all_masked_quick<KIND, MASK>(flat, mask_lo, mask_hi);
+                        const bool c = dirty ? (allm && (first || pkb == 0u)) : (first || pkb == kAllCols);
+                        fast = __all_sync(0xFFFFFFFFu, c);
+                        lm = dirty ? 0u : 0xFFFFFFFFu;
+                        if (fast && __all_sync(0xFFFFFFFFu, dirty)) continue;  // nothing but masked elements in the whole step
+                    }
+                    if (fast) {
+                        if (!anyd && !ragged) {
+#pragma unroll
+                            for (int u = 0; u < kRows2; ++u) {
+                                const int e = u % EPV;
+                                uint32_t w[NW];
+#pragma unroll
+                                for (int k = 0; k < NW; ++k) w[k] = flat[u * NW + k];
+                                if (XFORM) E::transform(w);
+#pragma unroll
+                                for (int k = 0; k < NW; ++k) { sw[k][u] = w[k]; abw[k][u] = prev[e][k] & w[k]; prev[e][k] = w[k]; }
+                            }
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < kRows2; ++u) {
+                                const int e = u % EPV;
+                                const bool exists = (unsigned)(u / EPV) < left;  // uniform
+                                uint32_t w[NW];
+#pragma unroll
+                                for (int k = 0; k < NW; ++k) w[k] = flat[u * NW + k];
+                                if (XFORM) E::transform(w);
+#pragma unroll
+                                for (int k = 0; k < NW; ++k) {
+                                    w[k] &= lm;  // (absent rows: transform of the neutral value, zero already)
+                                    sw[k][u] = w[k];
+                                    abw[k][u] = prev[e][k] & w[k];
+                                    prev[e][k] = exists ? w[k] : prev[e][k];  // the column's last row stays for the end of the walk
+                                }
+                            }
+                        }
+                        uint32_t rows_here = ragged ? left : (uint32_t)RS;
+                        if (first) {
+                            // row -1 is "masked": the b-stream loses row 0 of every column
+                            ev_reserve((uint32_t)EPV);
+#pragma unroll
+                            for (int e = 0; e < EPV; ++e) {
+                                ev_add_words<NW>(&ev, 0u, 0u, sw[0][e], NW == 2 ? sw[NW - 1][e] : 0u);
+                            }
+                            pkb = lm & kAllCols;
+                            pv_all = !anyd;
+                            rows_here -= 1u;
+                        }
+                        nvalid += (live && !dirty) ? rows_here * (uint32_t)EPV : 0u;
                     } else {
                         ev_reserve((uint32_t)kRows2);
-                        uint32_t vbits = 0, pand = 0xFFFFFFFFu;
+                        uint32_t vbits = 0;
 #pragma unroll
                         for (int u = 0; u < kRows2; ++u) {
                             const int e = u % EPV;
@@ -673,33 +777,26 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                             for (int k = 0; k < NW; ++k) w[k] = flat[u * NW + k];
                             uint32_t kk = ((unsigned)(u / EPV) < left) ? 0xFFFFFFFFu : 0u;  // the row exists ...
                             if (MASK != kMaskNone) kk &= keep_of(w);                         // ... and is not masked
+                            const uint32_t pke = 0u - ((pkb >> e) & 1u);                     // the row above: all-ones / 0
                             if (XFORM) E::transform(w);
                             uint32_t ca[NW], cb[NW], any_c = 0u;
 #pragma unroll
                             for (int k = 0; k < NW; ++k) {
                                 w[k] &= kk;
                                 ca[k] = prev[e][k] & ~kk;    // row above valid, this one masked / absent
-                                cb[k] = w[k] & ~pk[e];       // this row valid, the one above masked / absent
+                                cb[k] = w[k] & ~pke;         // this row valid, the one above masked / absent
                                 any_c |= ca[k] | cb[k];
                                 sw[k][u] = w[k];
                                 abw[k][u] = prev[e][k] & w[k];
                                 prev[e][k] = w[k];
                             }
-                            vbits |= (kk & pk[e]) & (1u << u);  // the pair (row above, this row) counts
-                            pk[e] = kk;
-                            if (__any_sync(0xFFFFFFFFu, any_c != 0u)) {
-                                ev.ecnt += any_c ? 1u : 0u;
-#pragma unroll
-                                for (int k = 0; k < NW; ++k) {
-                                    if (k == 0) { ev.template add<0, 0>(ca[0]); ev.template add<1, 0>(cb[0]); }
-                                    else { ev.template add<0, NW - 1>(ca[NW - 1]); ev.template add<1, NW - 1>(cb[NW - 1]); }
-                                }
-                            }
+                            vbits |= (kk & pke) & (1u << u);  // the pair (row above, this row) counts
+                            pkb = (pkb & ~(1u << e)) | (kk & (1u << e));
+                            if (__any_sync(0xFFFFFFFFu, any_c != 0u))
+                                ev_add_words<NW>(&ev, ca[0], NW == 2 ? ca[NW - 1] : 0u, cb[0], NW == 2 ? cb[NW - 1] : 0u);
                         }
                         nvalid += live ? (uint32_t)__popc(vbits) : 0u;
-#pragma unroll
-                        for (int e = 0; e < EPV; ++e) pand &= pk[e];
-                        pv_all = __all_sync(0xFFFFFFFFu, pand == 0xFFFFFFFFu);
+                        pv_all = __all_sync(0xFFFFFFFFu, pkb == kAllCols);
                     }
 #pragma unroll
                     for (int k = 0; k < NW; ++k) {
@@ -720,14 +817,7 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                     if (__any_sync(0xFFFFFFFFu, any_c != 0u)) {
                         ev_reserve((uint32_t)EPV);
 #pragma unroll
-                        for (int e = 0; e < EPV; ++e) {
-                            uint32_t c = 0u;
-#pragma unroll
-                            for (int k = 0; k < NW; ++k) c |= prev[e][k];
-                            ev.ecnt += c ? 1u : 0u;
-                            ev.template add<0, 0>(prev[e][0]);
-                            if (NW == 2) ev.template add<0, NW - 1>(prev[e][NW - 1]);
-                        }
+                        for (int e = 0; e < EPV; ++e) ev_add_words<NW>(&ev, prev[e][0], NW == 2 ? prev[e][NW - 1] : 0u, 0u, 0u);
                     }
                 }
                 slot_r = slot_w;  // the kAhead groups committed past the end of the column were empty
@@ -756,16 +846,17 @@ cudaError_t set_smem_once(K kern, size_t smem, std::atomic<unsigned long long>& 
 
 template <int KIND, int MASK, bool XFORM, bool LASTAX>
 cudaError_t launch_walk_ax(const void* x, const ChunkGrid& g, uint32_t mlo, uint32_t mhi, unsigned long long* counts,
-                           unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream, bool three) {
+                           unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream, bool three,
+                           const unsigned long long* dens) {
     constexpr int BYTES = Elem<KIND>::kBytes;
     constexpr bool RING = BYTES >= 4;
     if constexpr (RING) {
-        if (!three) {  // two streams + boundary corrections (the default for 4- and 8-byte types)
+        if (!three) {  // two streams + boundary corrections
             constexpr size_t smem2 = ring2_bytes<BYTES, LASTAX>();
             auto kern2 = k_pairs_chunked_walk2<KIND, MASK, XFORM, LASTAX>;
             static std::atomic<unsigned long long> attr_set2{0ull};
             if (cudaError_t e = set_smem_once(kern2, smem2, attr_set2)) return e;
-            kern2<<<grid, kWThreads, smem2, stream>>>(x, g, mlo, mhi, counts, items, groups);
+            kern2<<<grid, kWThreads, smem2, stream>>>(x, g, mlo, mhi, counts, items, groups, dens);
             return cudaGetLastError();
         }
     }
@@ -773,40 +864,42 @@ cudaError_t launch_walk_ax(const void* x, const ChunkGrid& g, uint32_t mlo, uint
     auto kern = k_pairs_chunked_walk<KIND, MASK, XFORM, RING, LASTAX>;
     static std::atomic<unsigned long long> attr_set{0ull};
     if (cudaError_t e = set_smem_once(kern, smem, attr_set)) return e;
-    kern<<<grid, kWThreads, smem, stream>>>(x, g, mlo, mhi, counts, items, groups);
+    kern<<<grid, kWThreads, smem, stream>>>(x, g, mlo, mhi, counts, items, groups, dens);
     return cudaGetLastError();
 }
 
 template <int KIND, int MASK, bool XFORM>
 cudaError_t launch_walk(const void* x, const ChunkGrid& g, uint32_t mlo, uint32_t mhi, unsigned long long* counts,
-                        unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream, bool three) {
+                        unsigned long long items, unsigned groups, unsigned grid, cudaStream_t stream, bool three,
+                        const unsigned long long* dens) {
     if constexpr (Elem<KIND>::kBytes >= 4) {
-        if (g.axis == kD - 1) return launch_walk_ax<KIND, MASK, XFORM, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+        if (g.axis == kD - 1) return launch_walk_ax<KIND, MASK, XFORM, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
     }
-    return launch_walk_ax<KIND, MASK, XFORM, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+    return launch_walk_ax<KIND, MASK, XFORM, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
 }
 
 template <int KIND>
 cudaError_t dispatch_walk(const void* x, const ChunkGrid& g, bool transform, int mask_mode, uint32_t mlo, uint32_t mhi,
                           unsigned long long* counts, unsigned long long items, unsigned groups, unsigned grid,
-                          cudaStream_t stream, bool three) {
+                          cudaStream_t stream, bool three,
+                        const unsigned long long* dens) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     if (transform) {
         if constexpr (isf) {
             switch (mask_mode) {
-                case kMaskNone: return launch_walk<KIND, kMaskNone, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
-                case kMaskNaN: return launch_walk<KIND, kMaskNaN, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
-                default: return launch_walk<KIND, kMaskValue, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+                case kMaskNone: return launch_walk<KIND, kMaskNone, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+                case kMaskNaN: return launch_walk<KIND, kMaskNaN, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+                default: return launch_walk<KIND, kMaskValue, true>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
             }
         }
         return cudaErrorInvalidValue;
     }
     switch (mask_mode) {
-        case kMaskNone: return launch_walk<KIND, kMaskNone, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+        case kMaskNone: return launch_walk<KIND, kMaskNone, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
         case kMaskNaN:
-            if constexpr (isf) return launch_walk<KIND, kMaskNaN, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+            if constexpr (isf) return launch_walk<KIND, kMaskNaN, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
             return cudaErrorInvalidValue;
-        default: return launch_walk<KIND, kMaskValue, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three);
+        default: return launch_walk<KIND, kMaskValue, false>(x, g, mlo, mhi, counts, items, groups, grid, stream, three, dens);
     }
 }
 
@@ -816,7 +909,7 @@ cudaError_t dispatch_walk(const void* x, const ChunkGrid& g, bool transform, int
 // *taken = false leaves everything to the odometer kernel of xbi_chunked.cu.
 cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
                                       int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream,
-                                      bool force, bool three, bool* taken) {
+                                      bool force, int flavour, bool* taken) {
     *taken = false;
     if (g.axis < 0 || nchunks == 0) return cudaSuccess;
     int dev = 0, sms = 148;
@@ -834,12 +927,13 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
         const long long epv = 16 / bytes;
         bool ok = g.chunk[kD - 1] % epv == 0;
         for (int d = g.lo; d < kD - 1; ++d) ok = ok && (g.stride[d] % epv == 0);
-        // ... and a chunk has enough columns to fill the lanes of a tile or two that way (4x4-column chunks: 4 live
-        // lanes of 32, 0.3 TB/s instead of 1.1)
+        // ... and a chunk has enough columns to fill some lanes of a tile that way.  The two-stream walkers keep
+        // lanes without a column on the fast step, so 8 live lanes are enough (float64, 10x10-column chunks: 1.87 TB/s
+        // with two columns per lane, 0.92 with one); the three-stream walkers wanted 64 vector columns
         unsigned long long c = 1;
         for (int d = 0; d < kD; ++d)
             if (d != g.axis) c *= g.chunk[d];
-        ok = ok && (force || c / (unsigned long long)epv >= 64);  // (force: the tests pin this path on small grids)
+        ok = ok && (force || c / (unsigned long long)epv >= (flavour == 2 ? 64ull : 8ull));  // (force: the tests pin this path on small grids)
         gg.vec16 = ok ? 1 : 0;
     }
     // the work inside a (full) chunk that the warps share: tiles of 32 lanes
@@ -859,16 +953,41 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
     const unsigned long long items = groups * nchunks;
     const unsigned grid = (unsigned)(sms * per_sm);
     const uint32_t mlo = (uint32_t)(mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(mask_bits >> 32);
+    auto run = [&](bool three, const unsigned long long* dens) -> cudaError_t {
+        switch (dtype) {
+            case XBI_U8: return dispatch_walk<kU8>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            case XBI_U16: return dispatch_walk<kU16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            case XBI_U32: return dispatch_walk<kU32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            case XBI_U64: return dispatch_walk<kU64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            case XBI_F16: return dispatch_walk<kF16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            case XBI_F32: return dispatch_walk<kF32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            case XBI_F64: return dispatch_walk<kF64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            default: return cudaErrorInvalidValue;
+        }
+    };
     cudaError_t e;
-    switch (dtype) {
-        case XBI_U8: e = dispatch_walk<kU8>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
-        case XBI_U16: e = dispatch_walk<kU16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
-        case XBI_U32: e = dispatch_walk<kU32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
-        case XBI_U64: e = dispatch_walk<kU64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
-        case XBI_F16: e = dispatch_walk<kF16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
-        case XBI_F32: e = dispatch_walk<kF32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
-        case XBI_F64: e = dispatch_walk<kF64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three); break;
-        default: return cudaErrorInvalidValue;
+    if (bytes < 4 || flavour == 2) {
+        e = run(true, nullptr);  // 1- and 2-byte types: three explicit streams, loads into registers
+    } else if (flavour == 1 || mask_mode == kMaskNone) {
+        e = run(false, nullptr);
+    } else {
+        // masked: sample the boundary density along the analysed axis, launch both, one returns at once
+        CountJob job = {};
+        job.x = x;
+        job.dtype = dtype;
+        job.transform = transform;
+        job.mask_mode = mask_mode;
+        job.mask_bits = mask_bits;
+        long long numel = 1;
+        for (int d = 0; d < kD; ++d) numel *= g.shape[d];
+        job.inner = g.stride[g.axis];
+        job.n = g.shape[g.axis];
+        job.outer = numel / (job.n * job.inner);
+        e = launch_mask_density_to(job, numel - job.inner, counts + kDensBnd, counts + kDensPairs, stream);
+        if (e != cudaSuccess) return e;
+        e = run(false, counts);
+        if (e != cudaSuccess) return e;
+        e = run(true, counts);
     }
     if (e != cudaSuccess) return e;
     note_fast_launch();

@@ -137,7 +137,7 @@ k_pairs_generic(const void* __restrict__ x, long long lo, long long count, long 
 template <int KIND, int MASK>
 __global__ void __launch_bounds__(kThreads)
 k_mask_density(const void* __restrict__ x, long long nsamples, long long stride, long long inner, uint32_t mask_lo,
-               uint32_t mask_hi, RawSums* __restrict__ plus) {
+               uint32_t mask_hi, unsigned long long* __restrict__ out_bnd, unsigned long long* __restrict__ out_pairs) {
     using E = Elem<KIND>;
     unsigned bnd = 0, pairs = 0;
     for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < nsamples; i += (long long)gridDim.x * kThreads) {
@@ -156,21 +156,22 @@ k_mask_density(const void* __restrict__ x, long long nsamples, long long stride,
         pairs += __shfl_xor_sync(0xFFFFFFFFu, pairs, o);
     }
     if ((threadIdx.x & 31u) == 0u) {
-        if (bnd) atomicAdd(&plus->pad[0], (unsigned long long)bnd);
-        if (pairs) atomicAdd(&plus->pad[1], (unsigned long long)pairs);
+        if (bnd) atomicAdd(out_bnd, (unsigned long long)bnd);
+        if (pairs) atomicAdd(out_pairs, (unsigned long long)pairs);
     }
 }
 
 template <int KIND>
-cudaError_t launch_density_kind(const CountJob& job, long long nsamples, long long stride, Workspace* ws, cudaStream_t stream) {
+cudaError_t launch_density_kind(const CountJob& job, long long nsamples, long long stride, unsigned long long* out_bnd,
+                                unsigned long long* out_pairs, cudaStream_t stream) {
     constexpr bool isf = (KIND == kF16 || KIND == kF32 || KIND == kF64);
     const unsigned grid = (unsigned)((nsamples + kThreads - 1) / kThreads < 592 ? (nsamples + kThreads - 1) / kThreads : 592);
     const uint32_t mlo = (uint32_t)(job.mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(job.mask_bits >> 32);
     if (job.mask_mode == kMaskNaN) {
-        if constexpr (isf) k_mask_density<KIND, kMaskNaN><<<grid, kThreads, 0, stream>>>(job.x, nsamples, stride, job.inner, mlo, mhi, &ws->plus);
+        if constexpr (isf) k_mask_density<KIND, kMaskNaN><<<grid, kThreads, 0, stream>>>(job.x, nsamples, stride, job.inner, mlo, mhi, out_bnd, out_pairs);
         else return cudaErrorInvalidValue;
     } else {
-        k_mask_density<KIND, kMaskValue><<<grid, kThreads, 0, stream>>>(job.x, nsamples, stride, job.inner, mlo, mhi, &ws->plus);
+        k_mask_density<KIND, kMaskValue><<<grid, kThreads, 0, stream>>>(job.x, nsamples, stride, job.inner, mlo, mhi, out_bnd, out_pairs);
     }
     note_launch();
     return cudaGetLastError();
@@ -249,19 +250,24 @@ cudaError_t launch_pairs_generic_edges(const CountJob& job, int64_t t_begin, int
 }
 
 cudaError_t launch_mask_density(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream) {
+    return launch_mask_density_to(job, npairs_flat, &ws->plus.pad[0], &ws->plus.pad[1], stream);
+}
+
+cudaError_t launch_mask_density_to(const CountJob& job, int64_t npairs_flat, unsigned long long* out_bnd,
+                                   unsigned long long* out_pairs, cudaStream_t stream) {
     if (job.mask_mode == kMaskNone || npairs_flat <= 0) return cudaSuccess;
     long long nsamples = npairs_flat < (1ll << 18) ? npairs_flat : (1ll << 18);
     long long stride = npairs_flat / nsamples;
     if (stride > 1) stride |= 1;  // odd: does not lock onto even row lengths
     while (stride > 1 && (nsamples - 1) * stride >= npairs_flat) --nsamples;
     switch (job.dtype) {
-        case XBI_U8: return launch_density_kind<kU8>(job, nsamples, stride, ws, stream);
-        case XBI_U16: return launch_density_kind<kU16>(job, nsamples, stride, ws, stream);
-        case XBI_U32: return launch_density_kind<kU32>(job, nsamples, stride, ws, stream);
-        case XBI_U64: return launch_density_kind<kU64>(job, nsamples, stride, ws, stream);
-        case XBI_F16: return launch_density_kind<kF16>(job, nsamples, stride, ws, stream);
-        case XBI_F32: return launch_density_kind<kF32>(job, nsamples, stride, ws, stream);
-        case XBI_F64: return launch_density_kind<kF64>(job, nsamples, stride, ws, stream);
+        case XBI_U8: return launch_density_kind<kU8>(job, nsamples, stride, out_bnd, out_pairs, stream);
+        case XBI_U16: return launch_density_kind<kU16>(job, nsamples, stride, out_bnd, out_pairs, stream);
+        case XBI_U32: return launch_density_kind<kU32>(job, nsamples, stride, out_bnd, out_pairs, stream);
+        case XBI_U64: return launch_density_kind<kU64>(job, nsamples, stride, out_bnd, out_pairs, stream);
+        case XBI_F16: return launch_density_kind<kF16>(job, nsamples, stride, out_bnd, out_pairs, stream);
+        case XBI_F32: return launch_density_kind<kF32>(job, nsamples, stride, out_bnd, out_pairs, stream);
+        case XBI_F64: return launch_density_kind<kF64>(job, nsamples, stride, out_bnd, out_pairs, stream);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -99,6 +99,9 @@ cudaError_t launch_pairs_xy(const CountJob& jy, Workspace* ws_y, Workspace* ws_x
 // Samples ~2^18 flat pairs and leaves (#pairs whose two elements differ in validity, #pairs sampled)
 // in ws->plus.pad[0], pad[1] for the masked fast kernels to choose their flavour.
 cudaError_t launch_mask_density(const CountJob& job, int64_t npairs_flat, Workspace* ws, cudaStream_t stream);
+// ... the two numbers added to any two (zeroed) device words
+cudaError_t launch_mask_density_to(const CountJob& job, int64_t npairs_flat, unsigned long long* out_bnd,
+                                   unsigned long long* out_pairs, cudaStream_t stream);
 
 
 // ---------------------------------------------------------------------------------
@@ -180,11 +183,12 @@ cudaError_t launch_pairs_chunked(const void* x, int dtype, const ChunkGrid& g, u
                                  int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream,
                                  unsigned flags = 0);
 // the fast formulation (xbi_chunked_walk.cu); *taken = false: the grid does not suit it, nothing was launched.
-// three: the walkers with three explicit streams under keep-masks also for 4- and 8-byte types (default: two
-// streams + boundary corrections)
+// flavour (4- and 8-byte types): 0 -- masked modes sample the density of validity boundaries and run the walkers on
+// two streams + boundary corrections or, for scattered masks, on three explicit streams under keep-masks;
+// 1 / 2 -- pinned to the two-stream / three-stream walkers (tests)
 cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid& g, unsigned nchunks, bool transform,
                                       int mask_mode, uint64_t mask_bits, unsigned long long* counts, cudaStream_t stream,
-                                      bool force, bool three, bool* taken);
+                                      bool force, int flavour, bool* taken);
 cudaError_t launch_bitround_chunked(void* x, int dtype, const ChunkGrid& g, const int* keepbits, cudaStream_t stream);
 
 // xbi_hostpool.cu: rows of row_bytes bytes copied host -> host by a small pool of threads

@@ -287,9 +287,10 @@ def count_pairs_chunked(x: torch.Tensor, chunk_shape, axis: int, *, transform: b
     if np_dtype.kind == "f" and transform:
         flags |= nat.SIGNED_EXPONENT
     if flavour is not None:  # testing: pin one of the two chunk-grid kernels
-        # ("walk3": the walkers with three explicit streams also for 4- / 8-byte types, whose default is two streams
-        # plus boundary corrections)
-        flags |= {"walk": nat.FORCE_WALK, "walk3": nat.FORCE_WALK | nat.FORCE_DENSE, "odometer": nat.FORCE_GENERIC}[flavour]
+        # (4- / 8-byte types: "walk" lets the sampled mask density choose between the walkers on two streams +
+        # boundary corrections and those on three explicit streams; "walk2" / "walk3" pin one of them)
+        flags |= {"walk": nat.FORCE_WALK, "walk2": nat.FORCE_WALK | nat.FORCE_SPARSE,
+                  "walk3": nat.FORCE_WALK | nat.FORCE_DENSE, "odometer": nat.FORCE_GENERIC}[flavour]
     with torch.cuda.device(x.device):
         if tables is None:
             rc = nat.lib().xbi_count_pairs_chunked(
