@@ -18,7 +18,9 @@ The same line carries ``configs.c2 / c3 / c4``: BASELINE configs[2..4] at sizes 
 (float64 ocean field with a land mask along latitude; one float32 (720,137,256,512) variable along
 all four dimensions with the significance filter; float16 / float32 bitinfo -> keepbits -> bitround
 on 5e9-element shares), each with GB/s, fraction of the measured copy peak and an in-run bit-exact
-check of a slab against oracle/fast_count (outside the timed regions).
+check of a slab against oracle/fast_count (outside the timed regions), and ``configs.chunks``: the
+per-chunk workflow of the reference's docs/chunking.ipynb (bitinformation, keepbits and bitround of
+every block of a chunked variable on its own) on a 3.1 GB month of the same field in 56 blocks.
 
 ``--impl reference`` times the reference's CPU algorithm (the numpy restatement in
 oracle/, the reference package itself cannot be imported in this image) on a bounded
@@ -889,6 +891,51 @@ def run_configs(args, dev, peak):
         }
     except Exception as e:
         out["c4"] = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+
+    # ---- chunks (docs/chunking.ipynb cells 8-10): get_bitinformation on every block of a chunked variable
+    # on its own -> keepbits per block -> bitround per block, one month of the configs[1] field cut into 7 x 8 blocks ----
+    try:
+        from xbitinfo_b200.chunked import keepbits_of_information_batched
+        from xbitinfo_b200.device import bitround_chunked_, count_pairs_chunked, information_batched
+
+        shape, chunk = (744, 721, 1440), (744, 103, 180)
+        x = _synth_nd(shape, torch.float32, 2, 21, dev)
+        nb = x.numel() * x.element_size()
+        res = {}
+        for axis, name in ((0, "dim_time"), (2, "dim_longitude")):
+            ms = timed(lambda: count_pairs_chunked(x, chunk, axis, masked_value=float("nan")))
+            res[name] = {"ms": ms, "value": nb / (ms * 1e-3) / 1e9, "unit": UNIT, "frac_of_measured_peak": nb / (ms * 1e-3) / 1e9 / peak}
+        y = x.clone()
+        state = {}
+
+        def workflow():
+            counts = count_pairs_chunked(x, chunk, 0, masked_value=float("nan"))
+            info = information_batched(counts, True, 0.99).cpu().numpy().reshape(-1, 32)
+            keep = np.clip(keepbits_of_information_batched(info, np.dtype("float32"), 0.99), 0, 23).astype("int32")
+            y.copy_(x)
+            bitround_chunked_(y, chunk, torch.from_numpy(keep).to(dev))
+            state["counts"], state["keep"] = counts, keep
+
+        ms_flow = timed(workflow)
+        # check: three blocks (first, one in the middle, the ragged last one) against fast_count on the host
+        got = state["counts"].cpu().numpy()
+        exact = True
+        for (cy, cx) in ((0, 0), (3, 4), (6, 7)):
+            blk = x[:, cy * 103:(cy + 1) * 103, cx * 180:(cx + 1) * 180].contiguous().cpu().numpy()
+            exact = exact and bool(np.array_equal(got[0, cy, cx], fc.count_pairs(blk, 0, masked_value=float("nan"))))
+        out["chunks"] = {
+            "workload": "per-chunk workflow of docs/chunking.ipynb on the device: float32 (744,721,1440) = 3.1 GB in 56 blocks of "
+                        "(744,103,180), masked_value=NaN; xbi_count_pairs_chunked alone along time / longitude, then count -> "
+                        "information -> keepbits per block (host) -> copy + bitround per block",
+            "count_pairs_chunked": res,
+            "workflow_ms": ms_flow, "workflow_bytes_GBps": 5 * nb / (ms_flow * 1e-3) / 1e9,  # count: 1 read; copy: read + write; round in place: read + write
+            "keepbits_min_max": [int(state["keep"].min()), int(state["keep"].max())],
+            "bit_exact_vs_fast_count": exact, "checked": "blocks (0,0), (3,4), (6,7) along time",
+        }
+        del x, y, state
+    except Exception as e:
+        out["chunks"] = {"error": f"{type(e).__name__}: {e}"}
     torch.cuda.empty_cache()
     return out
 

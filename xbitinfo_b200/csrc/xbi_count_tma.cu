@@ -194,7 +194,7 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
 
     // block totals; the boundary corrections of the masked modes are added to s_minus as they occur
     __shared__ unsigned long long s_sum[3][64];
-    __shared__ unsigned long long s_minus[2][64];  // boundary corrections of the a and b streams
+    __shared__ unsigned int s_minus[2][64];  // boundary corrections of the a and b streams (32-bit: see warp_event_push)
     __shared__ unsigned long long s_ninvalid;
     for (int i = threadIdx.x; i < 3 * 64; i += kThreads) (&s_sum[0][0])[i] = 0;
     for (int i = threadIdx.x; i < 2 * 64; i += kThreads) (&s_minus[0][0])[i] = 0;

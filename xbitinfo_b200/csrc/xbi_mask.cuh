@@ -215,10 +215,13 @@ __device__ __forceinline__ bool all_masked_quick(const uint32_t (&w)[N], uint32_
 // chain of dependent local loads and stores that 31 lanes waited for.)  All calls warp-converged.
 //   s_minus: shared [2][64] totals (stream a, stream b), bit number from the least significant bit, zeroed
 //   before the first event; fold = min(bits per element, 32): packed types fold their fields onto one another.
+//   The totals are 32-BIT words: a block never sees 2^32 elements (180 GB over 148 blocks), and a 32-bit shared
+//   atomic add is one fire-and-forget ATOMS.ADD, where the 64-bit one is a load / compare-and-swap spin loop
+//   (LDS.64 + ATOMS.CAST.SPIN.64 + branch) whose latency every event of a land-masked array paid in full.
 // ---------------------------------------------------------------------------------
 template <int STREAM, int NW>
 __device__ __forceinline__ void warp_event_push(bool have, const uint32_t (&v)[NW], uint32_t lane,
-                                                unsigned long long (*s_minus)[64], uint32_t fold) {
+                                                unsigned int (*s_minus)[64], uint32_t fold) {
     // STREAM 0: a valid / b masked (a-stream correction), 1: a masked / b valid
     unsigned hv = __ballot_sync(0xFFFFFFFFu, have);
     while (hv) {
@@ -226,7 +229,7 @@ __device__ __forceinline__ void warp_event_push(bool have, const uint32_t (&v)[N
         hv &= hv - 1u;
 #pragma unroll
         for (int k = 0; k < NW; ++k)
-            if ((__shfl_sync(0xFFFFFFFFu, v[k], src) >> lane) & 1u) atomicAdd(&s_minus[STREAM][k * 32 + (int)(lane % fold)], 1ull);
+            if ((__shfl_sync(0xFFFFFFFFu, v[k], src) >> lane) & 1u) atomicAdd(&s_minus[STREAM][k * 32 + (int)(lane % fold)], 1u);
     }
 }
 
