@@ -467,30 +467,31 @@ k_pairs_rows_tma(const __grid_constant__ CUtensorMap tmap, const char* __restric
             if (MASKED && __any_sync(0xFFFFFFFFu, may_contain_masked<KIND, MT>(w, mask_lo, mask_hi))) {
                 uint32_t keep[17], anyk = 0u;
 #pragma unroll
-                for (int i = 0; i < 17; ++i) { keep[i] = keep_word<KIND, MT>(w[i], mask_lo); anyk |= keep[i]; }
+                for (int i = 0; i < 17; ++i) { keep[i] = keep_word_fast<KIND, MT>(w[i], mask_lo); anyk |= keep[i]; }
                 if (__all_sync(0xFFFFFFFFu, anyk == 0u)) {
                     ninvalid += 16u * (4u / BYTES);
                     skip = true;
                 } else {
-                    uint32_t bnd = 0u;
+                    // invalid pairs: counted per field (at most 16 per field and stage), folded once; a word slot
+                    // goes through the boundary corrections only when some lane's validity changes inside it (round 1
+                    // pushed both streams of all 16 slots -- 32 ballots -- whenever any lane had any boundary: with 32
+                    // elements per thread nearly every warp of a land-masked float16 array holds a coast line)
+                    constexpr uint32_t kOnes = (BYTES == 2) ? 0x00010001u : 0x01010101u;
+                    uint32_t inv = 0u;
 #pragma unroll
                     for (int i = 0; i < 17; ++i) tw[i] &= keep[i];
 #pragma unroll
                     for (int i = 0; i < 16; ++i) {
                         const uint32_t ks = successor_word<BYTES>(keep[i], keep[i + 1]);
-                        ninvalid += count_fields<BYTES>(~(keep[i] & ks));
-                        bnd |= keep[i] ^ ks;
-                    }
-                    if (__any_sync(0xFFFFFFFFu, bnd != 0u)) {  // validity changes inside some thread's words: rare
-#pragma unroll
-                        for (int i = 0; i < 16; ++i) {
-                            const uint32_t ks = successor_word<BYTES>(keep[i], keep[i + 1]);
-                            const uint32_t va[1] = {tw[i] & keep[i] & ~ks};
-                            const uint32_t vb[1] = {successor_word<BYTES>(tw[i], tw[i + 1]) & ~keep[i] & ks};
+                        inv += ~(keep[i] & ks) & kOnes;
+                        if (__any_sync(0xFFFFFFFFu, keep[i] != ks)) {  // rare
+                            const uint32_t va[1] = {tw[i] & ~ks};                                            // a valid, b masked
+                            const uint32_t vb[1] = {successor_word<BYTES>(tw[i], tw[i + 1]) & ~keep[i]};   // a masked, b valid
                             warp_event_push<0>((keep[i] & ~ks) != 0u, va, lane, s_minus, kEvFold);
                             warp_event_push<1>((~keep[i] & ks) != 0u, vb, lane, s_minus, kEvFold);
                         }
                     }
+                    ninvalid += (BYTES == 2) ? ((inv & 0xFFFFu) + (inv >> 16)) : ((inv * 0x01010101u) >> 24);
                 }
             }
             if (!skip) {

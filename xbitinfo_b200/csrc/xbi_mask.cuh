@@ -52,6 +52,16 @@ __device__ __forceinline__ uint32_t keep_word(uint32_t w, uint32_t mask_lo) {  /
         return nz * 0xFFu;
     }
 }
+// the same, with the one-instruction form where the hardware has one: float16 NaN mask = packed "a == a" (HSET2)
+template <int KIND, int MASK>
+__device__ __forceinline__ uint32_t keep_word_fast(uint32_t w, uint32_t mask_lo) {
+    if constexpr (KIND == kF16 && MASK == kMaskNaN) {
+        const __half2 h = *reinterpret_cast<const __half2*>(&w);
+        return __heq2_mask(h, h);  // ordered compare: 0xFFFF per half unless NaN
+    } else {
+        return keep_word<KIND, MASK>(w, mask_lo);
+    }
+}
 template <int KIND, int MASK>
 __device__ __forceinline__ uint32_t keep_elem64(uint32_t lo, uint32_t hi, uint32_t mask_lo, uint32_t mask_hi) {
     if (MASK == kMaskNone) return 0xFFFFFFFFu;
