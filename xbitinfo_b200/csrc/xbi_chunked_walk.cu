@@ -477,6 +477,12 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
     // (made opaque: under register pressure ptxas otherwise re-derives these in every step)
     asm volatile("" : "+r"(lane), "+r"(warp), "+r"(ring0));
     uint32_t slot_w = 0, slot_r = 0;
+    // LASTAX, cooperative copies: addresses as 32-bit offsets in 16-byte units from `xa` (arrays below 64 GB)
+    const char* const xa = reinterpret_cast<const char*>(reinterpret_cast<uintptr_t>(x) & ~static_cast<uintptr_t>(15));
+    unsigned long long total_bytes = (unsigned long long)BYTES;
+#pragma unroll
+    for (int d = 0; d < kD; ++d) total_bytes *= (unsigned long long)g.shape[d];
+    const bool offsets_fit = ((total_bytes + 16ull) >> 36) == 0ull;
 
     const unsigned long long item_lo = (unsigned long long)blockIdx.x * items / gridDim.x;
     const unsigned long long item_hi = (unsigned long long)(blockIdx.x + 1) * items / gridDim.x;
@@ -630,25 +636,66 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                 const uint32_t nv_fast = live ? (uint32_t)kRows2 : 0u;
                 // LASTAX: 16-byte copies when every lane's run starts on a 16-byte boundary (warp-uniform)
                 const bool vec = LASTAX && __all_sync(0xFFFFFFFFu, !live || (reinterpret_cast<uintptr_t>(q) & 15u) == 0u);
+                // LASTAX with aligned runs: the warp copies COOPERATIVELY.  A lane copying its own run's 16-byte pieces
+                // makes every copy instruction touch 32 different lines (one per run): the L1 looks up one line per
+                // cycle, which capped the kernel near 2.8 TB/s.  Instead NP neighbouring lanes take the NP pieces of
+                // one run's step (64 / 128 contiguous bytes), so an instruction touches 32 / NP lines.  A lane then
+                // reads cells other lanes copied: __syncwarp after the wait and before a slot is overwritten.
+                constexpr int NP = kRows2 * BYTES / 16;  // 16-byte pieces of one run per step
+                constexpr int RPI = 32 / NP;             // runs per copy instruction of the warp
+                uint32_t co[LASTAX ? NP : 1];            // (start of run j * RPI + lane / NP, minus xa) / 16 + lane % NP
+                uint32_t colive = 0u;                    // bit j: that run exists
+                bool coop = false;
+                const uint32_t cbase = ring0 + (lane / NP) * kLanePitch + (lane % NP) * 16u;
+                if constexpr (LASTAX) {
+                    coop = vec && offsets_fit;
+                    if (coop) {
+                        const uint32_t my16 = (uint32_t)((unsigned long long)(q - xa) >> 4);
+                        const uint32_t lives = __ballot_sync(0xFFFFFFFFu, live);
+#pragma unroll
+                        for (int j = 0; j < NP; ++j) {
+                            const uint32_t r = (uint32_t)(j * RPI) + lane / NP;
+                            co[j] = __shfl_sync(0xFFFFFFFFu, my16, (int)r) + lane % NP;
+                            colive |= ((lives >> r) & 1u) << j;
+                        }
+                    }
+                    __syncwarp();  // every lane is done with the previous tile's cells
+                }
                 unsigned issued = 0;
                 auto issue = [&]() {
                     if (issued < nsteps) {
                         const unsigned left = ea - RS * issued;  // rows from this step on (uniform)
-                        if (live) {
-                            const uint32_t dst = cell + slot_w * kSlotBytes;
-                            if (left >= (unsigned)RS) {
-                                if (LASTAX && vec) {
+                        if constexpr (LASTAX) {
+                            if (coop && left >= (unsigned)RS) {
+                                const uint32_t dstw = cbase + slot_w * kSlotBytes;
 #pragma unroll
-                                    for (int v = 0; v < kRows2 * BYTES / 16; ++v)
-                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * v), "l"(q + 16 * v) : "memory");
-                                    q += kRows2 * BYTES;
+                                for (int j = 0; j < NP; ++j) {
+                                    if ((colive >> j) & 1u) {
+                                        const char* src = xa + 16ull * (unsigned long long)(co[j] + issued * (unsigned)NP);
+                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstw + (uint32_t)(j * RPI) * kLanePitch), "l"(src) : "memory");
+                                    }
+                                }
+                            } else if (live) {
+                                const uint32_t dst = cell + slot_w * kSlotBytes;
+                                const char* qs = q + (size_t)issued * (size_t)(kRows2 * BYTES);
+                                if (vec && left >= (unsigned)RS) {
+#pragma unroll
+                                    for (int v = 0; v < NP; ++v)
+                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * v), "l"(qs + 16 * v) : "memory");
                                 } else {
 #pragma unroll
-                                    for (int u = 0; u < RS; ++u) {
-                                        if constexpr (V16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * kRowP), "l"(q) : "memory");
-                                        else cpa_elem<BYTES>(dst + u * kRowP, q);
-                                        q += step_bytes;
-                                    }
+                                    for (int u = 0; u < RS; ++u)
+                                        if ((unsigned)u < left) cpa_elem<BYTES>(dst + u * kRowP, qs + u * BYTES);
+                                }
+                            }
+                        } else if (live) {
+                            const uint32_t dst = cell + slot_w * kSlotBytes;
+                            if (left >= (unsigned)RS) {
+#pragma unroll
+                                for (int u = 0; u < RS; ++u) {
+                                    if constexpr (V16) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + u * kRowP), "l"(q) : "memory");
+                                    else cpa_elem<BYTES>(dst + u * kRowP, q);
+                                    q += step_bytes;
                                 }
                             } else {
 #pragma unroll
@@ -670,8 +717,10 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                 for (int k = 0; k < kAhead; ++k) issue();
 #pragma unroll 1
                 for (unsigned s = 0; s < nsteps; ++s) {
+                    if (LASTAX) __syncwarp();  // the slot about to be refilled has been read by every lane
                     issue();
                     cpa_wait_w<kAhead>();
+                    if (LASTAX) __syncwarp();  // ... and the copies other lanes made for this one have landed
                     const unsigned left = ea - RS * s;  // rows from this step on (uniform)
                     const uint32_t src = cell + slot_r * kSlotBytes;
                     slot_r = (slot_r + 1 == kSlots) ? 0 : slot_r + 1;
@@ -969,6 +1018,14 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
     // two-stream walkers (first-row / last-row corrections) outweighs their cheaper steps -- 1.4 against 1.7 TB/s at
     // 32-element runs, 1.6 against 1.9 at 64
     if (flavour == 0 && bytes == 4 && g.axis == kD - 1 && g.chunk[kD - 1] <= 64) flavour = 2;
+    // ... and runs that do not start on 16-byte boundaries (element-sized copies, 32 lines per copy instruction):
+    // 0.66 against 1.76 TB/s at 131-element runs
+    if (flavour == 0 && bytes >= 4 && g.axis == kD - 1) {
+        const long long epv = 16 / bytes;
+        bool aligned = reinterpret_cast<uintptr_t>(x) % 16 == 0 && g.bounds[kD - 1] == nullptr && g.chunk[kD - 1] % epv == 0;
+        for (int d = g.lo; d < kD - 1; ++d) aligned = aligned && (g.stride[d] % epv == 0);
+        if (!aligned) flavour = 2;
+    }
     cudaError_t e;
     if (bytes < 4 || flavour == 2) {
         e = run(true, nullptr);  // 1- and 2-byte types: three explicit streams, loads into registers
