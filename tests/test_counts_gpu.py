@@ -343,6 +343,50 @@ def test_mask_probe_false_positives_float64():
         assert counts[0].sum() == npairs
 
 
+@pytest.mark.parametrize("axis", [0, 1])
+def test_mask_probe_false_positives_float32(axis):
+    """The float32 NaN probe multiplies three words per FMA lane (a * b + c): products beyond 3.4e38, infinities of
+    either sign and zeros next to them make NaNs out of NaN-free words.  Such stages only take the exact test; real
+    NaNs -- alone, next to infinities, next to zeros, at the neighbour word -- are never missed."""
+    rng = np.random.default_rng(26)
+    x = smooth_field(rng, (40, 4096), "float32", axis=1, scale=0.3, base=2.0)
+    x[1, 100:400] = 3e38            # every product overflows
+    x[2, 100:400] = -3e38           # ... to the other infinity
+    x[3, 10:300:2] = 0.0            # zero factors between ordinary values
+    x[4, 10:300:3] = 0.0
+    x[4, 11:300:3] = 3e38           # inf * 0 at the second level
+    x[5, 50] = np.inf
+    x[5, 51] = 0.0
+    x[5, 52] = -np.inf
+    x[6, 700:760] = np.nan
+    x[7, 15] = np.nan               # a lone NaN among zeros and huge values
+    x[7, 10:15] = 0.0
+    x[7, 16:22] = 3e38
+    x[8, 0:4096:16] = np.nan        # every thread's first word
+    x[9, 15:4096:16] = np.nan       # ... last word / the neighbour word of the thread before
+    x[10, 5::6] = np.nan            # one NaN per FMA group, every position in turn
+    x[11, 4::6] = np.nan
+    x[12, 3::6] = np.nan
+    x[13, 2::6] = np.nan
+    x[14, 1::6] = np.nan
+    x[15, 0::6] = np.nan
+    if axis == 0:
+        x = np.ascontiguousarray(x.T)
+    counts, _ = run_host(x, axis, masked_value=float("nan"))
+    ref_counts, npairs, _ = bo.bitinformation(x, axis, masked_value=float("nan"))
+    assert np.array_equal(counts, ref_counts)
+    assert counts[0].sum() == npairs
+    import torch
+
+    from xbitinfo_b200.device import PairCounter
+
+    pc = PairCounter(torch.float32, "cuda")
+    for flavour in ("sparse", "dense"):
+        pc.reset()
+        pc.add(torch.from_numpy(x).cuda(), axis, masked_value=float("nan"), flavour=flavour)
+        assert np.array_equal(pc.counts.cpu().numpy(), ref_counts), flavour
+
+
 def test_masked_zero_matches_bit_pattern_only():
     """masked_value=0.0 masks +0.0 but not -0.0 (bit identity)."""
     rng = np.random.default_rng(25)

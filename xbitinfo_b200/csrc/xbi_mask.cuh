@@ -105,6 +105,20 @@ __device__ __forceinline__ unsigned long long fma2_zero(uint32_t w0, uint32_t w1
     return r;
 }
 
+// {a0, a1} * {b0, b1} + {c0, c1}, IEEE
+__device__ __forceinline__ unsigned long long fma2_abc(uint32_t a0, uint32_t a1, uint32_t b0, uint32_t b1, uint32_t c0, uint32_t c1) {
+    unsigned long long r;
+    asm("{.reg .b64 a, b, c; mov.b64 a, {%1, %2}; mov.b64 b, {%3, %4}; mov.b64 c, {%5, %6}; fma.rn.f32x2 %0, a, b, c;}"
+        : "=l"(r)
+        : "r"(a0), "r"(a1), "r"(b0), "r"(b1), "r"(c0), "r"(c1));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2_pairs(unsigned long long a, unsigned long long b, unsigned long long c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 template <int KIND, int MASK, int N>
 __device__ __forceinline__ bool may_contain_masked(const uint32_t (&w)[N], uint32_t mask_lo, uint32_t mask_hi) {
     constexpr int BYTES = Elem<KIND>::kBytes;
@@ -115,13 +129,34 @@ __device__ __forceinline__ bool may_contain_masked(const uint32_t (&w)[N], uint3
             // exactly when the top eight exponent bits are ones (every double NaN/Inf, plus
             // finite |x| >= 2^1017)
             if (BYTES == 4) {
-                // words arrive in aligned register pairs (128-bit loads): FFMA2 on (w[2i], w[2i+1])
-                unsigned long long p[2] = {0ull, 0ull};
+                // Words arrive in aligned register pairs (128-bit loads).  THREE pairs per packed FMA: a * b + c is
+                // NaN whenever one of the three is; without a NaN among them it can only become one through an
+                // infinity (in the data, or a product beyond 3.4e38) meeting a zero factor or an opposite infinity --
+                // a false positive that costs the exact test, never a wrong count.  17 words: 4 FFMA2 + 1 FADD where
+                // x * 0 accumulated pair by pair took 8 + 4 -- issue slots are what the probe costs (the FMA pipe is
+                // idle in these kernels).
+                constexpr int G = (N + 5) / 6;
+                constexpr uint32_t kOne = 0x3F800000u;
+                unsigned long long g[G];
 #pragma unroll
-                for (int i = 0; i + 1 < N; i += 2) p[(i >> 1) & 1] = fma2_zero(w[i], w[i + 1], p[(i >> 1) & 1]);
-                float t = (__uint_as_float((uint32_t)p[0]) + __uint_as_float((uint32_t)(p[0] >> 32))) +
-                          (__uint_as_float((uint32_t)p[1]) + __uint_as_float((uint32_t)(p[1] >> 32)));
-                if (N & 1) t = fma_zero(w[N - 1], t);
+                for (int k = 0; k < G; ++k) {
+                    const int b = 6 * k;
+                    g[k] = fma2_abc(w[b], b + 1 < N ? w[b + 1] : 0u, b + 2 < N ? w[b + 2] : kOne, b + 3 < N ? w[b + 3] : kOne,
+                                    b + 4 < N ? w[b + 4] : 0u, b + 5 < N ? w[b + 5] : 0u);
+                }
+                int n = G;
+#pragma unroll
+                while (n > 1) {
+                    const int m = (n + 2) / 3;
+#pragma unroll
+                    for (int k = 0; k < m; ++k) {
+                        const int b = 3 * k;
+                        const unsigned long long one2 = ((unsigned long long)kOne << 32) | kOne;
+                        g[k] = fma2_pairs(g[b], b + 1 < n ? g[b + 1] : one2, b + 2 < n ? g[b + 2] : 0ull);
+                    }
+                    n = m;
+                }
+                const float t = __uint_as_float((uint32_t)g[0]) + __uint_as_float((uint32_t)(g[0] >> 32));
                 return !(t == t);
             }
             float s[4] = {0.f, 0.f, 0.f, 0.f};
