@@ -125,44 +125,48 @@ __device__ __forceinline__ bool may_contain_masked(const uint32_t (&w)[N], uint3
     if (MASK == kMaskNone) return false;
     if (MASK == kMaskNaN) {
         if (BYTES == 4 || BYTES == 8) {
-            // float32: the word itself; float64: the high word read as a float32 is NaN/Inf
-            // exactly when the top eight exponent bits are ones (every double NaN/Inf, plus
-            // finite |x| >= 2^1017)
-            if (BYTES == 4) {
-                // Words arrive in aligned register pairs (128-bit loads).  THREE pairs per packed FMA: a * b + c is
-                // NaN whenever one of the three is; without a NaN among them it can only become one through an
-                // infinity (in the data, or a product beyond 3.4e38) meeting a zero factor or an opposite infinity --
-                // a false positive that costs the exact test, never a wrong count.  17 words: 4 FFMA2 + 1 FADD where
-                // x * 0 accumulated pair by pair took 8 + 4 -- issue slots are what the probe costs (the FMA pipe is
-                // idle in these kernels).
-                constexpr int G = (N + 5) / 6;
-                constexpr uint32_t kOne = 0x3F800000u;
-                unsigned long long g[G];
+            // (the high word of a double read as a float32 is NaN/Inf exactly when the top eight exponent bits are ones:
+            // every double NaN/Inf, plus finite |x| >= 2^1017)
+            // float32: the word itself.  THREE values per FMA lane: a * b + c
+            // is NaN whenever one of the three is; without a NaN among them it can only become one through an infinity
+            // (in the data, or a product beyond 3.4e38) meeting a zero factor or an opposite infinity -- a false
+            // positive that costs the exact test, never a wrong count.  17 float32 words: 4 FFMA2 + 1 FADD where x * 0
+            // accumulated pair by pair took 8 + 4 -- issue slots are what the probe costs (the FMA pipe is idle in
+            // these kernels).
+            if (BYTES == 8) {
+                // (float64 keeps x * 0 accumulated over the high words: the column walkers' 8 high words per group gain
+                // nothing from the packed form -- configs[2] measured 1 % slower with it -- and the rows kernel is
+                // DRAM-bound in this mode)
+                float s[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-                for (int k = 0; k < G; ++k) {
-                    const int b = 6 * k;
-                    g[k] = fma2_abc(w[b], b + 1 < N ? w[b + 1] : 0u, b + 2 < N ? w[b + 2] : kOne, b + 3 < N ? w[b + 3] : kOne,
-                                    b + 4 < N ? w[b + 4] : 0u, b + 5 < N ? w[b + 5] : 0u);
-                }
-                int n = G;
-#pragma unroll
-                while (n > 1) {
-                    const int m = (n + 2) / 3;
-#pragma unroll
-                    for (int k = 0; k < m; ++k) {
-                        const int b = 3 * k;
-                        const unsigned long long one2 = ((unsigned long long)kOne << 32) | kOne;
-                        g[k] = fma2_pairs(g[b], b + 1 < n ? g[b + 1] : one2, b + 2 < n ? g[b + 2] : 0ull);
-                    }
-                    n = m;
-                }
-                const float t = __uint_as_float((uint32_t)g[0]) + __uint_as_float((uint32_t)(g[0] >> 32));
+                for (int i = 1, c = 0; i < N; i += 2, ++c) s[c & 3] = fma_zero(w[i], s[c & 3]);
+                const float t = (s[0] + s[1]) + (s[2] + s[3]);
                 return !(t == t);
             }
-            float s[4] = {0.f, 0.f, 0.f, 0.f};
+            constexpr int STEP = 1;
+            constexpr int M = N / STEP;  // values to probe
+            constexpr int G = (M + 5) / 6;
+            constexpr uint32_t kOne = 0x3F800000u;
+            auto val = [&](int i, uint32_t missing) -> uint32_t { return i < M ? w[i * STEP + STEP - 1] : missing; };
+            unsigned long long g[G];
 #pragma unroll
-            for (int i = 1, c = 0; i < N; i += 2, ++c) s[c & 3] = fma_zero(w[i], s[c & 3]);
-            const float t = (s[0] + s[1]) + (s[2] + s[3]);
+            for (int k = 0; k < G; ++k) {
+                const int b = 6 * k;
+                g[k] = fma2_abc(val(b, 0u), val(b + 1, 0u), val(b + 2, kOne), val(b + 3, kOne), val(b + 4, 0u), val(b + 5, 0u));
+            }
+            int n = G;
+#pragma unroll
+            while (n > 1) {
+                const int m = (n + 2) / 3;
+#pragma unroll
+                for (int k = 0; k < m; ++k) {
+                    const int b = 3 * k;
+                    const unsigned long long one2 = ((unsigned long long)kOne << 32) | kOne;
+                    g[k] = fma2_pairs(g[b], b + 1 < n ? g[b + 1] : one2, b + 2 < n ? g[b + 2] : 0ull);
+                }
+                n = m;
+            }
+            const float t = __uint_as_float((uint32_t)g[0]) + __uint_as_float((uint32_t)(g[0] >> 32));
             return !(t == t);
         } else {
             uint32_t s[2] = {0u, 0u};
