@@ -1,0 +1,9 @@
+#!/bin/bash
+# narrow chunks interleaved across the warps of a CTA
+mkdir -p gpurun_out
+python -m pytest tests/test_chunked_gpu.py -x -q > gpurun_out/chunk_tests.log 2>&1; echo "chunk tests rc=$?"; tail -2 gpurun_out/chunk_tests.log
+timeout 120 python scripts/fuzz_gpu.py --seconds 50 --seed 41 > gpurun_out/fuzz_gpu.log 2>&1; echo "fuzz rc=$?"; tail -2 gpurun_out/fuzz_gpu.log
+python scripts/perf_chunked.py --compare 2>&1 | grep "axis 0"
+python scripts/perf_chunked.py --compare --dtype float64 --shape 372,721,1440 2>&1 | grep "axis 0"
+python scripts/perf_chunked.py --compare --chunk 744,5,10 2>&1 | grep "axis"
+python scripts/perf_chunked.py --compare --chunk 744,16,16 2>&1 | grep "axis 0"
