@@ -988,51 +988,66 @@ cudaError_t launch_pairs_chunked_walk(const void* x, int dtype, const ChunkGrid&
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int per_sm = dtype_bytes(dtype) == 8 ? 1 : 2;
     const unsigned long long warps = (unsigned long long)sms * per_sm * kWWarps;
-    // outer axes, 4- / 8-byte types: a lane takes 16 bytes of a row when every row of every chunk is made of whole,
-    // aligned 16-byte vectors -- base pointer, every stride and the (regular) chunk length along the innermost
-    // dimension multiples of 16 bytes (ragged edge chunks fall back to one column per lane inside the kernel)
-    ChunkGrid gg = g;
-    gg.vec16 = 0;
     const int bytes = dtype_bytes(dtype);
-    if (bytes >= 4 && g.axis != kD - 1 && g.bounds[kD - 1] == nullptr && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
-        const long long epv = 16 / bytes;
-        bool ok = g.chunk[kD - 1] % epv == 0;
-        for (int d = g.lo; d < kD - 1; ++d) ok = ok && (g.stride[d] % epv == 0);
-        // ... and a chunk has enough columns to fill some lanes of a tile that way.  The two-stream walkers keep
-        // lanes without a column on the fast step, so 8 live lanes are enough (float64, 10x10-column chunks: 1.87 TB/s
-        // with two columns per lane, 0.92 with one); the three-stream walkers wanted 64 vector columns
-        unsigned long long c = 1;
+    // A plan per walker kernel: how many columns a lane takes, hence how many tiles (items) a chunk has.
+    // Outer axes, 4- / 8-byte types: a lane takes 16 bytes of a row when every row of every chunk is made of whole,
+    // aligned 16-byte vectors -- base pointer, every stride and the (regular) chunk length along the innermost
+    // dimension multiples of 16 bytes (ragged edge chunks fall back to one column per lane inside the kernel) -- and a
+    // chunk has enough columns to fill some lanes of a tile that way.  The two-stream walkers keep lanes without a
+    // column on the fast step, so 8 live lanes are enough (float64, 10x10-column chunks: 1.87 TB/s with two columns
+    // per lane, 0.92 with one); the three-stream walkers want 64 vector columns (4x4-column chunks: 4 live lanes of
+    // 32, 0.3 TB/s instead of 1.1).
+    struct Plan {
+        ChunkGrid gg;
+        unsigned long long units, items;
+    };
+    auto make_plan = [&](bool three) {
+        Plan pl;
+        pl.gg = g;
+        pl.gg.vec16 = 0;
+        if (bytes >= 4 && g.axis != kD - 1 && g.bounds[kD - 1] == nullptr && reinterpret_cast<uintptr_t>(x) % 16 == 0) {
+            const long long epv = 16 / bytes;
+            bool ok = g.chunk[kD - 1] % epv == 0;
+            for (int d = g.lo; d < kD - 1; ++d) ok = ok && (g.stride[d] % epv == 0);
+            unsigned long long c = 1;
+            for (int d = 0; d < kD; ++d)
+                if (d != g.axis) c *= g.chunk[d];
+            ok = ok && (force || c / (unsigned long long)epv >= (three ? 64ull : 8ull));  // (force: the tests pin this path on small grids)
+            pl.gg.vec16 = ok ? 1 : 0;
+        }
+        // the work inside a (full) chunk that the warps share: tiles of 32 lanes, one item each (edge chunks: some
+        // items stay empty)
+        unsigned long long cols = 1;
         for (int d = 0; d < kD; ++d)
-            if (d != g.axis) c *= g.chunk[d];
-        ok = ok && (force || c / (unsigned long long)epv >= (flavour == 2 ? 64ull : 8ull));  // (force: the tests pin this path on small grids)
-        gg.vec16 = ok ? 1 : 0;
-    }
-    // the work inside a (full) chunk that the warps share: tiles of 32 lanes
-    unsigned long long cols = 1;
-    for (int d = 0; d < kD; ++d)
-        if (d != g.axis) cols *= g.chunk[d];
-    if (gg.vec16) cols /= (unsigned long long)(16 / bytes);
-    const unsigned long long units = (cols + 31) / 32;
-    if (units * nchunks < 2 * warps && !force) return cudaSuccess;  // too few columns to occupy the GPU this way
+            if (d != g.axis) cols *= g.chunk[d];
+        if (pl.gg.vec16) cols /= (unsigned long long)(16 / bytes);
+        pl.units = (cols + 31) / 32;
+        pl.items = pl.units * nchunks;
+        return pl;
+    };
+    const Plan plan2 = make_plan(false), plan3 = make_plan(true);
+    const Plan& first = (bytes < 4 || flavour == 2) ? plan3 : plan2;  // the kernel that (most likely) runs
+    if (first.units * nchunks < 2 * warps && !force) return cudaSuccess;  // too few columns to occupy the GPU this way
     // the innermost dimension as analysed axis: lanes sit on neighbouring RUNS, each copy instruction touches 32
     // different sectors; worth it only while a lane uses up its sectors, i.e. runs of at least a sector or two
     if (g.axis == kD - 1 && ((unsigned long long)g.chunk[kD - 1] * dtype_bytes(dtype) < 64 || dtype_bytes(dtype) < 4) && !force)
         return cudaSuccess;
-    // items per chunk: one column tile each (edge chunks: some items stay empty)
-    unsigned long long groups = units;
-    if (groups > 0xFFFFFFFFull) return cudaSuccess;
-    const unsigned long long items = groups * nchunks;
+    if (plan2.units > 0xFFFFFFFFull || plan3.units > 0xFFFFFFFFull) return cudaSuccess;
     const unsigned grid = (unsigned)(sms * per_sm);
     const uint32_t mlo = (uint32_t)(mask_bits & 0xFFFFFFFFu), mhi = (uint32_t)(mask_bits >> 32);
     auto run = [&](bool three, const unsigned long long* dens) -> cudaError_t {
+        const Plan& pl = three ? plan3 : plan2;
+        const ChunkGrid& gg = pl.gg;
+        const unsigned long long items = pl.items;
+        const unsigned groups = (unsigned)pl.units;
         switch (dtype) {
-            case XBI_U8: return dispatch_walk<kU8>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
-            case XBI_U16: return dispatch_walk<kU16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
-            case XBI_U32: return dispatch_walk<kU32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
-            case XBI_U64: return dispatch_walk<kU64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
-            case XBI_F16: return dispatch_walk<kF16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
-            case XBI_F32: return dispatch_walk<kF32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
-            case XBI_F64: return dispatch_walk<kF64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, (unsigned)groups, grid, stream, three, dens);
+            case XBI_U8: return dispatch_walk<kU8>(x, gg, transform, mask_mode, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+            case XBI_U16: return dispatch_walk<kU16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+            case XBI_U32: return dispatch_walk<kU32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+            case XBI_U64: return dispatch_walk<kU64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+            case XBI_F16: return dispatch_walk<kF16>(x, gg, transform, mask_mode, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+            case XBI_F32: return dispatch_walk<kF32>(x, gg, transform, mask_mode, mlo, mhi, counts, items, groups, grid, stream, three, dens);
+            case XBI_F64: return dispatch_walk<kF64>(x, gg, transform, mask_mode, mlo, mhi, counts, items, groups, grid, stream, three, dens);
             default: return cudaErrorInvalidValue;
         }
     };
