@@ -97,7 +97,7 @@ template <int KIND, int MASK, bool XFORM, bool RING, bool LASTAX>
 __global__ void __launch_bounds__(kWThreads, Elem<KIND>::kWords == 1 ? 2 : 1)
 k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGrid g, uint32_t mask_lo, uint32_t mask_hi,
                      unsigned long long* __restrict__ counts, unsigned long long items, unsigned groups,
-                     const unsigned long long* dens) {
+                     const unsigned long long* dens, unsigned cblock) {
     if (dens != nullptr && !walk_density_is_scattered(dens)) return;  // the two-stream walkers take this array
     constexpr int BYTES = Elem<KIND>::kBytes;
     static_assert(!RING || BYTES >= 4, "cp.async moves 4 bytes at least");
@@ -193,7 +193,19 @@ k_pairs_chunked_walk(const void* __restrict__ x, const __grid_constant__ ChunkGr
     unsigned cur_chunk = 0xFFFFFFFFu;
     ChunkBox box;
     for (unsigned long long item = item_lo + warp; item < item_hi; item += kWWarps) {
-        const unsigned cid = (unsigned)(item / groups), grp = (unsigned)(item - (unsigned long long)cid * groups);
+        // (cblock > 1: the items of `cblock` neighbouring chunks interleaved tile by tile, see k_pairs_chunked_walk2)
+        unsigned cid, grp;
+        if (cblock <= 1u) {
+            cid = (unsigned)(item / groups);
+            grp = (unsigned)(item - (unsigned long long)cid * groups);
+        } else {
+            const unsigned long long per = (unsigned long long)cblock * groups;
+            const unsigned long long blk = item / per, r = item - blk * per;
+            const unsigned long long first = blk * cblock, nchunks = items / groups;
+            const unsigned bs = (unsigned)(nchunks - first < cblock ? nchunks - first : cblock);
+            grp = (unsigned)(r / bs);
+            cid = (unsigned)(first + (r - (unsigned long long)grp * bs));
+        }
         if (cid != cur_chunk) {
             if (cur_chunk != 0xFFFFFFFFu) flush_chunk(cur_chunk);
             cur_chunk = cid;
@@ -935,7 +947,10 @@ cudaError_t launch_walk_ax(const void* x, const ChunkGrid& g, uint32_t mlo, uint
     auto kern = k_pairs_chunked_walk<KIND, MASK, XFORM, RING, LASTAX>;
     static std::atomic<unsigned long long> attr_set{0ull};
     if (cudaError_t e = set_smem_once(kern, smem, attr_set)) return e;
-    kern<<<grid, kWThreads, smem, stream>>>(x, g, mlo, mhi, counts, items, groups, dens);
+    // chunks narrower than a tile along an outer axis: eight neighbouring chunks interleaved, as for the two-stream walkers
+    const unsigned lanes_per_row3 = g.chunk[kD - 1] / (g.vec16 ? (unsigned)(16 / BYTES) : 1u);
+    const unsigned cblock3 = (!LASTAX && g.axis != kD - 1 && lanes_per_row3 < 32u && g.bounds[kD - 1] == nullptr) ? 8u : 1u;
+    kern<<<grid, kWThreads, smem, stream>>>(x, g, mlo, mhi, counts, items, groups, dens, cblock3);
     return cudaGetLastError();
 }
 
