@@ -425,11 +425,19 @@ constexpr int kEvP = 6;              // planes of the correction counters: 63 ev
 
 template <bool LASTAX>
 struct Ring2 {
-    static constexpr int kSlots = LASTAX ? 5 : 6;
+    static constexpr int kSlots = 6;
 };
 template <int BYTES, bool LASTAX>
 constexpr size_t ring2_bytes() {
-    return 16 + (size_t)kWWarps * Ring2<LASTAX>::kSlots * 32 * (LASTAX ? kRows2 * BYTES + 16 : kRows2 * BYTES);
+    return 16 + (size_t)kWWarps * Ring2<LASTAX>::kSlots * 32 * (kRows2 * BYTES);
+}
+// LASTAX: a lane's cell is its 16 elements (64 / 128 bytes) with the 16-byte pieces XOR-swizzled by the lane number, so that
+// the 128-bit reads of a quarter warp (8 lanes, same piece) hit 8 different bank groups without padding the cells -- the
+// padding (+16 bytes per lane) cost the ring its sixth slot, and with 4 instead of 5 steps in flight the walkers along the
+// innermost axis waited on memory (`long_scoreboard` 3.06 warps per issue in ncu)
+template <int BYTES>
+__device__ __forceinline__ uint32_t ring2_swz16(uint32_t run) {  // 16 x the swizzle term of a run (a lane) of the tile
+    return BYTES == 4 ? ((run >> 1) & 3u) << 4 : (run & 7u) << 4;
 }
 
 // The correction planes live in LOCAL memory on purpose: they are touched at validity boundaries only, and the dozen
@@ -477,7 +485,7 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
     static_assert(BYTES >= 4, "4- and 8-byte element types");
     constexpr int kSlots = Ring2<LASTAX>::kSlots;
     constexpr int kAhead = kSlots - 1;
-    constexpr uint32_t kLanePitch = (uint32_t)(kRows2 * BYTES + 16);  // LASTAX: a lane's 16 elements + 16 (conflict-free 128-bit reads)
+    constexpr uint32_t kLanePitch = (uint32_t)(kRows2 * BYTES);  // LASTAX: a lane's 16 elements, pieces swizzled (ring2_swz16)
     constexpr uint32_t kSlotBytes = LASTAX ? 32u * kLanePitch : (uint32_t)kRows2 * 32u * (uint32_t)BYTES;
     using L = Ladder<3, 8, kLogR2>;
     using EP = EventPlanes<NW, kEvP>;
@@ -673,7 +681,12 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                 uint32_t co[LASTAX ? NP : 1];            // (start of run j * RPI + lane / NP, minus xa) / 16 + lane % NP
                 uint32_t colive = 0u;                    // bit j: that run exists
                 bool coop = false;
-                const uint32_t cbase = ring0 + (lane / NP) * kLanePitch + (lane % NP) * 16u;
+                // (cell of run j * RPI + lane / NP, piece lane % NP swizzled by that run's number: float32 -- the term
+                // does not depend on j; float64 -- it alternates with the parity of j)
+                const uint32_t cbase = ring0 + (lane / NP) * kLanePitch;
+                const uint32_t cpiece0 = ((lane % NP) << 4) ^ ring2_swz16<BYTES>(lane / NP);
+                const uint32_t cpiece1 = ((lane % NP) << 4) ^ ring2_swz16<BYTES>((uint32_t)RPI + lane / NP);
+                const uint32_t myswz = LASTAX ? ring2_swz16<BYTES>(lane) : 0u;
                 if constexpr (LASTAX) {
                     coop = vec && offsets_fit;
                     if (coop) {
@@ -699,7 +712,7 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                                 for (int j = 0; j < NP; ++j) {
                                     if ((colive >> j) & 1u) {
                                         const char* src = xa + 16ull * (unsigned long long)(co[j] + issued * (unsigned)NP);
-                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstw + (uint32_t)(j * RPI) * kLanePitch), "l"(src) : "memory");
+                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dstw + (uint32_t)(j * RPI) * kLanePitch + ((j & 1) ? cpiece1 : cpiece0)), "l"(src) : "memory");
                                     }
                                 }
                             } else if (live) {
@@ -708,11 +721,12 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                                 if (vec && left >= (unsigned)RS) {
 #pragma unroll
                                     for (int v = 0; v < NP; ++v)
-                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16 * v), "l"(qs + 16 * v) : "memory");
+                                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + ((16u * v) ^ myswz)), "l"(qs + 16 * v) : "memory");
                                 } else {
 #pragma unroll
                                     for (int u = 0; u < RS; ++u)
-                                        if ((unsigned)u < left) cpa_elem<BYTES>(dst + u * kRowP, qs + u * BYTES);
+                                        if ((unsigned)u < left)
+                                            cpa_elem<BYTES>(dst + (((uint32_t)(u * BYTES) & ~15u) ^ myswz) + ((uint32_t)(u * BYTES) & 15u), qs + u * BYTES);
                                 }
                             }
                         } else if (live) {
@@ -757,7 +771,7 @@ k_pairs_chunked_walk2(const void* __restrict__ x, const __grid_constant__ ChunkG
                         for (int v = 0; v < kRows2 * BYTES / 16; ++v) {
                             asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                                          : "=r"(flat[4 * v]), "=r"(flat[4 * v + 1]), "=r"(flat[4 * v + 2]), "=r"(flat[4 * v + 3])
-                                         : "r"(src + (LASTAX ? 16u * v : (uint32_t)v * kRowP)));
+                                         : "r"(src + (LASTAX ? ((16u * v) ^ myswz) : (uint32_t)v * kRowP)));
                         }
                     } else {
 #pragma unroll
